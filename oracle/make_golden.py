@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.pt from the real reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+The vectors pin oracle/cat_oracle.py (tests/test_oracle_golden.py) and, through it, the CUDA path.
+They are produced by the unmodified reference classes (InceptionDistiller, shrink, init_net) driven
+through set_input + optimize_parameters, exactly as trainer.py:128-133 does.
+"""
+import copy
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.ref_harness import build_reference_distiller, discriminator_arch, generator_arch  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+CASES = {
+    # pix2pix-style (scripts/pix2pix/cityscapes/train_inception_student_5p6B.sh): BatchNorm with
+    # running stats, aligned pairs, hinge GAN, 6-channel D input.
+    'pix2pix_bn_hinge': dict(norm='batch', gan_mode='hinge', dataset_mode='aligned',
+                             lambda_distill=0.5, lambda_recon=100.0, batch_size=3, height=32,
+                             width=32, frac=0.2),
+    # CycleGAN-style (scripts/cycle_gan/horse2zebra/train_inception_student_2p6B.sh):
+    # InstanceNorm (affine), unaligned, lsgan, recon against the teacher output, lambda_recon 5.
+    'cyclegan_in_lsgan': dict(norm='instance', gan_mode='lsgan', dataset_mode='unaligned',
+                              lambda_distill=1.0, lambda_recon=5.0, batch_size=2, height=32,
+                              width=48, frac=0.25),
+}
+
+
+def snap(sd):
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def make_case(name, cfg):
+    probe, _ = build_reference_distiller(norm=cfg['norm'], teacher_ngf=12, student_ngf=8, ndf=8,
+                                         height=cfg['height'], width=cfg['width'],
+                                         batch_size=cfg['batch_size'], do_shrink=False)
+    target = probe.netG_teacher.n_macs * cfg['frac']
+    model, opt = build_reference_distiller(norm=cfg['norm'], teacher_ngf=12, student_ngf=8, ndf=8,
+                                           height=cfg['height'], width=cfg['width'],
+                                           batch_size=cfg['batch_size'], target_flops=target,
+                                           gan_mode=cfg['gan_mode'],
+                                           dataset_mode=cfg['dataset_mode'],
+                                           lambda_distill=cfg['lambda_distill'],
+                                           lambda_recon=cfg['lambda_recon'])
+    # after the first evaluate_model the reference puts the student back in train mode
+    # (inception_distiller.py:280); the golden steps are recorded in that steady state.
+    model.netG_student.train()
+    # D/student weights: larger than N(0,0.02) so that activations/gradients are well scaled.
+    g = torch.Generator().manual_seed(7)
+    for net in (model.netG_student, model.netD):
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                m.weight.data = m.weight.data * 5.0
+                if m.bias is not None:
+                    m.bias.data = 0.05 * torch.randn(m.bias.shape, generator=g)
+    B, H, W = cfg['batch_size'], cfg['height'], cfg['width']
+    d_in = 6 if cfg['dataset_mode'] == 'aligned' else 3
+    fix = {
+        'name': name,
+        'teacher_arch': generator_arch(model.netG_teacher, opt),
+        'student_arch': generator_arch(model.netG_student, opt),
+        'D_arch': discriminator_arch(model.netD, opt, d_in),
+        'hp': dict(gan_mode=opt.gan_mode, aligned=opt.dataset_mode == 'aligned',
+                   lambda_recon=float(opt.lambda_recon), lambda_gan=float(opt.lambda_gan),
+                   lambda_distill=float(opt.lambda_distill), lr=float(opt.lr),
+                   beta1=float(opt.beta1), student_training=True),
+        'teacher_sd': snap(model.netG_teacher.state_dict()),
+        'student_sd0': snap(model.netG_student.state_dict()),
+        'D_sd0': snap(model.netD.state_dict()),
+        'steps': [],
+    }
+    gen = torch.Generator().manual_seed(233)
+    for it in range(2):
+        A = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
+        Bt = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
+        data = {'A': A, 'B': Bt, 'A_paths': ['x'] * B, 'B_paths': ['x'] * B}
+        model.set_input(data)
+        # optimize_parameters, split open only to snapshot gradients between the phases
+        model.forward()
+        model.set_requires_grad(model.netD, True)
+        model.optimizer_D.zero_grad()
+        model.backward_D()
+        D_grads = {k: p.grad.detach().clone() for k, p in model.netD.named_parameters()}
+        model.optimizer_D.step()
+        model.set_requires_grad(model.netD, False)
+        model.optimizer_G.zero_grad()
+        Sacts = {k.replace('cpu', ''): v for k, v in model.Sacts.items()}
+        for v in Sacts.values():
+            v.retain_grad()
+        model.backward_G(it)
+        S_grads = {k: p.grad.detach().clone() for k, p in model.netG_student.named_parameters()}
+        Sact_grads = {k: v.grad.detach().clone() for k, v in Sacts.items()}
+        model.optimizer_G.step()
+        step = {
+            'real_A': A, 'real_B': Bt,
+            'losses': {k: float(v) for k, v in model.get_current_losses().items()},
+            'student_sd_after': snap(model.netG_student.state_dict()),
+            'D_sd_after': snap(model.netD.state_dict()),
+        }
+        if it == 0:
+            step.update({
+                'Tfake_B': model.Tfake_B.detach().clone(), 'Sfake_B': model.Sfake_B.detach().clone(),
+                'Tacts': {k.replace('cpu', ''): v.detach().clone() for k, v in model.Tacts.items()},
+                'Sacts': {k: v.detach().clone() for k, v in Sacts.items()},
+                'Sact_grads': Sact_grads, 'S_grads': S_grads, 'D_grads': D_grads,
+            })
+        fix['steps'].append(step)
+    return fix
+
+
+def main():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for name, cfg in CASES.items():
+        fix = make_case(name, copy.deepcopy(cfg))
+        path = os.path.join(OUT_DIR, name + '.pt')
+        torch.save(fix, path)
+        print(name, 'student widths', fix['student_arch']['widths'], 'blocks',
+              fix['student_arch']['blocks'][:2], 'losses', fix['steps'][0]['losses'],
+              '-> %.2f MB' % (os.path.getsize(path) / 1e6))
+
+
+if __name__ == '__main__':
+    main()
