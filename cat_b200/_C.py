@@ -1,0 +1,118 @@
+"""ctypes binding of libcatb200.so (the C ABI declared in include/catb200.h).
+
+The library is built in-tree (cat_b200/lib/libcatb200.so) by ``__graft_entry__.build()`` or
+``make -C cat_b200/csrc``.  There is no CPU or PyTorch fallback: if the library is missing, or no sm_100
+device is present when a kernel is requested, this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libcatb200.so')
+
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH = 0, 1, 2, 3
+PAD_ZERO, PAD_REFLECT = 0, 1
+GAN_MODES = {'hinge': 0, 'lsgan': 1, 'vanilla': 2}
+
+
+class GatherUnit(C.Structure):
+    _fields_ = [('dr', C.c_int8), ('ds', C.c_int8), ('cu', C.c_int16)]
+
+
+class WeightUnit(C.Structure):
+    _fields_ = [('w_off', C.c_int32), ('sn_w', C.c_int32), ('sc_w', C.c_int32), ('nvalid', C.c_int32)]
+
+
+class IgemmDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        'N', 'H', 'W', 'ldx', 'x_coff', 'OH', 'OW', 'ldy', 'y_coff', 'o_step', 'o_ph', 'o_pw', 'OHs', 'OWs',
+        'sn', 'sd', 'pad_mode', 'n_units', 'n_rows', 'n_tile', 'act', 'accumulate', 'y_is_f32', 'reserved')]
+
+
+class CatbError(RuntimeError):
+    pass
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_DP = C.POINTER(IgemmDesc)
+
+# name -> argtypes (all return int unless listed in _SPECIAL)
+_PROTOS = {
+    'catb_init': [_I],
+    'catb_pack_weights': [_DP, _P, _P, _P, _P],
+    'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
+    'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
+    'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
+    'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
+    'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'catb_dwconv_bwd_data': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'catb_dwconv_bwd_weight': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'catb_norm_stats': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    'catb_norm_finalize': [_P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
+    'catb_norm_apply': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    'catb_norm_bwd_reduce': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    'catb_norm_bwd_apply': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I,
+                            _P, _P, _P],
+    'catb_nchw_to_nhwc': [_P, _I, _I, _I, _I, _P, _I, _I, _P],
+    'catb_nhwc_to_nchw': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    'catb_copy_channels': [_P, _I, _I, _P, _I, _I, _L, _I, _P],
+    'catb_act_bwd': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P],
+    'catb_channel_sum': [_P, _I, _I, _L, _I, _P, _P],
+    'catb_reflect_fold': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'catb_add': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _L, _I, _P],
+    'catb_gan_loss': [_P, _L, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P],
+    'catb_l1_loss': [_P, _I, _I, _P, _I, _I, _L, _I, _I, _F, _P, _P, _I, _I, _P, _I, _I, _P],
+    'catb_gram': [_P, _I, _I, _I, _L, _I, _P, _P],
+    'catb_ka_finish': [_P, _P, _I, _F, _P, _P, _P, _P],
+    'catb_ka_bwd': [_P, _I, _I, _I, _L, _I, _P, _P, _I, _I, _I, _P],
+    'catb_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P],
+}
+_SPECIAL = {
+    'catb_version': ([], C.c_char_p),
+    'catb_last_error_string': ([], C.c_char_p),
+    'catb_packed_weight_bytes': ([_I, _I, _I], C.c_size_t),
+}
+EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))
+
+_lib = None
+_inited_devices = set()
+
+
+def load():
+    """Load libcatb200.so and declare its prototypes (no GPU needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CatbError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                        f'or `make -C cat_b200/csrc` -- cat_b200 has no fallback path')
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, (argtypes, restype) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def init(device=0):
+    lib = load()
+    if device not in _inited_devices:
+        check(lib.catb_init(int(device)), 'catb_init')
+        _inited_devices.add(device)
+    return lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = load().catb_last_error_string().decode()
+        raise CatbError(f'{what} failed with status {status}: {msg}')
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    check(getattr(load(), name)(*args), name)

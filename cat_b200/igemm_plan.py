@@ -1,0 +1,208 @@
+"""Host-side description of the implicit GEMMs: K-unit tables and geometry descriptors.
+
+Every dense convolution of the CAT path (and its data / weight gradients) is expressed as
+    Y[row, n] = sum_units gather(X)[row, unit] . W[n, unit]
+where a *unit* is 8 consecutive channels of one filter tap (include/catb200.h, catb_gather_unit /
+catb_weight_unit).  This module builds the unit tables for
+  * nn.Conv2d forward (zero or reflect padding, stride 1/2)        -> conv_fprop_units
+  * its input gradient (optionally phase-decomposed for stride 2)   -> conv_dgrad_units
+  * nn.ConvTranspose2d forward / input gradient                     -> convT_fprop_units / convT_dgrad_units
+and K-concatenations of several convolutions that share an input or output buffer (the six branches
+of InvertedResidualChannels, reference models/modules/inception_modules.py:124-180,230-236).
+
+`emulate_fprop` / `emulate_wgrad` restate the device gather in plain torch so that the tables can be
+validated against F.conv2d on CPU (tests/test_plan_cpu.py); they are test helpers, not a fallback.
+"""
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+import torch
+
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+
+def cpad(c: int) -> int:
+    """Channel count padded to the 16-byte unit (8 bf16)."""
+    return (c + 7) // 8 * 8
+
+
+@dataclass
+class Units:
+    """Parallel lists: gather side (dr, ds, cu) and weight side (w_off, sn_w, sc_w, nvalid)."""
+    g: List[Tuple[int, int, int]] = field(default_factory=list)
+    w: List[Tuple[int, int, int, int]] = field(default_factory=list)
+
+    def __len__(self):
+        return len(self.g)
+
+    def extend(self, other: 'Units'):
+        self.g.extend(other.g)
+        self.w.extend(other.w)
+        return self
+
+    def phase(self, a: int, b: int) -> 'Units':
+        """Units that contribute to output rows/cols of parity (a, b) when sd == 2, sn == 1."""
+        out = Units()
+        for gu, wu in zip(self.g, self.w):
+            if (a + gu[0]) % 2 == 0 and (b + gu[1]) % 2 == 0:
+                out.g.append(gu)
+                out.w.append(wu)
+        return out
+
+
+def conv_fprop_units(w_off, Cout, Cin, R, S, pad, cu0=0) -> Units:
+    """nn.Conv2d weight [Cout, Cin, R, S] at arena offset w_off; input channels start at unit cu0 of
+    the gathered buffer.  GEMM rows = output channels.  Used for fprop and (same tables) wgrad."""
+    u = Units()
+    for r in range(R):
+        for s in range(S):
+            for cu in range(cpad(Cin) // 8):
+                u.g.append((r - pad, s - pad, cu0 + cu))
+                u.w.append((w_off + cu * 8 * R * S + r * S + s, Cin * R * S, R * S, max(0, min(8, Cin - cu * 8))))
+    return u
+
+
+def conv_dgrad_units(w_off, Cout, Cin, R, S, q, cu0=0) -> Units:
+    """Input gradient of the same convolution: gather dY with offset dr = q - r (q = pad for a direct
+    zero-padded gradient, q = 0 when the result is the gradient w.r.t. the *padded* frame of a reflect
+    padded conv, folded afterwards by catb_reflect_fold).  GEMM rows = input channels."""
+    u = Units()
+    for r in range(R):
+        for s in range(S):
+            for nu in range(cpad(Cout) // 8):
+                u.g.append((q - r, q - s, cu0 + nu))
+                u.w.append((w_off + nu * 8 * Cin * R * S + r * S + s, R * S, Cin * R * S, max(0, min(8, Cout - nu * 8))))
+    return u
+
+
+def convT_fprop_units(w_off, Cin, Cout, R, S, pad, cu0=0) -> Units:
+    """nn.ConvTranspose2d weight [Cin, Cout, R, S]: Y[oh] = sum X[(oh + pad - r)/stride] W[c, n, r]
+    (use with sn=1, sd=stride).  GEMM rows = output channels."""
+    u = Units()
+    for r in range(R):
+        for s in range(S):
+            for cu in range(cpad(Cin) // 8):
+                u.g.append((pad - r, pad - s, cu0 + cu))
+                u.w.append((w_off + cu * 8 * Cout * R * S + r * S + s, R * S, Cout * R * S, max(0, min(8, Cin - cu * 8))))
+    return u
+
+
+def convT_dgrad_units(w_off, Cin, Cout, R, S, pad, cu0=0) -> Units:
+    """Input gradient of the transposed conv = a strided correlation over dY (sn=stride, sd=1).
+    GEMM rows = input channels.  The same tables drive its weight gradient (lattice tensor = X)."""
+    u = Units()
+    for r in range(R):
+        for s in range(S):
+            for nu in range(cpad(Cout) // 8):
+                u.g.append((r - pad, s - pad, cu0 + nu))
+                u.w.append((w_off + nu * 8 * R * S + r * S + s, Cout * R * S, R * S, max(0, min(8, Cout - nu * 8))))
+    return u
+
+
+def choose_n_tile(n_rows: int) -> int:
+    """Rows of the packed weight image per CTA tile: a multiple of 16, at most 256, tiles balanced."""
+    np16 = (n_rows + 15) // 16 * 16
+    n_tiles = (np16 + 255) // 256
+    per = (np16 + n_tiles - 1) // n_tiles
+    return (per + 15) // 16 * 16
+
+
+@dataclass
+class Geometry:
+    """The integer fields of catb_igemm_desc that do not depend on the unit table."""
+    N: int
+    H: int
+    W: int
+    ldx: int
+    x_coff: int
+    OH: int
+    OW: int
+    ldy: int
+    y_coff: int
+    sn: int = 1
+    sd: int = 1
+    pad_mode: int = PAD_ZERO
+    o_step: int = 1
+    o_ph: int = 0
+    o_pw: int = 0
+
+    @property
+    def OHs(self):
+        return (self.OH - self.o_ph + self.o_step - 1) // self.o_step
+
+    @property
+    def OWs(self):
+        return (self.OW - self.o_pw + self.o_step - 1) // self.o_step
+
+
+# ------------------------------------------------------------------------------------------------
+# torch restatement of the device gather (test helper)
+# ------------------------------------------------------------------------------------------------
+def _reflect(i, L):
+    i = i.abs()
+    return torch.where(i >= L, 2 * (L - 1) - i, i)
+
+
+def _gather_unit(x, geo: Geometry, gu, rows):
+    """x: [N,H,W,ldx] float tensor; rows: (n, oh, ow) index tensors -> [M, 8] gathered values."""
+    n, oh, ow = rows
+    h = oh * geo.sn + gu[0]
+    w = ow * geo.sn + gu[1]
+    ok = torch.ones_like(h, dtype=torch.bool)
+    if geo.sd == 2:
+        ok &= (h % 2 == 0) & (w % 2 == 0)
+        h = torch.div(h, 2, rounding_mode='floor')
+        w = torch.div(w, 2, rounding_mode='floor')
+    if geo.pad_mode == PAD_REFLECT:
+        h, w = _reflect(h, geo.H), _reflect(w, geo.W)
+    ok &= (h >= 0) & (h < geo.H) & (w >= 0) & (w < geo.W)
+    hc, wc = h.clamp(0, geo.H - 1), w.clamp(0, geo.W - 1)
+    c0 = geo.x_coff + gu[2] * 8
+    vals = x[n, hc, wc, c0:c0 + 8]
+    return vals * ok.unsqueeze(1).to(vals.dtype)
+
+
+def _lattice_rows(geo: Geometry):
+    n = torch.arange(geo.N).view(-1, 1, 1)
+    oh = (geo.o_ph + torch.arange(geo.OHs) * geo.o_step).view(1, -1, 1)
+    ow = (geo.o_pw + torch.arange(geo.OWs) * geo.o_step).view(1, 1, -1)
+    n, oh, ow = torch.broadcast_tensors(n, oh, ow)
+    return n.reshape(-1), oh.reshape(-1), ow.reshape(-1)
+
+
+def emulate_fprop(geo: Geometry, units: Units, n_rows, x, arena, y, bias=None, accumulate=False):
+    """y[N,OH,OW,ldy] (float) slice [y_coff : y_coff+n_rows] (+)= gather(x) . W^T on the sub-lattice."""
+    rows = _lattice_rows(geo)
+    acc = torch.zeros(rows[0].numel(), n_rows, dtype=x.dtype)
+    ridx = torch.arange(n_rows)
+    for gu, wu in zip(units.g, units.w):
+        if wu[3] == 0:
+            continue
+        xg = _gather_unit(x, geo, gu, rows)[:, :wu[3]]
+        q = torch.arange(wu[3])
+        wmat = arena[wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]]
+        acc += xg @ wmat.T.to(x.dtype)
+    if bias is not None:
+        acc += bias.view(1, -1)
+    n, oh, ow = rows
+    if accumulate:
+        acc += y[n, oh, ow, geo.y_coff:geo.y_coff + n_rows]
+    y[n, oh, ow, geo.y_coff:geo.y_coff + n_rows] = acc
+    return y
+
+
+def emulate_wgrad(geo: Geometry, units: Units, n_rows, x, y, grad_arena):
+    """grad_arena[w(row c, unit, q)] += sum_rows y[row, c] * gather(x)[row, unit*8+q]."""
+    rows = _lattice_rows(geo)
+    n, oh, ow = rows
+    ymat = y[n, oh, ow, geo.y_coff:geo.y_coff + n_rows]
+    ridx = torch.arange(n_rows)
+    for gu, wu in zip(units.g, units.w):
+        if wu[3] == 0:
+            continue
+        xg = _gather_unit(x, geo, gu, rows)[:, :wu[3]]
+        contrib = ymat.T @ xg  # [n_rows, nvalid]
+        q = torch.arange(wu[3])
+        idx = wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]
+        grad_arena.index_put_((idx.reshape(-1),), contrib.reshape(-1).to(grad_arena.dtype), accumulate=True)
+    return grad_arena

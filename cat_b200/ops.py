@@ -1,0 +1,231 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw pointers + current stream out.
+
+PyTorch is used only for device memory and streams; every computation below is a kernel of
+libcatb200.so.  All wrappers enqueue on ``torch.cuda.current_stream()`` and never synchronise, so a
+sequence of calls can be captured into a CUDA graph.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _C
+from .igemm_plan import Geometry, Units, choose_n_tile, cpad
+
+ACT = {'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'leaky': _C.ACT_LEAKY02, 'tanh': _C.ACT_TANH}
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _C.CatbError('cat_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    _C.init(torch.cuda.current_device())
+
+
+class Act:
+    """A view of an NHWC bf16 activation buffer: channel slice [coff, coff+C) of pitch ld."""
+    __slots__ = ('t', 'N', 'H', 'W', 'ld', 'coff', 'C')
+
+    def __init__(self, t, coff=0, C=None):
+        assert t.dtype == BF16 and t.dim() == 4 and t.is_contiguous()
+        self.t = t
+        self.N, self.H, self.W, self.ld = t.shape
+        self.coff = coff
+        self.C = self.ld - coff if C is None else C
+        assert self.coff % 8 == 0 and self.C % 8 == 0 and self.coff + self.C <= self.ld
+
+    @staticmethod
+    def empty(N, H, W, C, device, zero=False):
+        Cp = cpad(C)
+        t = (torch.zeros if zero else torch.empty)(N, H, W, Cp, dtype=BF16, device=device)
+        return Act(t)
+
+    def slice(self, coff, C):
+        return Act(self.t, self.coff + coff, C)
+
+    @property
+    def pixels(self):
+        return self.N * self.H * self.W
+
+    @property
+    def HW(self):
+        return self.H * self.W
+
+    def args(self):
+        return _p(self.t), self.ld, self.coff
+
+
+_G_DT = np.dtype([('dr', 'i1'), ('ds', 'i1'), ('cu', '<i2')])
+
+
+def units_to_device(units: Units, device):
+    g = np.array(units.g, dtype=np.int64).reshape(-1, 3)
+    ga = np.zeros(len(units), dtype=_G_DT)
+    assert np.abs(g[:, :2]).max(initial=0) < 127 and g[:, 2].max(initial=0) < 32767
+    ga['dr'], ga['ds'], ga['cu'] = g[:, 0], g[:, 1], g[:, 2]
+    wa = np.array(units.w, dtype=np.int32).reshape(-1, 4)
+    gt = torch.from_numpy(ga.view(np.int32).copy()).to(device)
+    wt = torch.from_numpy(wa.copy()).to(device)
+    return gt, wt
+
+
+class Gemm:
+    """One implicit GEMM: geometry + unit tables (+ packed bf16 weights for the fprop direction)."""
+
+    def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True):
+        assert len(units) > 0 and n_rows > 0
+        self.geo, self.units, self.n_rows = geo, units, n_rows
+        self.n_units = len(units)
+        self.n_tile = choose_n_tile(n_rows)
+        self.gt, self.wt = units_to_device(units, device)
+        self.packed = None
+        if need_pack:
+            nbytes = _C.load().catb_packed_weight_bytes(n_rows, self.n_units, self.n_tile)
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def desc(self, act=0, accumulate=False, y_is_f32=False, geo=None):
+        g = geo or self.geo
+        d = _C.IgemmDesc()
+        d.N, d.H, d.W, d.ldx, d.x_coff = g.N, g.H, g.W, g.ldx, g.x_coff
+        d.OH, d.OW, d.ldy, d.y_coff = g.OH, g.OW, g.ldy, g.y_coff
+        d.o_step, d.o_ph, d.o_pw, d.OHs, d.OWs = g.o_step, g.o_ph, g.o_pw, g.OHs, g.OWs
+        d.sn, d.sd, d.pad_mode = g.sn, g.sd, g.pad_mode
+        d.n_units, d.n_rows, d.n_tile = self.n_units, self.n_rows, self.n_tile
+        d.act, d.accumulate, d.y_is_f32 = int(act), int(bool(accumulate)), int(bool(y_is_f32))
+        return d
+
+    def pack(self, arena):
+        d = self.desc()
+        _C.call('catb_pack_weights', C.byref(d), _p(self.wt), _p(arena), _p(self.packed), _stream())
+
+    def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False):
+        d = self.desc(act, accumulate, y_is_f32)
+        _C.call('catb_igemm_fprop', C.byref(d), _p(self.gt), _p(x), _p(self.packed), _p(bias), _p(y), _stream())
+
+    def wgrad(self, x, y, grad_arena):
+        d = self.desc()
+        _C.call('catb_igemm_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(grad_arena), _stream())
+
+    # SIMT restatements (tests only)
+    def ref_fprop(self, arena, x, y, bias=None, act=0, accumulate=False, y_is_f32=False):
+        d = self.desc(act, accumulate, y_is_f32)
+        _C.call('catb_ref_fprop', C.byref(d), _p(self.gt), _p(self.wt), _p(arena), _p(x), _p(bias), _p(y), _stream())
+
+    def ref_wgrad(self, x, y, grad_arena):
+        d = self.desc()
+        _C.call('catb_ref_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(grad_arena), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise / reduction wrappers
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(src, dst: Act):
+    N, Cc, H, W = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous() and (N, H, W) == (dst.N, dst.H, dst.W)
+    _C.call('catb_nchw_to_nhwc', _p(src), N, Cc, H, W, _p(dst.t), dst.ld, dst.coff, _stream())
+
+
+def nhwc_to_nchw(src: Act, Cc, out=None):
+    if out is None:
+        out = torch.empty(src.N, Cc, src.H, src.W, dtype=torch.float32, device=src.t.device)
+    _C.call('catb_nhwc_to_nchw', _p(src.t), src.ld, src.coff, src.N, Cc, src.H, src.W, _p(out), _stream())
+    return out
+
+
+def copy_channels(src: Act, dst: Act, Cc):
+    _C.call('catb_copy_channels', *src.args(), *dst.args(), src.pixels, Cc, _stream())
+
+
+def norm_stats(x: Act, per_sample, sums):
+    _C.call('catb_norm_stats', *x.args(), x.N, x.HW, x.C, int(per_sample), _p(sums), _stream())
+
+
+def norm_finalize(sums, G, Cc, count, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_rstd):
+    _C.call('catb_norm_finalize', _p(sums), G, Cc, float(count), float(eps), float(momentum), _p(gamma), _p(beta),
+            _p(rmean), _p(rvar), _p(scale), _p(shift), _p(mean_rstd), _stream())
+
+
+def norm_apply(x: Act, y: Act, scale, shift, per_sample, act, residual: Act = None):
+    r = residual.args() if residual is not None else (None, 0, 0)
+    _C.call('catb_norm_apply', *x.args(), *y.args(), *r, x.N, x.HW, x.C, int(per_sample), _p(scale), _p(shift),
+            int(act), _stream())
+
+
+def norm_bwd_reduce(dout: Act, out: Act, x: Act, per_sample, mean_rstd, act, red):
+    o = out.args() if out is not None else (None, 0, 0)
+    _C.call('catb_norm_bwd_reduce', *dout.args(), *o, *x.args(), x.N, x.HW, x.C, int(per_sample), _p(mean_rstd),
+            int(act), _p(red), _stream())
+
+
+def norm_bwd_apply(dout: Act, out: Act, x: Act, dx: Act, per_sample, mean_rstd, gamma, red, count, act, dgamma, dbeta):
+    o = out.args() if out is not None else (None, 0, 0)
+    _C.call('catb_norm_bwd_apply', *dout.args(), *o, *x.args(), *dx.args(), x.N, x.HW, x.C, int(per_sample),
+            _p(mean_rstd), _p(gamma), _p(red), float(count), int(act), _p(dgamma), _p(dbeta), _stream())
+
+
+def act_bwd(dout: Act, out: Act, dz: Act, act):
+    _C.call('catb_act_bwd', *dout.args(), *out.args(), *dz.args(), dout.pixels, dout.C, int(act), _stream())
+
+
+def channel_sum(x: Act, out):
+    _C.call('catb_channel_sum', *x.args(), x.pixels, x.C, _p(out), _stream())
+
+
+def reflect_fold(src: Act, dst: Act, p, add: Act = None):
+    a = add.args() if add is not None else (None, 0, 0)
+    _C.call('catb_reflect_fold', *src.args(), *dst.args(), *a, dst.N, dst.H, dst.W, dst.C, int(p), _stream())
+
+
+def add(a: Act, b: Act, dst: Act):
+    _C.call('catb_add', *a.args(), *b.args(), *dst.args(), a.pixels, a.C, _stream())
+
+
+def dwconv_fwd(x: Act, y: Act, ksize, w_off, arena):
+    _C.call('catb_dwconv_fwd', *x.args(), *y.args(), x.N, x.H, x.W, x.C, _p(ksize), _p(w_off), _p(arena), _stream())
+
+
+def dwconv_bwd_data(dy: Act, dx: Act, ksize, w_off, arena):
+    _C.call('catb_dwconv_bwd_data', *dy.args(), *dx.args(), dy.N, dy.H, dy.W, dy.C, _p(ksize), _p(w_off), _p(arena),
+            _stream())
+
+
+def dwconv_bwd_weight(x: Act, dy: Act, ksize, w_off, grad_arena):
+    _C.call('catb_dwconv_bwd_weight', *x.args(), *dy.args(), x.N, x.H, x.W, x.C, _p(ksize), _p(w_off),
+            _p(grad_arena), _stream())
+
+
+def gan_loss(pred, n, ld, mode, target_is_real, for_discriminator, grad_scale, loss, dpred: Act = None):
+    d = dpred.args() if dpred is not None else (None, 0, 0)
+    _C.call('catb_gan_loss', _p(pred), n, ld, _C.GAN_MODES[mode], int(target_is_real), int(for_discriminator),
+            float(grad_scale), _p(loss), *d, _stream())
+
+
+def l1_loss(a: Act, b: Act, Creal, grad_scale, loss, da: Act = None, extra: Act = None):
+    d = da.args() if da is not None else (None, 0, 0)
+    e = extra.args() if extra is not None else (None, 0, 0)
+    _C.call('catb_l1_loss', *a.args(), *b.args(), a.pixels, a.C, Creal, float(grad_scale), _p(loss), *d, *e, _stream())
+
+
+def gram(x: Act, G):
+    _C.call('catb_gram', *x.args(), x.N, x.HW, x.C, _p(G), _stream())
+
+
+def ka_finish(Gx, Gy, B, loss_scale, loss, ka_value, coef):
+    _C.call('catb_ka_finish', _p(Gx), _p(Gy), B, float(loss_scale), _p(loss), _p(ka_value), _p(coef), _stream())
+
+
+def ka_bwd(x: Act, coef, dx: Act, accumulate):
+    _C.call('catb_ka_bwd', *x.args(), x.N, x.HW, x.C, _p(coef), *dx.args(), int(accumulate), _stream())
+
+
+def adam(param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_count):
+    _C.call('catb_adam', _p(param), _p(grad), _p(m), _p(v), param.numel(), _p(lr), float(beta1), float(beta2),
+            float(eps), float(grad_scale), _p(step_count), _stream())

@@ -1,0 +1,195 @@
+/*
+ * catb200.h -- C ABI of libcatb200.so: hand-written sm_100a kernels for the CAT distillation hot path.
+ *
+ * The reference (snap-research/CAT) has no FFI/plugin layer of its own: every op on the path is a stock
+ * ATen call made from Python.  The entry points below are therefore the functions a
+ * reference-side binding (ctypes) would call *instead of* those ATen calls; each one
+ * cites the reference call site it replaces (paths relative to the reference root).
+ *
+ * Contract: the caller owns every buffer (including workspaces), the callee never
+ * allocates, never synchronises, only enqueues on the given stream, and returns 0 or a negative
+ * catb_status.  No C++ exceptions cross the boundary.  All descriptors are POD.
+ *
+ * Data layout: activations are NHWC bf16 with the channel count padded to a multiple of 8 ("Cp");
+ * padding channels are always zero.  A tensor may be a channel slice of a wider buffer: `ld*` is the
+ * pixel pitch in elements and `*_coff` the first channel of the slice (multiple of 8).
+ * Parameters, gradients and optimiser state are fp32 in the reference's own (PyTorch) layout.
+ */
+#ifndef CATB200_H_
+#define CATB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* catb_stream_t; /* cudaStream_t */
+
+typedef enum {
+  CATB_OK = 0,
+  CATB_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  CATB_ERR_CUDA = -2,    /* a CUDA runtime call failed; see catb_last_error_string() */
+  CATB_ERR_NO_DEVICE = -3
+} catb_status;
+
+enum { CATB_ACT_NONE = 0, CATB_ACT_RELU = 1, CATB_ACT_LEAKY02 = 2, CATB_ACT_TANH = 3 };
+enum { CATB_PAD_ZERO = 0, CATB_PAD_REFLECT = 1 };
+enum { CATB_GAN_HINGE = 0, CATB_GAN_LSGAN = 1, CATB_GAN_VANILLA = 2 };
+
+/* One 16-byte K-unit (8 consecutive channels of one tap) of an implicit-GEMM operand. */
+typedef struct {
+  int8_t dr, ds; /* tap offset added to (oh*sn, ow*sn) before the division by sd           */
+  int16_t cu;    /* channel offset inside the gathered pixel, in units of 8 channels        */
+} catb_gather_unit;
+
+/* Where the 8 k-elements of a unit live in the fp32 parameter / gradient arena. */
+typedef struct {
+  int32_t w_off;  /* element offset of (row 0, first channel of the unit, this tap)          */
+  int32_t sn_w;   /* element stride between GEMM rows (output channels)                      */
+  int32_t sc_w;   /* element stride between the 8 channels of the unit                       */
+  int32_t nvalid; /* number of real channels in the unit (0..8); the rest is zero padding    */
+} catb_weight_unit;
+
+/* Geometry shared by the implicit-GEMM kernels.  The "gathered" tensor X is read through the unit
+ * table; the "lattice" tensor Y is addressed one GEMM row per lattice point:
+ *   row m  <->  (n, i, j),  oh = o_ph + i*o_step,  ow = o_pw + j*o_step,
+ *   unit u <->  X[n, (oh*sn + dr_u)/sd, (ow*sn + ds_u)/sd, x_coff + 8*cu_u .. +8)
+ * with zero fill when the division is inexact or the coordinate is outside [0,H)x[0,W)
+ * (CATB_PAD_ZERO) or mirrored back inside (CATB_PAD_REFLECT, nn.ReflectionPad2d semantics). */
+typedef struct {
+  int32_t N, H, W;        /* gathered tensor X: batch and spatial size                       */
+  int32_t ldx, x_coff;    /* X pixel pitch (elements) and slice offset                       */
+  int32_t OH, OW;         /* lattice tensor Y: full spatial size                             */
+  int32_t ldy, y_coff;    /* Y pixel pitch and slice offset                                  */
+  int32_t o_step, o_ph, o_pw, OHs, OWs; /* sub-lattice covered by this launch                */
+  int32_t sn, sd;         /* gather numerator / denominator (1 or 2)                         */
+  int32_t pad_mode;       /* CATB_PAD_*                                                      */
+  int32_t n_units;        /* length of the unit tables; GEMM K = 8*n_units                   */
+  int32_t n_rows;         /* GEMM rows on the weight side: real output channels (fprop) /
+                             real lattice-tensor channels (wgrad)                            */
+  int32_t n_tile;         /* rows of the packed weight image per tile (multiple of 16, <=256)*/
+  int32_t act;            /* CATB_ACT_* applied in the fprop epilogue                        */
+  int32_t accumulate;     /* fprop: add to the existing contents of Y                        */
+  int32_t y_is_f32;       /* fprop: Y is fp32 instead of bf16                                */
+  int32_t reserved;
+} catb_igemm_desc;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* catb_version(void);
+const char* catb_last_error_string(void);
+/* Sets kernel attributes (opt-in shared memory); call once per device before any launch. */
+int catb_init(int device);
+/* Bytes of the packed bf16 weight image used by catb_igemm_fprop for (n_rows, n_units, n_tile). */
+size_t catb_packed_weight_bytes(int n_rows, int n_units, int n_tile);
+
+/* ---- implicit-GEMM convolution (tcgen05 / TMEM) -----------------------------------------------
+ * Replaces every dense F.conv2d / F.conv_transpose2d on the path and their input gradients:
+ *   models/modules/inception_architecture/inception_generator.py:37-56,116-132 (7x7 reflect stem/head,
+ *   3x3 s2 down, ConvTranspose 3x3 s2 up), models/modules/inception_modules.py:129-177 (block convs),
+ *   models/modules/discriminators.py:39-74 (4x4 PatchGAN convs); autograd's conv backward-data. */
+int catb_pack_weights(const catb_igemm_desc* d, const catb_weight_unit* wunits /*device*/,
+                      const float* arena /*device*/, void* packed /*device*/, catb_stream_t s);
+int catb_igemm_fprop(const catb_igemm_desc* d, const catb_gather_unit* units /*device*/, const void* x,
+                     const void* packed_w, const float* bias /*nullable*/, void* y, catb_stream_t s);
+/* Weight gradient: arena_grad[w] += sum_rows Y[row, c] * gather(X)[row, k]   (atomic fp32 adds).
+ * Replaces autograd's conv backward-weight for the same call sites. */
+int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
+                     const void* x, const void* y, float* arena_grad, catb_stream_t s);
+/* Slow SIMT restatements of the two kernels above (same descriptors); kept for on-device bisection
+ * in tests.  Not used by the product path. */
+int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
+                   const float* arena, const void* x, const float* bias, void* y, catb_stream_t s);
+int catb_ref_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
+                   const void* x, const void* y, float* arena_grad, catb_stream_t s);
+
+/* ---- depthwise convolution (reflect padded, per-channel kernel size) --------------------------
+ * models/modules/inception_modules.py:165-173 (ConvBNReLU(groups=midp)).  ksize[c] in {1,3,5,7};
+ * w_off[c] = element offset of the channel's k*k filter in the arena (-1: padding channel). */
+int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int N, int H, int W, int C,
+                    const int32_t* ksize, const int32_t* w_off, const float* arena, catb_stream_t s);
+int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* dx, int ldx, int x_coff, int N, int H, int W,
+                         int C, const int32_t* ksize, const int32_t* w_off, const float* arena, catb_stream_t s);
+int catb_dwconv_bwd_weight(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, int N, int H,
+                           int W, int C, const int32_t* ksize, const int32_t* w_off, float* arena_grad,
+                           catb_stream_t s);
+
+/* ---- normalisation (InstanceNorm2d / BatchNorm2d, models/networks.py:29-64) --------------------
+ * stats: sums[g*2*C + c] = sum x, sums[g*2*C + C + c] = sum x^2 with g = n (per_sample) or 0.
+ * The buffer must be zeroed by the caller (atomic accumulation). */
+int catb_norm_stats(const void* x, int ldx, int x_coff, int N, int HW, int C, int per_sample, float* sums,
+                    catb_stream_t s);
+/* scale/shift [G,C] from the sums (training) or from running stats (eval: sums == NULL).
+ * Training with running buffers also applies the momentum update with the unbiased variance
+ * (F.batch_norm semantics).  gamma/beta/running_* are arena offsets (-1: absent). */
+int catb_norm_finalize(const float* sums, int G, int C, float count, float eps, float momentum,
+                       const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* mean_rstd /* [G,2,C] saved for backward */,
+                       catb_stream_t s);
+/* y = act(x*scale + shift) (+ residual).  Replaces norm + ReLU/LeakyReLU (+ the residual add of
+ * inception_modules.py:235-236). */
+int catb_norm_apply(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, const void* residual,
+                    int ldr, int r_coff, int N, int HW, int C, int per_sample, const float* scale,
+                    const float* shift, int act, catb_stream_t s);
+/* Backward of act(norm(x)): pass 1 reduces sum(dz) and sum(dz*xhat) into red[G,2,C] (zeroed by the
+ * caller), pass 2 writes dx.  `out` is the saved activation output (act' is taken from it);
+ * act == NONE ignores it. */
+int catb_norm_bwd_reduce(const void* dout, int ldd, int d_coff, const void* out, int ldo, int o_coff,
+                         const void* x, int ldx, int x_coff, int N, int HW, int C, int per_sample,
+                         const float* mean_rstd, int act, float* red, catb_stream_t s);
+int catb_norm_bwd_apply(const void* dout, int ldd, int d_coff, const void* out, int ldo, int o_coff,
+                        const void* x, int ldx, int x_coff, void* dx, int ldg, int g_coff, int N, int HW, int C,
+                        int per_sample, const float* mean_rstd, const float* gamma, const float* red,
+                        float count, int act, float* dgamma, float* dbeta, catb_stream_t s);
+
+/* ---- element-wise helpers --------------------------------------------------------------------- */
+/* NCHW fp32 (reference layout) -> NHWC bf16 channel slice, and back. */
+int catb_nchw_to_nhwc(const float* src, int N, int C, int H, int W, void* dst, int ldd, int d_coff, catb_stream_t s);
+int catb_nhwc_to_nchw(const void* src, int lds, int s_coff, int N, int C, int H, int W, float* dst, catb_stream_t s);
+/* dst[..., d_coff:d_coff+C] = src[..., s_coff:s_coff+C] (torch.cat along channels,
+ * base_inception_distiller.py:295-296). */
+int catb_copy_channels(const void* src, int lds, int s_coff, void* dst, int ldd, int d_coff, long long pixels,
+                       int C, catb_stream_t s);
+/* dz = dout * act'(out) for activations without a norm (LeakyReLU after the first D conv, Tanh head). */
+int catb_act_bwd(const void* dout, int ldd, int d_coff, const void* out, int ldo, int o_coff, void* dz, int ldz,
+                 int z_coff, long long pixels, int C, int act, catb_stream_t s);
+/* per-channel sum over pixels of a bf16 tensor, atomically added to out[c] (conv bias gradients). */
+int catb_channel_sum(const void* x, int ldx, int x_coff, long long pixels, int C, float* out, catb_stream_t s);
+/* Adjoint of nn.ReflectionPad2d(p): dx[n,h,w,:] = sum of the padded-frame gradient entries that
+ * mirror onto (h,w) (+ add, optional).  src has spatial size (H+2p, W+2p). */
+int catb_reflect_fold(const void* src, int lds, int s_coff, void* dst, int ldd, int d_coff, const void* add,
+                      int lda, int a_coff, int N, int H, int W, int C, int p, catb_stream_t s);
+int catb_add(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, void* dst, int ldd, int d_coff,
+             long long pixels, int C, catb_stream_t s);
+
+/* ---- losses ----------------------------------------------------------------------------------- */
+/* GANLoss (models/modules/loss.py:52-99) on a fp32 prediction of n elements with element stride `ld`:
+ * *loss += value (atomic; caller zeroes); dpred (nullable) is written as bf16 rows of 8 channels with
+ * pitch ldg, channel g_coff carrying grad_scale * dloss/dpred and the other 7 channels zero. */
+int catb_gan_loss(const float* pred, long long n, int ld, int mode, int target_is_real, int for_discriminator,
+                  float grad_scale, float* loss, void* dpred, int ldg, int g_coff, catb_stream_t s);
+/* L1Loss (base_inception_distiller.py:171-172): *loss += mean|a-b|; da (bf16, nullable) =
+ * grad_scale*sign(a-b)/count + extra (optional bf16 tensor added, e.g. the GAN gradient). */
+int catb_l1_loss(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, long long pixels, int C,
+                 int Creal, float grad_scale, float* loss, void* da, int ldg, int g_coff, const void* extra,
+                 int lde, int e_coff, catb_stream_t s);
+/* KA (utils/common.py:38-46).  gram: G[B,B] += X X^T over K = pixels*C elements per sample (caller
+ * zeroes G).  ka_finish: value and the B x B coefficient matrix of dX = coef * X.  ka_bwd: dX (+)= coef X. */
+int catb_gram(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G, catb_stream_t s);
+int catb_ka_finish(const float* Gx, const float* Gy, int B, float loss_scale, float* loss /* += */,
+                   float* ka_value, float* coef, catb_stream_t s);
+int catb_ka_bwd(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, const float* coef,
+                void* dx, int ldg, int g_coff, int accumulate, catb_stream_t s);
+
+/* ---- optimiser -------------------------------------------------------------------------------- */
+/* torch.optim.Adam (base_inception_distiller.py:205-214) over a flat fp32 arena.  `step_count` is a
+ * device counter incremented by the kernel; `lr` is read from device memory so that a captured
+ * CUDA graph follows the scheduler (models/networks.py:80-87). */
+int catb_adam(float* param, const float* grad, float* m, float* v, long long n, const float* lr, float beta1,
+              float beta2, float eps, float grad_scale, int* step_count, catb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATB200_H_ */
