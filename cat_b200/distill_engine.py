@@ -1,0 +1,199 @@
+"""One CAT distillation step (teacher fwd, student fwd/bwd, discriminator update, KA / GAN / L1 losses,
+two Adam updates) on libcatb200 kernels.
+
+Restates InceptionDistiller.optimize_parameters (distillers/inception_distiller.py:179-188):
+    forward (:100-104) -> backward_D (base_inception_distiller.py:293-312) -> optimizer_D.step
+    -> backward_G (inception_distiller.py:159-177) -> optimizer_G.step
+with the same arithmetic order of the phases.  Deviations from the reference, all stated in DESIGN.md:
+bf16 activations / weights with fp32 accumulation, the two discriminator passes of backward_D are
+back-propagated one after the other instead of jointly (same gradients), conv biases that feed a
+normalisation layer are not updated (their gradient is analytically zero).
+"""
+import torch
+
+from . import ops
+from .engine import MAPPING_LAYERS, DisNet, GenNet
+from .igemm_plan import cpad
+from .ops import Act
+
+LOSS_NAMES = ['G_gan', 'G_distill', 'G_recon', 'D_fake', 'D_real', 'G_distill0', 'G_distill1', 'G_distill2',
+              'G_distill3']
+
+
+class DistillStep:
+    def __init__(self, teacher_arch, student_arch, D_arch, hp, B, H, W, device='cuda:0', world_size=1,
+                 use_cuda_graph=False):
+        ops.require_cuda()
+        self.hp, self.B, self.H, self.W, self.dev = dict(hp), B, H, W, device
+        self.world_size = world_size
+        self.aligned = bool(hp['aligned'])
+        assert D_arch['input_nc'] == (6 if self.aligned else 3)
+        self.T = GenNet(teacher_arch, B, H, W, device, training=False, need_grad=False)
+        self.S = GenNet(student_arch, B, H, W, device, training=hp.get('student_training', True), need_grad=True)
+        self.D = DisNet(D_arch, B, H, W, device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.real_A = torch.zeros(B, 3, H, W, **f32)
+        self.real_B = torch.zeros(B, 3, H, W, **f32)
+        self.xA = Act.empty(B, H, W, 3, device, zero=True)     # NHWC bf16 copies of the inputs
+        self.xB = Act.empty(B, H, W, 3, device, zero=True)
+        self.d_in_fake = Act.empty(B, H, W, D_arch['input_nc'], device, zero=True)
+        self.d_in_real = Act.empty(B, H, W, D_arch['input_nc'], device, zero=True)
+        self.dS = Act.empty(B, H, W, 3, device, zero=True)      # gradient w.r.t. the student output
+        self.dS_gan = Act.empty(B, H, W, 3, device, zero=True)
+        oh, ow = self.D.layers[-1].oh, self.D.layers[-1].ow
+        self.dpred = Act.empty(B, oh, ow, 8, device, zero=True)
+        self.losses = torch.zeros(16, **f32)                    # see LOSS_SLOTS
+        self.ka_vals = torch.zeros(4, **f32)
+        self.Gx = torch.zeros(4, B, B, **f32)
+        self.Gy = torch.zeros(4, B, B, **f32)
+        self.coef = torch.zeros(4, B, B, **f32)
+        self.lr_G = torch.full((1,), float(hp['lr']), **f32)
+        self.lr_D = torch.full((1,), float(hp['lr']), **f32)
+        self.step_G = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step_D = torch.zeros(1, dtype=torch.int32, device=device)
+        self.kernel_launches = None
+        self._graphs = None
+        self.use_cuda_graph = use_cuda_graph
+
+    LOSS_SLOTS = {'D_fake': 0, 'D_real': 1, 'G_gan': 2, 'G_recon': 3, 'G_distill': 4}
+
+    # ---- state ---------------------------------------------------------------------------------
+    def load(self, teacher_sd, student_sd, D_sd):
+        self.T.load_state_dict(teacher_sd)
+        self.S.load_state_dict(student_sd)
+        self.D.load_state_dict(D_sd)
+
+    def set_input(self, real_A, real_B):
+        """Host or device NCHW fp32 tensors -> the persistent device buffers (the H2D copy of
+        BaseInceptionDistiller.set_input, base_inception_distiller.py:271-280)."""
+        self.real_A.copy_(real_A, non_blocking=True)
+        self.real_B.copy_(real_B, non_blocking=True)
+
+    def set_lr(self, lr_G, lr_D=None):
+        self.lr_G.fill_(float(lr_G))
+        self.lr_D.fill_(float(lr_G if lr_D is None else lr_D))
+
+    # ---- phases --------------------------------------------------------------------------------
+    def _forward_generators(self):
+        ops.nchw_to_nhwc(self.real_A, self.xA)
+        ops.nchw_to_nhwc(self.real_B, self.xB)
+        self.T.forward(self.xA)
+        self.S.forward(self.xA)
+
+    def _d_inputs(self):
+        if self.aligned:
+            ops.copy_channels(self.xA, self.d_in_fake, 3)
+            ops.copy_channels(self.S.out, _chan_view(self.d_in_fake, 3), 3)
+            ops.copy_channels(self.xA, self.d_in_real, 3)
+            ops.copy_channels(self.xB, _chan_view(self.d_in_real, 3), 3)
+            return self.d_in_fake, self.d_in_real
+        return self.S.out, self.xB
+
+    def _phase_D(self):
+        hp, D = self.hp, self.D
+        fake, real = self._d_inputs()
+        D.arena.g.zero_()
+        D.forward(fake)
+        ops.gan_loss(D.pred, D.pred_n, 8, hp['gan_mode'], False, True, 0.5, self.losses[0:1], self.dpred)
+        D.backward(self.dpred, param_grads=True, input_grad=False)
+        D.forward(real)
+        ops.gan_loss(D.pred, D.pred_n, 8, hp['gan_mode'], True, True, 0.5, self.losses[1:2], self.dpred)
+        D.backward(self.dpred, param_grads=True, input_grad=False)
+
+    def _adam(self, net, lr, step):
+        a = net.arena
+        ops.adam(a.p, a.g, a.m, a.v, lr, self.hp['beta1'], 0.999, 1e-8, 1.0 / self.world_size, step)
+        net.pack_weights()
+
+    def _phase_G(self):
+        hp, D, S, T = self.hp, self.D, self.S, self.T
+        fake, _ = self._d_inputs()
+        S.arena.g.zero_()
+        D.forward(fake)
+        ops.gan_loss(D.pred, D.pred_n, 8, hp['gan_mode'], True, False, hp['lambda_gan'], self.losses[2:3], self.dpred)
+        d_in = D.backward(self.dpred, param_grads=False, input_grad=True)
+        if self.aligned:
+            ops.copy_channels(_chan_view(d_in, 3), self.dS_gan, 3)
+            extra, target = self.dS_gan, self.xB
+        else:
+            extra, target = d_in, T.out
+        ops.l1_loss(S.out, target, 3, hp['lambda_recon'], self.losses[3:4], self.dS, extra)
+        act_grads = {}
+        if hp['lambda_distill'] > 0:
+            self.Gx.zero_()
+            self.Gy.zero_()
+            scale = -hp['lambda_distill'] * hp.get('ka_scale', 1.0)
+            for i, n in enumerate(MAPPING_LAYERS):
+                ops.gram(S.acts[n], self.Gx[i])
+                ops.gram(T.acts[n], self.Gy[i])
+                ops.ka_finish(self.Gx[i], self.Gy[i], self.B, scale, self.losses[4:5], self.ka_vals[i:i + 1], self.coef[i])
+                act_grads[n] = (lambda dact, i=i, n=n: ops.ka_bwd(S.acts[n], self.coef[i], dact, True))
+        S.backward(self.dS, act_grads)
+
+    def _allreduce(self, net):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(net.arena.g)
+
+    # ---- the step ------------------------------------------------------------------------------
+    def _part1(self):
+        self.losses.zero_()
+        self._forward_generators()
+        self._phase_D()
+
+    def _part2(self):
+        self._adam(self.D, self.lr_D, self.step_D)
+        self._phase_G()
+
+    def _part3(self):
+        self._adam(self.S, self.lr_G, self.step_G)
+
+    def step(self):
+        """optimize_parameters(): three launch segments separated by the two gradient all-reduces."""
+        if self.use_cuda_graph:
+            if self._graphs is None:
+                self._capture()
+            g1, g2, g3 = self._graphs
+            g1.replay()
+            self._allreduce(self.D)
+            g2.replay()
+            self._allreduce(self.S)
+            g3.replay()
+        else:
+            self._part1()
+            self._allreduce(self.D)
+            self._part2()
+            self._allreduce(self.S)
+            self._part3()
+
+    def _capture(self):
+        # warm-up outside capture (kernel attribute setup, allocator), then capture the three segments
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        graphs = []
+        with torch.cuda.stream(s):
+            for part in (self._part1, self._part2, self._part3):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    part()
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(s)
+        self._graphs = graphs
+
+    def get_losses(self):
+        """Synchronises (float() on device scalars), like get_current_losses (base_model.py:166-188)."""
+        l = self.losses.tolist()
+        k = self.ka_vals.tolist()
+        hp = self.hp
+        scale = hp.get('ka_scale', 1.0)
+        out = {'D_fake': l[0], 'D_real': l[1], 'G_gan': l[2] * hp['lambda_gan'], 'G_recon': l[3] * hp['lambda_recon'], 'G_distill': l[4]}
+        for i in range(4):
+            out['G_distill%d' % i] = -k[i] * scale
+        return out
+
+
+def _chan_view(act: Act, c):
+    """View of `act` whose slice starts at channel c (may be unaligned; only for copy_channels)."""
+    v = Act(act.t)
+    v.coff, v.C = act.coff + c, act.ld - act.coff - c
+    return v

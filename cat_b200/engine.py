@@ -1,0 +1,708 @@
+"""Execution engine for the CAT distillation step on libcatb200 kernels.
+
+The reference runs the step as ~600 eager ATen calls under autograd.  Here each network
+is compiled once, for a fixed batch shape, into a static sequence of kernel launches with a hand-derived
+backward; every buffer is pre-allocated, nothing synchronises, so the whole step can be replayed from a
+CUDA graph.  Parameters live in flat fp32 arenas (reference layout per tensor, so ``state_dict``s
+round-trip), gradients / Adam state in parallel arenas (one NCCL all-reduce per optimiser).
+
+Networks restated here (same maths as the reference modules, different execution):
+  GenNet  -- InceptionGenerator (models/modules/inception_architecture/inception_generator.py:37-142)
+             with InvertedResidualChannels blocks (models/modules/inception_modules.py:124-236)
+  DisNet  -- NLayerDiscriminator (models/modules/discriminators.py:14-79)
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import igemm_plan as P
+from . import ops
+from .igemm_plan import cpad
+from .ops import ACT, Act, Gemm
+
+MAPPING_LAYERS = ['down_sampling.9', 'features.2', 'features.5', 'features.8']
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter arenas
+# ------------------------------------------------------------------------------------------------
+class Arena:
+    """Flat fp32 storage for a set of named tensors.  Entries may be padded (norm vectors are padded
+    to the 8-channel unit so that kernels can index the padded channel range directly)."""
+
+    def __init__(self, with_grad):
+        self.entries = OrderedDict()  # name -> (offset, shape, padded_len, pad_value)
+        self.size = 8
+        self.with_grad = with_grad
+        self.p = self.g = self.m = self.v = None
+
+    def alloc(self, name, shape, pad_to=None, pad_value=0.0):
+        n = int(math.prod(shape))
+        L = max(n, pad_to or n)
+        assert name not in self.entries, name
+        self.entries[name] = (self.size, tuple(shape), L, pad_value)
+        self.size += L
+        return self.entries[name][0]
+
+    def finalize(self, device):
+        total = self.size + 64
+        self.p = torch.zeros(total, dtype=torch.float32, device=device)
+        for (off, shape, L, pv) in self.entries.values():
+            n = int(math.prod(shape))
+            if L > n and pv != 0.0:
+                self.p[off + n:off + L] = pv
+        if self.with_grad:
+            self.g = torch.zeros_like(self.p)
+            self.m = torch.zeros_like(self.p)
+            self.v = torch.zeros_like(self.p)
+
+    def off(self, name):
+        return self.entries[name][0]
+
+    def has(self, name):
+        return name in self.entries
+
+    def view(self, name, which='p'):
+        off, shape, L, _ = self.entries[name]
+        n = int(math.prod(shape))
+        return getattr(self, which)[off:off + n].view(shape)
+
+    def padded(self, name, which='p'):
+        off, shape, L, _ = self.entries[name]
+        return getattr(self, which)[off:off + L]
+
+    def span(self, first, last, which='p'):
+        """Contiguous slice covering entries first..last (allocated back to back)."""
+        o0 = self.entries[first][0]
+        o1, _, L1, _ = self.entries[last]
+        return getattr(self, which)[o0:o1 + L1]
+
+    def load_state_dict(self, sd, prefix=''):
+        for name in self.entries:
+            key = prefix + name
+            if key in sd:
+                self.view(name).copy_(sd[key].to(torch.float32))
+
+    def state_dict(self, prefix=''):
+        return OrderedDict((prefix + n, self.view(n).detach().clone().cpu()) for n in self.entries)
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation layer over a channel range of a (raw, activated) buffer pair
+# ------------------------------------------------------------------------------------------------
+class Norm:
+    def __init__(self, dev, N, HW, Cp, kind, eps, momentum, training, track, gamma=None, beta=None, rmean=None,
+                 rvar=None, dgamma=None, dbeta=None):
+        self.per_sample = kind == 'instance'
+        if self.per_sample and track:
+            raise NotImplementedError('InstanceNorm with running statistics is not on the CAT distillation path')
+        self.N, self.HW, self.Cp = N, HW, Cp
+        self.G = N if self.per_sample else 1
+        self.count = HW if self.per_sample else N * HW
+        self.eps, self.momentum = eps, momentum
+        self.batch_stats = self.per_sample or training or not track
+        self.training, self.track = training, track
+        self.gamma, self.beta, self.rmean, self.rvar = gamma, beta, rmean, rvar
+        self.dgamma, self.dbeta = dgamma, dbeta
+        f = dict(dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(self.G, 2, Cp, **f)
+        self.scale = torch.empty(self.G, Cp, **f)
+        self.shift = torch.empty(self.G, Cp, **f)
+        self.mean_rstd = torch.empty(self.G, 2, Cp, **f)
+        self.red = torch.zeros(self.G, 2, Cp, **f)
+        self._frozen = False
+
+    def forward(self, x: Act, y: Act, act, residual=None):
+        if self.batch_stats:
+            self.sums.zero_()
+            ops.norm_stats(x, self.per_sample, self.sums)
+            upd = self.training and self.track
+            ops.norm_finalize(self.sums, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
+                              self.rmean if upd else None, self.rvar if upd else None, self.scale, self.shift,
+                              self.mean_rstd)
+        elif not self._frozen:
+            ops.norm_finalize(None, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
+                              self.rmean, self.rvar, self.scale, self.shift, self.mean_rstd)
+            self._frozen = not self.training  # eval-mode affine of a frozen net is computed once
+        ops.norm_apply(x, y, self.scale, self.shift, self.per_sample, act, residual)
+
+    def backward(self, dout: Act, out, x: Act, dx: Act, act, param_grads=True):
+        if not self.batch_stats:
+            raise NotImplementedError('backward through eval-mode BatchNorm (the reference\'s first-step quirk, '
+                                      'SURVEY.md section 7) is not supported')
+        self.red.zero_()
+        ops.norm_bwd_reduce(dout, out, x, self.per_sample, self.mean_rstd, act, self.red)
+        ops.norm_bwd_apply(dout, out, x, dx, self.per_sample, self.mean_rstd, self.gamma, self.red, self.count, act,
+                           self.dgamma if param_grads else None, self.dbeta if param_grads else None)
+
+
+class _NormSpec:
+    """Allocation helper that keeps gamma / beta / running stats of several norm layers contiguous and
+    in the same (padded) channel order as the activation slices they normalise."""
+
+    def __init__(self, arena: Arena, bufs: Arena, arch):
+        self.arena, self.bufs, self.arch = arena, bufs, arch
+
+    def alloc_group(self, prefixes_and_C):
+        a, b, arch = self.arena, self.bufs, self.arch
+        track = arch['norm'] == 'batch' and arch['track_running_stats']
+        if arch['affine']:
+            for p, C in prefixes_and_C:
+                a.alloc(p + '.weight', (C,), cpad(C), 1.0)
+            for p, C in prefixes_and_C:
+                a.alloc(p + '.bias', (C,), cpad(C), 0.0)
+        if track:
+            for p, C in prefixes_and_C:
+                b.alloc(p + '.running_mean', (C,), cpad(C), 0.0)
+            for p, C in prefixes_and_C:
+                b.alloc(p + '.running_var', (C,), cpad(C), 1.0)
+            for p, C in prefixes_and_C:
+                b.alloc(p + '.num_batches_tracked', (1,))
+
+    def make(self, dev, N, HW, prefixes_and_C, training):
+        a, b, arch = self.arena, self.bufs, self.arch
+        track = arch['norm'] == 'batch' and arch['track_running_stats']
+        first, last = prefixes_and_C[0][0], prefixes_and_C[-1][0]
+        Cp = sum(cpad(C) for _, C in prefixes_and_C)
+        kw = {}
+        if arch['affine']:
+            kw['gamma'] = a.span(first + '.weight', last + '.weight')
+            kw['beta'] = a.span(first + '.bias', last + '.bias')
+            if a.with_grad:
+                kw['dgamma'] = a.span(first + '.weight', last + '.weight', 'g')
+                kw['dbeta'] = a.span(first + '.bias', last + '.bias', 'g')
+        if track:
+            kw['rmean'] = b.span(first + '.running_mean', last + '.running_mean')
+            kw['rvar'] = b.span(first + '.running_var', last + '.running_var')
+        for t in kw.values():
+            assert t.numel() == Cp
+        return Norm(dev, N, HW, Cp, arch['norm'], arch['eps'], arch['momentum'], training, track, **kw)
+
+
+def _strided_dgrad(geo_kw, units, n_rows, dev, stride):
+    """Input-gradient GEMMs of a stride-`stride` zero-padded conv: one launch (stride 1) or one per
+    output parity class with only the taps that hit it (4-phase sub-pixel decomposition)."""
+    if stride == 1:
+        return [Gemm(P.Geometry(**geo_kw), units, n_rows, dev)]
+    gemms = []
+    for a in range(2):
+        for b in range(2):
+            ph = units.phase(a, b)
+            if len(ph):
+                gemms.append(Gemm(P.Geometry(**geo_kw, sn=1, sd=2, o_step=2, o_ph=a, o_pw=b), ph, n_rows, dev))
+    return gemms
+
+
+# ------------------------------------------------------------------------------------------------
+# generator
+# ------------------------------------------------------------------------------------------------
+class _Block:
+    pass
+
+
+class GenNet:
+    """InceptionGenerator compiled for a fixed (B, H, W)."""
+
+    def __init__(self, arch, B, H, W, device, training, need_grad):
+        assert H % 4 == 0 and W % 4 == 0, 'the generator down-samples twice'
+        self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
+        self.training, self.need_grad = training, need_grad
+        self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
+        self.ns = _NormSpec(self.arena, self.bufs, arch)
+        self.use_bias = arch['use_bias']
+        self._alloc_params()
+        self.arena.finalize(device)
+        self.bufs.finalize(device)
+        self._build()
+
+    # ---- parameters --------------------------------------------------------------------------
+    def _conv_alloc(self, name, shape, bias, transposed=False):
+        """Conv2d weight [Cout,Cin,k,k] (ConvTranspose2d: [Cin,Cout,k,k]) and optional bias [Cout]."""
+        self.arena.alloc(name + '.weight', shape)
+        if bias:
+            self.arena.alloc(name + '.bias', (shape[1] if transposed else shape[0],))
+
+    def _alloc_params(self):
+        A, ub = self.arch, self.use_bias
+        c0, c1, c2, c3, c4 = A['widths']
+        ks = A['kernel_sizes']
+        self._conv_alloc('down_sampling.1', (c0, A['input_nc'], 7, 7), ub)
+        self.ns.alloc_group([('down_sampling.2', c0)])
+        self._conv_alloc('down_sampling.4', (c1, c0, 3, 3), ub)
+        self.ns.alloc_group([('down_sampling.5', c1)])
+        self._conv_alloc('down_sampling.7', (c2, c1, 3, 3), ub)
+        self.ns.alloc_group([('down_sampling.8', c2)])
+        for i, blk in enumerate(A['blocks']):
+            pre = f'features.{i}'
+            res = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(blk['res'], ks) if mk[0] > 0))]
+            dw = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(blk['dw'], ks) if mk[0] > 0))]
+            for j, m, k in res:
+                self._conv_alloc(f'{pre}.res_ops.{j}.1.0', (m, c2, k, k), ub)
+                self._conv_alloc(f'{pre}.res_ops.{j}.4', (c2, m, k, k), ub)
+            for j, m, k in dw:
+                self._conv_alloc(f'{pre}.dw_ops.{j}.0.0', (m, c2, 1, 1), ub)
+                self._conv_alloc(f'{pre}.dw_ops.{j}.2.0', (m, 1, k, k), ub)
+                self._conv_alloc(f'{pre}.dw_ops.{j}.4', (c2, m, 1, 1), ub)
+            grpA = [(f'{pre}.res_ops.{j}.1.1', m) for j, m, k in res] + [(f'{pre}.dw_ops.{j}.0.1', m) for j, m, k in dw]
+            grpB = [(f'{pre}.dw_ops.{j}.2.1', m) for j, m, k in dw]
+            if grpA:
+                self.ns.alloc_group(grpA)
+            if grpB:
+                self.ns.alloc_group(grpB)
+            if res or dw:
+                self.ns.alloc_group([(f'{pre}.pw_bn', c2)])
+        self._conv_alloc('up_sampling.0', (c2, c3, 3, 3), ub, transposed=True)
+        self.ns.alloc_group([('up_sampling.1', c3)])
+        self._conv_alloc('up_sampling.3', (c3, c4, 3, 3), ub, transposed=True)
+        self.ns.alloc_group([('up_sampling.4', c4)])
+        self._conv_alloc('up_sampling.7', (A['output_nc'], c4, 7, 7), True)
+
+    def load_state_dict(self, sd):
+        self.arena.load_state_dict(sd)
+        self.bufs.load_state_dict(sd)
+        self.pack_weights()
+
+    def state_dict(self):
+        sd = self.arena.state_dict()
+        sd.update(self.bufs.state_dict())
+        return sd
+
+    # ---- graph construction --------------------------------------------------------------------
+    def _act(self, H, W, C, zero=False):
+        return Act.empty(self.B, H, W, C, self.dev, zero=zero)
+
+    def _build(self):
+        A, B, H, W, dev = self.arch, self.B, self.H, self.W, self.dev
+        ar, ng, tr = self.arena, self.need_grad, self.training
+        c0, c1, c2, c3, c4 = A['widths']
+        cin, cout = A['input_nc'], A['output_nc']
+        ks = A['kernel_sizes']
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        self.fprop_gemms, self.bwd_gemms = [], []   # everything that needs packed weights
+
+        def G(geo, units, n_rows, bwd=False):
+            g = Gemm(geo, units, n_rows, dev)
+            (self.bwd_gemms if bwd else self.fprop_gemms).append(g)
+            return g
+
+        # ---- stem / down-sampling
+        self.x_in = None  # set per forward (shared NHWC input)
+        self.y0, self.a0 = self._act(H, W, c0), self._act(H, W, c0)
+        self.g_stem = G(P.Geometry(B, H, W, cpad(cin), 0, H, W, cpad(c0), 0, pad_mode=P.PAD_REFLECT),
+                        P.conv_fprop_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 3), c0)
+        self.n_stem = self.ns.make(dev, B, H * W, [('down_sampling.2', c0)], tr)
+        self.y1, self.a1 = self._act(H2, W2, c1), self._act(H2, W2, c1)
+        self.g_d1 = G(P.Geometry(B, H, W, cpad(c0), 0, H2, W2, cpad(c1), 0, sn=2),
+                      P.conv_fprop_units(ar.off('down_sampling.4.weight'), c1, c0, 3, 3, 1), c1)
+        self.n_d1 = self.ns.make(dev, B, H2 * W2, [('down_sampling.5', c1)], tr)
+        self.y2, self.a2 = self._act(H4, W4, c2), self._act(H4, W4, c2)
+        self.g_d2 = G(P.Geometry(B, H2, W2, cpad(c1), 0, H4, W4, cpad(c2), 0, sn=2),
+                      P.conv_fprop_units(ar.off('down_sampling.7.weight'), c2, c1, 3, 3, 1), c2)
+        self.n_d2 = self.ns.make(dev, B, H4 * W4, [('down_sampling.8', c2)], tr)
+
+        # ---- residual blocks
+        C, Cp = c2, cpad(c2)
+        self.blocks = []
+        x = self.a2
+        maxL = maxLpad = 0
+        for i, blk in enumerate(A['blocks']):
+            pre = f'features.{i}'
+            b = _Block()
+            b.x = x
+            b.res = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(blk['res'], ks) if mk[0] > 0))]
+            b.dw = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(blk['dw'], ks) if mk[0] > 0))]
+            b.empty = not b.res and not b.dw
+            if b.empty:  # forward returns x unchanged (inception_modules.py:231-232)
+                b.out = x
+                self.blocks.append(b)
+                continue
+            # channel slices of the mid buffer: [res first-stage | dw first-stage | dw second-stage]
+            off = 0
+            b.res_sl, b.dw1_sl, b.dw2_sl = [], [], []
+            for _, m, _k in b.res:
+                b.res_sl.append(off)
+                off += cpad(m)
+            b.LR = off
+            for _, m, _k in b.dw:
+                b.dw1_sl.append(off)
+                off += cpad(m)
+            b.LA = off
+            for _, m, _k in b.dw:
+                b.dw2_sl.append(off)
+                off += cpad(m)
+            b.L = off
+            maxL = max(maxL, b.L)
+            b.mid_raw = self._act(H4, W4, b.L, zero=True)
+            b.mid_act = self._act(H4, W4, b.L, zero=True)
+            b.tmp, b.out = self._act(H4, W4, C), self._act(H4, W4, C)
+            # stage 1: one GEMM per branch, all reading x
+            b.s1 = []
+            for (j, m, k), sl in zip(b.res, b.res_sl):
+                wn = f'{pre}.res_ops.{j}.1.0.weight'
+                g = G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl, pad_mode=P.PAD_REFLECT),
+                      P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m)
+                b.s1.append((g, sl, m, k, wn))
+            for (j, m, k), sl in zip(b.dw, b.dw1_sl):
+                wn = f'{pre}.dw_ops.{j}.0.0.weight'
+                g = G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0), m)
+                b.s1.append((g, sl, m, 1, wn))
+            grpA = [(f'{pre}.res_ops.{j}.1.1', m) for j, m, k in b.res] + [(f'{pre}.dw_ops.{j}.0.1', m) for j, m, k in b.dw]
+            b.nA = self.ns.make(dev, B, H4 * W4, grpA, tr)
+            # depthwise convs over the dw slices
+            if b.dw:
+                Cdw = b.L - b.LA
+                ksz = torch.ones(Cdw, dtype=torch.int32)
+                wof = torch.full((Cdw,), -1, dtype=torch.int32)
+                for (j, m, k), sl in zip(b.dw, b.dw2_sl):
+                    o = sl - b.LA
+                    ksz[o:o + cpad(m)] = k
+                    wof[o:o + m] = ar.off(f'{pre}.dw_ops.{j}.2.0.weight') + torch.arange(m, dtype=torch.int32) * k * k
+                b.dw_k, b.dw_w = ksz.to(dev), wof.to(dev)
+                b.nB = self.ns.make(dev, B, H4 * W4, [(f'{pre}.dw_ops.{j}.2.1', m) for j, m, k in b.dw], tr)
+            # stage 2: ONE GEMM, K-concatenation of every branch's last conv
+            u2 = P.Units()
+            for (j, m, k), sl in zip(b.res, b.res_sl):
+                u2.extend(P.conv_fprop_units(ar.off(f'{pre}.res_ops.{j}.4.weight'), C, m, k, k, (k - 1) // 2, cu0=sl // 8))
+            for (j, m, k), sl in zip(b.dw, b.dw2_sl):
+                u2.extend(P.conv_fprop_units(ar.off(f'{pre}.dw_ops.{j}.4.weight'), C, m, 1, 1, 0, cu0=sl // 8))
+            b.g2 = G(P.Geometry(B, H4, W4, b.L, 0, H4, W4, Cp, 0, pad_mode=P.PAD_REFLECT), u2, C)
+            b.npw = self.ns.make(dev, B, H4 * W4, [(f'{pre}.pw_bn', C)], tr)
+            if ng:
+                # stage-2 input gradients: one GEMM per branch (padded frame + fold for k > 1)
+                b.d2 = []
+                for (j, m, k), sl in zip(b.res, b.res_sl):
+                    p = (k - 1) // 2
+                    un = P.conv_dgrad_units(ar.off(f'{pre}.res_ops.{j}.4.weight'), C, m, k, k, 0)
+                    if p > 0:
+                        maxLpad = max(maxLpad, (H4 + 2 * p) * (W4 + 2 * p) * cpad(m))
+                        g = G(P.Geometry(B, H4, W4, Cp, 0, H4 + 2 * p, W4 + 2 * p, cpad(m), 0), un, m, bwd=True)
+                    else:
+                        g = G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), un, m, bwd=True)
+                    b.d2.append((g, sl, m, p))
+                for (j, m, k), sl in zip(b.dw, b.dw2_sl):
+                    un = P.conv_dgrad_units(ar.off(f'{pre}.dw_ops.{j}.4.weight'), C, m, 1, 1, 0)
+                    b.d2.append((G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), un, m, bwd=True), sl, m, 0))
+                # stage-1 input gradient: ONE GEMM over the concatenated first-stage gradients
+                b.P1 = max([(k - 1) // 2 for _, _, k in b.res] + [0])
+                u1 = P.Units()
+                for (j, m, k), sl in zip(b.res, b.res_sl):
+                    q = (k - 1) // 2 - b.P1
+                    u1.extend(P.conv_dgrad_units(ar.off(f'{pre}.res_ops.{j}.1.0.weight'), m, C, k, k, q, cu0=sl // 8))
+                for (j, m, k), sl in zip(b.dw, b.dw1_sl):
+                    u1.extend(P.conv_dgrad_units(ar.off(f'{pre}.dw_ops.{j}.0.0.weight'), m, C, 1, 1, -b.P1, cu0=sl // 8))
+                Hp, Wp = H4 + 2 * b.P1, W4 + 2 * b.P1
+                b.g1d = G(P.Geometry(B, H4, W4, b.L, 0, Hp, Wp, Cp, 0), u1, C, bwd=True)
+            self.blocks.append(b)
+            x = b.out
+        self.feat_out = x
+
+        # ---- up-sampling (ConvTranspose 3x3 s2 p1 op1 as four sub-pixel phases) and head
+        def up(prefix_conv, prefix_norm, xin_C, out_C, h, w):
+            y, a = self._act(2 * h, 2 * w, out_C), self._act(2 * h, 2 * w, out_C)
+            fu = P.convT_fprop_units(ar.off(prefix_conv + '.weight'), xin_C, out_C, 3, 3, 1)
+            gs = []
+            for pa in range(2):
+                for pb in range(2):
+                    gs.append(G(P.Geometry(B, h, w, cpad(xin_C), 0, 2 * h, 2 * w, cpad(out_C), 0, sn=1, sd=2, o_step=2,
+                                           o_ph=pa, o_pw=pb), fu.phase(pa, pb), out_C))
+            n = self.ns.make(dev, B, 4 * h * w, [(prefix_norm, out_C)], tr)
+            bu = P.convT_dgrad_units(ar.off(prefix_conv + '.weight'), xin_C, out_C, 3, 3, 1)
+            gb = G(P.Geometry(B, 2 * h, 2 * w, cpad(out_C), 0, h, w, cpad(xin_C), 0, sn=2, sd=1), bu, xin_C, bwd=True) if ng else None
+            return y, a, gs, n, gb
+
+        self.yu1, self.au1, self.g_u1, self.n_u1, self.gb_u1 = up('up_sampling.0', 'up_sampling.1', c2, c3, H4, W4)
+        self.yu2, self.au2, self.g_u2, self.n_u2, self.gb_u2 = up('up_sampling.3', 'up_sampling.4', c3, c4, H2, W2)
+        self.out = self._act(H, W, cout)
+        self.g_head = G(P.Geometry(B, H, W, cpad(c4), 0, H, W, cpad(cout), 0, pad_mode=P.PAD_REFLECT),
+                        P.conv_fprop_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 3), cout)
+        self.head_bias = ar.view('up_sampling.7.bias')
+
+        self.acts = {'down_sampling.9': self.a2}
+        for i in (2, 5, 8):
+            self.acts[f'features.{i}'] = self.blocks[i].out
+
+        if ng:
+            f = dict(dtype=torch.bfloat16, device=dev)
+            # gradient workspaces shared by all blocks
+            self.ws_dmid_act = torch.zeros(B * H4 * W4 * max(maxL, 8), **f)
+            self.ws_dmid_raw = torch.zeros(B * H4 * W4 * max(maxL, 8), **f)
+            self.ws_frame = torch.zeros(B * max(maxLpad, 8), **f)
+            self.ws_dtmp = self._act(H4, W4, C)
+            self.ws_dxp = torch.zeros(B * (H4 + 6) * (W4 + 6) * Cp, **f)
+            self.dfeat = [self._act(H4, W4, C), self._act(H4, W4, C)]   # ping-pong d(block output)
+            # head / up / down gradient buffers
+            self.d_head_z = self._act(H, W, cout)
+            self.d_head_frame = Act.empty(B, H + 6, W + 6, c4, dev)
+            self.gb_head = G(P.Geometry(B, H, W, cpad(cout), 0, H + 6, W + 6, cpad(c4), 0),
+                             P.conv_dgrad_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 0), c4, bwd=True)
+            self.d_au2, self.d_yu2 = self._act(H, W, c4), self._act(H, W, c4)
+            self.d_au1, self.d_yu1 = self._act(H2, W2, c3), self._act(H2, W2, c3)
+            self.d_y2, self.d_a1, self.d_y1, self.d_a0, self.d_y0 = (self._act(H4, W4, c2), self._act(H2, W2, c1),
+                                                                       self._act(H2, W2, c1), self._act(H, W, c0),
+                                                                       self._act(H, W, c0))
+            self.gb_d2 = _strided_dgrad(dict(N=B, H=H4, W=W4, ldx=cpad(c2), x_coff=0, OH=H2, OW=W2, ldy=cpad(c1), y_coff=0),
+                                        P.conv_dgrad_units(ar.off('down_sampling.7.weight'), c2, c1, 3, 3, 1), c1, dev, 2)
+            self.gb_d1 = _strided_dgrad(dict(N=B, H=H2, W=W2, ldx=cpad(c1), x_coff=0, OH=H, OW=W, ldy=cpad(c0), y_coff=0),
+                                        P.conv_dgrad_units(ar.off('down_sampling.4.weight'), c1, c0, 3, 3, 1), c0, dev, 2)
+            self.bwd_gemms += self.gb_d2 + self.gb_d1
+
+    def _ws(self, flat, H, W, C):
+        return Act(flat[:self.B * H * W * C].view(self.B, H, W, C))
+
+    def pack_weights(self):
+        for g in self.fprop_gemms + self.bwd_gemms:
+            g.pack(self.arena.p)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x_in: Act):
+        """x_in: NHWC bf16 input image [B,H,W,cpad(input_nc)].  Returns the output Act (tanh applied)."""
+        self.x_in = x_in
+        relu, none = ACT['relu'], ACT['none']
+        self.g_stem.fprop(x_in.t, self.y0.t)
+        self.n_stem.forward(self.y0, self.a0, relu)
+        self.g_d1.fprop(self.a0.t, self.y1.t)
+        self.n_d1.forward(self.y1, self.a1, relu)
+        self.g_d2.fprop(self.a1.t, self.y2.t)
+        self.n_d2.forward(self.y2, self.a2, relu)
+        for b in self.blocks:
+            if b.empty:
+                continue
+            for (g, sl, m, k, wn) in b.s1:
+                g.fprop(b.x.t, b.mid_raw.t)
+            b.nA.forward(b.mid_raw.slice(0, b.LA), b.mid_act.slice(0, b.LA), relu)
+            if b.dw:
+                ops.dwconv_fwd(b.mid_act.slice(b.LR, b.LA - b.LR), b.mid_raw.slice(b.LA, b.L - b.LA), b.dw_k, b.dw_w,
+                               self.arena.p)
+                b.nB.forward(b.mid_raw.slice(b.LA, b.L - b.LA), b.mid_act.slice(b.LA, b.L - b.LA), relu)
+            b.g2.fprop(b.mid_act.t, b.tmp.t)
+            b.npw.forward(b.tmp, b.out, none, residual=b.x)
+        for g in self.g_u1:
+            g.fprop(self.feat_out.t, self.yu1.t)
+        self.n_u1.forward(self.yu1, self.au1, relu)
+        for g in self.g_u2:
+            g.fprop(self.au1.t, self.yu2.t)
+        self.n_u2.forward(self.yu2, self.au2, relu)
+        self.g_head.fprop(self.au2.t, self.out.t, bias=self.head_bias, act=ACT['tanh'])
+        return self.out
+
+    # ---- backward ------------------------------------------------------------------------------
+    def backward(self, d_out: Act, act_grads=None):
+        """d_out: gradient w.r.t. the tanh output.  act_grads: {mapping layer: callable(Act)} invoked to
+        accumulate extra gradient (the KA loss) into d(activation) at the four mapping layers."""
+        assert self.need_grad
+        relu, none, ar = ACT['relu'], ACT['none'], self.arena
+        act_grads = act_grads or {}
+        B, H, W = self.B, self.H, self.W
+        c0, c1, c2, c3, c4 = self.arch['widths']
+        H4, W4 = H // 4, W // 4
+        Cp = cpad(c2)
+        # head: tanh, 7x7 reflect conv
+        ops.act_bwd(d_out, self.out, self.d_head_z, ACT['tanh'])
+        self.g_head.wgrad(self.au2.t, self.d_head_z.t, ar.g)
+        ops.channel_sum(self.d_head_z, ar.view('up_sampling.7.bias', 'g'))
+        self.gb_head.fprop(self.d_head_z.t, self.d_head_frame.t)
+        ops.reflect_fold(self.d_head_frame, self.d_au2, 3)
+        # up 2
+        self.n_u2.backward(self.d_au2, self.au2, self.yu2, self.d_yu2, relu)
+        self.gb_u2.wgrad(self.d_yu2.t, self.au1.t, ar.g)
+        self.gb_u2.fprop(self.d_yu2.t, self.d_au1.t)
+        # up 1
+        self.n_u1.backward(self.d_au1, self.au1, self.yu1, self.d_yu1, relu)
+        self.gb_u1.wgrad(self.d_yu1.t, self.feat_out.t, ar.g)
+        cur = self.dfeat[0]
+        self.gb_u1.fprop(self.d_yu1.t, cur.t)
+        nxt_i = 1
+        for i in range(len(self.blocks) - 1, -1, -1):
+            b = self.blocks[i]
+            name = f'features.{i}'
+            if name in act_grads:
+                act_grads[name](cur)
+            if b.empty:
+                continue
+            dmid_act = self._ws(self.ws_dmid_act, H4, W4, b.L)
+            dmid_raw = self._ws(self.ws_dmid_raw, H4, W4, b.L)
+            # x + pw_bn(tmp): norm backward without activation
+            b.npw.backward(cur, None, b.tmp, self.ws_dtmp, none)
+            b.g2.wgrad(b.mid_act.t, self.ws_dtmp.t, ar.g)
+            for (g, sl, m, p) in b.d2:
+                if p > 0:
+                    fr = self._ws(self.ws_frame, H4 + 2 * p, W4 + 2 * p, cpad(m))
+                    g.fprop(self.ws_dtmp.t, fr.t)
+                    ops.reflect_fold(fr, dmid_act.slice(sl, cpad(m)), p)
+                else:
+                    g.fprop(self.ws_dtmp.t, dmid_act.t)
+            if b.dw:
+                nB = b.L - b.LA
+                b.nB.backward(dmid_act.slice(b.LA, nB), b.mid_act.slice(b.LA, nB), b.mid_raw.slice(b.LA, nB),
+                              dmid_raw.slice(b.LA, nB), relu)
+                ops.dwconv_bwd_weight(b.mid_act.slice(b.LR, b.LA - b.LR), dmid_raw.slice(b.LA, nB), b.dw_k, b.dw_w, ar.g)
+                ops.dwconv_bwd_data(dmid_raw.slice(b.LA, nB), dmid_act.slice(b.LR, b.LA - b.LR), b.dw_k, b.dw_w, ar.p)
+            b.nA.backward(dmid_act.slice(0, b.LA), b.mid_act.slice(0, b.LA), b.mid_raw.slice(0, b.LA),
+                          dmid_raw.slice(0, b.LA), relu)
+            for (g, sl, m, k, wn) in b.s1:
+                g.wgrad(b.x.t, dmid_raw.t, ar.g)
+            nxt = self.dfeat[nxt_i]
+            if b.P1 > 0:
+                fr = self._ws(self.ws_dxp, H4 + 2 * b.P1, W4 + 2 * b.P1, Cp)
+                b.g1d.fprop(dmid_raw.t, fr.t)
+                ops.reflect_fold(fr, nxt, b.P1, add=cur)
+            else:
+                b.g1d.fprop(dmid_raw.t, nxt.t)
+                ops.add(nxt, cur, nxt)
+            cur, nxt_i = nxt, 1 - nxt_i
+        if 'down_sampling.9' in act_grads:
+            act_grads['down_sampling.9'](cur)
+        # down 2, down 1, stem (no input gradient needed for the image)
+        self.n_d2.backward(cur, self.a2, self.y2, self.d_y2, relu)
+        self.g_d2.wgrad(self.a1.t, self.d_y2.t, ar.g)
+        for g in self.gb_d2:
+            g.fprop(self.d_y2.t, self.d_a1.t)
+        self.n_d1.backward(self.d_a1, self.a1, self.y1, self.d_y1, relu)
+        self.g_d1.wgrad(self.a0.t, self.d_y1.t, ar.g)
+        for g in self.gb_d1:
+            g.fprop(self.d_y1.t, self.d_a0.t)
+        self.n_stem.backward(self.d_a0, self.a0, self.y0, self.d_y0, relu)
+        self.g_stem.wgrad(self.x_in.t, self.d_y0.t, ar.g)
+
+
+# ------------------------------------------------------------------------------------------------
+# discriminator
+# ------------------------------------------------------------------------------------------------
+def discriminator_layers(arch):
+    """(seq index of the conv, cin, cout, stride, has_norm, has_act) -- discriminators.py:37-75."""
+    ndf, n_layers = arch['ndf'], arch['n_layers']
+    layers = [(0, arch['input_nc'], ndf, 2, False, True)]
+    idx, mult = 2, 1
+    for n in range(1, n_layers):
+        prev, mult = mult, min(2 ** n, 8)
+        layers.append((idx, ndf * prev, ndf * mult, 2, True, True))
+        idx += 3
+    prev, mult = mult, min(2 ** n_layers, 8)
+    layers.append((idx, ndf * prev, ndf * mult, 1, True, True))
+    idx += 3
+    layers.append((idx, ndf * mult, 1, 1, False, False))
+    return layers
+
+
+class _DLayer:
+    pass
+
+
+class DisNet:
+    """NLayerDiscriminator (70x70 PatchGAN) compiled for a fixed (B, H, W); always in train mode on the
+    distillation path (netD is never put in eval(), base_inception_distiller.py:144-169)."""
+
+    def __init__(self, arch, B, H, W, device):
+        self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
+        self.arena, self.bufs = Arena(True), Arena(False)
+        self.ns = _NormSpec(self.arena, self.bufs, arch)
+        self.layers = []
+        h, w = H, W
+        for (ci, cin, cout, stride, has_norm, has_act) in discriminator_layers(arch):
+            L = _DLayer()
+            L.ci, L.cin, L.cout, L.stride, L.has_norm, L.has_act = ci, cin, cout, stride, has_norm, has_act
+            L.h, L.w = h, w
+            L.oh = (h + 2 - 4) // stride + 1
+            L.ow = (w + 2 - 4) // stride + 1
+            L.has_bias = not has_norm  # biases in front of a norm layer are mathematically inert
+            self.arena.alloc(f'model.{ci}.weight', (cout, cin, 4, 4))
+            if not has_norm or arch['use_bias']:
+                self.arena.alloc(f'model.{ci}.bias', (cout,))
+            if has_norm:
+                self.ns.alloc_group([(f'model.{ci + 1}', cout)])
+            h, w = L.oh, L.ow
+            self.layers.append(L)
+        self.arena.finalize(device)
+        self.bufs.finalize(device)
+        ar, dev = self.arena, device
+        self.fprop_gemms, self.bwd_gemms = [], []
+        self.d_in = Act.empty(B, H, W, arch['input_nc'], dev)  # gradient w.r.t. the input image
+        prev_C = arch['input_nc']
+        for li, L in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            wn = f'model.{L.ci}.weight'
+            L.units = P.conv_fprop_units(ar.off(wn), L.cout, L.cin, 4, 4, 1)
+            L.y_f32 = last
+            if last:
+                L.y = torch.zeros(B, L.oh, L.ow, 8, dtype=torch.float32, device=dev)
+                ldy = 8
+            else:
+                L.yraw = Act.empty(B, L.oh, L.ow, L.cout, dev)
+                L.a = Act.empty(B, L.oh, L.ow, L.cout, dev) if L.has_norm else L.yraw
+                ldy = cpad(L.cout)
+            L.g = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.oh, L.ow, ldy, 0, sn=L.stride), L.units, L.cout, dev)
+            self.fprop_gemms.append(L.g)
+            L.bias = ar.view(f'model.{L.ci}.bias') if L.has_bias else None
+            L.dbias = ar.view(f'model.{L.ci}.bias', 'g') if L.has_bias else None
+            if L.has_norm:
+                L.norm = self.ns.make(dev, B, L.oh * L.ow, [(f'model.{L.ci + 1}', L.cout)], True)
+            # backward buffers
+            L.dy = Act.empty(B, L.oh, L.ow, L.cout, dev)       # gradient w.r.t. the conv output
+            L.da = Act.empty(B, L.oh, L.ow, L.cout, dev) if not last else None  # w.r.t. the activation
+            geo_kw = dict(N=B, H=L.oh, W=L.ow, ldx=cpad(L.cout), x_coff=0, OH=L.h, OW=L.w, ldy=cpad(L.cin), y_coff=0)
+            L.gb = _strided_dgrad(geo_kw, P.conv_dgrad_units(ar.off(wn), L.cout, L.cin, 4, 4, 1), L.cin, dev, L.stride)
+            self.bwd_gemms += L.gb
+            # wgrad geometry: lattice tensor = dy (bf16, pitch cpad(cout))
+            L.gw = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.oh, L.ow, cpad(L.cout), 0, sn=L.stride), L.units,
+                        L.cout, dev, need_pack=False)
+        self.pred = self.layers[-1].y
+        self.pred_n = B * self.layers[-1].oh * self.layers[-1].ow
+
+    def load_state_dict(self, sd):
+        self.arena.load_state_dict(sd)
+        self.bufs.load_state_dict(sd)
+        self.pack_weights()
+
+    def state_dict(self):
+        sd = self.arena.state_dict()
+        sd.update(self.bufs.state_dict())
+        return sd
+
+    def pack_weights(self):
+        for g in self.fprop_gemms + self.bwd_gemms:
+            g.pack(self.arena.p)
+
+    def forward(self, x: Act):
+        self.x = x
+        cur = x
+        for L in self.layers:
+            if L.y_f32:
+                L.g.fprop(cur.t, L.y, bias=L.bias, y_is_f32=True)
+            elif L.has_norm:
+                L.g.fprop(cur.t, L.yraw.t)
+                L.norm.forward(L.yraw, L.a, ACT['leaky'])
+                cur = L.a
+            else:
+                L.g.fprop(cur.t, L.yraw.t, bias=L.bias, act=ACT['leaky'])
+                cur = L.yraw
+        return self.pred
+
+    def backward(self, dpred: Act, param_grads, input_grad):
+        """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0)."""
+        ar = self.arena
+        d = dpred
+        for li in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[li]
+            x_in = self.layers[li - 1].a if li > 0 else self.x
+            if L.y_f32:
+                dy = d
+            elif L.has_norm:
+                L.norm.backward(d, L.a, L.yraw, L.dy, ACT['leaky'], param_grads=param_grads)
+                dy = L.dy
+            else:
+                ops.act_bwd(d, L.yraw, L.dy, ACT['leaky'])
+                dy = L.dy
+            if param_grads:
+                L.gw.wgrad(x_in.t, dy.t, ar.g)
+                if L.has_bias:
+                    ops.channel_sum(dy, L.dbias)
+            if li > 0:
+                tgt = self.layers[li - 1].da
+                for g in L.gb:
+                    g.fprop(dy.t, tgt.t)
+                d = tgt
+            elif input_grad:
+                for g in L.gb:
+                    g.fprop(dy.t, self.d_in.t)
+        return self.d_in
