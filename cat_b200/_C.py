@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libcatb200.so')
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 GAN_MODES = {'hinge': 0, 'lsgan': 1, 'vanilla': 2}
+RECON_KINDS = {'l1': 0, 'l2': 1, 'smooth_l1': 2}
 
 
 class GatherUnit(C.Structure):
@@ -61,7 +62,7 @@ _PROTOS = {
     'catb_reflect_fold': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'catb_add': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _L, _I, _P],
     'catb_gan_loss': [_P, _L, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P],
-    'catb_l1_loss': [_P, _I, _I, _P, _I, _I, _L, _I, _I, _F, _P, _P, _I, _I, _P, _I, _I, _P],
+    'catb_recon_loss': [_P, _I, _I, _P, _I, _I, _L, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _I, _P],
     'catb_gram': [_P, _I, _I, _I, _L, _I, _P, _P],
     'catb_ka_finish': [_P, _P, _I, _F, _P, _P, _P, _P],
     'catb_ka_bwd': [_P, _I, _I, _I, _L, _I, _P, _P, _I, _I, _I, _P],

@@ -519,8 +519,8 @@ __global__ void gan_loss_kernel(const float* __restrict__ pred, long long n, int
   if (threadIdx.x == 0) atomicAdd(loss, t * inv_n);
 }
 
-__global__ void l1_loss_kernel(const __nv_bfloat16* __restrict__ a, int lda, int a_coff, const __nv_bfloat16* __restrict__ b,
-                               int ldb, int b_coff, long long pixels, int C, int Creal, float grad_scale, float* loss,
+__global__ void recon_loss_kernel(const __nv_bfloat16* __restrict__ a, int lda, int a_coff, const __nv_bfloat16* __restrict__ b,
+                               int ldb, int b_coff, long long pixels, int C, int Creal, int kind, float grad_scale, float* loss,
                                __nv_bfloat16* da, int ldg, int g_coff, const __nv_bfloat16* extra, int lde, int e_coff) {
   __shared__ float sh[32];
   const int U = C / 8;
@@ -538,8 +538,19 @@ __global__ void l1_loss_kernel(const __nv_bfloat16* __restrict__ a, int lda, int
     for (int q = 0; q < 8; ++q) {
       const float dlt = x.v[q] - y.v[q];
       const bool real = u * 8 + q < Creal;
-      if (real) acc += fabsf(dlt);
-      g.v[q] = real ? grad_scale * inv * (dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f)) : 0.f;
+      float l, dl;
+      if (kind == 1) {  // MSE
+        l = dlt * dlt;
+        dl = 2.f * dlt;
+      } else if (kind == 2 && fabsf(dlt) < 1.f) {  // smooth L1, quadratic zone
+        l = 0.5f * dlt * dlt;
+        dl = dlt;
+      } else {  // L1 (and the linear zone of smooth L1)
+        l = fabsf(dlt) - (kind == 2 ? 0.5f : 0.f);
+        dl = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+      }
+      if (real) acc += l;
+      g.v[q] = real ? grad_scale * inv * dl : 0.f;
     }
     if (da != nullptr) {
       if (extra != nullptr) {
@@ -890,17 +901,18 @@ extern "C" int catb_gan_loss(const float* pred, long long n, int ld, int mode, i
   return check_launch("gan_loss");
 }
 
-extern "C" int catb_l1_loss(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, long long pixels,
-                            int C, int Creal, float grad_scale, float* loss, void* da, int ldg, int g_coff,
-                            const void* extra, int lde, int e_coff, catb_stream_t s) {
+extern "C" int catb_recon_loss(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, long long pixels,
+                               int C, int Creal, int kind, float grad_scale, float* loss, void* da, int ldg, int g_coff,
+                               const void* extra, int lde, int e_coff, catb_stream_t s) {
+  CATB_REQUIRE(kind >= 0 && kind <= 2, "unknown reconstruction loss kind %d", kind);
   CHK_SLICE(lda, a_coff, C);
   CHK_SLICE(ldb, b_coff, C);
   CATB_REQUIRE(Creal > 0 && Creal <= C, "bad real channel count");
-  l1_loss_kernel<<<grid_for(pixels * (C / 8), 256, 148 * 4), 256, 0, S(s)>>>(
+  recon_loss_kernel<<<grid_for(pixels * (C / 8), 256, 148 * 4), 256, 0, S(s)>>>(
       static_cast<const __nv_bfloat16*>(a), lda, a_coff, static_cast<const __nv_bfloat16*>(b), ldb, b_coff, pixels, C,
-      Creal, grad_scale, loss, static_cast<__nv_bfloat16*>(da), ldg, g_coff, static_cast<const __nv_bfloat16*>(extra),
+      Creal, kind, grad_scale, loss, static_cast<__nv_bfloat16*>(da), ldg, g_coff, static_cast<const __nv_bfloat16*>(extra),
       lde, e_coff);
-  return check_launch("l1_loss");
+  return check_launch("recon_loss");
 }
 
 extern "C" int catb_gram(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G,

@@ -208,10 +208,11 @@ def gan_loss(pred, n, ld, mode, target_is_real, for_discriminator, grad_scale, l
             float(grad_scale), _p(loss), *d, _stream())
 
 
-def l1_loss(a: Act, b: Act, Creal, grad_scale, loss, da: Act = None, extra: Act = None):
+def recon_loss(a: Act, b: Act, Creal, kind, grad_scale, loss, da: Act = None, extra: Act = None):
     d = da.args() if da is not None else (None, 0, 0)
     e = extra.args() if extra is not None else (None, 0, 0)
-    _C.call('catb_l1_loss', *a.args(), *b.args(), a.pixels, a.C, Creal, float(grad_scale), _p(loss), *d, *e, _stream())
+    _C.call('catb_recon_loss', *a.args(), *b.args(), a.pixels, a.C, Creal, _C.RECON_KINDS[kind], float(grad_scale),
+            _p(loss), *d, *e, _stream())
 
 
 def gram(x: Act, G):

@@ -169,11 +169,12 @@ int catb_add(const void* a, int lda, int a_coff, const void* b, int ldb, int b_c
  * pitch ldg, channel g_coff carrying grad_scale * dloss/dpred and the other 7 channels zero. */
 int catb_gan_loss(const float* pred, long long n, int ld, int mode, int target_is_real, int for_discriminator,
                   float grad_scale, float* loss, void* dpred, int ldg, int g_coff, catb_stream_t s);
-/* L1Loss (base_inception_distiller.py:171-172): *loss += mean|a-b|; da (bf16, nullable) =
- * grad_scale*sign(a-b)/count + extra (optional bf16 tensor added, e.g. the GAN gradient). */
-int catb_l1_loss(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, long long pixels, int C,
-                 int Creal, float grad_scale, float* loss, void* da, int ldg, int g_coff, const void* extra,
-                 int lde, int e_coff, catb_stream_t s);
+/* Reconstruction loss (base_inception_distiller.py:171-176): kind 0 = L1Loss, 1 = MSELoss,
+ * 2 = SmoothL1Loss (beta 1).  *loss += mean over the Creal real channels; da (bf16, nullable) =
+ * grad_scale * dloss/da + extra (optional bf16 tensor added, e.g. the GAN gradient). */
+int catb_recon_loss(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff, long long pixels, int C,
+                    int Creal, int kind, float grad_scale, float* loss, void* da, int ldg, int g_coff,
+                    const void* extra, int lde, int e_coff, catb_stream_t s);
 /* KA (utils/common.py:38-46).  gram: G[B,B] += X X^T over K = pixels*C elements per sample (caller
  * zeroes G).  ka_finish: value and the B x B coefficient matrix of dX = coef * X.  ka_bwd: dX (+)= coef X. */
 int catb_gram(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G, catb_stream_t s);

@@ -174,6 +174,11 @@ def gan_loss(mode, pred, target_is_real, for_discriminator=True):
     raise NotImplementedError(mode)
 
 
+def recon_loss(kind, a, b):
+    """criterionRecon (distillers/base_inception_distiller.py:171-176): L1Loss | MSELoss | SmoothL1Loss."""
+    return {'l1': F.l1_loss, 'l2': F.mse_loss, 'smooth_l1': F.smooth_l1_loss}[kind](a, b)
+
+
 def ka(X, Y):
     """KA(X, Y) (utils/common.py:38-46): <XX^T, YY^T>_F / (||XX^T||_F ||YY^T||_F).  The
     denominator is evaluated as a product of two square roots (identical in exact arithmetic;
@@ -252,6 +257,7 @@ def distill_step(state, real_A, real_B, hp):
                               capture=Sacts)
     for a in Sacts.values():
         a.retain_grad()
+    Sfake.retain_grad()
     out['Tfake_B'], out['Sfake_B'] = Tfake, Sfake.detach().clone()
     out['Tacts'] = {k: v for k, v in Tacts.items()}
     out['Sacts'] = {k: v.detach().clone() for k, v in Sacts.items()}
@@ -267,13 +273,16 @@ def distill_step(state, real_A, real_B, hp):
     else:
         fake, real = Sfake.detach(), real_B.detach()
     pred_fake = discriminator_forward(D_sd, D_arch, fake, training=True)
+    pred_fake.retain_grad()
     loss_D_fake = gan_loss(hp['gan_mode'], pred_fake, False, True)
     pred_real = discriminator_forward(D_sd, D_arch, real, training=True)
+    pred_real.retain_grad()
     loss_D_real = gan_loss(hp['gan_mode'], pred_real, True, True)
     loss_D = (loss_D_fake + loss_D_real) * 0.5
     loss_D.backward()
     out['loss_D_fake'], out['loss_D_real'] = loss_D_fake.detach(), loss_D_real.detach()
     out['pred_fake_D'] = pred_fake.detach()
+    out['dpred_fake'], out['dpred_real'] = pred_fake.grad.detach().clone(), pred_real.grad.detach().clone()
     out['D_grads'] = {k: p.grad.detach().clone() for k, p in D_params.items()}
     with torch.no_grad():
         adam_update(D_params, out['D_grads'], state['adam_D'], hp['lr'], hp['beta1'])
@@ -283,10 +292,10 @@ def distill_step(state, real_A, real_B, hp):
         p.requires_grad_(False)
         p.grad = None
     if hp['aligned']:
-        loss_G_recon = F.l1_loss(Sfake, real_B) * hp['lambda_recon']
+        loss_G_recon = recon_loss(hp.get('recon_loss_type', 'l1'), Sfake, real_B) * hp['lambda_recon']
         fake = torch.cat((real_A, Sfake), 1)
     else:
-        loss_G_recon = F.l1_loss(Sfake, Tfake) * hp['lambda_recon']
+        loss_G_recon = recon_loss(hp.get('recon_loss_type', 'l1'), Sfake, Tfake) * hp['lambda_recon']
         fake = Sfake
     pred_fake = discriminator_forward(D_sd, D_arch, fake, training=True)
     loss_G_gan = gan_loss(hp['gan_mode'], pred_fake, True, False) * hp['lambda_gan']
@@ -300,6 +309,7 @@ def distill_step(state, real_A, real_B, hp):
     out['loss_G_distill'] = loss_G_distill.detach()
     out['loss_G_distill_terms'] = [t.detach() for t in distill_terms]
     out['Sact_grads'] = {k: v.grad.detach().clone() for k, v in Sacts.items()}
+    out['Sfake_grad'] = Sfake.grad.detach().clone()
     out['S_grads'] = {k: p.grad.detach().clone() for k, p in S_params.items()}
     with torch.no_grad():
         adam_update(S_params, out['S_grads'], state['adam_G'], hp['lr'], hp['beta1'])

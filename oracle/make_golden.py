@@ -27,6 +27,12 @@ CASES = {
     'cyclegan_in_lsgan': dict(norm='instance', gan_mode='lsgan', dataset_mode='unaligned',
                               lambda_distill=1.0, lambda_recon=5.0, batch_size=2, height=32,
                               width=48, frac=0.25),
+    # smooth losses everywhere (--recon_loss_type l2, lsgan): gradients are Lipschitz in the forward
+    # values, so this case pins the whole backward pass tightly (the sign() of L1 and the hinge mask
+    # amplify rounding differences of the forward pass).
+    'pix2pix_bn_lsgan_l2': dict(norm='batch', gan_mode='lsgan', dataset_mode='aligned', lambda_distill=0.5,
+                                lambda_recon=100.0, batch_size=4, height=32, width=32, frac=0.2,
+                                recon_loss_type='l2'),
 }
 
 
@@ -45,7 +51,8 @@ def make_case(name, cfg):
                                            gan_mode=cfg['gan_mode'],
                                            dataset_mode=cfg['dataset_mode'],
                                            lambda_distill=cfg['lambda_distill'],
-                                           lambda_recon=cfg['lambda_recon'])
+                                           lambda_recon=cfg['lambda_recon'],
+                                           recon_loss_type=cfg.get('recon_loss_type', 'l1'))
     # after the first evaluate_model the reference puts the student back in train mode
     # (inception_distiller.py:280); the golden steps are recorded in that steady state.
     model.netG_student.train()
@@ -67,7 +74,7 @@ def make_case(name, cfg):
         'hp': dict(gan_mode=opt.gan_mode, aligned=opt.dataset_mode == 'aligned',
                    lambda_recon=float(opt.lambda_recon), lambda_gan=float(opt.lambda_gan),
                    lambda_distill=float(opt.lambda_distill), lr=float(opt.lr),
-                   beta1=float(opt.beta1), student_training=True),
+                   beta1=float(opt.beta1), student_training=True, recon_loss_type=opt.recon_loss_type),
         'teacher_sd': snap(model.netG_teacher.state_dict()),
         'student_sd0': snap(model.netG_student.state_dict()),
         'D_sd0': snap(model.netD.state_dict()),
@@ -114,7 +121,10 @@ def make_case(name, cfg):
 
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
+    only = sys.argv[1:]
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         fix = make_case(name, copy.deepcopy(cfg))
         path = os.path.join(OUT_DIR, name + '.pt')
         torch.save(fix, path)

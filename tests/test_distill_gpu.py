@@ -1,12 +1,19 @@
-"""End-to-end parity of the CUDA distillation step against the CPU oracle (which is itself pinned to
-the reference by tests/test_oracle_golden.py), on the committed golden fixtures.
+"""End-to-end parity of the CUDA distillation step against the CPU oracle (itself pinned to the
+reference by tests/test_oracle_golden.py) on the committed golden fixtures.
 
-Stated tolerance (bf16 operands / activations, fp32 accumulation, networks ~40 convs deep):
+Stated tolerances (bf16 operands / activations, fp32 accumulation, networks ~40 convs deep):
   * activations / outputs: relative L2 error <= 3e-2
   * losses: |delta| <= 2e-2 * max(1, |loss|);  KA terms: |delta| <= 5e-3
-  * parameter gradients: relative L2 error over all parameters of a network <= 6e-2
-  * post-Adam weights: within 2.1*lr of the oracle (Adam normalises the update to +-lr, so a sign
-    flip of a near-zero gradient moves a weight by at most 2*lr) and mean |delta| <= 0.15*lr
+  * parameter gradients, relative L2 error over all parameters of a network:
+      - <= 6e-2 when the loss gradients are smooth functions of the forward values (the l2/lsgan
+        fixture) or when the oracle's loss gradients d(loss)/d(pred), d(loss)/d(Sfake) are injected;
+      - <= 0.5 otherwise: sign(S - B) of the L1 loss and the hinge mask flip wherever the ~1% forward
+        rounding difference crosses zero / the margin; flipping a fraction f of the signs changes the
+        gradient by sqrt(4 f) in relative L2 (f = 1% -> 20%).  This is conditioning of the loss, not of
+        the kernels, and it is why the injected variant exists.
+  * post-Adam weights (smooth / injected runs): within 2.1*lr*(step+1) of the oracle (Adam normalises
+    every update to ~lr, so a sign flip of a near-zero gradient moves a weight by up to 2*lr) and mean
+    |delta| <= 0.15*lr*(step+1)
 """
 import os
 
@@ -15,7 +22,8 @@ import torch
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
-CASES = ['pix2pix_bn_hinge', 'cyclegan_in_lsgan']
+CASES = ['pix2pix_bn_lsgan_l2', 'pix2pix_bn_hinge', 'cyclegan_in_lsgan']
+SMOOTH = {'pix2pix_bn_lsgan_l2'}
 
 
 def rel_l2(a, b):
@@ -33,7 +41,7 @@ def _inert_biases(sd, tag):
     return {k for k in conv_biases if k not in ('model.0.bias', 'model.%d.bias' % last)}
 
 
-def _run(golden_dir, name, use_graph):
+def _run(golden_dir, name, use_graph, inject):
     from cat_b200 import ops
     from cat_b200.distill_engine import DistillStep
     from oracle import cat_oracle as O
@@ -49,6 +57,17 @@ def _run(golden_dir, name, use_graph):
     report = {}
     for it, step in enumerate(fix['steps']):
         ref = O.distill_step(state, step['real_A'], step['real_B'], fix['hp'])
+        if inject:
+            def put_pred(key):
+                def fn(act, key=key):
+                    act.t.zero_()
+                    act.t[..., 0] = ref[key][:, 0].to(act.t.device, torch.bfloat16)
+                return fn
+
+            def put_dS(act):
+                act.t.zero_()
+                act.t[..., :3] = ref['Sfake_grad'].permute(0, 2, 3, 1).to(act.t.device, torch.bfloat16)
+            eng.debug_hooks = {'dpred_fake': put_pred('dpred_fake'), 'dpred_real': put_pred('dpred_real'), 'dS': put_dS}
         eng.set_input(step['real_A'], step['real_B'])
         eng.step()
         torch.cuda.synchronize()
@@ -60,11 +79,10 @@ def _run(golden_dir, name, use_graph):
                 Ct, Cs = ref['Tacts'][n].shape[1], ref['Sacts'][n].shape[1]
                 report['Tact ' + n] = rel_l2(ops.nhwc_to_nchw(eng.T.acts[n], Ct).cpu(), ref['Tacts'][n])
                 report['Sact ' + n] = rel_l2(ops.nhwc_to_nchw(eng.S.acts[n], Cs).cpu(), ref['Sacts'][n])
-            # gradients (all parameters of a network concatenated)
             for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
                 mine, theirs = [], []
                 for k, g in grads.items():
-                    if net.arena.has(k):
+                    if net.arena.has(k) and k not in _inert_biases(grads, tag):
                         mine.append(net.arena.view(k, 'g').flatten().cpu())
                         theirs.append(g.flatten())
                 report[tag + '_grads'] = rel_l2(torch.cat(mine), torch.cat(theirs))
@@ -80,9 +98,7 @@ def _run(golden_dir, name, use_graph):
             inert = _inert_biases(sd, tag)
             mine_sd = net.state_dict()
             for k, v in sd.items():
-                if not v.is_floating_point() or k not in mine_sd or k.endswith('num_batches_tracked'):
-                    continue
-                if k in inert:
+                if not v.is_floating_point() or k not in mine_sd or k.endswith('num_batches_tracked') or k in inert:
                     continue
                 dlt = (mine_sd[k].double() - v.detach().double()).abs()
                 if k.endswith('running_mean') or k.endswith('running_var'):
@@ -96,17 +112,28 @@ def _run(golden_dir, name, use_graph):
     return report
 
 
-@pytest.mark.parametrize('name', CASES)
-@pytest.mark.parametrize('use_graph', [False, True])
-def test_distill_step_matches_oracle(golden_dir, name, use_graph):
-    rep = _run(golden_dir, name, use_graph)
-    print(name, 'graph' if use_graph else 'eager', {k: round(v, 4) for k, v in rep.items()})
+def _check(rep, strict):
     for k, v in rep.items():
         if k.startswith(('Tfake', 'Sfake', 'Tact', 'Sact')):
             assert v <= 3e-2, (k, v)
         elif k.endswith('_grads'):
-            assert v <= 6e-2, (k, v)
-        elif '_w_worst' in k:
+            assert v <= (6e-2 if strict else 0.5), (k, v)
+        elif strict and '_w_worst' in k:
             assert v <= 2.1 * (int(k[-1]) + 1), (k, v)
-        elif '_w_mean' in k:
+        elif strict and '_w_mean' in k:
             assert v <= 0.15 * (int(k[-1]) + 1), (k, v)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_distill_step_with_injected_loss_gradients(golden_dir, name):
+    rep = _run(golden_dir, name, use_graph=False, inject=True)
+    print(name, 'injected', {k: round(v, 4) for k, v in rep.items()})
+    _check(rep, strict=True)
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_distill_step_matches_oracle(golden_dir, name, use_graph):
+    rep = _run(golden_dir, name, use_graph, inject=False)
+    print(name, 'graph' if use_graph else 'eager', {k: round(v, 4) for k, v in rep.items()})
+    _check(rep, strict=name in SMOOTH)

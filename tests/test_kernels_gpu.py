@@ -376,10 +376,19 @@ def test_gan_and_l1_losses(mode):
     extra = torch.randn(2, 3, 8, 9) * 1e-3
     loss = torch.zeros(1, device=DEV)
     da = ops.Act.empty(2, 8, 9, 8, DEV)
-    ops.l1_loss(ops.Act(to_dev_nhwc(a)), ops.Act(to_dev_nhwc(b)), 3, 100.0, loss, da, ops.Act(to_dev_nhwc(extra)))
+    ops.recon_loss(ops.Act(to_dev_nhwc(a)), ops.Act(to_dev_nhwc(b)), 3, 'l1', 100.0, loss, da, ops.Act(to_dev_nhwc(extra)))
     torch.cuda.synchronize()
     assert abs(float(loss) * 100.0 - float(ref)) < 1e-4 * float(ref)
     assert rel_err(from_dev_nhwc(da.t, 3), ar.grad + bf(extra)) < 6e-3
+    for kind, fn in (('l2', F.mse_loss), ('smooth_l1', F.smooth_l1_loss)):
+        ar = bf(a * 1.5).requires_grad_(True)
+        ref = fn(ar, bf(b)) * 10.0
+        ref.backward()
+        loss.zero_()
+        ops.recon_loss(ops.Act(to_dev_nhwc(a * 1.5)), ops.Act(to_dev_nhwc(b)), 3, kind, 10.0, loss, da)
+        torch.cuda.synchronize()
+        assert abs(float(loss) * 10.0 - float(ref)) < 1e-4 * float(ref), kind
+        assert rel_err(from_dev_nhwc(da.t, 3), ar.grad) < 6e-3, kind
 
 
 @pytest.mark.parametrize('B,Cs,Ct,H,W', [(2, 5, 16, 8, 8), (16, 62, 256, 16, 16), (1, 8, 8, 4, 4), (32, 24, 48, 8, 8)])

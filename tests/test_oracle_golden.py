@@ -7,7 +7,7 @@ import torch
 
 from oracle import cat_oracle as O
 
-CASES = ['pix2pix_bn_hinge', 'cyclegan_in_lsgan']
+CASES = ['pix2pix_bn_hinge', 'cyclegan_in_lsgan', 'pix2pix_bn_lsgan_l2']
 
 
 def _close(a, b, rtol=2e-4, atol=2e-5, what=''):
