@@ -1,0 +1,331 @@
+"""Benchmark of the CAT distillation step (BASELINE.json metric: distill-step images/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload pix2pix_5p6B]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one InceptionDistiller.optimize_parameters (teacher fwd, student fwd/bwd, 3 D fwd + 2 D bwd + 1 D
+dgrad, KA/GAN/L1 losses, two Adam updates) on a synthetic batch of the BASELINE.json configs[1] shape:
+pix2pix student pruned to 5.6e9 MACs (channel counts from the reference's own shrink(), committed under
+tests/golden/), teacher ngf 64, PatchGAN ndf 128, 256x256, batch 16 per GPU.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='cat_b200', choices=['cat_b200', 'reference'])
+    ap.add_argument('--workload', default='pix2pix_5p6B')
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
+    ap.add_argument('--height', type=int, default=256)
+    ap.add_argument('--width', type=int, default=256)
+    ap.add_argument('--cpu-batch', type=int, default=2, help='images per step of the bounded CPU sample')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-gemms', action='store_true', help='print the per-GEMM timing table to stderr')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.samples if len(r) >= 7]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = sorted(float(r[0]) for r in rows)
+        reasons = []
+        for i, name in ((3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')):
+            if any(r[i].lower().startswith('active') for r in rows):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons,
+                'power_w_max': max(float(r[2]) for r in rows), 'samples': len(rows)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline (the oracle port of the reference path, timed on the host cores)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_steps(arch, hp, B, H, W, steps, warmup):
+    """Times oracle.cat_oracle.distill_step (CPU restatement of optimize_parameters) on a bounded sample
+    of the workload: same networks and resolution, `B` images per step."""
+    from cat_b200 import workload as WL
+    from oracle import cat_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = dict(teacher_sd=WL.init_generator(arch['teacher_arch'], 0, 'uniform'),
+                 student_sd=WL.init_generator(arch['student_arch'], 1), D_sd=WL.init_discriminator(arch['D_arch'], 2),
+                 teacher_arch=arch['teacher_arch'], student_arch=arch['student_arch'], D_arch=arch['D_arch'],
+                 adam_G={}, adam_D={})
+    a, b = WL.synthetic_batch(B, H, W, 233)
+    for _ in range(warmup):
+        O.distill_step(state, a, b, hp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.distill_step(state, a, b, hp)
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from cat_b200 import workload as WL
+    arch = WL.load_arch(args.workload)
+    hp = dict(arch['hp'])
+    B = args.cpu_batch
+    ips, dt, cores = cpu_reference_steps(arch, hp, B, args.height, args.width, args.steps, args.warmup)
+    sample = f'{B} images/step at {args.height}x{args.width}, same networks; CPU oracle port of optimize_parameters'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'distill-step images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, arch, B, 1),
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(args, arch, B, world):
+    return {'workload': f'{args.workload}: pix2pix inception student distill step (teacher ngf64 + pruned student '
+                        f'{arch["student_macs"] / 1e9:.2f} GMAC + PatchGAN ndf{arch["D_arch"]["ndf"]}), '
+                        f'{args.height}x{args.width}, batch {B}/GPU',
+            'global_batch': B * world, 'height': args.height, 'width': args.width, 'parallelism': f'dp{world}',
+            'l2': 'per-step working set (~GBs of activations) exceeds the 126 MB L2; no explicit flush'}
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-GEMM instrumentation (roofline of the dominant kernel)
+# ----------------------------------------------------------------------------------------------------
+class GemmProfiler:
+    def __init__(self):
+        self.records = []
+
+    def install(self):
+        from cat_b200 import ops
+        prof = self
+        self._orig = (ops.Gemm.fprop, ops.Gemm.wgrad)
+
+        def flops(g):
+            nv = sum(w[3] for w in g.units.w)
+            return 2.0 * g.geo.N * g.geo.OHs * g.geo.OWs * g.n_rows * nv
+
+        def wrap(fn, kind):
+            def inner(g, *a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(g, *a, **k)
+                e1.record()
+                prof.records.append((kind, g, flops(g), e0, e1))
+            return inner
+        ops.Gemm.fprop, ops.Gemm.wgrad = wrap(self._orig[0], 'fprop'), wrap(self._orig[1], 'wgrad')
+
+    def remove(self):
+        from cat_b200 import ops
+        ops.Gemm.fprop, ops.Gemm.wgrad = self._orig
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        per = {}
+        for kind, g, fl, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += fl
+            a[1] += ms
+            a[2] += 1
+            key = (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs)
+            p = per.setdefault(key, [0.0, 0.0, 0])
+            p[0] += fl
+            p[1] += ms
+            p[2] += 1
+        return agg, per
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    from cat_b200 import _C, ops
+    from cat_b200 import workload as WL
+    from cat_b200.distill_engine import DistillStep
+    from cat_b200.engine import GenNet
+
+    arch = WL.load_arch(args.workload)
+    hp = dict(arch['hp'])
+    hp['ka_scale'] = float(world)   # the reference sums the per-replica KA terms (inception_distiller.py:145-148)
+    B, H, W = args.batch, args.height, args.width
+    eng = DistillStep(arch['teacher_arch'], arch['student_arch'], arch['D_arch'], hp, B, H, W, device=dev,
+                      world_size=world, use_cuda_graph=not args.no_graph)
+    t_sd = WL.init_generator(arch['teacher_arch'], 0, 'uniform')
+    a_host, b_host = WL.synthetic_batch(B, H, W, 233 + rank, pin=True)
+    if arch['teacher_arch']['norm'] == 'batch' and arch['teacher_arch']['track_running_stats']:
+        # synthetic "trained" teacher: running statistics calibrated on one synthetic batch
+        cal_arch = dict(arch['teacher_arch'], momentum=1.0)
+        cal = GenNet(cal_arch, B, H, W, dev, training=True, need_grad=False)
+        cal.load_state_dict(t_sd)
+        xa = ops.Act.empty(B, H, W, 3, dev, zero=True)
+        ops.nchw_to_nhwc(a_host.to(dev), xa)
+        cal.forward(xa)
+        torch.cuda.synchronize()
+        t_sd = cal.state_dict()
+        del cal
+    eng.load(t_sd, WL.init_generator(arch['student_arch'], 1), WL.init_discriminator(arch['D_arch'], 2))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    eng.set_input(a_host, b_host)
+    for _ in range(args.warmup):
+        eng.step()
+    launches0 = _C.LAUNCH_COUNT[0]
+    if not args.no_graph:
+        launches_per_step = eng.launches_per_step
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if args.no_graph:
+        launches_per_step = (_C.LAUNCH_COUNT[0] - launches0) // args.steps
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the losses, every step
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        eng.set_input(a_host, b_host)
+        eng.step()
+        losses = eng.get_losses()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    bad = [k for k, v in losses.items() if v != v]
+    if bad:
+        raise RuntimeError(f'non-finite losses after the timed steps: {bad}')
+
+    # ---- roofline of the dominant kernel: one instrumented eager step (CUDA events around every GEMM launch)
+    roof = None
+    if rank == 0:
+        prof = GemmProfiler()
+        prof.install()
+        eng.use_cuda_graph = False
+        eng.step()
+        agg, per = prof.summary()
+        prof.remove()
+        eng.use_cuda_graph = not args.no_graph
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+        fl, tms, n = agg['fprop']
+        achieved = fl / (tms * 1e-3) / 1e12
+        step_ms_eager = sum(v[1] for v in agg.values())
+        roof = {'bound': 'tensor', 'kernel': 'igemm_fprop_kernel (tcgen05 implicit-GEMM conv/dgrad)',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'launches': n, 'kernel_ms_per_step': tms,
+                'share_of_gemm_time': tms / step_ms_eager,
+                'wgrad': {'achieved': agg['wgrad'][0] / (agg['wgrad'][1] * 1e-3) / 1e12, 'launches': agg['wgrad'][2],
+                          'kernel_ms_per_step': agg['wgrad'][1]} if 'wgrad' in agg else None}
+        if args.profile_gemms:
+            rows = sorted(per.items(), key=lambda kv: -kv[1][1])[:40]
+            for (kind, n_rows, n_units, M), (f, t, c) in rows:
+                print(f'{kind:6s} rows {n_rows:5d} units {n_units:5d} M {M:8d} x{c:3d}  {t:8.3f} ms  {f / (t * 1e-3) / 1e12:8.1f} TF/s',
+                      file=sys.stderr)
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, dt, cores = cpu_reference_steps(arch, dict(arch['hp']), args.cpu_batch, H, W, 2, 1)
+        cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{args.cpu_batch} images/step at {H}x{W}, 1 warm-up + 2 timed steps of the CPU oracle '
+                         f'(same networks), {dt:.2f} s/step'}
+
+    if rank == 0:
+        imgs = B * world * args.steps
+        macs = WL.macs_per_image(arch, H, W)
+        value = imgs / (ms * 1e-3)
+        print(json.dumps({
+            'metric': 'distill-step images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': workload_config(args, arch, B, world),
+            'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
+                    'h2d_bytes_per_step': 2 * B * 3 * H * W * 4, 'd2h_bytes_per_step': (16 + 4) * 4},
+            'gpu_launches': launches_per_step * args.steps * 2 + launches_per_step,
+            'launches_per_step': launches_per_step,
+            'algorithmic_gflop_per_image': 2 * macs['step'] / 1e9,
+            'model_tflops': 2 * macs['step'] * value / 1e12,
+            'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
+            'losses': {k: round(v, 5) for k, v in losses.items()},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -114,6 +114,10 @@ def check(status, what=''):
         raise CatbError(f'{what} failed with status {status}: {msg}')
 
 
+LAUNCH_COUNT = [0]  # entry-point calls so far (each enqueues one kernel; catb_adam enqueues two)
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and raise on a non-zero status."""
+    LAUNCH_COUNT[0] += 2 if name == 'catb_adam' else 1
     check(getattr(load(), name)(*args), name)
