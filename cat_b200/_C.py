@@ -30,6 +30,14 @@ class IgemmDesc(C.Structure):
         'sn', 'sd', 'pad_mode', 'n_units', 'n_rows', 'n_tile', 'act', 'accumulate', 'y_is_f32', 'reserved')]
 
 
+class HaloDesc(C.Structure):
+    _fields_ = [('n_steps', C.c_int32), ('n_chunks', C.c_int32), ('n_planes', C.c_int32),
+                ('plane_pa', C.c_int32 * 4), ('plane_pb', C.c_int32 * 4), ('plane_y0', C.c_int32 * 4),
+                ('plane_x0', C.c_int32 * 4), ('mul', C.c_int32), ('TW', C.c_int32), ('n_strips', C.c_int32),
+                ('Wf', C.c_int32), ('Lh', C.c_int32),
+                ('Ymax', C.c_int32), ('Xmax', C.c_int32), ('m_sub', C.c_int32)]
+
+
 class CatbError(RuntimeError):
     pass
 
@@ -43,6 +51,7 @@ _PROTOS = {
     'catb_pack_weights': [_DP, _P, _P, _P, _P],
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
+    'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
@@ -72,6 +81,7 @@ _SPECIAL = {
     'catb_version': ([], C.c_char_p),
     'catb_last_error_string': ([], C.c_char_p),
     'catb_packed_weight_bytes': ([_I, _I, _I], C.c_size_t),
+    'catb_igemm_halo_fits': ([_I, _I, _I, _I], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))
 

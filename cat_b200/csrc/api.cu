@@ -25,6 +25,7 @@ int check_launch(const char* what) {
 }
 
 int init_igemm_attributes();
+int init_halo_attributes();
 
 }  // namespace catb
 
@@ -51,5 +52,6 @@ extern "C" int catb_init(int device) {
     catb::set_error("cudaSetDevice(%d) failed", device);
     return CATB_ERR_CUDA;
   }
-  return catb::init_igemm_attributes();
+  if (int e = catb::init_igemm_attributes()) return e;
+  return catb::init_halo_attributes();
 }

@@ -1,0 +1,314 @@
+// Implicit-GEMM convolution v2: shared-memory halo tile + shifted-window UMMA descriptors.
+//
+// v1 (igemm.cu) re-gathers the activation tile from L2 once per filter tap; profiling showed every shape
+// bound by that gather (~2.5 TB/s L2->SM irrespective of N).  Here a CTA owns 128*m_sub consecutive
+// positions of ONE image in "pitch space" (m = i*Wf + j, Wf = lattice width + tap extent) and stages, once
+// per 64-channel chunk, the contiguous range of frame pixels those positions touch (the halo, one copy per
+// input parity plane for stride-2 convs).  A filter tap is then just a row offset into that buffer: the A
+// descriptor of tap (dy,dx) starts at halo_row = plane*Lh + dy*Wf + dx, all taps of the chunk reuse the
+// same shared-memory bytes, and the gather traffic drops by the tap count (25x for 5x5, 16x for 4x4, ...).
+// A window that does not start on a 1024-byte swizzle-atom boundary is described with the matrix
+// descriptor's base-offset field ((start >> 7) & 7).
+//
+// Warp roles as in v1: warps 0-3 fill the halo then run the epilogue, warp 4 issues tcgen05.mma for every
+// (chunk, tap, sub-tile), warp 5 streams the pre-swizzled weight tile of each (chunk, tap) step with one
+// bulk copy.  Up to two 128-row sub-tiles share every weight tile (halves weight traffic per FLOP).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace catb {
+
+constexpr int kHThreads = 192;
+constexpr int kHHeader = 1024;
+constexpr int kHMaxBStages = 6;
+
+struct HaloParams {
+  catb_igemm_desc d;
+  catb_halo_desc h;
+  const catb_halo_step* steps;
+  const catb_halo_chunk* chunks;
+  const __nv_bfloat16* x;
+  const uint8_t* wpk;
+  const float* bias;
+  void* y;
+  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = make_sw128_desc(smem_addr, lbo_bytes, sbo_bytes);
+  d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;  // matrix base offset inside the 1024-byte swizzle atom
+  return d;
+}
+
+__global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);  // [2]
+  uint64_t* a_empty = a_full + 2;                         // [2]
+  uint64_t* b_full = a_full + 4;                          // [kHMaxBStages]
+  uint64_t* b_empty = b_full + kHMaxBStages;              // [kHMaxBStages]
+  uint64_t* accum = b_empty + kHMaxBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  uint8_t* a_base = smem + kHHeader;
+  uint8_t* b_base = a_base + static_cast<size_t>(p.a_bufs) * p.halo_bytes;
+
+  const catb_igemm_desc& d = p.d;
+  const catb_halo_desc& h = p.h;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_img = p.tiles_per_image * h.n_strips;   // tiles_per_image = tiles per (image, strip)
+  const int n_img = blockIdx.x / per_img;
+  const int strip = (blockIdx.x - n_img * per_img) / p.tiles_per_image;
+  const int m0 = (blockIdx.x - n_img * per_img - strip * p.tiles_per_image) * (128 * h.m_sub);
+  const int strip_x = strip * h.TW;
+  const int tile_n = blockIdx.y;
+  const int b_bytes = d.n_tile * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.b_stages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- halo producer
+    const int total_rows = h.n_planes * h.Lh;
+    const int ul = threadIdx.x & 7, rsub = threadIdx.x >> 3;  // 16 rows per pass, 8 lanes per row
+    const int Hf = d.OHs + h.Ymax;                              // frame height
+    const size_t img_base = static_cast<size_t>(n_img) * d.H * d.W;
+    for (int c = 0; c < h.n_chunks; ++c) {
+      const int buf = c % p.a_bufs;
+      const uint32_t ph = (c / p.a_bufs) & 1;
+      const catb_halo_chunk ch = p.chunks[c];
+      const bool uvalid = ul < ch.n_units;
+      const __nv_bfloat16* xc = p.x + d.x_coff + (ch.cu0 + ul) * 8;
+      uint8_t* abuf = a_base + static_cast<size_t>(buf) * p.halo_bytes;
+      mbar_wait(&a_empty[buf], ph ^ 1);
+      for (int row0 = 0; row0 < total_rows; row0 += 64) {
+        uint4 v[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row0 + it * 16 + rsub;
+          v[it] = make_uint4(0, 0, 0, 0);
+          if (row < total_rows && uvalid) {
+            const int plane = row / h.Lh;
+            const int q = m0 + (row - plane * h.Lh);
+            const int fy = q / h.Wf, fx = q - fy * h.Wf;
+            if (fy < Hf) {
+              int iy = h.mul * (fy + h.plane_y0[plane]) + h.plane_pa[plane];
+              int ix = h.mul * (fx + h.plane_x0[plane] + strip_x) + h.plane_pb[plane];
+              bool ok;
+              if (d.pad_mode == CATB_PAD_REFLECT) {
+                ok = (iy > -d.H) & (iy < 2 * d.H - 1) & (ix > -d.W) & (ix < 2 * d.W - 1);
+                iy = reflect_idx(iy, d.H);
+                ix = reflect_idx(ix, d.W);
+              } else {
+                ok = (iy >= 0) & (iy < d.H) & (ix >= 0) & (ix < d.W);
+              }
+              if (ok) v[it] = ldg16(xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx);
+            }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row0 + it * 16 + rsub;
+          if (row < total_rows) st16(abuf + static_cast<size_t>(row) * 128 + ((ul ^ (row & 7)) << 4), v[it]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[buf]);
+    }
+
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(accum, 0);
+    tcgen05_fence_after();
+    for (int sub = 0; sub < h.m_sub; ++sub) {
+      const int m = m0 + sub * 128 + warp * 32 + lane;
+      const int i = m / h.Wf, j = m - i * h.Wf;
+      const int jg = strip_x + j;
+      const bool rvalid = (i < d.OHs) & (j < h.TW) & (jg < d.OWs);
+      const size_t ypix = (static_cast<size_t>(n_img) * d.OH + (d.o_ph + i * d.o_step)) * d.OW + (d.o_pw + jg * d.o_step);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + sub * d.n_tile;
+      for (int cc = 0; cc < d.n_tile / 16; ++cc) {
+        float acc[16];
+        tmem_ld16(trow + cc * 16, acc);
+        const int col0 = tile_n * d.n_tile + cc * 16;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + g * 8;
+          if (!rvalid || col >= p.n_store) continue;
+          f8 o;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float t = acc[g * 8 + q];
+            if (p.bias != nullptr && col + q < d.n_rows) t += __ldg(p.bias + col + q);
+            o.v[q] = t;
+          }
+          if (d.y_is_f32) {
+            float* yp = reinterpret_cast<float*>(p.y) + ypix * d.ldy + d.y_coff + col;
+            if (d.accumulate) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o.v[q] += yp[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o.v[q] = apply_act(o.v[q], d.act);
+            *reinterpret_cast<float4*>(yp) = make_float4(o.v[0], o.v[1], o.v[2], o.v[3]);
+            *reinterpret_cast<float4*>(yp + 4) = make_float4(o.v[4], o.v[5], o.v[6], o.v[7]);
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + ypix * d.ldy + d.y_coff + col;
+            if (d.accumulate) {
+              const f8 old = unpack8(ld16(yp));
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o.v[q] += old.v[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o.v[q] = apply_act(o.v[q], d.act);
+            st16(yp, pack8(o));
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int sg = 0;  // global step counter (ring position of the weight tiles)
+      for (int c = 0; c < h.n_chunks; ++c) {
+        const int buf = c % p.a_bufs;
+        const uint32_t ph = (c / p.a_bufs) & 1;
+        const catb_halo_chunk ch = p.chunks[c];
+        mbar_wait(&a_full[buf], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(a_base + static_cast<size_t>(buf) * p.halo_bytes);
+        for (int s = ch.first_step; s < ch.first_step + ch.n_steps; ++s, ++sg) {
+          const int st = sg % p.b_stages;
+          const uint32_t phb = (sg / p.b_stages) & 1;
+          const int a_row = p.steps[s].a_row;
+          mbar_wait(&b_full[st], phb);
+          tcgen05_fence_after();
+          const uint32_t b_addr = smem_u32(b_base + static_cast<size_t>(st) * b_bytes);
+          for (int sub = 0; sub < h.m_sub; ++sub) {
+            const uint32_t wa = a_addr + static_cast<uint32_t>(a_row + sub * 128) * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024);
+              const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(tmem_base + sub * d.n_tile, adesc, bdesc, p.idesc, (sg | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&b_empty[st]);
+        }
+        umma_commit(&a_empty[buf]);
+      }
+      umma_commit(accum);
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- weight loader
+    if (lane == 0) {
+      const uint8_t* src = p.wpk + static_cast<size_t>(tile_n) * h.n_steps * b_bytes;
+      for (int sg = 0; sg < h.n_steps; ++sg) {
+        const int st = sg % p.b_stages;
+        const uint32_t phb = (sg / p.b_stages) & 1;
+        mbar_wait(&b_empty[st], phb ^ 1);
+        mbar_arrive_expect_tx(&b_full[st], b_bytes);
+        bulk_g2s(b_base + static_cast<size_t>(st) * b_bytes, src + static_cast<size_t>(sg) * b_bytes, b_bytes, &b_full[st]);
+      }
+    }
+    __syncwarp();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+}
+
+int init_halo_attributes() {
+  const cudaError_t e =
+      cudaFuncSetAttribute(igemm_halo_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(halo): %s", cudaGetErrorString(e));
+    return CATB_ERR_CUDA;
+  }
+  return CATB_OK;
+}
+
+}  // namespace catb
+
+using namespace catb;
+
+// Shared-memory plan: returns 0 and fills a_bufs / b_stages, or -1 when the halo does not fit.
+static int halo_smem_plan(int halo_bytes, int b_bytes, int* a_bufs, int* b_stages, size_t* total) {
+  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kHHeader;
+  int ab = 2;
+  if (2 * halo_bytes + 3 * b_bytes > limit) ab = 1;
+  int bs = (limit - ab * halo_bytes) / b_bytes;
+  if (bs > kHMaxBStages) bs = kHMaxBStages;
+  if (bs < 2) return -1;
+  *a_bufs = ab;
+  *b_stages = bs;
+  *total = 1024 + kHHeader + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes;
+  return 0;
+}
+
+extern "C" int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub) {
+  const int halo_bytes = (n_planes * Lh * 128 + 1023) / 1024 * 1024;
+  int ab, bs;
+  size_t total;
+  if (m_sub * n_tile > 512) return 0;
+  return halo_smem_plan(halo_bytes, n_tile * 128, &ab, &bs, &total) == 0 ? 1 : 0;
+}
+
+extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
+                                     const catb_halo_chunk* chunks, const void* x, const void* packed_w,
+                                     const float* bias, void* y, catb_stream_t s) {
+  CATB_REQUIRE(d != nullptr && h != nullptr, "null descriptor");
+  CATB_REQUIRE(d->n_tile % 16 == 0 && d->n_tile >= 16 && d->n_tile <= 256, "n_tile must be a multiple of 16 in [16,256]");
+  CATB_REQUIRE(h->m_sub >= 1 && h->m_sub <= 2 && h->m_sub * d->n_tile <= 512, "m_sub * n_tile must fit 512 TMEM columns");
+  CATB_REQUIRE(h->n_planes >= 1 && h->n_planes <= 4 && h->n_steps > 0 && h->n_chunks > 0, "bad halo plan");
+  CATB_REQUIRE(h->TW > 0 && h->n_strips == (d->OWs + h->TW - 1) / h->TW && h->Wf == h->TW + h->Xmax &&
+                   h->Lh == 128 * h->m_sub + h->Ymax * h->Wf + h->Xmax,
+               "inconsistent halo geometry");
+  CATB_REQUIRE(d->n_units == h->n_steps * 8, "unit table must hold 8 units per step");
+  CATB_REQUIRE(d->ldx % 8 == 0 && d->x_coff % 8 == 0 && d->ldy % 8 == 0 && d->y_coff % 8 == 0, "pitches must be multiples of 8");
+  HaloParams p;
+  p.d = *d;
+  p.h = *h;
+  p.steps = steps;
+  p.chunks = chunks;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.wpk = static_cast<const uint8_t*>(packed_w);
+  p.bias = bias;
+  p.y = y;
+  p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
+  size_t smem = 0;
+  CATB_REQUIRE(halo_smem_plan(p.halo_bytes, d->n_tile * 128, &p.a_bufs, &p.b_stages, &smem) == 0,
+               "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
+  if (h->n_chunks == 1) p.a_bufs = 1;
+  const int positions = d->OHs * h->Wf;
+  p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);
+  uint32_t cols = 32;
+  while (static_cast<int>(cols) < h->m_sub * d->n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_store = (d->n_rows + 7) / 8 * 8;
+  p.idesc = make_idesc_bf16(128, d->n_tile, 0, 0);
+  const int n_tiles = (d->n_rows + d->n_tile - 1) / d->n_tile;
+  dim3 grid(p.tiles_per_image * h->n_strips * d->N, n_tiles, 1);
+  igemm_halo_fprop_kernel<<<grid, kHThreads, smem, static_cast<cudaStream_t>(s)>>>(p);
+  return check_launch("igemm_halo_fprop");
+}

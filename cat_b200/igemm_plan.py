@@ -206,3 +206,153 @@ def emulate_wgrad(geo: Geometry, units: Units, n_rows, x, y, grad_arena):
         idx = wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]
         grad_arena.index_put_((idx.reshape(-1),), contrib.reshape(-1).to(grad_arena.dtype), accumulate=True)
     return grad_arena
+
+
+# ------------------------------------------------------------------------------------------------
+# halo plan (v2 kernel): every input pixel is staged ONCE per CTA, taps address shifted windows
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class HaloPlan:
+    """Metadata of catb_igemm_halo_fprop for one (Geometry, Units) pair.
+
+    The lattice of an image is cut into vertical strips of TW columns; inside a strip, position (i, j) is
+    flattened in *pitch space* m = i*Wf + j with Wf = TW + Xmax (columns j >= TW are garbage positions whose
+    results are dropped).  A CTA owns `m_sub`*128 consecutive positions of one (image, strip) and stages, per
+    64-channel chunk and parity plane p, the frame rows [m0, m0 + Lh), where frame pixel (fy, fx) of plane p
+    is input pixel (mul*(fy + y0[p]) + pa[p], mul*(fx + x0[p] + strip*TW) + pb[p]).
+    GEMM step s = (chunk, tap): A rows = halo rows plane*Lh + dy*Wf + dx + (m - m0); B = packed tile s."""
+    units: Units                              # re-ordered, chunk aligned: 8 units per step
+    steps: List[Tuple[int, int, int, int]]    # (chunk index, plane, dy, dx)
+    chunks: List[Tuple[int, int, int, int]]   # (cu0, n_units, first_step, n_steps)
+    planes: List[Tuple[int, int, int, int]]   # (pa, pb, y0, x0)
+    mul: int
+    OWs: int
+    Ymax: int
+    Xmax: int
+    TW: int = 0
+    m_sub: int = 1
+
+    def __post_init__(self):
+        if self.TW == 0:
+            self.TW = self.OWs
+
+    @property
+    def n_strips(self):
+        return (self.OWs + self.TW - 1) // self.TW
+
+    @property
+    def Wf(self):
+        return self.TW + self.Xmax
+
+    @property
+    def Lh(self):
+        return 128 * self.m_sub + self.Ymax * self.Wf + self.Xmax
+
+    def halo_bytes(self):
+        return len(self.planes) * self.Lh * 128
+
+
+def make_halo_plan(geo: Geometry, units: Units):
+    """Returns a HaloPlan, or None when the gather is not a shifted-window pattern."""
+    if geo.sd == 2:
+        if not (geo.sn == 1 and geo.o_step == 2):
+            return None   # un-decomposed fractional stride: parity differs per output pixel
+        eff = [((geo.o_ph + g[0]), (geo.o_pw + g[1])) for g in units.g]
+        if any(a % 2 or b % 2 for a, b in eff):
+            return None
+        taps = [(a // 2, b // 2, 0, 0) for a, b in eff]
+        mul = 1
+    elif geo.sn == 2:
+        if geo.o_step != 1:
+            return None
+        taps = [((g[0] - g[0] % 2) // 2, (g[1] - g[1] % 2) // 2, g[0] % 2, g[1] % 2) for g in units.g]
+        mul = 2
+    else:
+        if geo.o_step != 1:
+            return None
+        taps = [(g[0], g[1], 0, 0) for g in units.g]
+        mul = 1
+    par = sorted({(t[2], t[3]) for t in taps})
+    planes, Ymax, Xmax = [], 0, 0
+    for (pa, pb) in par:
+        ys = [t[0] for t in taps if (t[2], t[3]) == (pa, pb)]
+        xs = [t[1] for t in taps if (t[2], t[3]) == (pa, pb)]
+        planes.append((pa, pb, min(ys), min(xs)))
+        Ymax, Xmax = max(Ymax, max(ys) - min(ys)), max(Xmax, max(xs) - min(xs))
+    # group units by 64-channel chunk of the gathered buffer, then by tap
+    by_chunk = {}
+    for (gu, wu, t) in zip(units.g, units.w, taps):
+        cc, j = divmod(gu[2], 8)
+        slot = by_chunk.setdefault(cc, {}).setdefault(t, {})
+        assert j not in slot, 'duplicate (channel unit, tap) in a halo GEMM'
+        slot[j] = (gu, wu)
+    new_units, steps, chunks = Units(), [], []
+    for cc in sorted(by_chunk):
+        first = len(steps)
+        present = sorted({j for t in by_chunk[cc].values() for j in t})
+        n_units = present[-1] + 1
+        for t in sorted(by_chunk[cc]):
+            pi = par.index((t[2], t[3]))
+            steps.append((len(chunks), pi, t[0] - planes[pi][2], t[1] - planes[pi][3]))
+            for j in range(8):
+                if j in by_chunk[cc][t]:
+                    gu, wu = by_chunk[cc][t][j]
+                    new_units.g.append(gu)
+                    new_units.w.append(wu)
+                else:  # padding unit: zero weights, never gathered
+                    ref = next(iter(by_chunk[cc][t].values()))[0]
+                    new_units.g.append((ref[0], ref[1], cc * 8 + j))
+                    new_units.w.append((0, 0, 0, 0))
+        chunks.append((cc * 8, n_units, first, len(steps) - first))
+    return HaloPlan(new_units, steps, chunks, planes, mul, geo.OWs, Ymax, Xmax)
+
+
+def emulate_halo_fprop(geo: Geometry, plan: HaloPlan, n_rows, x, arena, y, bias=None):
+    """Torch restatement of the v2 device algorithm (halo fill + shifted windows), test helper."""
+    Lh, Wf, TW = plan.Lh, plan.Wf, plan.TW
+    M = 128 * plan.m_sub
+    npos = geo.OHs * Wf
+    Hf = geo.OHs + plan.Ymax
+    ridx = torch.arange(n_rows)
+    for n in range(geo.N):
+        for strip in range(plan.n_strips):
+            for m0 in range(0, npos, M):
+                acc = torch.zeros(M, n_rows, dtype=x.dtype)
+                for (cu0, n_units, first, nsteps) in plan.chunks:
+                    halo = torch.zeros(len(plan.planes), Lh, 64, dtype=x.dtype)
+                    h = torch.arange(Lh)
+                    fy, fx = torch.div(m0 + h, Wf, rounding_mode='floor'), (m0 + h) % Wf
+                    for pi, (pa, pb, y0, x0) in enumerate(plan.planes):
+                        iy = plan.mul * (fy + y0) + pa
+                        ix = plan.mul * (fx + x0 + strip * TW) + pb
+                        if geo.pad_mode == PAD_REFLECT:
+                            ok = (iy > -geo.H) & (iy < 2 * geo.H - 1) & (ix > -geo.W) & (ix < 2 * geo.W - 1)
+                            iyr, ixr = _reflect(iy, geo.H), _reflect(ix, geo.W)
+                        else:
+                            iyr, ixr = iy, ix
+                            ok = (iyr >= 0) & (iyr < geo.H) & (ixr >= 0) & (ixr < geo.W)
+                        ok &= fy < Hf
+                        c0 = geo.x_coff + cu0 * 8
+                        vals = x[n, iyr.clamp(0, geo.H - 1), ixr.clamp(0, geo.W - 1), c0:c0 + n_units * 8]
+                        halo[pi, :, :n_units * 8] = vals * ok.unsqueeze(1).to(x.dtype)
+                    for s in range(first, first + nsteps):
+                        _, plane, dy, dx = plan.steps[s]
+                        a_off = dy * Wf + dx
+                        A = halo[plane, a_off:a_off + M]                    # [M, 64]
+                        Bm = torch.zeros(n_rows, 64, dtype=x.dtype)
+                        for j in range(8):
+                            wu = plan.units.w[s * 8 + j]
+                            if wu[3]:
+                                q = torch.arange(wu[3])
+                                Bm[:, j * 8:j * 8 + wu[3]] = arena[wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]]
+                        acc += A @ Bm.T
+                if bias is not None:
+                    acc += bias.view(1, -1)
+                m = m0 + torch.arange(M)
+                i, j = torch.div(m, Wf, rounding_mode='floor'), m % Wf
+                jg = strip * TW + j
+                ok = (i < geo.OHs) & (j < TW) & (jg < geo.OWs)
+                oh = geo.o_ph + i[ok] * geo.o_step
+                ow = geo.o_pw + jg[ok] * geo.o_step
+                y[n, oh, ow, geo.y_coff:geo.y_coff + n_rows] = acc[ok]
+    return y

@@ -5,12 +5,13 @@ libcatb200.so.  All wrappers enqueue on ``torch.cuda.current_stream()`` and neve
 sequence of calls can be captured into a CUDA graph.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import _C
-from .igemm_plan import Geometry, Units, choose_n_tile, cpad
+from .igemm_plan import Geometry, Units, choose_n_tile, cpad, make_halo_plan
 
 ACT = {'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'leaky': _C.ACT_LEAKY02, 'tanh': _C.ACT_TANH}
 BF16 = torch.bfloat16
@@ -77,38 +78,89 @@ def units_to_device(units: Units, device):
     return gt, wt
 
 
-class Gemm:
-    """One implicit GEMM: geometry + unit tables (+ packed bf16 weights for the fprop direction)."""
+USE_HALO = os.environ.get('CATB_NO_HALO', '0') != '1'   # v2 (halo) forward kernel unless disabled
 
-    def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True):
+
+class Gemm:
+    """One implicit GEMM: geometry + unit tables (+ packed bf16 weights for the fprop direction).
+
+    The forward direction runs the v2 halo kernel whenever the gather is a shifted-window pattern and the
+    halo tile fits in shared memory (make_halo_plan / catb_igemm_halo_fits), else the v1 gather-per-tap
+    kernel.  Both read the same packed weights; wgrad always uses the original unit order."""
+
+    def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True, halo=None, force_tile=None):
+        """force_tile=(TW, m_sub) pins the halo tiling (tests); by default the widest strip / largest
+        sub-tile count that fits in shared memory and still fills the GPU is chosen."""
         assert len(units) > 0 and n_rows > 0
         self.geo, self.units, self.n_rows = geo, units, n_rows
         self.n_units = len(units)
         self.n_tile = choose_n_tile(n_rows)
         self.gt, self.wt = units_to_device(units, device)
         self.packed = None
+        self.halo = None
+        self.f_units, self.f_gt, self.f_wt = units, self.gt, self.wt   # tables of the forward direction
         if need_pack:
-            nbytes = _C.load().catb_packed_weight_bytes(n_rows, self.n_units, self.n_tile)
+            lib = _C.load()
+            plan = make_halo_plan(geo, units) if (USE_HALO if halo is None else halo) else None
+            if plan is not None:
+                n_tiles_n = (n_rows + self.n_tile - 1) // self.n_tile
+                chosen = None
+                for tw in [geo.OWs] + [t for t in (64, 32, 16) if t < geo.OWs]:   # full width first, then strips
+                    plan.TW = tw
+                    for m_sub in (2, 1):
+                        plan.m_sub = m_sub
+                        tiles = (geo.OHs * plan.Wf + 128 * m_sub - 1) // (128 * m_sub)
+                        ctas = geo.N * plan.n_strips * tiles * n_tiles_n
+                        if lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, m_sub) and \
+                                (m_sub == 1 or ctas >= 2 * 148):
+                            chosen = (tw, m_sub)
+                            break
+                    if chosen:
+                        break
+                if force_tile is not None:
+                    plan.TW, plan.m_sub = force_tile
+                    chosen = force_tile if lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, plan.m_sub) else None
+                if chosen is None:
+                    plan = None
+            if plan is not None:
+                self.halo = plan
+                self.f_units = plan.units
+                self.f_gt, self.f_wt = units_to_device(plan.units, device)
+                hd = _C.HaloDesc()
+                hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
+                for i, (pa, pb, y0, x0) in enumerate(plan.planes):
+                    hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
+                hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
+                hd.Ymax, hd.Xmax, hd.m_sub = plan.Ymax, plan.Xmax, plan.m_sub
+                self.hdesc = hd
+                st = np.array([[pl * plan.Lh + dy * plan.Wf + dx, ci] for (ci, pl, dy, dx) in plan.steps], dtype=np.int32)
+                self.h_steps = torch.from_numpy(st).to(device)
+                self.h_chunks = torch.from_numpy(np.array(plan.chunks, dtype=np.int32)).to(device)
+            nbytes = lib.catb_packed_weight_bytes(n_rows, len(self.f_units), self.n_tile)
             self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
 
-    def desc(self, act=0, accumulate=False, y_is_f32=False, geo=None):
+    def desc(self, act=0, accumulate=False, y_is_f32=False, geo=None, n_units=None):
         g = geo or self.geo
         d = _C.IgemmDesc()
         d.N, d.H, d.W, d.ldx, d.x_coff = g.N, g.H, g.W, g.ldx, g.x_coff
         d.OH, d.OW, d.ldy, d.y_coff = g.OH, g.OW, g.ldy, g.y_coff
         d.o_step, d.o_ph, d.o_pw, d.OHs, d.OWs = g.o_step, g.o_ph, g.o_pw, g.OHs, g.OWs
         d.sn, d.sd, d.pad_mode = g.sn, g.sd, g.pad_mode
-        d.n_units, d.n_rows, d.n_tile = self.n_units, self.n_rows, self.n_tile
+        d.n_units, d.n_rows, d.n_tile = (self.n_units if n_units is None else n_units), self.n_rows, self.n_tile
         d.act, d.accumulate, d.y_is_f32 = int(act), int(bool(accumulate)), int(bool(y_is_f32))
         return d
 
     def pack(self, arena):
-        d = self.desc()
-        _C.call('catb_pack_weights', C.byref(d), _p(self.wt), _p(arena), _p(self.packed), _stream())
+        d = self.desc(n_units=len(self.f_units))
+        _C.call('catb_pack_weights', C.byref(d), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
 
-    def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False):
-        d = self.desc(act, accumulate, y_is_f32)
-        _C.call('catb_igemm_fprop', C.byref(d), _p(self.gt), _p(x), _p(self.packed), _p(bias), _p(y), _stream())
+    def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
+        d = self.desc(act, accumulate, y_is_f32, n_units=len(self.f_units))
+        if self.halo is not None and not force_v1:
+            _C.call('catb_igemm_halo_fprop', C.byref(d), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks), _p(x),
+                    _p(self.packed), _p(bias), _p(y), _stream())
+        else:
+            _C.call('catb_igemm_fprop', C.byref(d), _p(self.f_gt), _p(x), _p(self.packed), _p(bias), _p(y), _stream())
 
     def wgrad(self, x, y, grad_arena):
         d = self.desc()

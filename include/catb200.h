@@ -97,6 +97,36 @@ int catb_igemm_fprop(const catb_igemm_desc* d, const catb_gather_unit* units /*d
  * Replaces autograd's conv backward-weight for the same call sites. */
 int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
                      const void* x, const void* y, float* arena_grad, catb_stream_t s);
+/* v2 forward kernel: the CTA stages each input pixel ONCE per 64-channel chunk in a shared-memory halo
+ * tile and every filter tap addresses a shifted window of it (see cat_b200/csrc/igemm_halo.cu).  Same
+ * packed weights and unit table as catb_igemm_fprop, with the table ordered chunk-major, 8 units per
+ * (chunk, tap) step (cat_b200/igemm_plan.py: make_halo_plan).  Lattice positions are enumerated in pitch
+ * space m = i*Wf + j inside vertical strips of TW lattice columns; frame pixel (fy, fx) of plane p is
+ * input pixel (mul*(fy+y0[p]) + pa[p], mul*(fx+x0[p]+strip*TW) + pb[p]) under the padding rule. */
+typedef struct {
+  int32_t a_row; /* halo row of lattice position m0 for this step: plane*Lh + dy*Wf + dx */
+  int32_t chunk; /* index into the chunk table                                               */
+} catb_halo_step;
+typedef struct {
+  int32_t cu0, n_units;         /* first 8-channel unit of the chunk in the gathered pixel, units used */
+  int32_t first_step, n_steps;  /* the chunk's (tap) steps are contiguous in the step table            */
+} catb_halo_chunk;
+typedef struct {
+  int32_t n_steps, n_chunks, n_planes;
+  int32_t plane_pa[4], plane_pb[4]; /* input parity of the plane (stride-2 convs), else 0              */
+  int32_t plane_y0[4], plane_x0[4]; /* frame origin of the plane                                        */
+  int32_t mul;                      /* frame -> input: (mul*(fy+y0)+pa, mul*(fx+x0+strip*TW)+pb)        */
+  int32_t TW, n_strips;             /* lattice columns per vertical strip, strips per image             */
+  int32_t Wf, Lh;                   /* frame pitch TW+Xmax; halo rows per plane 128*m_sub+Ymax*Wf+Xmax  */
+  int32_t Ymax, Xmax;               /* tap extent in frame rows / columns                               */
+  int32_t m_sub;                    /* 128-row sub-tiles per CTA (1 or 2) sharing every weight tile     */
+} catb_halo_desc;
+/* 1 when the halo tile + weight ring fit in shared memory / TMEM for these parameters, else 0. */
+int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub);
+int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
+                          const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
+                          const float* bias /*nullable*/, void* y, catb_stream_t s);
+
 /* Slow SIMT restatements of the two kernels above (same descriptors); kept for on-device bisection
  * in tests.  Not used by the product path. */
 int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,

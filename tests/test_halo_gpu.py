@@ -1,0 +1,146 @@
+"""GPU parity of the v2 (halo / shifted-window) forward kernel: against torch (fp64 on bf16-rounded
+operands) and bit-for-bit against the v1 gather-per-tap kernel, which reads the same packed weights and
+accumulates the same products in fp32 (only the summation order of the K steps differs)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cat_b200 import igemm_plan as P
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _init():
+    from cat_b200 import ops
+    ops.require_cuda()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def to_dev_nhwc(x, ld=None, coff=0):
+    N, C, H, W = x.shape
+    ld = ld or P.cpad(C)
+    out = torch.zeros(N, H, W, ld, dtype=torch.bfloat16)
+    out[..., coff:coff + C] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.to(DEV)
+
+
+def from_dev_nhwc(t, C, coff=0):
+    return t[..., coff:coff + C].permute(0, 3, 1, 2).to(torch.float64).cpu()
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+CASES = [
+    # k, stride, pad, mode, Cin, Cout, N, H, W
+    (3, 1, 1, 'zero', 5, 7, 2, 10, 12),
+    (5, 1, 2, 'reflect', 72, 42, 2, 16, 16),     # two channel chunks, second one partial
+    (7, 1, 3, 'reflect', 64, 3, 1, 24, 40),      # generator head
+    (7, 1, 3, 'reflect', 3, 17, 2, 20, 24),      # generator stem
+    (1, 1, 0, 'zero', 24, 40, 2, 8, 8),
+    (3, 2, 1, 'zero', 17, 31, 2, 16, 16),        # 4 parity planes
+    (4, 2, 1, 'zero', 64, 128, 2, 16, 16),
+    (4, 1, 1, 'zero', 128, 1, 2, 9, 9),
+    (4, 1, 1, 'zero', 128, 300, 1, 12, 12),      # two N tiles
+    (5, 1, 2, 'reflect', 256, 48, 1, 16, 16),
+]
+
+
+@pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,N,H,W', CASES)
+@pytest.mark.parametrize('tile', ['auto', 'msub2', 'strips'])
+def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
+    from cat_b200 import ops
+    torch.manual_seed(k * 100 + Cin)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, k, k) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout)
+    xb, wb = bf(x).requires_grad_(True), bf(w)
+    xin = F.pad(xb, (pad,) * 4, mode='reflect') if mode == 'reflect' else xb
+    y_ref = F.conv2d(xin, wb, b.double(), stride=stride, padding=0 if mode == 'reflect' else pad)
+    OH, OW = y_ref.shape[2:]
+    arena = torch.cat([torch.zeros(5), w.flatten()]).to(DEV)
+    pm = P.PAD_REFLECT if mode == 'reflect' else P.PAD_ZERO
+    units = P.conv_fprop_units(5, Cout, Cin, k, k, pad)
+    ldy = P.cpad(Cout) + 8
+    geo = P.Geometry(N, H, W, P.cpad(Cin), 0, OH, OW, ldy, 8, sn=stride, pad_mode=pm)
+    force = {'auto': None, 'msub2': (OW, 2), 'strips': (max(4, OW // 3), 1)}[tile]
+    gm = ops.Gemm(geo, units, Cout, DEV, force_tile=force)
+    assert gm.halo is not None, 'every conv of the path must qualify for the halo kernel'
+    gm.pack(arena)
+    xd, bias = to_dev_nhwc(x), b.to(DEV)
+    y2 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
+    gm.fprop(xd, y2, bias=bias, act=ops.ACT['leaky'])
+    y1 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
+    gm.fprop(xd, y1, bias=bias, act=ops.ACT['leaky'], force_v1=True)
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(y_ref.detach(), 0.2)
+    assert rel_err(from_dev_nhwc(y1, Cout, 8), ref) < 6e-3, 'v1 on the chunk-aligned table'
+    assert rel_err(from_dev_nhwc(y2, Cout, 8), ref) < 6e-3, 'v2 halo kernel vs torch'
+    assert float((y1.float() - y2.float()).abs().max()) <= 2 ** -7 * float(ref.abs().max()), 'v2 vs v1'
+    assert float(y2[..., :8].float().min()) == 7.0 and float(y2[..., :8].float().max()) == 7.0
+    # fp32 output with accumulate
+    yf = torch.ones(N, OH, OW, ldy, dtype=torch.float32, device=DEV)
+    gm.fprop(xd, yf, bias=bias, accumulate=True, y_is_f32=True)
+    torch.cuda.synchronize()
+    assert rel_err(yf[..., 8:8 + Cout].permute(0, 3, 1, 2).double().cpu(), y_ref.detach() + 1.0) < 2e-5
+    # input gradient through the halo kernel (zero-padded convs: direct / 4 phases)
+    if mode == 'zero':
+        dy = torch.randn(N, Cout, OH, OW)
+        y_ref.backward(bf(dy))
+        dyd = to_dev_nhwc(dy)
+        du = P.conv_dgrad_units(5, Cout, Cin, k, k, pad)
+        dx = torch.zeros(N, H, W, P.cpad(Cin), dtype=torch.bfloat16, device=DEV)
+        if stride == 1:
+            gd = ops.Gemm(P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0), du, Cin, DEV)
+            assert gd.halo is not None
+            gd.pack(arena)
+            gd.fprop(dyd, dx)
+        else:
+            for a in range(2):
+                for c in range(2):
+                    ph = du.phase(a, c)
+                    if len(ph) == 0:
+                        continue
+                    g = P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0, sn=1, sd=2, o_step=2, o_ph=a, o_pw=c)
+                    gd = ops.Gemm(g, ph, Cin, DEV)
+                    assert gd.halo is not None
+                    gd.pack(arena)
+                    gd.fprop(dyd, dx)
+        torch.cuda.synchronize()
+        assert rel_err(from_dev_nhwc(dx, Cin), xb.grad) < 6e-3, 'halo dgrad'
+
+
+def test_halo_k_concat_block_stage2():
+    """Stage-2 GEMM of a residual block: K-concatenation of 1x1 / 3x3 / 5x5 convs over channel slices."""
+    from cat_b200 import ops
+    torch.manual_seed(2)
+    N, H, W, C = 2, 16, 16, 62
+    mids, ks = [17, 9, 70, 5], [1, 3, 5, 1]
+    xs = [torch.randn(N, m, H, W) for m in mids]
+    ws = [torch.randn(C, m, k, k) / math.sqrt(m * k * k) for m, k in zip(mids, ks)]
+    ref = sum(F.conv2d(F.pad(bf(x), ((k - 1) // 2,) * 4, mode='reflect') if k > 1 else bf(x), bf(w)) for x, w, k in zip(xs, ws, ks))
+    arena = torch.cat([torch.zeros(3)] + [w.flatten() for w in ws]).to(DEV)
+    ld = sum(P.cpad(m) for m in mids)
+    buf = torch.zeros(N, H, W, ld, dtype=torch.bfloat16)
+    units, cu0, off = P.Units(), 0, 3
+    for x, w, k, m in zip(xs, ws, ks, mids):
+        buf[..., cu0 * 8:cu0 * 8 + m] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        units.extend(P.conv_fprop_units(off, C, m, k, k, (k - 1) // 2, cu0=cu0))
+        cu0 += P.cpad(m) // 8
+        off += w.numel()
+    g = P.Geometry(N, H, W, ld, 0, H, W, P.cpad(C), 0, pad_mode=P.PAD_REFLECT)
+    gm = ops.Gemm(g, units, C, DEV)
+    assert gm.halo is not None
+    gm.pack(arena)
+    y = torch.zeros(N, H, W, P.cpad(C), dtype=torch.bfloat16, device=DEV)
+    gm.fprop(buf.to(DEV), y)
+    torch.cuda.synchronize()
+    assert rel_err(from_dev_nhwc(y, C), ref) < 6e-3

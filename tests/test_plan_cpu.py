@@ -155,3 +155,83 @@ def test_choose_n_tile():
         assert t % 16 == 0 and 16 <= t <= 256
         tiles = (n + t - 1) // t
         assert tiles * t >= n and (tiles - 1) * t < n
+
+
+@pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,H,W', [
+    (3, 1, 1, 'zero', 5, 7, 10, 12), (5, 1, 2, 'reflect', 70, 4, 12, 9), (7, 1, 3, 'reflect', 3, 17, 9, 11),
+    (1, 1, 0, 'zero', 130, 10, 8, 8), (3, 2, 1, 'zero', 6, 11, 10, 12), (4, 2, 1, 'zero', 72, 8, 12, 10),
+    (4, 1, 1, 'zero', 8, 1, 7, 9)])
+@pytest.mark.parametrize('m_sub', [1, 2])
+def test_halo_plan_conv_and_dgrad(k, stride, pad, mode, Cin, Cout, H, W, m_sub):
+    torch.manual_seed(0)
+    N = 2
+    x = torch.randn(N, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, dtype=torch.float64)
+    b = torch.randn(Cout, dtype=torch.float64)
+    xin = F.pad(x, (pad,) * 4, mode='reflect') if mode == 'reflect' else x
+    y_ref = F.conv2d(xin, w, b, stride=stride, padding=0 if mode == 'reflect' else pad)
+    OH, OW = y_ref.shape[2:]
+    arena, (w_off,) = make_arena(w)
+    units = P.conv_fprop_units(w_off, Cout, Cin, k, k, pad)
+    geo = P.Geometry(N, H, W, P.cpad(Cin), 0, OH, OW, P.cpad(Cout), 0, sn=stride,
+                     pad_mode=P.PAD_REFLECT if mode == 'reflect' else P.PAD_ZERO)
+    plan = P.make_halo_plan(geo, units)
+    assert plan is not None
+    plan.m_sub = m_sub
+    y = torch.zeros(N, OH, OW, geo.ldy, dtype=torch.float64)
+    P.emulate_halo_fprop(geo, plan, Cout, to_nhwc(x.detach()), arena, y, bias=b)
+    assert torch.allclose(from_nhwc(y, Cout), y_ref.detach(), atol=1e-10)
+    for tw in (4, 5):  # vertical strips (wide images whose full-width halo would not fit in shared memory)
+        plan.TW = tw
+        y = torch.zeros(N, OH, OW, geo.ldy, dtype=torch.float64)
+        P.emulate_halo_fprop(geo, plan, Cout, to_nhwc(x.detach()), arena, y, bias=b)
+        assert torch.allclose(from_nhwc(y, Cout), y_ref.detach(), atol=1e-10), tw
+    plan.TW = plan.OWs
+    # the re-ordered table must still drive the v1 gather kernel identically
+    y1 = torch.zeros_like(y)
+    P.emulate_fprop(geo, plan.units, Cout, to_nhwc(x.detach()), arena, y1, bias=b)
+    assert torch.allclose(y1, y, atol=1e-10)
+    if mode == 'zero':
+        dy = torch.randn_like(y_ref)
+        y_ref.backward(dy)
+        du = P.conv_dgrad_units(w_off, Cout, Cin, k, k, pad)
+        dx = torch.zeros(N, H, W, P.cpad(Cin), dtype=torch.float64)
+        if stride == 1:
+            g = P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0)
+            pl = P.make_halo_plan(g, du)
+            pl.m_sub = m_sub
+            P.emulate_halo_fprop(g, pl, Cin, to_nhwc(dy), arena, dx)
+        else:
+            for a in range(2):
+                for c in range(2):
+                    ph = du.phase(a, c)
+                    if len(ph) == 0:
+                        continue
+                    g = P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0, sn=1, sd=2, o_step=2, o_ph=a, o_pw=c)
+                    pl = P.make_halo_plan(g, ph)
+                    assert pl is not None
+                    pl.m_sub = m_sub
+                    P.emulate_halo_fprop(g, pl, Cin, to_nhwc(dy), arena, dx)
+        assert torch.allclose(from_nhwc(dx, Cin), x.grad, atol=1e-9)
+
+
+def test_halo_plan_k_concat():
+    torch.manual_seed(2)
+    N, H, W, C = 1, 9, 8, 6
+    mids, ks = [3, 9, 70], [1, 3, 5]
+    xs = [torch.randn(N, m, H, W, dtype=torch.float64) for m in mids]
+    ws = [torch.randn(C, m, k, k, dtype=torch.float64) for m, k in zip(mids, ks)]
+    ref = sum(F.conv2d(F.pad(x, ((k - 1) // 2,) * 4, mode='reflect') if k > 1 else x, w) for x, w, k in zip(xs, ws, ks))
+    arena, offs = make_arena(*ws)
+    ld = sum(P.cpad(m) for m in mids)
+    buf = torch.zeros(N, H, W, ld, dtype=torch.float64)
+    units, cu0 = P.Units(), 0
+    for x, w, k, m, off in zip(xs, ws, ks, mids, offs):
+        buf[..., cu0 * 8:cu0 * 8 + m] = x.permute(0, 2, 3, 1)
+        units.extend(P.conv_fprop_units(off, C, m, k, k, (k - 1) // 2, cu0=cu0))
+        cu0 += P.cpad(m) // 8
+    g = P.Geometry(N, H, W, ld, 0, H, W, P.cpad(C), 0, pad_mode=P.PAD_REFLECT)
+    plan = P.make_halo_plan(g, units)
+    y = torch.zeros(N, H, W, P.cpad(C), dtype=torch.float64)
+    P.emulate_halo_fprop(g, plan, C, buf, arena, y)
+    assert torch.allclose(from_nhwc(y, C), ref, atol=1e-10)
