@@ -14,6 +14,7 @@
 // (chunk, tap, sub-tile), warp 5 streams the pre-swizzled weight tile of each (chunk, tap) step with one
 // bulk copy.  Up to two 128-row sub-tiles share every weight tile (halves weight traffic per FLOP).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -32,15 +33,25 @@ struct HaloParams {
   const uint8_t* wpk;
   const float* bias;
   void* y;
-  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes;
+  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, bo_mode;
   uint32_t idesc;
 };
 
-__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       int bo_mode) {
   uint64_t d = make_sw128_desc(smem_addr, lbo_bytes, sbo_bytes);
-  d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;  // matrix base offset inside the 1024-byte swizzle atom
+  const uint32_t phase = (smem_addr >> 7) & 7u;  // row phase of the window start inside the 1024-byte swizzle atom
+  const uint32_t bo = bo_mode == 1 ? phase : (bo_mode == 2 ? ((8u - phase) & 7u) : 0u);
+  d |= static_cast<uint64_t>(bo) << 49;  // matrix-descriptor base offset
   return d;
 }
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -88,7 +99,6 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
 
   if (warp < 4) {
     // ---------------------------------------------------------------- halo producer
-    const int total_rows = h.n_planes * h.Lh;
     const int ul = threadIdx.x & 7, rsub = threadIdx.x >> 3;  // 16 rows per pass, 8 lanes per row
     const int Hf = d.OHs + h.Ymax;                              // frame height
     const size_t img_base = static_cast<size_t>(n_img) * d.H * d.W;
@@ -100,37 +110,36 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       const __nv_bfloat16* xc = p.x + d.x_coff + (ch.cu0 + ul) * 8;
       uint8_t* abuf = a_base + static_cast<size_t>(buf) * p.halo_bytes;
       mbar_wait(&a_empty[buf], ph ^ 1);
-      for (int row0 = 0; row0 < total_rows; row0 += 64) {
-        uint4 v[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = row0 + it * 16 + rsub;
-          v[it] = make_uint4(0, 0, 0, 0);
-          if (row < total_rows && uvalid) {
-            const int plane = row / h.Lh;
-            const int q = m0 + (row - plane * h.Lh);
-            const int fy = q / h.Wf, fx = q - fy * h.Wf;
-            if (fy < Hf) {
-              int iy = h.mul * (fy + h.plane_y0[plane]) + h.plane_pa[plane];
-              int ix = h.mul * (fx + h.plane_x0[plane] + strip_x) + h.plane_pb[plane];
-              bool ok;
-              if (d.pad_mode == CATB_PAD_REFLECT) {
-                ok = (iy > -d.H) & (iy < 2 * d.H - 1) & (ix > -d.W) & (ix < 2 * d.W - 1);
-                iy = reflect_idx(iy, d.H);
-                ix = reflect_idx(ix, d.W);
-              } else {
-                ok = (iy >= 0) & (iy < d.H) & (ix >= 0) & (ix < d.W);
-              }
-              if (ok) v[it] = ldg16(xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx);
-            }
+      // Every thread issues all of its 16-byte copies back to back with cp.async (LDGSTS, zero-fill for
+      // padding / out-of-frame pixels): hundreds of loads in flight per SM, no register staging.
+      for (int plane = 0; plane < h.n_planes; ++plane) {
+        const int y0 = h.plane_y0[plane], x0 = h.plane_x0[plane] + strip_x;
+        const int pa = h.plane_pa[plane], pb = h.plane_pb[plane];
+        int fy = (m0 + rsub) / h.Wf;
+        int fx = (m0 + rsub) - fy * h.Wf;
+        uint8_t* prow = abuf + static_cast<size_t>(plane) * h.Lh * 128;
+        for (int hr = rsub; hr < h.Lh; hr += 16) {
+          int iy = h.mul * (fy + y0) + pa;
+          int ix = h.mul * (fx + x0) + pb;
+          bool ok = uvalid & (fy < Hf);
+          if (d.pad_mode == CATB_PAD_REFLECT) {
+            ok &= (iy > -d.H) & (iy < 2 * d.H - 1) & (ix > -d.W) & (ix < 2 * d.W - 1);
+            iy = reflect_idx(iy, d.H);
+            ix = reflect_idx(ix, d.W);
+          } else {
+            ok &= (iy >= 0) & (iy < d.H) & (ix >= 0) & (ix < d.W);
+          }
+          const __nv_bfloat16* src = ok ? xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx : p.x;
+          const int row = plane * h.Lh + hr;  // swizzle phase follows the absolute row in the buffer
+          cp_async16_zfill(prow + static_cast<size_t>(hr) * 128 + ((ul ^ (row & 7)) << 4), src, ok);
+          fx += 16;
+          while (fx >= h.Wf) {
+            fx -= h.Wf;
+            ++fy;
           }
         }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = row0 + it * 16 + rsub;
-          if (row < total_rows) st16(abuf + static_cast<size_t>(row) * 128 + ((ul ^ (row & 7)) << 4), v[it]);
-        }
       }
+      cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
     }
@@ -206,7 +215,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
             const uint32_t wa = a_addr + static_cast<uint32_t>(a_row + sub * 128) * 128u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024);
+              const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024, p.bo_mode);
               const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
               umma_bf16(tmem_base + sub * d.n_tile, adesc, bdesc, p.idesc, (sg | k) != 0 ? 1u : 0u);
             }
@@ -296,10 +305,19 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   p.bias = bias;
   p.y = y;
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
+  {
+    const char* e = getenv("CATB_HALO_BO");  // experiment switch for the descriptor base-offset convention
+    p.bo_mode = e ? atoi(e) : 0;
+  }
   size_t smem = 0;
   CATB_REQUIRE(halo_smem_plan(p.halo_bytes, d->n_tile * 128, &p.a_bufs, &p.b_stages, &smem) == 0,
                "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
-  if (h->n_chunks == 1) p.a_bufs = 1;
+  // Ask only for what this launch can use, so that small problems co-schedule several CTAs per SM
+  // (the kernel is not persistent: prologue / epilogue of one CTA overlap the MMAs of its neighbours).
+  if (p.a_bufs > h->n_chunks) p.a_bufs = h->n_chunks;
+  if (p.b_stages > h->n_steps) p.b_stages = h->n_steps;
+  if (p.b_stages > 4 && 2 * (kHHeader + 1024 + p.a_bufs * p.halo_bytes + 4 * d->n_tile * 128) <= 226 * 1024) p.b_stages = 4;
+  smem = 1024 + kHHeader + static_cast<size_t>(p.a_bufs) * p.halo_bytes + static_cast<size_t>(p.b_stages) * d->n_tile * 128;
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);
   uint32_t cols = 32;

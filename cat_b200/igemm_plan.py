@@ -299,9 +299,9 @@ def make_halo_plan(geo: Geometry, units: Units):
                     gu, wu = by_chunk[cc][t][j]
                     new_units.g.append(gu)
                     new_units.w.append(wu)
-                else:  # padding unit: zero weights, never gathered
+                else:  # padding unit: zero weights; points at a real unit so that the v1 gather stays in bounds
                     ref = next(iter(by_chunk[cc][t].values()))[0]
-                    new_units.g.append((ref[0], ref[1], cc * 8 + j))
+                    new_units.g.append((ref[0], ref[1], ref[2]))
                     new_units.w.append((0, 0, 0, 0))
         chunks.append((cc * 8, n_units, first, len(steps) - first))
     return HaloPlan(new_units, steps, chunks, planes, mul, geo.OWs, Ymax, Xmax)

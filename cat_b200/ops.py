@@ -79,6 +79,7 @@ def units_to_device(units: Units, device):
 
 
 USE_HALO = os.environ.get('CATB_NO_HALO', '0') != '1'   # v2 (halo) forward kernel unless disabled
+AUTOTUNE = os.environ.get('CATB_NO_AUTOTUNE', '0') != '1'  # pick v1 / v2 per GEMM by timing the first call
 
 
 class Gemm:
@@ -98,6 +99,8 @@ class Gemm:
         self.gt, self.wt = units_to_device(units, device)
         self.packed = None
         self.halo = None
+        self.choice = None      # 'v1' | 'v2' once tuned; None = v2 whenever a halo plan exists
+        self.tuned_ms = None
         self.f_units, self.f_gt, self.f_wt = units, self.gt, self.wt   # tables of the forward direction
         if need_pack:
             lib = _C.load()
@@ -154,9 +157,29 @@ class Gemm:
         d = self.desc(n_units=len(self.f_units))
         _C.call('catb_pack_weights', C.byref(d), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
 
+    def _launch_timed(self, fn, reps=2):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
         d = self.desc(act, accumulate, y_is_f32, n_units=len(self.f_units))
-        if self.halo is not None and not force_v1:
+        if AUTOTUNE and self.halo is not None and self.choice is None and not force_v1 and not accumulate \
+                and not torch.cuda.is_current_stream_capturing():
+            # both kernels compute the same GEMM from the same packed weights: time them once on the real
+            # operands of the first call (idempotent, the output is simply rewritten) and keep the faster one
+            args = (_p(x), _p(self.packed), _p(bias), _p(y), _stream())
+            t2 = self._launch_timed(lambda: _C.call('catb_igemm_halo_fprop', C.byref(d), C.byref(self.hdesc),
+                                                    _p(self.h_steps), _p(self.h_chunks), *args))
+            t1 = self._launch_timed(lambda: _C.call('catb_igemm_fprop', C.byref(d), _p(self.f_gt), *args))
+            self.choice = 'v2' if t2 <= t1 else 'v1'
+            self.tuned_ms = (t1, t2)
+        if self.halo is not None and not force_v1 and self.choice != 'v1':
             _C.call('catb_igemm_halo_fprop', C.byref(d), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks), _p(x),
                     _p(self.packed), _p(bias), _p(y), _stream())
         else:

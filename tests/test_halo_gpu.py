@@ -74,6 +74,7 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
     force = {'auto': None, 'msub2': (OW, 2), 'strips': (max(4, OW // 3), 1)}[tile]
     gm = ops.Gemm(geo, units, Cout, DEV, force_tile=force)
     assert gm.halo is not None, 'every conv of the path must qualify for the halo kernel'
+    gm.choice = 'v2'   # pin the kernel under test (the engine autotunes v1 / v2 per GEMM)
     gm.pack(arena)
     xd, bias = to_dev_nhwc(x), b.to(DEV)
     y2 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
@@ -101,6 +102,7 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
         if stride == 1:
             gd = ops.Gemm(P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0), du, Cin, DEV)
             assert gd.halo is not None
+            gd.choice = 'v2'
             gd.pack(arena)
             gd.fprop(dyd, dx)
         else:
@@ -112,6 +114,7 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
                     g = P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0, sn=1, sd=2, o_step=2, o_ph=a, o_pw=c)
                     gd = ops.Gemm(g, ph, Cin, DEV)
                     assert gd.halo is not None
+                    gd.choice = 'v2'
                     gd.pack(arena)
                     gd.fprop(dyd, dx)
         torch.cuda.synchronize()
@@ -139,6 +142,7 @@ def test_halo_k_concat_block_stage2():
     g = P.Geometry(N, H, W, ld, 0, H, W, P.cpad(C), 0, pad_mode=P.PAD_REFLECT)
     gm = ops.Gemm(g, units, C, DEV)
     assert gm.halo is not None
+    gm.choice = 'v2'
     gm.pack(arena)
     y = torch.zeros(N, H, W, P.cpad(C), dtype=torch.bfloat16, device=DEV)
     gm.fprop(buf.to(DEV), y)
