@@ -26,6 +26,7 @@ int check_launch(const char* what) {
 
 int init_igemm_attributes();
 int init_halo_attributes();
+int init_simt_attributes();
 
 }  // namespace catb
 
@@ -53,5 +54,6 @@ extern "C" int catb_init(int device) {
     return CATB_ERR_CUDA;
   }
   if (int e = catb::init_igemm_attributes()) return e;
-  return catb::init_halo_attributes();
+  if (int e = catb::init_halo_attributes()) return e;
+  return catb::init_simt_attributes();
 }

@@ -19,9 +19,25 @@ static inline int grid_for(long long work, int block, int max_blocks = 148 * 16)
 // ------------------------------------------------------------------------------------------------
 // depthwise convolution, reflect padding (k-1)/2, per-unit kernel size
 // ------------------------------------------------------------------------------------------------
+// Filters of the whole channel range are staged once per block in shared memory as w_s[tap][C]
+// (49 taps max, zero for padding channels / unused taps), then every thread handles one (pixel, 8-channel
+// unit): 16-byte activation loads, two float4 filter loads per tap.
+constexpr int kDwMaxTaps = 49;
+__device__ __forceinline__ void dw_stage_filters(float* w_s, int C, const int32_t* ksize, const int32_t* w_off,
+                                                 const float* arena) {
+  for (int i = threadIdx.x; i < C * kDwMaxTaps; i += blockDim.x) {
+    const int tap = i / C, c = i - tap * C;
+    const int k = ksize[c], wo = w_off[c];
+    w_s[i] = (wo >= 0 && tap < k * k) ? arena[wo + tap] : 0.f;
+  }
+  __syncthreads();
+}
+
 __global__ void dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, __nv_bfloat16* __restrict__ y,
                                   int ldy, int y_coff, int N, int H, int W, int C, const int32_t* __restrict__ ksize,
                                   const int32_t* __restrict__ w_off, const float* __restrict__ arena) {
+  extern __shared__ float w_s[];
+  dw_stage_filters(w_s, C, ksize, w_off, arena);
   const int U = C / 8;
   const long long total = static_cast<long long>(N) * H * W * U;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -36,17 +52,15 @@ __global__ void dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, 
     f8 acc;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
-    int wo[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) wo[q] = w_off[u * 8 + q];
     for (int r = 0; r < k; ++r) {
       const int ih = reflect_idx(h - p + r, H);
       for (int s = 0; s < k; ++s) {
         const int iw = reflect_idx(w - p + s, W);
         const f8 xv = unpack8(ldg16(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * ldx + x_coff + u * 8));
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (wo[q] >= 0) acc.v[q] += xv.v[q] * __ldg(arena + wo[q] + r * k + s);
+        const float4 wa = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8 + 4);
+        acc.v[0] += xv.v[0] * wa.x; acc.v[1] += xv.v[1] * wa.y; acc.v[2] += xv.v[2] * wa.z; acc.v[3] += xv.v[3] * wa.w;
+        acc.v[4] += xv.v[4] * wb.x; acc.v[5] += xv.v[5] * wb.y; acc.v[6] += xv.v[6] * wb.z; acc.v[7] += xv.v[7] * wb.w;
       }
     }
     st16(y + static_cast<size_t>(pix) * ldy + y_coff + u * 8, pack8(acc));
@@ -67,6 +81,8 @@ __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int
                                        __nv_bfloat16* __restrict__ dx, int ldx, int x_coff, int N, int H, int W, int C,
                                        const int32_t* __restrict__ ksize, const int32_t* __restrict__ w_off,
                                        const float* __restrict__ arena) {
+  extern __shared__ float w_s[];
+  dw_stage_filters(w_s, C, ksize, w_off, arena);
   const int U = C / 8;
   const long long total = static_cast<long long>(N) * H * W * U;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -78,9 +94,6 @@ __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int
     const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
     const int k = ksize[u * 8];
     const int p = (k - 1) / 2;
-    int wo[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) wo[q] = w_off[u * 8 + q];
     f8 acc;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
@@ -95,9 +108,9 @@ __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int
             const int ow = ws[b] + p - s;
             if (ow < 0 || ow >= W) continue;
             const f8 g = unpack8(ldg16(dy + ((static_cast<size_t>(n) * H + oh) * W + ow) * ldy + y_coff + u * 8));
+            const float* wp = w_s + (r * k + s) * C + u * 8;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (wo[q] >= 0) acc.v[q] += g.v[q] * __ldg(arena + wo[q] + r * k + s);
+            for (int q = 0; q < 8; ++q) acc.v[q] += g.v[q] * wp[q];
           }
       }
     st16(dx + static_cast<size_t>(pix) * ldx + x_coff + u * 8, pack8(acc));
@@ -700,6 +713,16 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+int init_simt_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(dwconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(dwconv): %s", cudaGetErrorString(e));
+    return CATB_ERR_CUDA;
+  }
+  return CATB_OK;
+}
+
 }  // namespace catb
 
 using namespace catb;
@@ -713,7 +736,8 @@ extern "C" int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int 
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  dwconv_fwd_kernel<<<grid_for(total, 256), 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
+  CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
+  dwconv_fwd_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
                                                              static_cast<__nv_bfloat16*>(y), ldy, y_coff, N, H, W, C,
                                                              ksize, w_off, arena);
   return check_launch("dwconv_fwd");
@@ -725,7 +749,8 @@ extern "C" int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* d
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  dwconv_bwd_data_kernel<<<grid_for(total, 256), 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, y_coff,
+  CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
+  dwconv_bwd_data_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, y_coff,
                                                                   static_cast<__nv_bfloat16*>(dx), ldx, x_coff, N, H, W,
                                                                   C, ksize, w_off, arena);
   return check_launch("dwconv_bwd_data");

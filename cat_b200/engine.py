@@ -112,10 +112,12 @@ class Norm:
         self.mean_rstd = torch.empty(self.G, 2, Cp, **f)
         self.red = torch.zeros(self.G, 2, Cp, **f)
         self._frozen = False
+        self.pooled = False   # True once sums / red live in a per-network pool that is zeroed once per pass
 
     def forward(self, x: Act, y: Act, act, residual=None):
         if self.batch_stats:
-            self.sums.zero_()
+            if not self.pooled:
+                self.sums.zero_()
             ops.norm_stats(x, self.per_sample, self.sums)
             upd = self.training and self.track
             ops.norm_finalize(self.sums, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
@@ -131,10 +133,28 @@ class Norm:
         if not self.batch_stats:
             raise NotImplementedError('backward through eval-mode BatchNorm (the reference\'s first-step quirk, '
                                       'SURVEY.md section 7) is not supported')
-        self.red.zero_()
+        if not self.pooled:
+            self.red.zero_()
         ops.norm_bwd_reduce(dout, out, x, self.per_sample, self.mean_rstd, act, self.red)
         ops.norm_bwd_apply(dout, out, x, dx, self.per_sample, self.mean_rstd, self.gamma, self.red, self.count, act,
                            self.dgamma if param_grads else None, self.dbeta if param_grads else None)
+
+
+def pool_norm_buffers(norms, dev):
+    """Move the atomic-accumulation buffers of all norm layers of a network into two flat tensors, so that
+    one memset per forward / backward pass replaces two per layer."""
+    n_s = sum(n.sums.numel() for n in norms)
+    n_r = sum(n.red.numel() for n in norms)
+    pool_s = torch.zeros(max(n_s, 1), dtype=torch.float32, device=dev)
+    pool_r = torch.zeros(max(n_r, 1), dtype=torch.float32, device=dev)
+    o_s = o_r = 0
+    for n in norms:
+        n.sums = pool_s[o_s:o_s + n.sums.numel()].view(n.sums.shape)
+        n.red = pool_r[o_r:o_r + n.red.numel()].view(n.red.shape)
+        o_s += n.sums.numel()
+        o_r += n.red.numel()
+        n.pooled = True
+    return pool_s, pool_r
 
 
 class _NormSpec:
@@ -143,6 +163,7 @@ class _NormSpec:
 
     def __init__(self, arena: Arena, bufs: Arena, arch):
         self.arena, self.bufs, self.arch = arena, bufs, arch
+        self.created = []
 
     def alloc_group(self, prefixes_and_C):
         a, b, arch = self.arena, self.bufs, self.arch
@@ -177,7 +198,9 @@ class _NormSpec:
             kw['rvar'] = b.span(first + '.running_var', last + '.running_var')
         for t in kw.values():
             assert t.numel() == Cp
-        return Norm(dev, N, HW, Cp, arch['norm'], arch['eps'], arch['momentum'], training, track, **kw)
+        n = Norm(dev, N, HW, Cp, arch['norm'], arch['eps'], arch['momentum'], training, track, **kw)
+        self.created.append(n)
+        return n
 
 
 def _strided_dgrad(geo_kw, units, n_rows, dev, stride):
@@ -215,6 +238,7 @@ class GenNet:
         self.arena.finalize(device)
         self.bufs.finalize(device)
         self._build()
+        self.pool_sums, self.pool_red = pool_norm_buffers(self.ns.created, device)
 
     # ---- parameters --------------------------------------------------------------------------
     def _conv_alloc(self, name, shape, bias, transposed=False):
@@ -459,6 +483,7 @@ class GenNet:
         """x_in: NHWC bf16 input image [B,H,W,cpad(input_nc)].  Returns the output Act (tanh applied)."""
         self.x_in = x_in
         relu, none = ACT['relu'], ACT['none']
+        self.pool_sums.zero_()
         self.g_stem.fprop(x_in.t, self.y0.t)
         self.n_stem.forward(self.y0, self.a0, relu)
         self.g_d1.fprop(self.a0.t, self.y1.t)
@@ -492,6 +517,7 @@ class GenNet:
         accumulate extra gradient (the KA loss) into d(activation) at the four mapping layers."""
         assert self.need_grad
         relu, none, ar = ACT['relu'], ACT['none'], self.arena
+        self.pool_red.zero_()
         act_grads = act_grads or {}
         B, H, W = self.B, self.H, self.W
         c0, c1, c2, c3, c4 = self.arch['widths']
@@ -646,6 +672,7 @@ class DisNet:
             # wgrad geometry: lattice tensor = dy (bf16, pitch cpad(cout))
             L.gw = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.oh, L.ow, cpad(L.cout), 0, sn=L.stride), L.units,
                         L.cout, dev, need_pack=False)
+        self.pool_sums, self.pool_red = pool_norm_buffers(self.ns.created, dev)
         self.pred = self.layers[-1].y
         self.pred_n = B * self.layers[-1].oh * self.layers[-1].ow
 
@@ -666,6 +693,7 @@ class DisNet:
     def forward(self, x: Act):
         self.x = x
         cur = x
+        self.pool_sums.zero_()
         for L in self.layers:
             if L.y_f32:
                 L.g.fprop(cur.t, L.y, bias=L.bias, y_is_f32=True)
@@ -682,6 +710,7 @@ class DisNet:
         """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0)."""
         ar = self.arena
         d = dpred
+        self.pool_red.zero_()
         for li in range(len(self.layers) - 1, -1, -1):
             L = self.layers[li]
             x_in = self.layers[li - 1].a if li > 0 else self.x

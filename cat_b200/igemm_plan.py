@@ -279,31 +279,37 @@ def make_halo_plan(geo: Geometry, units: Units):
         xs = [t[1] for t in taps if (t[2], t[3]) == (pa, pb)]
         planes.append((pa, pb, min(ys), min(xs)))
         Ymax, Xmax = max(Ymax, max(ys) - min(ys)), max(Xmax, max(xs) - min(xs))
-    # group units by 64-channel chunk of the gathered buffer, then by tap
-    by_chunk = {}
+    # Channel chunks: runs of up to 8 consecutive channel units that share the same tap set (so a
+    # K-concatenation of convs with different kernel sizes is cut at the slice boundaries and no step
+    # multiplies a slice by taps it does not have), each chunk = one staged halo of <= 64 channels.
+    by_cu = {}
     for (gu, wu, t) in zip(units.g, units.w, taps):
-        cc, j = divmod(gu[2], 8)
-        slot = by_chunk.setdefault(cc, {}).setdefault(t, {})
-        assert j not in slot, 'duplicate (channel unit, tap) in a halo GEMM'
-        slot[j] = (gu, wu)
+        slot = by_cu.setdefault(gu[2], {})
+        assert t not in slot, 'duplicate (channel unit, tap) in a halo GEMM'
+        slot[t] = (gu, wu)
+    groups = []
+    for cu in sorted(by_cu):
+        tapset = frozenset(by_cu[cu])
+        if groups and len(groups[-1][1]) < 8 and groups[-1][1][-1] + 1 == cu and groups[-1][0] == tapset:
+            groups[-1][1].append(cu)
+        else:
+            groups.append((tapset, [cu]))
     new_units, steps, chunks = Units(), [], []
-    for cc in sorted(by_chunk):
+    for tapset, cus in groups:
         first = len(steps)
-        present = sorted({j for t in by_chunk[cc].values() for j in t})
-        n_units = present[-1] + 1
-        for t in sorted(by_chunk[cc]):
+        for t in sorted(tapset):
             pi = par.index((t[2], t[3]))
             steps.append((len(chunks), pi, t[0] - planes[pi][2], t[1] - planes[pi][3]))
             for j in range(8):
-                if j in by_chunk[cc][t]:
-                    gu, wu = by_chunk[cc][t][j]
+                if j < len(cus):
+                    gu, wu = by_cu[cus[j]][t]
                     new_units.g.append(gu)
                     new_units.w.append(wu)
-                else:  # padding unit: zero weights; points at a real unit so that the v1 gather stays in bounds
-                    ref = next(iter(by_chunk[cc][t].values()))[0]
+                else:  # padding unit: zero weights (points at a real unit: stays in bounds if ever gathered)
+                    ref = by_cu[cus[0]][t][0]
                     new_units.g.append((ref[0], ref[1], ref[2]))
                     new_units.w.append((0, 0, 0, 0))
-        chunks.append((cc * 8, n_units, first, len(steps) - first))
+        chunks.append((cus[0], len(cus), first, len(steps) - first))
     return HaloPlan(new_units, steps, chunks, planes, mul, geo.OWs, Ymax, Xmax)
 
 

@@ -139,8 +139,12 @@ class Gemm:
                 st = np.array([[pl * plan.Lh + dy * plan.Wf + dx, ci] for (ci, pl, dy, dx) in plan.steps], dtype=np.int32)
                 self.h_steps = torch.from_numpy(st).to(device)
                 self.h_chunks = torch.from_numpy(np.array(plan.chunks, dtype=np.int32)).to(device)
-            nbytes = lib.catb_packed_weight_bytes(n_rows, len(self.f_units), self.n_tile)
-            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            # v1 reads the compact original table, v2 the chunk-aligned one: two packed images until tuned
+            self.packed_v1 = torch.empty(lib.catb_packed_weight_bytes(n_rows, self.n_units, self.n_tile),
+                                         dtype=torch.uint8, device=device)
+            if self.halo is not None:
+                self.packed = torch.empty(lib.catb_packed_weight_bytes(n_rows, len(self.f_units), self.n_tile),
+                                          dtype=torch.uint8, device=device)
 
     def desc(self, act=0, accumulate=False, y_is_f32=False, geo=None, n_units=None):
         g = geo or self.geo
@@ -154,8 +158,12 @@ class Gemm:
         return d
 
     def pack(self, arena):
-        d = self.desc(n_units=len(self.f_units))
-        _C.call('catb_pack_weights', C.byref(d), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
+        if self.halo is None or self.choice != 'v2':
+            d = self.desc()
+            _C.call('catb_pack_weights', C.byref(d), _p(self.wt), _p(arena), _p(self.packed_v1), _stream())
+        if self.halo is not None and self.choice != 'v1':
+            d = self.desc(n_units=len(self.f_units))
+            _C.call('catb_pack_weights', C.byref(d), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
 
     def _launch_timed(self, fn, reps=2):
         fn()
@@ -168,22 +176,31 @@ class Gemm:
         return e0.elapsed_time(e1) / reps
 
     def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
-        d = self.desc(act, accumulate, y_is_f32, n_units=len(self.f_units))
+        d1 = self.desc(act, accumulate, y_is_f32)
+        d2 = self.desc(act, accumulate, y_is_f32, n_units=len(self.f_units))
+
+        def v1():
+            _C.call('catb_igemm_fprop', C.byref(d1), _p(self.gt), _p(x), _p(self.packed_v1), _p(bias), _p(y), _stream())
+
+        def v2():
+            _C.call('catb_igemm_halo_fprop', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
+                    _p(x), _p(self.packed), _p(bias), _p(y), _stream())
+
         if AUTOTUNE and self.halo is not None and self.choice is None and not force_v1 and not accumulate \
                 and not torch.cuda.is_current_stream_capturing():
-            # both kernels compute the same GEMM from the same packed weights: time them once on the real
-            # operands of the first call (idempotent, the output is simply rewritten) and keep the faster one
-            args = (_p(x), _p(self.packed), _p(bias), _p(y), _stream())
-            t2 = self._launch_timed(lambda: _C.call('catb_igemm_halo_fprop', C.byref(d), C.byref(self.hdesc),
-                                                    _p(self.h_steps), _p(self.h_chunks), *args))
-            t1 = self._launch_timed(lambda: _C.call('catb_igemm_fprop', C.byref(d), _p(self.f_gt), *args))
+            # both kernels compute the same GEMM: time them once on the real operands of the first call
+            # (idempotent, the output is simply rewritten) and keep the faster one
+            t2, t1 = self._launch_timed(v2), self._launch_timed(v1)
             self.choice = 'v2' if t2 <= t1 else 'v1'
             self.tuned_ms = (t1, t2)
+            if self.choice == 'v2':
+                self.packed_v1 = None
+            else:
+                self.packed = None
         if self.halo is not None and not force_v1 and self.choice != 'v1':
-            _C.call('catb_igemm_halo_fprop', C.byref(d), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks), _p(x),
-                    _p(self.packed), _p(bias), _p(y), _stream())
+            v2()
         else:
-            _C.call('catb_igemm_fprop', C.byref(d), _p(self.f_gt), _p(x), _p(self.packed), _p(bias), _p(y), _stream())
+            v1()
 
     def wgrad(self, x, y, grad_arena):
         d = self.desc()

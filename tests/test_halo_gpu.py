@@ -74,8 +74,8 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
     force = {'auto': None, 'msub2': (OW, 2), 'strips': (max(4, OW // 3), 1)}[tile]
     gm = ops.Gemm(geo, units, Cout, DEV, force_tile=force)
     assert gm.halo is not None, 'every conv of the path must qualify for the halo kernel'
-    gm.choice = 'v2'   # pin the kernel under test (the engine autotunes v1 / v2 per GEMM)
-    gm.pack(arena)
+    gm.pack(arena)     # packs both weight images (v1: compact table, v2: chunk-aligned table)
+    gm.choice = 'v2'   # then pin the kernel under test (the engine autotunes v1 / v2 per GEMM)
     xd, bias = to_dev_nhwc(x), b.to(DEV)
     y2 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
     gm.fprop(xd, y2, bias=bias, act=ops.ACT['leaky'])
