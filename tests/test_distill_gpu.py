@@ -145,4 +145,4 @@ def test_distill_step_matches_oracle(golden_dir, name, use_graph, kernels):
         elif '_w_mean' in k:
             assert v <= (0.1 if kernels == 'v1' else 0.25) * (int(k[-1]) + 1), ('emu', k, v)
         else:
-            assert v <= (2e-2 if kernels == 'v1' else 3e-2), ('emu', k, v)
+            assert v <= 3e-2, ('emu', k, v)
