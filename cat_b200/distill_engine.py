@@ -11,7 +11,7 @@ normalisation layer are not updated (their gradient is analytically zero).
 """
 import torch
 
-from . import ops
+from . import ops, parallel
 from .engine import MAPPING_LAYERS, DisNet, GenNet
 from .igemm_plan import cpad
 from .ops import Act
@@ -101,7 +101,7 @@ class DistillStep:
 
     def _adam(self, net, lr, step):
         a = net.arena
-        ops.adam(a.p, a.g, a.m, a.v, lr, self.hp['beta1'], 0.999, 1e-8, 1.0 / self.world_size, step)
+        ops.adam(a.p, a.g, a.m, a.v, lr, self.hp['beta1'], 0.999, 1e-8, parallel.grad_scale(self.world_size), step)
         net.pack_weights()
 
     def _phase_G(self):
@@ -131,9 +131,7 @@ class DistillStep:
         S.backward(self.dS, act_grads)
 
     def _allreduce(self, net):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(net.arena.g)
+        parallel.reduce_gradients(net.arena.g, self.world_size)
 
     # ---- the step ------------------------------------------------------------------------------
     def _part1(self):

@@ -1,0 +1,19 @@
+"""Reference distiller protocol on the CUDA engine (distillers/__init__.py:13-41: name -> class lookup)."""
+
+
+def find_distiller_using_name(distiller_name):
+    if distiller_name == 'inception':
+        from .inception_distiller import InceptionDistiller
+        return InceptionDistiller
+    raise NotImplementedError('distiller [%s] is not available in cat_b200 yet (spade is the next section-8 row)' % distiller_name)
+
+
+def get_option_setter(distiller_name):
+    return find_distiller_using_name(distiller_name).modify_commandline_options
+
+
+def create_distiller(opt, verbose=True):
+    distiller = find_distiller_using_name(opt.distiller)(opt)
+    if verbose:
+        print('distiller [%s] was created' % type(distiller).__name__)
+    return distiller

@@ -1,0 +1,218 @@
+"""Mirror of the reference distiller protocol (distillers/inception_distiller.py:32-281 and
+distillers/base_inception_distiller.py:28-403) on top of the fused CUDA step.
+
+What ``trainer.py:79-175`` calls is kept name for name: ``InceptionDistiller(opt)``, ``setup``, ``set_input``,
+``optimize_parameters``, ``get_current_losses``, ``save_networks`` / ``load_networks``, ``update_learning_rate``,
+``print_networks``, ``test``; attributes ``netG_teacher / netG_student / netD / netAs``, ``optimizers``,
+``Tfake_B / Sfake_B``, ``loss_*``.  The networks are the module-tree mirrors of cat_b200.models.networks whose
+parameters alias the engine arenas, so checkpoints written here load in the reference and vice versa.
+Out of scope: FID / mIoU evaluation (``evaluate_model`` raises), data loading, logging.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from ..distill_engine import DistillStep
+from ..engine import MAPPING_LAYERS
+from ..models import networks
+
+
+class _ArenaOptimizer:
+    """Stand-in for torch.optim.Adam over an engine arena: exposes what the reference touches
+    (param_groups[0]['lr'], state_dict / load_state_dict for save_networks / load_optimizer)."""
+
+    def __init__(self, lr, betas):
+        self.param_groups = [{'lr': lr, 'betas': betas}]
+        self.net = None
+        self.step_counter = None
+
+    def bind(self, net, step_counter):
+        self.net, self.step_counter = net, step_counter
+
+    def state_dict(self):
+        if self.net is None:
+            return {'state': {}, 'param_groups': self.param_groups}
+        a = self.net.arena
+        return {'exp_avg': a.m.detach().cpu(), 'exp_avg_sq': a.v.detach().cpu(), 'step': int(self.step_counter.item()),
+                'layout': {k: (v[0], v[1]) for k, v in a.entries.items()}, 'param_groups': self.param_groups}
+
+    def load_state_dict(self, sd):
+        if self.net is not None and 'exp_avg' in sd:
+            self.net.arena.m.copy_(sd['exp_avg'])
+            self.net.arena.v.copy_(sd['exp_avg_sq'])
+            self.step_counter.fill_(int(sd['step']))
+
+
+class InceptionDistiller:
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        """The flags of base_inception_distiller.py:30-101 and inception_distiller.py:34-76 that the step uses."""
+        assert is_train
+        parser.add_argument('--teacher_netG', type=str, default='inception_9blocks')
+        parser.add_argument('--student_netG', type=str, default='inception_9blocks')
+        parser.add_argument('--teacher_ngf', type=int, default=64)
+        parser.add_argument('--student_ngf', type=int, default=48)
+        parser.add_argument('--restore_teacher_G_path', type=str, required=True)
+        parser.add_argument('--restore_student_G_path', type=str, default=None)
+        parser.add_argument('--restore_D_path', type=str, default=None)
+        parser.add_argument('--restore_O_path', type=str, default=None)
+        parser.add_argument('--recon_loss_type', type=str, default='l1', choices=['l1', 'l2', 'smooth_l1'])
+        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka'])
+        parser.add_argument('--lambda_distill', type=float, default=1)
+        parser.add_argument('--lambda_recon', type=float, default=100)
+        parser.add_argument('--lambda_gan', type=float, default=1)
+        parser.add_argument('--target_flops', type=float, default=0)
+        parser.set_defaults(norm='instance', dataset_mode='aligned', teacher_netG='inception_9blocks',
+                            student_netG='inception_9blocks')
+        return parser
+
+    def __init__(self, opt):
+        assert opt.isTrain
+        self.opt = opt
+        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0]))
+        if not self.gpu_ids or not torch.cuda.is_available():
+            raise RuntimeError('cat_b200.InceptionDistiller needs a CUDA device (sm_100a); there is no CPU path')
+        self.device = torch.device('cuda:%d' % self.gpu_ids[0])
+        self.save_dir = os.path.join(getattr(opt, 'log_dir', '.'), 'checkpoints')
+        if getattr(opt, 'distill_G_loss_type', 'ka') != 'ka':
+            raise NotImplementedError("only --distill_G_loss_type ka (the CAT kernel-alignment loss) is implemented")
+        if opt.recon_loss_type == 'vgg':
+            raise NotImplementedError('VGG reconstruction loss is not on the inception distillation scripts')
+        self.loss_names = ['G_gan', 'G_distill', 'G_recon', 'D_fake', 'D_real'] + ['G_distill%d' % i for i in range(4)]
+        self.model_names = ['netG_student', 'netG_teacher', 'netD']
+        self.visual_names = ['real_A', 'Sfake_B', 'Tfake_B', 'real_B']
+        self.image_paths = []
+        ids = self.gpu_ids[:1]
+        self.netG_teacher = networks.define_G(opt.input_nc, opt.output_nc, opt.teacher_ngf, opt.teacher_netG, opt.norm,
+                                              0, opt.init_type, opt.init_gain, ids, opt=opt)
+        arch_S = getattr(opt, 'student_arch', None)  # pruned architecture (what shrink_model produces)
+        if arch_S is not None:
+            self.netG_student = networks.init_net(networks.InceptionGenerator.from_arch(arch_S), opt.init_type,
+                                                  opt.init_gain, ids)
+        else:
+            self.netG_student = networks.define_G(opt.input_nc, opt.output_nc, opt.student_ngf, opt.student_netG,
+                                                  opt.norm, 0, opt.init_type, opt.init_gain, ids, opt=opt)
+        d_in = opt.input_nc + opt.output_nc if opt.dataset_mode in ('aligned', 'cityscapes') else opt.output_nc
+        self.netD = networks.define_D(d_in, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, opt.init_type, opt.init_gain,
+                                      ids, opt=opt)
+        self.netG_teacher.eval()
+        self.mapping_layers = list(MAPPING_LAYERS)
+        # adaptor convs: parameters of optimizer_G in the reference, unused under the 'ka' loss
+        self.netAs = [nn.Conv2d(opt.student_ngf * 4, opt.teacher_ngf * 4, kernel_size=1).to(self.device) for _ in range(4)]
+        self.optimizer_G = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
+        self.optimizer_D = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
+        self.optimizers = [self.optimizer_G, self.optimizer_D]
+        self.Tacts, self.Sacts = {}, {}
+        self.engine = None
+        self.is_best = False
+        self._epoch = 0
+
+    # ---- protocol -------------------------------------------------------------------------------
+    def setup(self, opt, verbose=True):
+        self.load_networks(verbose)
+        if verbose:
+            self.print_networks()
+
+    def _hp(self):
+        o = self.opt
+        return dict(gan_mode=o.gan_mode, aligned=o.dataset_mode in ('aligned', 'cityscapes'), lambda_recon=o.lambda_recon,
+                    lambda_gan=o.lambda_gan, lambda_distill=o.lambda_distill, lr=o.lr, beta1=o.beta1,
+                    student_training=self.netG_student.training, recon_loss_type=o.recon_loss_type,
+                    ka_scale=float(getattr(o, 'world_size', 1)))
+
+    def _ensure_engine(self, B, H, W):
+        if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
+            return
+        eng = DistillStep(self.netG_teacher.arch(), self.netG_student.arch(), self.netD.arch(), self._hp(), B, H, W,
+                          device=str(self.device), world_size=int(getattr(self.opt, 'world_size', 1)),
+                          use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
+        for module, net in ((self.netG_teacher, eng.T), (self.netG_student, eng.S), (self.netD, eng.D)):
+            module.bind(net)               # copies the module's weights in, then re-points them at the arena
+            net.pack_weights()
+        self.optimizer_G.bind(eng.S, eng.step_G)
+        self.optimizer_D.bind(eng.D, eng.step_D)
+        self.engine = eng
+
+    def set_input(self, input):
+        AtoB = getattr(self.opt, 'direction', 'AtoB') == 'AtoB'
+        self.real_A = input['A' if AtoB else 'B']
+        self.real_B = input['B' if AtoB else 'A']
+        self.image_paths = input.get('A_paths' if AtoB else 'B_paths', [])
+        B, _, H, W = self.real_A.shape
+        self._ensure_engine(B, H, W)
+        self.engine.set_input(self.real_A, self.real_B)
+
+    def optimize_parameters(self, steps):
+        self.engine.step()
+        self._losses = None
+
+    def forward(self, teacher_forward=True):
+        """Inference of both generators on the current input (test() in the reference)."""
+        with torch.no_grad():
+            if teacher_forward:
+                self.Tfake_B = self.netG_teacher(self.engine.real_A)
+            self.Sfake_B = self.netG_student(self.engine.real_A)
+
+    def test(self, teacher_forward=True):
+        self.forward(teacher_forward)
+
+    def get_current_losses(self):
+        L = self.engine.get_losses()   # one device synchronisation, like float(loss) in base_model.py:187
+        out = OrderedDict()
+        for name in self.loss_names:
+            key = ('Specific_loss/' if any(ch.isdigit() for ch in name) else ('D_loss/' if name.startswith('D_') else 'G_loss/')) + name
+            out[key] = L[name]
+            setattr(self, 'loss_' + name, L[name])
+        return out
+
+    def update_learning_rate(self, logger=None):
+        """'linear' policy of models/networks.py:80-87, stepped once per epoch (trainer.py:175)."""
+        o = self.opt
+        self._epoch += 1
+        scale = 1.0 - max(0, self._epoch + 1 - o.nepochs) / float(o.nepochs_decay + 1)
+        lr = o.lr * scale
+        for opt_ in self.optimizers:
+            opt_.param_groups[0]['lr'] = lr
+        if self.engine is not None:
+            self.engine.set_lr(lr)
+        msg = 'learning rate = %.7f' % lr
+        logger.print_info(msg + '\n') if logger is not None else print(msg)
+
+    def evaluate_model(self, step):
+        raise NotImplementedError('FID / mIoU evaluation (metric/) is outside the distillation hot path')
+
+    def add_mapping_hook(self):
+        pass   # the engine exposes the four mapped activations natively (engine.S.acts / engine.T.acts)
+
+    def remove_mapping_hook(self):
+        pass
+
+    def print_networks(self):
+        for name in self.model_names:
+            net = getattr(self, name)
+            n = sum(p.numel() for p in net.parameters())
+            print('[Network %s] Total number of parameters : %.3f M' % (name, n / 1e6))
+
+    # ---- checkpoints (same file names and key layout as base_inception_distiller.py:342-396) -------
+    def load_networks(self, verbose=True, teacher_only=False, restore_pretrain=True):
+        def load(net, path):
+            if path is not None:
+                net.load_state_dict(torch.load(path, map_location='cpu'))
+                if verbose:
+                    print('Load network at %s' % path)
+        load(self.netG_teacher, getattr(self.opt, 'restore_teacher_G_path', None))
+        load(self.netG_student, getattr(self.opt, 'restore_student_G_path', None))
+        load(self.netD, getattr(self.opt, 'restore_D_path', None))
+
+    def save_networks(self, epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
+        def cpu_sd(net):
+            return OrderedDict((k, v.detach().cpu().clone()) for k, v in net.state_dict().items())
+        torch.save(cpu_sd(self.netG_student), os.path.join(self.save_dir, '%s_net_G.pth' % epoch))
+        torch.save(cpu_sd(self.netD), os.path.join(self.save_dir, '%s_net_D.pth' % epoch))
+        for i, net in enumerate(self.netAs):
+            torch.save(cpu_sd(net), os.path.join(self.save_dir, '%s_net_A-%d.pth' % (epoch, i)))
+        for i, optimizer in enumerate(self.optimizers):
+            torch.save(optimizer.state_dict(), os.path.join(self.save_dir, '%s_optim-%d.pth' % (epoch, i)))

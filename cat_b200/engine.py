@@ -227,16 +227,23 @@ class _Block:
 class GenNet:
     """InceptionGenerator compiled for a fixed (B, H, W)."""
 
-    def __init__(self, arch, B, H, W, device, training, need_grad):
+    def __init__(self, arch, B, H, W, device, training, need_grad, share=None):
+        """share: another GenNet of the same architecture whose parameter / buffer arenas are reused (e.g. an
+        eval-mode or different-resolution compilation of the same weights)."""
         assert H % 4 == 0 and W % 4 == 0, 'the generator down-samples twice'
         self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
         self.training, self.need_grad = training, need_grad
-        self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
-        self.ns = _NormSpec(self.arena, self.bufs, arch)
         self.use_bias = arch['use_bias']
-        self._alloc_params()
-        self.arena.finalize(device)
-        self.bufs.finalize(device)
+        if share is not None:
+            assert share.arch == arch and (share.arena.with_grad or not need_grad)
+            self.arena, self.bufs = share.arena, share.bufs
+            self.ns = _NormSpec(self.arena, self.bufs, arch)
+        else:
+            self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
+            self.ns = _NormSpec(self.arena, self.bufs, arch)
+            self._alloc_params()
+            self.arena.finalize(device)
+            self.bufs.finalize(device)
         self._build()
         self.pool_sums, self.pool_red = pool_norm_buffers(self.ns.created, device)
 

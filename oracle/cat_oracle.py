@@ -258,7 +258,7 @@ def _is_param(key):
     return key.endswith('.weight') or key.endswith('.bias')
 
 
-def distill_step(state, real_A, real_B, hp):
+def distill_step(state, real_A, real_B, hp, grad_hook=None):
     """One InceptionDistiller.optimize_parameters (distillers/inception_distiller.py:179-188):
     forward (:100-104), backward_D (base_inception_distiller.py:293-312), optimizer_D.step,
     backward_G (inception_distiller.py:159-177), optimizer_G.step.
@@ -312,6 +312,8 @@ def distill_step(state, real_A, real_B, hp):
     out['dpred_fake'], out['dpred_real'] = pred_fake.grad.detach().clone(), pred_real.grad.detach().clone()
     out['D_grads'] = {k: p.grad.detach().clone() for k, p in D_params.items()}
     with torch.no_grad():
+        if grad_hook is not None:   # data-parallel tests: reduce the gradients across ranks before the update
+            out['D_grads'] = grad_hook('D', out['D_grads'])
         adam_update(D_params, out['D_grads'], state['adam_D'], hp['lr'], hp['beta1'])
 
     # ---- backward_G (inception_distiller.py:159-177), D frozen (:185)
@@ -339,6 +341,8 @@ def distill_step(state, real_A, real_B, hp):
     out['Sfake_grad'] = Sfake.grad.detach().clone()
     out['S_grads'] = {k: p.grad.detach().clone() for k, p in S_params.items()}
     with torch.no_grad():
+        if grad_hook is not None:
+            out['S_grads'] = grad_hook('S', out['S_grads'])
         adam_update(S_params, out['S_grads'], state['adam_G'], hp['lr'], hp['beta1'])
     for p in S_params.values():
         p.requires_grad_(False)
