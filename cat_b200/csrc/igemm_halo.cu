@@ -22,7 +22,7 @@ namespace catb {
 
 constexpr int kHThreads = 192;
 constexpr int kHHeader = 1024;
-constexpr int kHMaxBStages = 6;
+constexpr int kHMaxBStages = 24;  // small weight tiles need many copies in flight (a 6 KB tile per ~1.5 us round trip otherwise)
 
 struct HaloParams {
   catb_igemm_desc d;
@@ -316,7 +316,13 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   // (the kernel is not persistent: prologue / epilogue of one CTA overlap the MMAs of its neighbours).
   if (p.a_bufs > h->n_chunks) p.a_bufs = h->n_chunks;
   if (p.b_stages > h->n_steps) p.b_stages = h->n_steps;
-  if (p.b_stages > 4 && 2 * (kHHeader + 1024 + p.a_bufs * p.halo_bytes + 4 * d->n_tile * 128) <= 226 * 1024) p.b_stages = 4;
+  {
+    // keep >= ~64 KB of weight tiles in flight (bulk-copy latency ~1.5 us), but not more stages than that needs
+    const int b_bytes = d->n_tile * 128;
+    int want = (64 * 1024 + b_bytes - 1) / b_bytes;
+    if (want < 4) want = 4;
+    if (p.b_stages > want) p.b_stages = want;
+  }
   smem = 1024 + kHHeader + static_cast<size_t>(p.a_bufs) * p.halo_bytes + static_cast<size_t>(p.b_stages) * d->n_tile * 128;
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);
