@@ -52,6 +52,7 @@ _PROTOS = {
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],
+    'catb_igemm_halo_wgrad': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
@@ -82,6 +83,7 @@ _SPECIAL = {
     'catb_last_error_string': ([], C.c_char_p),
     'catb_packed_weight_bytes': ([_I, _I, _I], C.c_size_t),
     'catb_igemm_halo_fits': ([_I, _I, _I, _I], C.c_int),
+    'catb_igemm_halo_wgrad_fits': ([_I, _I], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))
 

@@ -27,6 +27,7 @@ int check_launch(const char* what) {
 int init_igemm_attributes();
 int init_halo_attributes();
 int init_simt_attributes();
+int init_halo_wgrad_attributes();
 
 }  // namespace catb
 
@@ -55,5 +56,6 @@ extern "C" int catb_init(int device) {
   }
   if (int e = catb::init_igemm_attributes()) return e;
   if (int e = catb::init_halo_attributes()) return e;
-  return catb::init_simt_attributes();
+  if (int e = catb::init_simt_attributes()) return e;
+  return catb::init_halo_wgrad_attributes();
 }

@@ -82,6 +82,18 @@ USE_HALO = os.environ.get('CATB_NO_HALO', '0') != '1'   # v2 (halo) forward kern
 AUTOTUNE = os.environ.get('CATB_NO_AUTOTUNE', '0') != '1'  # pick v1 / v2 per GEMM by timing the first call
 
 
+_SCRATCH = {}
+
+
+def _scratch_like(t):
+    """A reusable zero-initialised scratch tensor shaped like `t` (autotuning of accumulating kernels)."""
+    key = (t.device, t.numel(), t.dtype)
+    if key not in _SCRATCH:
+        _SCRATCH.clear()
+        _SCRATCH[key] = torch.zeros_like(t)
+    return _SCRATCH[key]
+
+
 class Gemm:
     """One implicit GEMM: geometry + unit tables (+ packed bf16 weights for the fprop direction).
 
@@ -101,6 +113,7 @@ class Gemm:
         self.halo = None
         self.choice = None      # 'v1' | 'v2' once tuned; None = v2 whenever a halo plan exists
         self.tuned_ms = None
+        self.w_ready, self.w_halo, self.w_choice, self.w_tuned_ms = False, None, None, None
         self.f_units, self.f_gt, self.f_wt = units, self.gt, self.wt   # tables of the forward direction
         if need_pack:
             lib = _C.load()
@@ -221,9 +234,68 @@ class Gemm:
         else:
             v1()
 
-    def wgrad(self, x, y, grad_arena):
+    def _wgrad_plan(self):
+        """Halo plan of the weight-gradient direction (built lazily: not every Gemm computes one)."""
+        if self.w_ready:
+            return
+        self.w_ready = True
+        self.w_halo = None
+        if not USE_HALO:
+            return
+        lib = _C.load()
+        plan = make_halo_plan(self.geo, self.units)
+        if plan is None:
+            return
+        plan.m_sub = 1
+        for tw in [self.geo.OWs] + [t for t in (64, 32, 16) if t < self.geo.OWs]:
+            plan.TW = tw
+            if lib.catb_igemm_halo_wgrad_fits(len(plan.planes), plan.Lh):
+                break
+        else:
+            return
+        dev = self.gt.device
+        hd = _C.HaloDesc()
+        hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
+        for i, (pa, pb, y0, x0) in enumerate(plan.planes):
+            hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
+        hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
+        hd.Ymax, hd.Xmax, hd.m_sub = plan.Ymax, plan.Xmax, 1
+        st = np.array([[pl * plan.Lh + dy * plan.Wf + dx, ci] for (ci, pl, dy, dx) in plan.steps], dtype=np.int32)
+        groups = []
+        for ci, (cu0, nu, first, ns) in enumerate(plan.chunks):   # groups of <= 8 taps: 8 x 64 TMEM columns
+            for g0 in range(0, ns, 8):
+                groups.append([ci, first + g0, min(8, ns - g0), 0])
+        self.w_halo = plan
+        self.w_hdesc = hd
+        self.w_steps = torch.from_numpy(st).to(dev)
+        self.w_chunks = torch.from_numpy(np.array(plan.chunks, dtype=np.int32)).to(dev)
+        self.w_groups = torch.from_numpy(np.array(groups, dtype=np.int32)).to(dev)
+        self.w_ngroups = len(groups)
+        self.w_wt = units_to_device(plan.units, dev)[1]
+
+    def wgrad(self, x, y, grad_arena, force_v1=False):
+        self._wgrad_plan()
         d = self.desc()
-        _C.call('catb_igemm_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(grad_arena), _stream())
+
+        def v1(g):
+            _C.call('catb_igemm_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(g), _stream())
+
+        def v2(g):
+            _C.call('catb_igemm_halo_wgrad', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
+                    _p(self.w_groups), self.w_ngroups, _p(self.w_wt), _p(x), _p(y), _p(g), _stream())
+
+        if AUTOTUNE and self.w_halo is not None and self.w_choice is None and not force_v1 \
+                and not torch.cuda.is_current_stream_capturing():
+            # wgrad accumulates with atomics, so the two kernels are timed on a scratch copy of the arena
+            scratch = _scratch_like(grad_arena)
+            t2 = self._launch_timed(lambda: v2(scratch))
+            t1 = self._launch_timed(lambda: v1(scratch))
+            self.w_choice = 'v2' if t2 <= t1 else 'v1'
+            self.w_tuned_ms = (t1, t2)
+        if self.w_halo is not None and not force_v1 and self.w_choice != 'v1':
+            v2(grad_arena)
+        else:
+            v1(grad_arena)
 
     # SIMT restatements (tests only)
     def ref_fprop(self, arena, x, y, bias=None, act=0, accumulate=False, y_is_f32=False):

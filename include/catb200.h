@@ -127,6 +127,19 @@ int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, con
                           const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
                           const float* bias /*nullable*/, void* y, catb_stream_t s);
 
+/* v2 weight gradient on the same halo plan (m_sub = 1): a CTA handles one 128-channel tile of the lattice
+ * tensor, one channel chunk of X and one group of <= 8 consecutive steps (taps) of that chunk, each tap
+ * accumulating in its own 64 TMEM columns (cat_b200/csrc/igemm_halo_wgrad.cu).  `wunits` holds 8 weight
+ * units per step (the chunk-aligned table of make_halo_plan). */
+typedef struct {
+  int32_t chunk, first_step, n_steps, reserved;
+} catb_halo_wgroup;
+int catb_igemm_halo_wgrad_fits(int n_planes, int Lh);
+int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
+                          const catb_halo_chunk* chunks /*device*/, const catb_halo_wgroup* groups /*device*/,
+                          int n_groups, const catb_weight_unit* wunits /*device*/, const void* x, const void* y,
+                          float* arena_grad, catb_stream_t s);
+
 /* Slow SIMT restatements of the two kernels above (same descriptors); kept for on-device bisection
  * in tests.  Not used by the product path. */
 int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,

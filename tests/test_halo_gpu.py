@@ -121,6 +121,39 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
         assert rel_err(from_dev_nhwc(dx, Cin), xb.grad) < 6e-3, 'halo dgrad'
 
 
+@pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,N,H,W', CASES + [(3, 1, 1, 'zero', 40, 200, 2, 12, 12)])
+def test_halo_wgrad(k, stride, pad, mode, Cin, Cout, N, H, W):
+    """v2 weight gradient (MN-major shifted windows, one TMEM accumulator per tap) vs torch and vs v1."""
+    from cat_b200 import ops
+    torch.manual_seed(k * 10 + Cout)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, k, k)
+    xb, wb = bf(x), bf(w).requires_grad_(True)
+    xin = F.pad(xb, (pad,) * 4, mode='reflect') if mode == 'reflect' else xb
+    y_ref = F.conv2d(xin, wb, None, stride=stride, padding=0 if mode == 'reflect' else pad)
+    OH, OW = y_ref.shape[2:]
+    dy = torch.randn(N, Cout, OH, OW)
+    y_ref.backward(bf(dy))
+    pm = P.PAD_REFLECT if mode == 'reflect' else P.PAD_ZERO
+    units = P.conv_fprop_units(5, Cout, Cin, k, k, pad)
+    geo = P.Geometry(N, H, W, P.cpad(Cin), 0, OH, OW, P.cpad(Cout) + 8, 8, sn=stride, pad_mode=pm)
+    gw = ops.Gemm(geo, units, Cout, DEV, need_pack=False)
+    xd, dyd = to_dev_nhwc(x), to_dev_nhwc(dy, P.cpad(Cout) + 8, 8)
+    g2 = torch.zeros(5 + w.numel() + 64, device=DEV)
+    g1 = torch.zeros_like(g2)
+    gw._wgrad_plan()
+    assert gw.w_halo is not None
+    gw.w_choice = 'v2'
+    gw.wgrad(xd, dyd, g2)
+    gw.wgrad(xd, dyd, g1, force_v1=True)
+    torch.cuda.synchronize()
+    got2 = g2[5:5 + w.numel()].view_as(w).double().cpu()
+    got1 = g1[5:5 + w.numel()].view_as(w).double().cpu()
+    assert rel_err(got1, wb.grad) < 2e-4, 'v1 wgrad'
+    assert rel_err(got2, wb.grad) < 2e-4, 'v2 (halo) wgrad'
+    assert float(g2[:5].abs().max()) == 0 and float(g2[5 + w.numel():].abs().max()) == 0
+
+
 def test_halo_k_concat_block_stage2():
     """Stage-2 GEMM of a residual block: K-concatenation of 1x1 / 3x3 / 5x5 convs over channel slices."""
     from cat_b200 import ops
