@@ -49,6 +49,7 @@ _DP = C.POINTER(IgemmDesc)
 _PROTOS = {
     'catb_init': [_I],
     'catb_pack_weights': [_DP, _P, _P, _P, _P],
+    'catb_pack_weights_rows': [_DP, _P, _P, _P, _I, _I, _I, _P],
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],

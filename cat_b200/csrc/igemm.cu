@@ -394,26 +394,29 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_wgrad_kernel(const WgradPar
 // ------------------------------------------------------------------------------------------------
 // weight packing: fp32 arena (reference layout) -> bf16 smem-image tiles [tile_n][chunk][row][128B sw]
 // ------------------------------------------------------------------------------------------------
+// Writes image rows [row0, row0 + span) of the packed weights: the first `nreal` of them from the arena
+// (row r <-> arena row r of this segment's tensor), the rest as zero padding.  A plain conv is one segment
+// covering the whole image; an N-concatenation of several convs (the six branch convs of a residual block
+// sharing one input) is packed segment by segment, each with its own weight-unit table.
 __global__ void pack_weights_kernel(catb_igemm_desc d, const catb_weight_unit* __restrict__ wunits,
-                                    const float* __restrict__ arena, uint8_t* __restrict__ packed, int n_tiles,
-                                    int n_chunks) {
-  const long long total = static_cast<long long>(n_tiles) * d.n_tile * n_chunks * 8;
+                                    const float* __restrict__ arena, uint8_t* __restrict__ packed, int n_chunks,
+                                    int row0, int span, int nreal) {
+  const long long total = static_cast<long long>(span) * n_chunks * 8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ul = static_cast<int>(idx & 7);
     long long t = idx >> 3;
-    const int row = static_cast<int>(t % d.n_tile);
-    t /= d.n_tile;
-    const int chunk = static_cast<int>(t % n_chunks);
-    const int tile = static_cast<int>(t / n_chunks);
-    const int n = tile * d.n_tile + row;
+    const int r = static_cast<int>(t % span);
+    const int chunk = static_cast<int>(t / span);
+    const int n = row0 + r;
+    const int tile = n / d.n_tile, row = n - tile * d.n_tile;
     const int u = chunk * 8 + ul;
     f8 o;
 #pragma unroll
     for (int q = 0; q < 8; ++q) o.v[q] = 0.f;
-    if (n < d.n_rows && u < d.n_units) {
+    if (r < nreal && u < d.n_units) {
       const catb_weight_unit wu = wunits[u];
-      const float* base = arena + wu.w_off + static_cast<long long>(n) * wu.sn_w;
+      const float* base = arena + wu.w_off + static_cast<long long>(r) * wu.sn_w;
       for (int q = 0; q < wu.nvalid; ++q) o.v[q] = base[q * wu.sc_w];
     }
     uint8_t* dst = packed + (static_cast<size_t>(tile) * n_chunks + chunk) * d.n_tile * 128 + row * 128 +
@@ -526,17 +529,29 @@ extern "C" size_t catb_packed_weight_bytes(int n_rows, int n_units, int n_tile) 
   return static_cast<size_t>(n_tiles) * n_tile * n_chunks * 128;
 }
 
-extern "C" int catb_pack_weights(const catb_igemm_desc* d, const catb_weight_unit* wunits, const float* arena,
-                                 void* packed, catb_stream_t s) {
+extern "C" int catb_pack_weights_rows(const catb_igemm_desc* d, const catb_weight_unit* wunits, const float* arena,
+                                      void* packed, int row0, int span, int nreal, catb_stream_t s) {
   if (int e = validate_desc(d)) return e;
   CATB_REQUIRE(d->n_tile % 16 == 0 && d->n_tile >= 16 && d->n_tile <= 256, "n_tile must be a multiple of 16 in [16,256]");
   const int n_tiles = (d->n_rows + d->n_tile - 1) / d->n_tile;
+  CATB_REQUIRE(row0 >= 0 && span > 0 && nreal >= 0 && nreal <= span && row0 + span <= n_tiles * d->n_tile,
+               "row segment [%d,+%d) outside the packed image", row0, span);
   const int n_chunks = (d->n_units + 7) / 8;
-  const long long total = static_cast<long long>(n_tiles) * d->n_tile * n_chunks * 8;
+  const long long total = static_cast<long long>(span) * n_chunks * 8;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
-  pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(*d, wunits, arena,
-                                                                         static_cast<uint8_t*>(packed), n_tiles, n_chunks);
+  pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(*d, wunits, arena, static_cast<uint8_t*>(packed),
+                                                                         n_chunks, row0, span, nreal);
   return check_launch("pack_weights");
+}
+
+extern "C" int catb_pack_weights(const catb_igemm_desc* d, const catb_weight_unit* wunits, const float* arena,
+                                 void* packed, catb_stream_t s) {
+  if (d == nullptr) {
+    set_error("null descriptor");
+    return CATB_ERR_INVALID;
+  }
+  const int n_tiles = (d->n_rows + d->n_tile - 1) / (d->n_tile > 0 ? d->n_tile : 1);
+  return catb_pack_weights_rows(d, wunits, arena, packed, 0, n_tiles * d->n_tile, d->n_rows, s);
 }
 
 extern "C" int catb_igemm_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const void* x,

@@ -367,17 +367,31 @@ class GenNet:
             b.mid_raw = self._act(H4, W4, b.L, zero=True)
             b.mid_act = self._act(H4, W4, b.L, zero=True)
             b.tmp, b.out = self._act(H4, W4, C), self._act(H4, W4, C)
-            # stage 1: one GEMM per branch, all reading x
+            # stage 1: the first convs of all branches read x.  Forward: ONE GEMM, the branches N-concatenated
+            # (each embedded in the largest branch's tap grid, its rows packed from its own weight tensor);
+            # the per-branch GEMM objects are kept for the weight gradients.
             b.s1 = []
+            multi = len(b.res) + len(b.dw) > 1
             for (j, m, k), sl in zip(b.res, b.res_sl):
                 wn = f'{pre}.res_ops.{j}.1.0.weight'
-                g = G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl, pad_mode=P.PAD_REFLECT),
-                      P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m)
+                g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl, pad_mode=P.PAD_REFLECT),
+                         P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m, dev, need_pack=not multi)
                 b.s1.append((g, sl, m, k, wn))
             for (j, m, k), sl in zip(b.dw, b.dw1_sl):
                 wn = f'{pre}.dw_ops.{j}.0.0.weight'
-                g = G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0), m)
+                g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0), m,
+                         dev, need_pack=not multi)
                 b.s1.append((g, sl, m, 1, wn))
+            b.s1_fused = None
+            if multi:
+                kmax = max(k for (_, _, _, k, _) in b.s1)
+                base = P.conv_embedded_units(0, b.LA, C, kmax, kmax)   # gather side shared by all segments
+                segs = [(sl, cpad(m), m, P.conv_embedded_units(ar.off(wn), m, C, k, kmax)) for (_, sl, m, k, wn) in b.s1]
+                b.s1_fused = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0, pad_mode=P.PAD_REFLECT), base, b.LA, dev,
+                                  segments=segs)
+                self.fprop_gemms.append(b.s1_fused)
+            else:
+                self.fprop_gemms.append(b.s1[0][0])
             grpA = [(f'{pre}.res_ops.{j}.1.1', m) for j, m, k in b.res] + [(f'{pre}.dw_ops.{j}.0.1', m) for j, m, k in b.dw]
             b.nA = self.ns.make(dev, B, H4 * W4, grpA, tr)
             # depthwise convs over the dw slices
@@ -500,8 +514,10 @@ class GenNet:
         for b in self.blocks:
             if b.empty:
                 continue
-            for (g, sl, m, k, wn) in b.s1:
-                g.fprop(b.x.t, b.mid_raw.t)
+            if b.s1_fused is not None:
+                b.s1_fused.fprop(b.x.t, b.mid_raw.t)
+            else:
+                b.s1[0][0].fprop(b.x.t, b.mid_raw.t)
             b.nA.forward(b.mid_raw.slice(0, b.LA), b.mid_act.slice(0, b.LA), relu)
             if b.dw:
                 ops.dwconv_fwd(b.mid_act.slice(b.LR, b.LA - b.LR), b.mid_raw.slice(b.LA, b.L - b.LA), b.dw_k, b.dw_w,

@@ -62,6 +62,28 @@ def conv_fprop_units(w_off, Cout, Cin, R, S, pad, cu0=0) -> Units:
     return u
 
 
+def conv_embedded_units(w_off, Cout, Cin, k, Kmax, cu0=0) -> Units:
+    """A k x k conv (padding (k-1)/2) expressed on the tap grid of a Kmax x Kmax conv (padding (Kmax-1)/2):
+    same gather side as conv_fprop_units(., ., Cin, Kmax, Kmax, (Kmax-1)/2), weight side pointing at the
+    k x k tensor for the central taps and empty (nvalid = 0) for the outer ring.  Exact under reflect or
+    zero padding because the outer taps carry zero weight.  Used to N-concatenate the first-stage convs
+    of a residual block (kernel sizes 1/3/5 reading the same input) into one GEMM."""
+    assert (Kmax - k) % 2 == 0 and k <= Kmax
+    off, pad = (Kmax - k) // 2, (Kmax - 1) // 2
+    u = Units()
+    for r in range(Kmax):
+        for s in range(Kmax):
+            rb, sb = r - off, s - off
+            inside = 0 <= rb < k and 0 <= sb < k
+            for cu in range(cpad(Cin) // 8):
+                u.g.append((r - pad, s - pad, cu0 + cu))
+                if inside:
+                    u.w.append((w_off + cu * 8 * k * k + rb * k + sb, Cin * k * k, k * k, max(0, min(8, Cin - cu * 8))))
+                else:
+                    u.w.append((0, 0, 0, 0))
+    return u
+
+
 def conv_dgrad_units(w_off, Cout, Cin, R, S, q, cu0=0) -> Units:
     """Input gradient of the same convolution: gather dY with offset dr = q - r (q = pad for a direct
     zero-padded gradient, q = 0 when the result is the gradient w.r.t. the *padded* frame of a reflect

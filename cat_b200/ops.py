@@ -101,10 +101,14 @@ class Gemm:
     halo tile fits in shared memory (make_halo_plan / catb_igemm_halo_fits), else the v1 gather-per-tap
     kernel.  Both read the same packed weights; wgrad always uses the original unit order."""
 
-    def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True, halo=None, force_tile=None):
+    def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True, halo=None, force_tile=None,
+                 segments=None):
         """force_tile=(TW, m_sub) pins the halo tiling (tests); by default the widest strip / largest
-        sub-tile count that fits in shared memory and still fills the GPU is chosen."""
+        sub-tile count that fits in shared memory and still fills the GPU is chosen.
+        segments=[(row0, span, nreal, Units)] describes an N-concatenation: every segment shares the gather
+        side of `units` and supplies its own weight side for image rows [row0, row0+span)."""
         assert len(units) > 0 and n_rows > 0
+        self.segments = None
         self.geo, self.units, self.n_rows = geo, units, n_rows
         self.n_units = len(units)
         self.n_tile = choose_n_tile(n_rows)
@@ -160,11 +164,18 @@ class Gemm:
                         break
                 self._use_tiling(pick)
             # v1 reads the compact original table, v2 the chunk-aligned one: two packed images until tuned
-            self.packed_v1 = torch.empty(lib.catb_packed_weight_bytes(n_rows, self.n_units, self.n_tile),
+            self.packed_v1 = torch.zeros(lib.catb_packed_weight_bytes(n_rows, self.n_units, self.n_tile),
                                          dtype=torch.uint8, device=device)
             if self.halo is not None:
-                self.packed = torch.empty(lib.catb_packed_weight_bytes(n_rows, len(self.f_units), self.n_tile),
+                self.packed = torch.zeros(lib.catb_packed_weight_bytes(n_rows, len(self.f_units), self.n_tile),
                                           dtype=torch.uint8, device=device)
+            if segments is not None:
+                self.segments = []
+                for (row0, span, nreal, su) in segments:
+                    assert su.g == units.g, 'segments must share the gather side of the GEMM'
+                    wt1 = units_to_device(su, device)[1]
+                    wt2 = units_to_device(make_halo_plan(geo, su).units, device)[1] if self.halo is not None else None
+                    self.segments.append((row0, span, nreal, wt1, wt2))
 
     def _use_tiling(self, t):
         tw, ms, hd, steps = t
@@ -183,12 +194,20 @@ class Gemm:
         return d
 
     def pack(self, arena):
-        if self.halo is None or self.choice != 'v2':
-            d = self.desc()
-            _C.call('catb_pack_weights', C.byref(d), _p(self.wt), _p(arena), _p(self.packed_v1), _stream())
-        if self.halo is not None and self.choice != 'v1':
-            d = self.desc(n_units=len(self.f_units))
-            _C.call('catb_pack_weights', C.byref(d), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
+        do1 = self.halo is None or self.choice != 'v2'
+        do2 = self.halo is not None and self.choice != 'v1'
+        d1, d2 = self.desc(), self.desc(n_units=len(self.f_units))
+        if self.segments is None:
+            if do1:
+                _C.call('catb_pack_weights', C.byref(d1), _p(self.wt), _p(arena), _p(self.packed_v1), _stream())
+            if do2:
+                _C.call('catb_pack_weights', C.byref(d2), _p(self.f_wt), _p(arena), _p(self.packed), _stream())
+            return
+        for (row0, span, nreal, wt1, wt2) in self.segments:
+            if do1:
+                _C.call('catb_pack_weights_rows', C.byref(d1), _p(wt1), _p(arena), _p(self.packed_v1), row0, span, nreal, _stream())
+            if do2:
+                _C.call('catb_pack_weights_rows', C.byref(d2), _p(wt2), _p(arena), _p(self.packed), row0, span, nreal, _stream())
 
     def _launch_timed(self, fn, reps=2):
         fn()

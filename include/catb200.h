@@ -91,6 +91,12 @@ size_t catb_packed_weight_bytes(int n_rows, int n_units, int n_tile);
  *   models/modules/discriminators.py:39-74 (4x4 PatchGAN convs); autograd's conv backward-data. */
 int catb_pack_weights(const catb_igemm_desc* d, const catb_weight_unit* wunits /*device*/,
                       const float* arena /*device*/, void* packed /*device*/, catb_stream_t s);
+/* Row-segment variant for N-concatenated GEMMs (several convs sharing one gathered input, e.g. the six
+ * first-stage convs of inception_modules.py:129-163): fills image rows [row0, row0+span) -- the first
+ * `nreal` from this segment's weights, the rest with zeros -- using this segment's weight-unit table
+ * (nvalid = 0 for taps the segment's kernel does not have).  d->n_rows is the row count of the whole image. */
+int catb_pack_weights_rows(const catb_igemm_desc* d, const catb_weight_unit* wunits /*device*/, const float* arena,
+                           void* packed, int row0, int span, int nreal, catb_stream_t s);
 int catb_igemm_fprop(const catb_igemm_desc* d, const catb_gather_unit* units /*device*/, const void* x,
                      const void* packed_w, const float* bias /*nullable*/, void* y, catb_stream_t s);
 /* Weight gradient: arena_grad[w] += sum_rows Y[row, c] * gather(X)[row, k]   (atomic fp32 adds).
