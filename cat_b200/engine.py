@@ -224,6 +224,14 @@ class _Block:
     pass
 
 
+def _stage1_order(res, dw):
+    """Slice order of the first-stage outputs in the mid buffer: all 1x1 convs first (the k=1 res branch and
+    the first conv of every dw branch -- they share one N-concatenated GEMM), then the k>1 res branches.
+    Entries: (kind, j, m, k_of_first_conv)."""
+    return ([('res', j, m, k) for (j, m, k) in res if k == 1] + [('dw', j, m, 1) for (j, m, k) in dw] +
+            [('res', j, m, k) for (j, m, k) in res if k > 1])
+
+
 class GenNet:
     """InceptionGenerator compiled for a fixed (B, H, W)."""
 
@@ -275,7 +283,8 @@ class GenNet:
                 self._conv_alloc(f'{pre}.dw_ops.{j}.0.0', (m, c2, 1, 1), ub)
                 self._conv_alloc(f'{pre}.dw_ops.{j}.2.0', (m, 1, k, k), ub)
                 self._conv_alloc(f'{pre}.dw_ops.{j}.4', (c2, m, 1, 1), ub)
-            grpA = [(f'{pre}.res_ops.{j}.1.1', m) for j, m, k in res] + [(f'{pre}.dw_ops.{j}.0.1', m) for j, m, k in dw]
+            grpA = [(f'{pre}.res_ops.{j}.1.1' if kind == 'res' else f'{pre}.dw_ops.{j}.0.1', m)
+                    for (kind, j, m, _k) in _stage1_order(res, dw)]
             grpB = [(f'{pre}.dw_ops.{j}.2.1', m) for j, m, k in dw]
             if grpA:
                 self.ns.alloc_group(grpA)
@@ -348,15 +357,19 @@ class GenNet:
                 b.out = x
                 self.blocks.append(b)
                 continue
-            # channel slices of the mid buffer: [res first-stage | dw first-stage | dw second-stage]
+            # channel slices of the mid buffer: [1x1 first-stage convs (res k=1, dw) | res k>1 | dw second-stage]
             off = 0
-            b.res_sl, b.dw1_sl, b.dw2_sl = [], [], []
-            for _, m, _k in b.res:
-                b.res_sl.append(off)
-                off += cpad(m)
-            b.LR = off
-            for _, m, _k in b.dw:
-                b.dw1_sl.append(off)
+            b.res_sl, b.dw1_sl, b.dw2_sl = [None] * len(b.res), [None] * len(b.dw), []
+            b.order = _stage1_order(b.res, b.dw)
+            b.D0 = b.D1 = 0   # the dw first-stage slices are contiguous: [D0, D1)
+            for (kind, j, m, _k) in b.order:
+                if kind == 'res':
+                    b.res_sl[j] = off
+                else:
+                    if j == 0:
+                        b.D0 = off
+                    b.dw1_sl[j] = off
+                    b.D1 = off + cpad(m)
                 off += cpad(m)
             b.LA = off
             for _, m, _k in b.dw:
@@ -367,32 +380,32 @@ class GenNet:
             b.mid_raw = self._act(H4, W4, b.L, zero=True)
             b.mid_act = self._act(H4, W4, b.L, zero=True)
             b.tmp, b.out = self._act(H4, W4, C), self._act(H4, W4, C)
-            # stage 1: the first convs of all branches read x.  Forward: ONE GEMM, the branches N-concatenated
-            # (each embedded in the largest branch's tap grid, its rows packed from its own weight tensor);
-            # the per-branch GEMM objects are kept for the weight gradients.
-            b.s1 = []
-            multi = len(b.res) + len(b.dw) > 1
-            for (j, m, k), sl in zip(b.res, b.res_sl):
-                wn = f'{pre}.res_ops.{j}.1.0.weight'
+            # stage 1: the first convs of all branches read x.  Forward: the 1x1 convs (k=1 res branch + the
+            # first conv of every dw branch) are N-concatenated into ONE GEMM (rows packed from each weight
+            # tensor, catb_pack_weights_rows); each k>1 res branch is its own GEMM.  The per-branch objects
+            # are kept for the weight gradients.
+            b.s1, b.s1_fwd = [], []
+            ones = [(kind, j, m) for (kind, j, m, k) in b.order if k == 1]
+            for (kind, j, m, k) in b.order:
+                if kind == 'res':
+                    wn, sl = f'{pre}.res_ops.{j}.1.0.weight', b.res_sl[j]
+                else:
+                    wn, sl = f'{pre}.dw_ops.{j}.0.0.weight', b.dw1_sl[j]
+                fused = k == 1 and len(ones) > 1
                 g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl, pad_mode=P.PAD_REFLECT),
-                         P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m, dev, need_pack=not multi)
+                         P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m, dev, need_pack=not fused)
                 b.s1.append((g, sl, m, k, wn))
-            for (j, m, k), sl in zip(b.dw, b.dw1_sl):
-                wn = f'{pre}.dw_ops.{j}.0.0.weight'
-                g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0), m,
-                         dev, need_pack=not multi)
-                b.s1.append((g, sl, m, 1, wn))
-            b.s1_fused = None
-            if multi:
-                kmax = max(k for (_, _, _, k, _) in b.s1)
-                base = P.conv_embedded_units(0, b.LA, C, kmax, kmax)   # gather side shared by all segments
-                segs = [(sl, cpad(m), m, P.conv_embedded_units(ar.off(wn), m, C, k, kmax)) for (_, sl, m, k, wn) in b.s1]
-                b.s1_fused = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0, pad_mode=P.PAD_REFLECT), base, b.LA, dev,
-                                  segments=segs)
-                self.fprop_gemms.append(b.s1_fused)
-            else:
-                self.fprop_gemms.append(b.s1[0][0])
-            grpA = [(f'{pre}.res_ops.{j}.1.1', m) for j, m, k in b.res] + [(f'{pre}.dw_ops.{j}.0.1', m) for j, m, k in b.dw]
+                if not fused:
+                    b.s1_fwd.append(g)
+                    self.fprop_gemms.append(g)
+            if len(ones) > 1:
+                rows = sum(cpad(m) for (_, _, m) in ones)      # the 1x1 slices start at channel 0 and are contiguous
+                base = P.conv_fprop_units(0, rows, C, 1, 1, 0)
+                segs = [(sl, cpad(m), m, P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0)) for (_, sl, m, k, wn) in b.s1 if k == 1]
+                g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0), base, rows, dev, segments=segs)
+                b.s1_fwd.insert(0, g)
+                self.fprop_gemms.append(g)
+            grpA = [(f'{pre}.res_ops.{j}.1.1' if kind == 'res' else f'{pre}.dw_ops.{j}.0.1', m) for (kind, j, m, _k) in b.order]
             b.nA = self.ns.make(dev, B, H4 * W4, grpA, tr)
             # depthwise convs over the dw slices
             if b.dw:
@@ -514,13 +527,11 @@ class GenNet:
         for b in self.blocks:
             if b.empty:
                 continue
-            if b.s1_fused is not None:
-                b.s1_fused.fprop(b.x.t, b.mid_raw.t)
-            else:
-                b.s1[0][0].fprop(b.x.t, b.mid_raw.t)
+            for g in b.s1_fwd:
+                g.fprop(b.x.t, b.mid_raw.t)
             b.nA.forward(b.mid_raw.slice(0, b.LA), b.mid_act.slice(0, b.LA), relu)
             if b.dw:
-                ops.dwconv_fwd(b.mid_act.slice(b.LR, b.LA - b.LR), b.mid_raw.slice(b.LA, b.L - b.LA), b.dw_k, b.dw_w,
+                ops.dwconv_fwd(b.mid_act.slice(b.D0, b.D1 - b.D0), b.mid_raw.slice(b.LA, b.L - b.LA), b.dw_k, b.dw_w,
                                self.arena.p)
                 b.nB.forward(b.mid_raw.slice(b.LA, b.L - b.LA), b.mid_act.slice(b.LA, b.L - b.LA), relu)
             b.g2.fprop(b.mid_act.t, b.tmp.t)
@@ -585,8 +596,8 @@ class GenNet:
                 nB = b.L - b.LA
                 b.nB.backward(dmid_act.slice(b.LA, nB), b.mid_act.slice(b.LA, nB), b.mid_raw.slice(b.LA, nB),
                               dmid_raw.slice(b.LA, nB), relu)
-                ops.dwconv_bwd_weight(b.mid_act.slice(b.LR, b.LA - b.LR), dmid_raw.slice(b.LA, nB), b.dw_k, b.dw_w, ar.g)
-                ops.dwconv_bwd_data(dmid_raw.slice(b.LA, nB), dmid_act.slice(b.LR, b.LA - b.LR), b.dw_k, b.dw_w, ar.p)
+                ops.dwconv_bwd_weight(b.mid_act.slice(b.D0, b.D1 - b.D0), dmid_raw.slice(b.LA, nB), b.dw_k, b.dw_w, ar.g)
+                ops.dwconv_bwd_data(dmid_raw.slice(b.LA, nB), dmid_act.slice(b.D0, b.D1 - b.D0), b.dw_k, b.dw_w, ar.p)
             b.nA.backward(dmid_act.slice(0, b.LA), b.mid_act.slice(0, b.LA), b.mid_raw.slice(0, b.LA),
                           dmid_raw.slice(0, b.LA), relu)
             for (g, sl, m, k, wn) in b.s1:
