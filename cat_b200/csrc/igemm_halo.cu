@@ -7,8 +7,10 @@
 // input parity plane for stride-2 convs).  A filter tap is then just a row offset into that buffer: the A
 // descriptor of tap (dy,dx) starts at halo_row = plane*Lh + dy*Wf + dx, all taps of the chunk reuse the
 // same shared-memory bytes, and the gather traffic drops by the tap count (25x for 5x5, 16x for 4x4, ...).
-// A window that does not start on a 1024-byte swizzle-atom boundary is described with the matrix
-// descriptor's base-offset field ((start >> 7) & 7).
+// A window may start at any 128-byte row of the (1024-byte aligned) tile: the SW128 XOR is taken from the
+// absolute shared-memory address bits, so the descriptor's base-offset field stays 0 (measured on B200; the
+// other reading of the PTX text, base_offset = (start >> 7) & 7, gives wrong results -- CATB_HALO_BO=1 keeps
+// it selectable for that experiment).
 //
 // Warp roles as in v1: warps 0-3 fill the halo then run the epilogue, warp 4 issues tcgen05.mma for every
 // (chunk, tap, sub-tile), warp 5 streams the pre-swizzled weight tile of each (chunk, tap) step with one
