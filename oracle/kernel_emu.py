@@ -1,0 +1,382 @@
+"""CPU restatement of every libcatb200 entry point used by the engines -- TEST INFRASTRUCTURE ONLY.
+
+Like the rest of oracle/, this file is a checker, never a product path: it lets the `-m "not gpu"` suite run
+the *host logic* of cat_b200 (launch sequences, hand-derived backward passes, buffer plumbing, table
+construction) on CPU tensors by swapping the kernel wrappers of ``cat_b200.ops`` for torch restatements of
+the same contracts (include/catb200.h).  Nothing under cat_b200/ imports it; without ``emulated_kernels()``
+the package still raises when the CUDA library / an sm_100 device is missing.
+
+Numerics mirror the device: bf16 storage (round to nearest even on every store), fp32 arithmetic, fp32
+statistics and losses.  Summation order differs (no atomics here), so GPU and emulation agree to rounding,
+not bit for bit.
+"""
+import contextlib
+import dataclasses
+
+import torch
+import torch.nn.functional as F
+
+from cat_b200 import igemm_plan as P
+from cat_b200 import ops, _C
+from cat_b200.igemm_plan import cpad
+
+BF16 = torch.bfloat16
+
+
+def _get(a):
+    return a.t[..., a.coff:a.coff + a.C].float()
+
+
+def _put(a, val):
+    a.t[..., a.coff:a.coff + a.C] = val.to(BF16)
+
+
+def _act(v, act):
+    if act == _C.ACT_RELU:
+        return torch.relu(v)
+    if act == _C.ACT_LEAKY02:
+        return F.leaky_relu(v, 0.2)
+    if act == _C.ACT_TANH:
+        return torch.tanh(v)
+    return v
+
+
+def _act_grad_from_out(o, act):
+    if act == _C.ACT_RELU:
+        return (o > 0).float()
+    if act == _C.ACT_LEAKY02:
+        return torch.where(o > 0, torch.ones_like(o), torch.full_like(o, 0.2))
+    if act == _C.ACT_TANH:
+        return 1.0 - o * o
+    return torch.ones_like(o)
+
+
+# ---- implicit GEMMs ------------------------------------------------------------------------------
+def _gemm_init(orig):
+    def init(self, geo, units, n_rows, device, need_pack=True, halo=None, force_tile=None, segments=None):
+        orig(self, geo, units, n_rows, device, need_pack=need_pack, halo=False, force_tile=None, segments=segments)
+        self._emu_segments = segments
+        self._emu_w = None
+    return init
+
+
+def _gemm_pack(self, arena):
+    # the device packs a bf16 image of the weights: a snapshot, re-taken only by the next pack()
+    self._emu_w = arena.detach().to(BF16).float()
+
+
+def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
+    assert self._emu_w is not None, 'fprop before pack()'
+    assert y.dtype == (torch.float32 if y_is_f32 else BF16)
+    geo = self.geo
+    xf, yf = x.float(), y.float()
+    n, oh, ow = P._lattice_rows(geo)
+    if self._emu_segments is None:
+        P.emulate_fprop(geo, self.units, self.n_rows, xf, self._emu_w, yf, bias, accumulate)
+    else:
+        assert bias is None
+        for (row0, span, nreal, su) in self._emu_segments:
+            g2 = dataclasses.replace(geo, y_coff=geo.y_coff + row0)
+            P.emulate_fprop(g2, su, nreal, xf, self._emu_w, yf, None, accumulate)
+            if not accumulate:
+                yf[n, oh, ow, g2.y_coff + nreal:g2.y_coff + span] = 0
+    c0 = geo.y_coff
+    yf[n, oh, ow, c0:c0 + self.n_rows] = _act(yf[n, oh, ow, c0:c0 + self.n_rows], act)
+    if not accumulate and self._emu_segments is None:
+        top = min(c0 + cpad(self.n_rows), geo.ldy)
+        yf[n, oh, ow, c0 + self.n_rows:top] = 0
+    y.copy_(yf.to(y.dtype))
+
+
+def _gemm_wgrad(self, x, y, grad_arena, force_v1=False):
+    P.emulate_wgrad(self.geo, self.units, self.n_rows, x.float(), y.float(), grad_arena)
+
+
+# ---- layout / element-wise -----------------------------------------------------------------------
+def nchw_to_nhwc(src, dst):
+    N, Cc, H, W = src.shape
+    v = torch.zeros(N, H, W, dst.C)
+    v[..., :Cc] = src.permute(0, 2, 3, 1)
+    _put(dst, v)
+
+
+def nhwc_to_nchw(src, Cc, out=None):
+    v = _get(src)[..., :Cc].permute(0, 3, 1, 2).contiguous()
+    if out is None:
+        return v
+    out.copy_(v)
+    return out
+
+
+def copy_channels(src, dst, Cc):
+    dst.t[..., dst.coff:dst.coff + Cc] = src.t[..., src.coff:src.coff + Cc]
+
+
+def act_bwd(dout, out, dz, act):
+    _put(dz, _get(dout) * _act_grad_from_out(_get(out), act))
+
+
+def channel_sum(x, out):
+    n = min(out.numel(), x.C)   # the device adds the (zero) padding channels to whatever follows in the arena
+    out[:n] += _get(x).sum((0, 1, 2))[:n]
+
+
+def reflect_fold(src, dst, p, add=None):
+    g = _get(src).permute(0, 3, 1, 2).double()
+    xx = torch.zeros(dst.N, dst.C, dst.H, dst.W, dtype=torch.float64, requires_grad=True)
+    F.pad(xx, (p,) * 4, mode='reflect').backward(g)
+    v = xx.grad.permute(0, 2, 3, 1).float()
+    if add is not None:
+        v = v + _get(add)
+    _put(dst, v)
+
+
+def add(a, b, dst):
+    _put(dst, _get(a) + _get(b))
+
+
+# ---- normalisation -------------------------------------------------------------------------------
+def norm_stats(x, per_sample, sums):
+    v = _get(x)
+    if per_sample:
+        sums[:, 0, :] += v.sum((1, 2))
+        sums[:, 1, :] += (v * v).sum((1, 2))
+    else:
+        sums[0, 0, :] += v.sum((0, 1, 2))
+        sums[0, 1, :] += (v * v).sum((0, 1, 2))
+
+
+def norm_finalize(sums, G, Cc, count, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_rstd):
+    if sums is not None:
+        s = sums.view(G, 2, Cc).double()
+        mean = s[:, 0] / count
+        var = (s[:, 1] / count - mean * mean).clamp_min(0)
+        mean, var = mean.float(), var.float()
+        if rmean is not None and G == 1:
+            unbiased = var[0] * count / (count - 1) if count > 1 else var[0]
+            rmean.mul_(1 - momentum).add_(momentum * mean[0])
+            rvar.mul_(1 - momentum).add_(momentum * unbiased)
+    else:
+        mean, var = rmean.view(1, Cc).clone(), rvar.view(1, Cc).clone()
+    rstd = torch.rsqrt(var + eps)
+    ga = gamma.view(1, Cc) if gamma is not None else 1.0
+    be = beta.view(1, Cc) if beta is not None else 0.0
+    scale.view(G, Cc).copy_(ga * rstd)
+    shift.view(G, Cc).copy_(be - mean * ga * rstd)
+    if mean_rstd is not None:
+        mean_rstd.view(G, 2, Cc)[:, 0] = mean
+        mean_rstd.view(G, 2, Cc)[:, 1] = rstd
+
+
+def _bc(t, per_sample, N, C):
+    """[G,C] -> broadcastable over [N,H,W,C]."""
+    return t.view(-1, C)[:N if per_sample else 1].view(-1, 1, 1, C)
+
+
+def norm_apply(x, y, scale, shift, per_sample, act, residual=None):
+    v = _act(_get(x) * _bc(scale, per_sample, x.N, x.C) + _bc(shift, per_sample, x.N, x.C), act)
+    if residual is not None:
+        v = v + _get(residual)
+    _put(y, v)
+
+
+def _dz_xhat(dout, out, x, per_sample, mean_rstd, act):
+    C = x.C
+    mr = mean_rstd.view(-1, 2, C)
+    mu, rs = _bc(mr[:, 0].contiguous(), per_sample, x.N, C), _bc(mr[:, 1].contiguous(), per_sample, x.N, C)
+    dz = _get(dout)
+    if act != _C.ACT_NONE:
+        dz = dz * _act_grad_from_out(_get(out), act)
+    return dz, (_get(x) - mu) * rs, rs
+
+
+def norm_bwd_reduce(dout, out, x, per_sample, mean_rstd, act, red):
+    dz, xh, _ = _dz_xhat(dout, out, x, per_sample, mean_rstd, act)
+    if per_sample:
+        red[:, 0, :] += dz.sum((1, 2))
+        red[:, 1, :] += (dz * xh).sum((1, 2))
+    else:
+        red[0, 0, :] += dz.sum((0, 1, 2))
+        red[0, 1, :] += (dz * xh).sum((0, 1, 2))
+
+
+def norm_bwd_apply(dout, out, x, dx, per_sample, mean_rstd, gamma, red, count, act, dgamma, dbeta):
+    C = x.C
+    dz, xh, rs = _dz_xhat(dout, out, x, per_sample, mean_rstd, act)
+    r = red.view(-1, 2, C)
+    if dbeta is not None:
+        dbeta[:C] += r[:, 0].sum(0)
+    if dgamma is not None:
+        dgamma[:C] += r[:, 1].sum(0)
+    s1 = _bc(r[:, 0].contiguous(), per_sample, x.N, C)
+    s2 = _bc(r[:, 1].contiguous(), per_sample, x.N, C)
+    ga = gamma.view(1, 1, 1, C) if gamma is not None else 1.0
+    _put(dx, ga * rs * (dz - s1 / count - xh * s2 / count))
+
+
+# ---- depthwise -----------------------------------------------------------------------------------
+def _dw_groups(ksize, w_off):
+    """Runs of channels sharing a kernel size: (c0, c1, k)."""
+    ks = ksize.tolist()
+    runs, c0 = [], 0
+    for c in range(1, len(ks) + 1):
+        if c == len(ks) or ks[c] != ks[c0]:
+            runs.append((c0, c, ks[c0]))
+            c0 = c
+    return runs
+
+
+def _dw_weights(arena, w_off, c0, c1, k):
+    w = torch.zeros(c1 - c0, 1, k, k)
+    for c in range(c0, c1):
+        o = int(w_off[c])
+        if o >= 0:
+            w[c - c0, 0] = arena[o:o + k * k].view(k, k)
+    return w
+
+
+def _dw_run(x, w, k, pad_mode):
+    p = (k - 1) // 2
+    if p and pad_mode == 'reflect':
+        return F.conv2d(F.pad(x, (p,) * 4, mode='reflect'), w, groups=w.shape[0])
+    return F.conv2d(x, w, padding=p, groups=w.shape[0])
+
+
+def dwconv_fwd(x, y, ksize, w_off, arena, pad_mode='reflect'):
+    xv = _get(x).permute(0, 3, 1, 2)
+    out = torch.zeros_like(xv)
+    for (c0, c1, k) in _dw_groups(ksize, w_off):
+        out[:, c0:c1] = _dw_run(xv[:, c0:c1], _dw_weights(arena, w_off, c0, c1, k), k, pad_mode)
+    _put(y, out.permute(0, 2, 3, 1))
+
+
+def dwconv_bwd_data(dy, dx, ksize, w_off, arena, pad_mode='reflect'):
+    dyv = _get(dy).permute(0, 3, 1, 2)
+    out = torch.zeros_like(dyv)
+    for (c0, c1, k) in _dw_groups(ksize, w_off):
+        xx = torch.zeros_like(dyv[:, c0:c1]).requires_grad_(True)
+        _dw_run(xx, _dw_weights(arena, w_off, c0, c1, k), k, pad_mode).backward(dyv[:, c0:c1])
+        out[:, c0:c1] = xx.grad
+    _put(dx, out.permute(0, 2, 3, 1))
+
+
+def dwconv_bwd_weight(x, dy, ksize, w_off, grad_arena, pad_mode='reflect'):
+    xv, dyv = _get(x).permute(0, 3, 1, 2), _get(dy).permute(0, 3, 1, 2)
+    for (c0, c1, k) in _dw_groups(ksize, w_off):
+        w = torch.zeros(c1 - c0, 1, k, k, requires_grad=True)
+        _dw_run(xv[:, c0:c1], w, k, pad_mode).backward(dyv[:, c0:c1])
+        for c in range(c0, c1):
+            o = int(w_off[c])
+            if o >= 0:
+                grad_arena[o:o + k * k] += w.grad[c - c0, 0].reshape(-1)
+
+
+# ---- losses --------------------------------------------------------------------------------------
+def gan_loss(pred, n, ld, mode, target_is_real, for_discriminator, grad_scale, loss, dpred=None):
+    p = pred.reshape(-1)[::ld][:n].float()
+    if mode == 'hinge':
+        if for_discriminator:
+            t = p - 1 if target_is_real else -p - 1
+            l = torch.where(t < 0, -t, torch.zeros_like(t))
+            g = torch.where(t < 0, torch.full_like(t, -1.0 if target_is_real else 1.0), torch.zeros_like(t))
+        else:
+            l, g = -p, torch.full_like(p, -1.0)
+    elif mode == 'lsgan':
+        t = 1.0 if target_is_real else 0.0
+        l, g = (p - t) ** 2, 2 * (p - t)
+    else:
+        t = 1.0 if target_is_real else 0.0
+        l = p.clamp_min(0) - p * t + torch.log1p(torch.exp(-p.abs()))
+        g = torch.sigmoid(p) - t
+    loss += l.sum() / n
+    if dpred is not None:
+        rows = dpred.t.view(-1, dpred.ld)
+        rows[:n, dpred.coff:dpred.coff + 8] = 0
+        rows[:n, dpred.coff] = (g / n * grad_scale).to(BF16)
+
+
+def recon_loss(a, b, Creal, kind, grad_scale, loss, da=None, extra=None):
+    x, y = _get(a), _get(b)
+    d = (x - y)
+    real = torch.zeros(a.C)
+    real[:Creal] = 1.0
+    inv = 1.0 / (a.pixels * Creal)
+    if kind == 'l2':
+        l, dl = d * d, 2 * d
+    elif kind == 'smooth_l1':
+        quad = d.abs() < 1
+        l = torch.where(quad, 0.5 * d * d, d.abs() - 0.5)
+        dl = torch.where(quad, d, torch.sign(d))
+    else:
+        l, dl = d.abs(), torch.sign(d)
+    loss += (l * real).sum() * inv
+    if da is not None:
+        g = grad_scale * inv * dl * real
+        if extra is not None:
+            g = g + _get(extra)
+        _put(da, g)
+
+
+def gram(x, G):
+    v = _get(x).reshape(x.N, -1)
+    G += v @ v.T
+
+
+def ka_finish(Gx, Gy, B, loss_scale, loss, ka_value, coef):
+    num, sx, sy = (Gx * Gy).sum(), (Gx * Gx).sum(), (Gy * Gy).sum()
+    nx, ny = sx.sqrt(), sy.sqrt()
+    ka = num / (nx * ny)
+    if ka_value is not None:
+        ka_value.fill_(float(ka))
+    if loss is not None:
+        loss += loss_scale * ka
+    if coef is not None:
+        coef.copy_(loss_scale * 2.0 * (Gy / (nx * ny) - Gx * num / (nx ** 3 * ny)))
+
+
+def ka_bwd(x, coef, dx, accumulate):
+    v = _get(x)
+    g = torch.einsum('bj,jhwc->bhwc', coef, v)
+    if accumulate:
+        g = g + _get(dx)
+    _put(dx, g)
+
+
+def adam(param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_count):
+    step_count += 1
+    t = float(step_count)
+    bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
+    g = grad * grad_scale
+    m.mul_(beta1).add_((1 - beta1) * g)
+    v.mul_(beta2).add_((1 - beta2) * g * g)
+    param.sub_(float(lr) / bc1 * m / (v.sqrt() / (bc2 ** 0.5) + eps))
+
+
+_PATCHED = ['nchw_to_nhwc', 'nhwc_to_nchw', 'copy_channels', 'act_bwd', 'channel_sum', 'reflect_fold', 'add',
+            'norm_stats', 'norm_finalize', 'norm_apply', 'norm_bwd_reduce', 'norm_bwd_apply', 'dwconv_fwd',
+            'dwconv_bwd_data', 'dwconv_bwd_weight', 'gan_loss', 'recon_loss', 'gram', 'ka_finish', 'ka_bwd', 'adam']
+
+
+@contextlib.contextmanager
+def emulated_kernels():
+    """Swap the kernel wrappers of cat_b200.ops for the CPU restatements above (tests only)."""
+    saved = {n: getattr(ops, n) for n in _PATCHED if hasattr(ops, n)}
+    saved_gemm = {n: getattr(ops.Gemm, n) for n in ('__init__', 'pack', 'fprop', 'wgrad')}
+    saved_req = ops.require_cuda
+    try:
+        g = globals()
+        for n in _PATCHED:
+            setattr(ops, n, g[n])
+        ops.Gemm.__init__ = _gemm_init(saved_gemm['__init__'])
+        ops.Gemm.pack, ops.Gemm.fprop, ops.Gemm.wgrad = _gemm_pack, _gemm_fprop, _gemm_wgrad
+        ops.require_cuda = lambda: None
+        yield
+    finally:
+        for n in _PATCHED:
+            if n in saved:
+                setattr(ops, n, saved[n])
+            elif hasattr(ops, n):
+                delattr(ops, n)
+        for n, f in saved_gemm.items():
+            setattr(ops.Gemm, n, f)
+        ops.require_cuda = saved_req

@@ -1,0 +1,60 @@
+"""Host logic of the distillation engine on CPU: the launch sequence, hand-derived backward and buffer
+plumbing of cat_b200.distill_engine.DistillStep are executed with every kernel wrapper swapped for its
+torch restatement (oracle/kernel_emu.py, test infrastructure) and compared with the bf16-emulating oracle.
+The GPU suite (tests/test_distill_gpu.py) runs the same comparison through libcatb200.so."""
+import os
+
+import pytest
+import torch
+
+CASES = ['pix2pix_bn_lsgan_l2', 'pix2pix_bn_hinge', 'cyclegan_in_lsgan']
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('name', CASES)
+def test_distill_step_host_logic(golden_dir, name):
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    fix = torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+    step = fix['steps'][0]
+    B, _, H, W = step['real_A'].shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
+              D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
+              D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    with O.emulate_bf16():
+        ref = O.distill_step(st, step['real_A'], step['real_B'], fix['hp'])
+    with emulated_kernels():
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(step['real_A'], step['real_B'])
+        eng.step()
+        assert rel_l2(ops.nhwc_to_nchw(eng.T.out, 3), ref['Tfake_B']) < 3e-2
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), ref['Sfake_B']) < 3e-2
+        L = eng.get_losses()
+    for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'),
+                     ('loss_G_recon', 'G_recon'), ('loss_G_distill', 'G_distill')):
+        r = float(ref[k_ref])
+        assert abs(L[k] - r) <= 1e-2 * max(1.0, abs(r)), (k, L[k], r)
+    for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
+        mine, theirs = [], []
+        for k, g in grads.items():
+            if net.arena.has(k):
+                mine.append(net.arena.view(k, 'g').flatten())
+                theirs.append(g.flatten())
+        assert rel_l2(torch.cat(mine), torch.cat(theirs)) < 0.35, tag
+
+
+def test_product_path_still_requires_cuda():
+    """Outside the emulation context the package must refuse to run without a CUDA device."""
+    from cat_b200 import ops, _C
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_C.CatbError):
+        ops.require_cuda()
