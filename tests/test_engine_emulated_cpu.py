@@ -41,7 +41,7 @@ def test_distill_step_host_logic(golden_dir, name):
     for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'),
                      ('loss_G_recon', 'G_recon'), ('loss_G_distill', 'G_distill')):
         r = float(ref[k_ref])
-        assert abs(L[k] - r) <= 1e-2 * max(1.0, abs(r)), (k, L[k], r)
+        assert abs(L[k] - r) <= 2e-2 * max(1.0, abs(r)), (k, L[k], r)
     for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
         mine, theirs = [], []
         for k, g in grads.items():
