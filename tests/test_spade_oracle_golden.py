@@ -1,0 +1,55 @@
+"""Pin oracle/spade_oracle.py against golden vectors produced by the real reference SPADEDistiller
+(oracle/make_golden_spade.py).  fp32 on both sides, same algorithm -> tight tolerances."""
+import os
+
+import torch
+
+from oracle import spade_oracle as SO
+from oracle.cat_oracle import clone_sd
+
+LOSS_KEYS = [('loss_G_gan', 'G_loss/G_gan'), ('loss_G_feat', 'G_loss/G_feat'), ('loss_G_vgg', 'G_loss/G_vgg'),
+             ('loss_G_distill', 'G_loss/G_distill'), ('loss_D_real', 'D_loss/D_real'), ('loss_D_fake', 'D_loss/D_fake')]
+
+
+def spade_state(fix):
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    check = float(sum(v.double().abs().sum() for v in vgg.values()))
+    assert abs(check - fix['vgg_check']) < 1e-6 * fix['vgg_check'], 'seeded VGG19 weights differ from the fixture\'s'
+    return dict(teacher_sd=clone_sd(fix['teacher_sd']), student_sd=clone_sd(fix['student_sd0']), D_sd=clone_sd(fix['D_sd0']),
+                vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+                adam_G={}, adam_D={})
+
+
+def test_two_spade_steps_match_reference(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    state, hp = spade_state(fix), fix['hp']
+    for it, s in enumerate(fix['steps']):
+        seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+        assert torch.equal(seg, s['seg'].float())          # one-hot + edges: bit exact
+        out = SO.spade_distill_step(state, seg, s['image'], hp)
+        for mine, theirs in LOSS_KEYS:
+            r = s['losses'][theirs]
+            assert abs(float(out[mine]) - r) < 1e-4 * max(1.0, abs(r)), (it, mine, float(out[mine]), r)
+        for i in range(3):
+            assert abs(float(out['loss_G_distill_terms'][i]) - s['losses']['Specific_loss/G_distill%d' % i]) < 1e-4
+        if it:
+            continue
+        # biases in front of a BatchNorm have an analytically zero gradient (the reference holds rounding noise
+        # there): the floor is tied to the global gradient scale
+        for name in ('S_grads', 'D_grads'):
+            scale = max(float(g.abs().max()) for g in s[name].values())
+            assert set(out[name]) == set(s[name])
+            for k, g in s[name].items():
+                err = float((out[name][k] - g).abs().max())
+                assert err <= 1e-3 * float(g.abs().max()) + 1e-5 * scale, (name, k, err)
+        for k, v in s['student_buffers_after'].items():
+            if v.is_floating_point():
+                assert float((state['student_sd'][k] - v).abs().max()) < 1e-4, k
+        for k, v in s['D_buffers_after'].items():     # spectral-norm u / v after two power iterations
+            assert float((state['D_sd'][k] - v).abs().max()) < 1e-4, k
+        # Adam (beta1 = 0) turns the noise gradients of the inert biases into +-lr-sized steps of arbitrary sign,
+        # so the parameter checksum is only comparable to that band
+        cs = float(sum(v.double().abs().sum() for k, v in state['D_sd'].items() if SO._is_param(k)))
+        assert abs(cs - s['D_param_checksum_after']) < 1e-3
+        cs = float(sum(v.double().abs().sum() for k, v in state['student_sd'].items() if SO._is_param(k)))
+        assert abs(cs - s['student_param_checksum_after']) < 1e-2
