@@ -56,9 +56,9 @@ _PROTOS = {
     'catb_igemm_halo_wgrad': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
-    'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    'catb_dwconv_bwd_data': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    'catb_dwconv_bwd_weight': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    'catb_dwconv_bwd_data': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    'catb_dwconv_bwd_weight': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     'catb_norm_stats': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     'catb_norm_finalize': [_P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     'catb_norm_apply': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
@@ -78,6 +78,23 @@ _PROTOS = {
     'catb_ka_finish': [_P, _P, _I, _F, _P, _P, _P, _P],
     'catb_ka_bwd': [_P, _I, _I, _I, _L, _I, _P, _P, _I, _I, _I, _P],
     'catb_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P],
+    # SPADE path
+    'catb_resize_nearest': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    'catb_upsample2x_bwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    'catb_spade_modulate': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _L, _I, _P, _P, _I, _P],
+    'catb_spade_modulate_bwd': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I,
+                                _L, _I, _P, _P, _I, _P],
+    'catb_act_fwd': [_P, _I, _I, _P, _I, _I, _L, _I, _I, _P],
+    'catb_avgpool3s2': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P],
+    'catb_avgpool3s2_bwd': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    'catb_maxpool2': [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P],
+    'catb_maxpool2_bwd': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    'catb_onehot_edges': [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    'catb_gather_sum_f32': [_P, _P, _I, _I, _P, _P],
+    'catb_scatter_add_f32': [_P, _P, _I, _I, _P, _P],
+    'catb_fma_vec': [_P, _P, _P, _I, _P],
+    'catb_sn_forward': [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P],
+    'catb_sn_backward': [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     'catb_version': ([], C.c_char_p),
@@ -127,10 +144,10 @@ def check(status, what=''):
         raise CatbError(f'{what} failed with status {status}: {msg}')
 
 
-LAUNCH_COUNT = [0]  # entry-point calls so far (each enqueues one kernel; catb_adam enqueues two)
+LAUNCH_COUNT = [0]  # kernels enqueued so far (one per entry-point call; catb_adam 2, catb_sn_forward 5, catb_sn_backward 2)
 
 
 def call(name, *args):
     """Invoke an int-returning entry point and raise on a non-zero status."""
-    LAUNCH_COUNT[0] += 2 if name == 'catb_adam' else 1
+    LAUNCH_COUNT[0] += {'catb_adam': 2, 'catb_sn_forward': 5, 'catb_sn_backward': 2}.get(name, 1)
     check(getattr(load(), name)(*args), name)

@@ -35,7 +35,7 @@ __device__ __forceinline__ void dw_stage_filters(float* w_s, int C, const int32_
 
 __global__ void dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, __nv_bfloat16* __restrict__ y,
                                   int ldy, int y_coff, int N, int H, int W, int C, const int32_t* __restrict__ ksize,
-                                  const int32_t* __restrict__ w_off, const float* __restrict__ arena) {
+                                  const int32_t* __restrict__ w_off, const float* __restrict__ arena, int zero_pad) {
   extern __shared__ float w_s[];
   dw_stage_filters(w_s, C, ksize, w_off, arena);
   const int U = C / 8;
@@ -53,9 +53,11 @@ __global__ void dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, 
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
     for (int r = 0; r < k; ++r) {
-      const int ih = reflect_idx(h - p + r, H);
+      if (zero_pad && (h - p + r < 0 || h - p + r >= H)) continue;
+      const int ih = zero_pad ? h - p + r : reflect_idx(h - p + r, H);
       for (int s = 0; s < k; ++s) {
-        const int iw = reflect_idx(w - p + s, W);
+        if (zero_pad && (w - p + s < 0 || w - p + s >= W)) continue;
+        const int iw = zero_pad ? w - p + s : reflect_idx(w - p + s, W);
         const f8 xv = unpack8(ldg16(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * ldx + x_coff + u * 8));
         const float4 wa = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8);
         const float4 wb = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8 + 4);
@@ -80,7 +82,7 @@ __device__ __forceinline__ int reflect_sources(int i, int L, int p, int* src) {
 __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int ldy, int y_coff,
                                        __nv_bfloat16* __restrict__ dx, int ldx, int x_coff, int N, int H, int W, int C,
                                        const int32_t* __restrict__ ksize, const int32_t* __restrict__ w_off,
-                                       const float* __restrict__ arena) {
+                                       const float* __restrict__ arena, int zero_pad) {
   extern __shared__ float w_s[];
   dw_stage_filters(w_s, C, ksize, w_off, arena);
   const int U = C / 8;
@@ -98,7 +100,8 @@ __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
     int hs[3], ws[3];
-    const int nh = reflect_sources(h, H, p, hs), nw = reflect_sources(w, W, p, ws);
+    // zero padding: only the pixel itself maps onto (h, w)
+    const int nh = reflect_sources(h, H, zero_pad ? 0 : p, hs), nw = reflect_sources(w, W, zero_pad ? 0 : p, ws);
     for (int a = 0; a < nh; ++a)
       for (int r = 0; r < k; ++r) {
         const int oh = hs[a] + p - r;
@@ -121,7 +124,7 @@ __global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int
 __global__ void dwconv_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff,
                                          const __nv_bfloat16* __restrict__ dy, int ldy, int y_coff, int N, int H, int W,
                                          const int32_t* __restrict__ ksize, const int32_t* __restrict__ w_off,
-                                         float* __restrict__ grad) {
+                                         float* __restrict__ grad, int zero_pad) {
   __shared__ float part[8][8];
   const int u = blockIdx.y;
   const int k = ksize[u * 8];
@@ -138,7 +141,8 @@ __global__ void dwconv_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x, in
         const int w = static_cast<int>(pix % W);
         const int h = static_cast<int>((pix / W) % H);
         const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-        const int ih = reflect_idx(h - p + r, H), iw = reflect_idx(w - p + s, W);
+        if (zero_pad && (h - p + r < 0 || h - p + r >= H || w - p + s < 0 || w - p + s >= W)) continue;
+        const int ih = zero_pad ? h - p + r : reflect_idx(h - p + r, H), iw = zero_pad ? w - p + s : reflect_idx(w - p + s, W);
         const f8 g = unpack8(ldg16(dy + static_cast<size_t>(pix) * ldy + y_coff + u * 8));
         const f8 xv = unpack8(ldg16(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * ldx + x_coff + u * 8));
 #pragma unroll
@@ -567,7 +571,7 @@ __global__ void recon_loss_kernel(const __nv_bfloat16* __restrict__ a, int lda, 
     }
     if (da != nullptr) {
       if (extra != nullptr) {
-        const f8 e = unpack8(ldg16(extra + pix * lde + e_coff + u * 8));
+        const f8 e = unpack8(ld16(extra + pix * lde + e_coff + u * 8));  // may alias da: coherent load
 #pragma unroll
         for (int q = 0; q < 8; ++q) g.v[q] += e.v[q];
       }
@@ -732,40 +736,41 @@ using namespace catb;
                "bad channel slice (ld=%d coff=%d C=%d)", (int)(ld), (int)(coff), (int)(C))
 
 extern "C" int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int N, int H, int W,
-                               int C, const int32_t* ksize, const int32_t* w_off, const float* arena, catb_stream_t s) {
+                               int C, const int32_t* ksize, const int32_t* w_off, const float* arena, int pad_mode,
+                               catb_stream_t s) {
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
   CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
   dwconv_fwd_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
                                                              static_cast<__nv_bfloat16*>(y), ldy, y_coff, N, H, W, C,
-                                                             ksize, w_off, arena);
+                                                             ksize, w_off, arena, pad_mode == CATB_PAD_ZERO);
   return check_launch("dwconv_fwd");
 }
 
 extern "C" int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* dx, int ldx, int x_coff, int N, int H,
                                     int W, int C, const int32_t* ksize, const int32_t* w_off, const float* arena,
-                                    catb_stream_t s) {
+                                    int pad_mode, catb_stream_t s) {
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
   CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
   dwconv_bwd_data_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, y_coff,
                                                                   static_cast<__nv_bfloat16*>(dx), ldx, x_coff, N, H, W,
-                                                                  C, ksize, w_off, arena);
+                                                                  C, ksize, w_off, arena, pad_mode == CATB_PAD_ZERO);
   return check_launch("dwconv_bwd_data");
 }
 
 extern "C" int catb_dwconv_bwd_weight(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, int N,
                                       int H, int W, int C, const int32_t* ksize, const int32_t* w_off,
-                                      float* arena_grad, catb_stream_t s) {
+                                      float* arena_grad, int pad_mode, catb_stream_t s) {
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long pixels = static_cast<long long>(N) * H * W;
   dim3 grid(grid_for(pixels, 256, 64), C / 8, 1);
   dwconv_bwd_weight_kernel<<<grid, 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
                                                     static_cast<const __nv_bfloat16*>(dy), ldy, y_coff, N, H, W, ksize,
-                                                    w_off, arena_grad);
+                                                    w_off, arena_grad, pad_mode == CATB_PAD_ZERO);
   return check_launch("dwconv_bwd_weight");
 }
 

@@ -481,7 +481,7 @@ class GenNet:
             self.acts[f'features.{i}'] = self.blocks[i].out
 
         if ng:
-            f = dict(dtype=torch.bfloat16, device=dev)
+            f = dict(dtype=ops.BF16, device=dev)
             # gradient workspaces shared by all blocks
             self.ws_dmid_act = torch.zeros(B * H4 * W4 * max(maxL, 8), **f)
             self.ws_dmid_raw = torch.zeros(B * H4 * W4 * max(maxL, 8), **f)
@@ -653,36 +653,50 @@ class DisNet:
     """NLayerDiscriminator (70x70 PatchGAN) compiled for a fixed (B, H, W); always in train mode on the
     distillation path (netD is never put in eval(), base_inception_distiller.py:144-169)."""
 
-    def __init__(self, arch, B, H, W, device):
+    def __init__(self, arch, B, H, W, device, layers=None, pad=1, names=None, arenas=None):
+        """layers / pad / names / arenas generalise the class to the sub-discriminators of the SPADE
+        MultiscaleDiscriminator (discriminators.py:129-180; cat_b200/spade_engine.py): `names(ci)` returns the
+        (weight, bias, norm-prefix) keys of conv ci, `arenas=(arena, bufs)` are shared, not yet finalised arenas
+        owned by the caller, who then calls build() after finalising them."""
         self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
-        self.arena, self.bufs = Arena(True), Arena(False)
+        self.pad = pad
+        self.names = names or (lambda ci: (f'model.{ci}.weight', f'model.{ci}.bias', f'model.{ci + 1}'))
+        own = arenas is None
+        self.arena, self.bufs = (Arena(True), Arena(False)) if own else arenas
         self.ns = _NormSpec(self.arena, self.bufs, arch)
         self.layers = []
         h, w = H, W
-        for (ci, cin, cout, stride, has_norm, has_act) in discriminator_layers(arch):
+        for (ci, cin, cout, stride, has_norm, has_act) in (layers or discriminator_layers(arch)):
             L = _DLayer()
             L.ci, L.cin, L.cout, L.stride, L.has_norm, L.has_act = ci, cin, cout, stride, has_norm, has_act
             L.h, L.w = h, w
-            L.oh = (h + 2 - 4) // stride + 1
-            L.ow = (w + 2 - 4) // stride + 1
+            L.oh = (h + 2 * pad - 4) // stride + 1
+            L.ow = (w + 2 * pad - 4) // stride + 1
             L.has_bias = not has_norm  # biases in front of a norm layer are mathematically inert
-            self.arena.alloc(f'model.{ci}.weight', (cout, cin, 4, 4))
+            L.wn, L.bn, L.nn = self.names(ci)
+            self.arena.alloc(L.wn, (cout, cin, 4, 4))
             if not has_norm or arch['use_bias']:
-                self.arena.alloc(f'model.{ci}.bias', (cout,))
+                self.arena.alloc(L.bn, (cout,))
             if has_norm:
-                self.ns.alloc_group([(f'model.{ci + 1}', cout)])
+                self.ns.alloc_group([(L.nn, cout)])
             h, w = L.oh, L.ow
             self.layers.append(L)
-        self.arena.finalize(device)
-        self.bufs.finalize(device)
+        self.w_src = None       # effective weights the GEMM images are packed from (default: the parameters)
+        if own:
+            self.arena.finalize(device)
+            self.bufs.finalize(device)
+            self.build()
+
+    def build(self):
+        arch, B, H, W, device, pad = self.arch, self.B, self.H, self.W, self.dev, self.pad
         ar, dev = self.arena, device
         self.fprop_gemms, self.bwd_gemms = [], []
         self.d_in = Act.empty(B, H, W, arch['input_nc'], dev)  # gradient w.r.t. the input image
         prev_C = arch['input_nc']
         for li, L in enumerate(self.layers):
             last = li == len(self.layers) - 1
-            wn = f'model.{L.ci}.weight'
-            L.units = P.conv_fprop_units(ar.off(wn), L.cout, L.cin, 4, 4, 1)
+            wn = L.wn
+            L.units = P.conv_fprop_units(ar.off(wn), L.cout, L.cin, 4, 4, pad)
             L.y_f32 = last
             if last:
                 L.y = torch.zeros(B, L.oh, L.ow, 8, dtype=torch.float32, device=dev)
@@ -693,15 +707,15 @@ class DisNet:
                 ldy = cpad(L.cout)
             L.g = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.oh, L.ow, ldy, 0, sn=L.stride), L.units, L.cout, dev)
             self.fprop_gemms.append(L.g)
-            L.bias = ar.view(f'model.{L.ci}.bias') if L.has_bias else None
-            L.dbias = ar.view(f'model.{L.ci}.bias', 'g') if L.has_bias else None
+            L.bias = ar.view(L.bn) if L.has_bias else None
+            L.dbias = ar.view(L.bn, 'g') if L.has_bias else None
             if L.has_norm:
-                L.norm = self.ns.make(dev, B, L.oh * L.ow, [(f'model.{L.ci + 1}', L.cout)], True)
+                L.norm = self.ns.make(dev, B, L.oh * L.ow, [(L.nn, L.cout)], True)
             # backward buffers
             L.dy = Act.empty(B, L.oh, L.ow, L.cout, dev)       # gradient w.r.t. the conv output
             L.da = Act.empty(B, L.oh, L.ow, L.cout, dev) if not last else None  # w.r.t. the activation
             geo_kw = dict(N=B, H=L.oh, W=L.ow, ldx=cpad(L.cout), x_coff=0, OH=L.h, OW=L.w, ldy=cpad(L.cin), y_coff=0)
-            L.gb = _strided_dgrad(geo_kw, P.conv_dgrad_units(ar.off(wn), L.cout, L.cin, 4, 4, 1), L.cin, dev, L.stride)
+            L.gb = _strided_dgrad(geo_kw, P.conv_dgrad_units(ar.off(wn), L.cout, L.cin, 4, 4, pad), L.cin, dev, L.stride)
             self.bwd_gemms += L.gb
             # wgrad geometry: lattice tensor = dy (bf16, pitch cpad(cout))
             L.gw = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.oh, L.ow, cpad(L.cout), 0, sn=L.stride), L.units,
@@ -721,8 +735,9 @@ class DisNet:
         return sd
 
     def pack_weights(self):
+        src = self.arena.p if self.w_src is None else self.w_src
         for g in self.fprop_gemms + self.bwd_gemms:
-            g.pack(self.arena.p)
+            g.pack(src)
 
     def forward(self, x: Act):
         self.x = x
@@ -740,14 +755,18 @@ class DisNet:
                 cur = L.yraw
         return self.pred
 
-    def backward(self, dpred: Act, param_grads, input_grad):
-        """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0)."""
+    def backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None):
+        """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0).
+        act_grad_hook(li, d): called with the gradient w.r.t. the activation output of layer li before it is
+        back-propagated (the feature-matching loss of the SPADE path adds its term there)."""
         ar = self.arena
         d = dpred
         self.pool_red.zero_()
         for li in range(len(self.layers) - 1, -1, -1):
             L = self.layers[li]
             x_in = self.layers[li - 1].a if li > 0 else self.x
+            if act_grad_hook is not None and not L.y_f32:
+                act_grad_hook(li, d)
             if L.y_f32:
                 dy = d
             elif L.has_norm:

@@ -205,7 +205,7 @@ def emulate_fprop(geo: Geometry, units: Units, n_rows, x, arena, y, bias=None, a
         wmat = arena[wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]]
         acc += xg @ wmat.T.to(x.dtype)
     if bias is not None:
-        acc += bias.view(1, -1)
+        acc += bias[:n_rows].view(1, -1)
     n, oh, ow = rows
     if accumulate:
         acc += y[n, oh, ow, geo.y_coff:geo.y_coff + n_rows]
@@ -375,7 +375,7 @@ def emulate_halo_fprop(geo: Geometry, plan: HaloPlan, n_rows, x, arena, y, bias=
                                 Bm[:, j * 8:j * 8 + wu[3]] = arena[wu[0] + ridx.view(-1, 1) * wu[1] + q.view(1, -1) * wu[2]]
                         acc += A @ Bm.T
                 if bias is not None:
-                    acc += bias.view(1, -1)
+                    acc += bias[:n_rows].view(1, -1)
                 m = m0 + torch.arange(M)
                 i, j = torch.div(m, Wf, rounding_mode='floor'), m % Wf
                 jg = strip * TW + j

@@ -390,18 +390,19 @@ def add(a: Act, b: Act, dst: Act):
     _C.call('catb_add', *a.args(), *b.args(), *dst.args(), a.pixels, a.C, _stream())
 
 
-def dwconv_fwd(x: Act, y: Act, ksize, w_off, arena):
-    _C.call('catb_dwconv_fwd', *x.args(), *y.args(), x.N, x.H, x.W, x.C, _p(ksize), _p(w_off), _p(arena), _stream())
-
-
-def dwconv_bwd_data(dy: Act, dx: Act, ksize, w_off, arena):
-    _C.call('catb_dwconv_bwd_data', *dy.args(), *dx.args(), dy.N, dy.H, dy.W, dy.C, _p(ksize), _p(w_off), _p(arena),
+def dwconv_fwd(x: Act, y: Act, ksize, w_off, arena, pad_mode=_C.PAD_REFLECT):
+    _C.call('catb_dwconv_fwd', *x.args(), *y.args(), x.N, x.H, x.W, x.C, _p(ksize), _p(w_off), _p(arena), int(pad_mode),
             _stream())
 
 
-def dwconv_bwd_weight(x: Act, dy: Act, ksize, w_off, grad_arena):
+def dwconv_bwd_data(dy: Act, dx: Act, ksize, w_off, arena, pad_mode=_C.PAD_REFLECT):
+    _C.call('catb_dwconv_bwd_data', *dy.args(), *dx.args(), dy.N, dy.H, dy.W, dy.C, _p(ksize), _p(w_off), _p(arena),
+            int(pad_mode), _stream())
+
+
+def dwconv_bwd_weight(x: Act, dy: Act, ksize, w_off, grad_arena, pad_mode=_C.PAD_REFLECT):
     _C.call('catb_dwconv_bwd_weight', *x.args(), *dy.args(), x.N, x.H, x.W, x.C, _p(ksize), _p(w_off),
-            _p(grad_arena), _stream())
+            _p(grad_arena), int(pad_mode), _stream())
 
 
 def gan_loss(pred, n, ld, mode, target_is_real, for_discriminator, grad_scale, loss, dpred: Act = None):
@@ -432,3 +433,81 @@ def ka_bwd(x: Act, coef, dx: Act, accumulate):
 def adam(param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_count):
     _C.call('catb_adam', _p(param), _p(grad), _p(m), _p(v), param.numel(), _p(lr), float(beta1), float(beta2),
             float(eps), float(grad_scale), _p(step_count), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# SPADE path wrappers
+# ------------------------------------------------------------------------------------------------
+def resize_nearest(x: Act, y: Act):
+    assert x.N == y.N and x.C == y.C
+    _C.call('catb_resize_nearest', *x.args(), x.H, x.W, *y.args(), y.N, y.H, y.W, y.C, _stream())
+
+
+def upsample2x_bwd(dy: Act, dx: Act):
+    assert dy.H == 2 * dx.H and dy.W == 2 * dx.W and dy.C == dx.C
+    _C.call('catb_upsample2x_bwd', *dy.args(), *dx.args(), dx.N, dx.H, dx.W, dx.C, _stream())
+
+
+def spade_modulate(x: Act, gamma: Act, beta: Act, y: Act, scale, shift, act):
+    _C.call('catb_spade_modulate', *x.args(), *gamma.args(), *beta.args(), *y.args(), x.pixels, x.C, _p(scale), _p(shift),
+            int(act), _stream())
+
+
+def spade_modulate_bwd(dy: Act, y: Act, x: Act, gamma: Act, dgamma: Act, dbeta: Act, dn: Act, scale, shift, act):
+    _C.call('catb_spade_modulate_bwd', *dy.args(), *y.args(), *x.args(), *gamma.args(), *dgamma.args(), *dbeta.args(),
+            *dn.args(), x.pixels, x.C, _p(scale), _p(shift), int(act), _stream())
+
+
+def act_fwd(x: Act, y: Act, act):
+    _C.call('catb_act_fwd', *x.args(), *y.args(), x.pixels, x.C, int(act), _stream())
+
+
+def avgpool3s2(x: Act, y: Act):
+    assert y.H == (x.H + 1) // 2 and y.W == (x.W + 1) // 2 and x.C == y.C
+    _C.call('catb_avgpool3s2', *x.args(), x.H, x.W, *y.args(), x.N, x.C, _stream())
+
+
+def avgpool3s2_bwd(dy: Act, dx: Act, add: Act = None):
+    a = add.args() if add is not None else (None, 0, 0)
+    _C.call('catb_avgpool3s2_bwd', *dy.args(), *a, *dx.args(), dx.N, dx.H, dx.W, dx.C, _stream())
+
+
+def maxpool2(x: Act, y: Act):
+    assert y.H == x.H // 2 and y.W == x.W // 2 and x.C == y.C
+    _C.call('catb_maxpool2', *x.args(), x.H, x.W, *y.args(), x.N, x.C, _stream())
+
+
+def maxpool2_bwd(dy: Act, x: Act, dx: Act):
+    _C.call('catb_maxpool2_bwd', *dy.args(), *x.args(), *dx.args(), x.N, x.H, x.W, x.C, _stream())
+
+
+def onehot_edges(label, instance, n_label, y: Act):
+    """label / instance: int32 [N,H,W] device tensors (instance may be None)."""
+    assert label.dtype == torch.int32 and label.is_contiguous() and (instance is None or instance.dtype == torch.int32)
+    _C.call('catb_onehot_edges', _p(label), _p(instance), y.N, y.H, y.W, int(n_label), *y.args(), _stream())
+
+
+def gather_sum(arena, idx, out):
+    """idx: int32 [K, n] arena offsets (-1: none); out[i] = sum_k arena[idx[k, i]]."""
+    K, n = idx.shape
+    assert out.numel() >= n
+    _C.call('catb_gather_sum_f32', _p(arena), _p(idx), K, n, _p(out), _stream())
+
+
+def scatter_add(src, idx, grad_arena):
+    K, n = idx.shape
+    _C.call('catb_scatter_add_f32', _p(src), _p(idx), K, n, _p(grad_arena), _stream())
+
+
+def fma_vec(shift, bias, scale):
+    _C.call('catb_fma_vec', _p(shift), _p(bias), _p(scale), shift.numel(), _stream())
+
+
+def sn_forward(table, n, max_rows, max_cols, arena, bufs, training, tmp, sigma, w_eff):
+    _C.call('catb_sn_forward', _p(table), n, max_rows, max_cols, _p(arena), _p(bufs), int(training), _p(tmp), _p(sigma),
+            _p(w_eff), _stream())
+
+
+def sn_backward(table, n, max_rows, max_cols, grad, w_eff, bufs, sigma, cdot):
+    _C.call('catb_sn_backward', _p(table), n, max_rows, max_cols, _p(grad), _p(w_eff), _p(bufs), _p(sigma), _p(cdot),
+            _stream())

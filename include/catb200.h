@@ -153,15 +153,18 @@ int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, cons
 int catb_ref_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
                    const void* x, const void* y, float* arena_grad, catb_stream_t s);
 
-/* ---- depthwise convolution (reflect padded, per-channel kernel size) --------------------------
- * models/modules/inception_modules.py:165-173 (ConvBNReLU(groups=midp)).  ksize[c] in {1,3,5,7};
- * w_off[c] = element offset of the channel's k*k filter in the arena (-1: padding channel). */
+/* ---- depthwise convolution (per-channel kernel size, padding (k-1)/2) ---------------------------
+ * models/modules/inception_modules.py:165-173 (ConvBNReLU(groups=midp), reflect padded: pad_mode
+ * CATB_PAD_REFLECT) and :441-452 / :700-712 (ConvSyncBNReLU(groups=midp) of the SPADE blocks, zero padded:
+ * CATB_PAD_ZERO).  ksize[c] in {1,3,5,7}; w_off[c] = element offset of the channel's k*k filter in the arena
+ * (-1: padding channel). */
 int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int N, int H, int W, int C,
-                    const int32_t* ksize, const int32_t* w_off, const float* arena, catb_stream_t s);
+                    const int32_t* ksize, const int32_t* w_off, const float* arena, int pad_mode, catb_stream_t s);
 int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* dx, int ldx, int x_coff, int N, int H, int W,
-                         int C, const int32_t* ksize, const int32_t* w_off, const float* arena, catb_stream_t s);
+                         int C, const int32_t* ksize, const int32_t* w_off, const float* arena, int pad_mode,
+                         catb_stream_t s);
 int catb_dwconv_bwd_weight(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, int N, int H,
-                           int W, int C, const int32_t* ksize, const int32_t* w_off, float* arena_grad,
+                           int W, int C, const int32_t* ksize, const int32_t* w_off, float* arena_grad, int pad_mode,
                            catb_stream_t s);
 
 /* ---- normalisation (InstanceNorm2d / BatchNorm2d, models/networks.py:29-64) --------------------
@@ -238,6 +241,68 @@ int catb_ka_bwd(const void* x, int ldx, int x_coff, int B, long long pixels_per_
  * CUDA graph follows the scheduler (models/networks.py:80-87). */
 int catb_adam(float* param, const float* grad, float* m, float* v, long long n, const float* lr, float beta1,
               float beta2, float eps, float grad_scale, int* step_count, catb_stream_t s);
+
+/* ---- SPADE distillation path ----------------------------------------- */
+/* F.interpolate(mode='nearest') / nn.Upsample(scale_factor=2) (inception_spade_generator.py:68,79-113;
+ * inception_modules.py:750) on an NHWC bf16 slice: y[n,oh,ow] = x[n, floor(oh*H/OH), floor(ow*W/OW)]. */
+int catb_resize_nearest(const void* x, int ldx, int x_coff, int H, int W, void* y, int ldy, int y_coff, int N,
+                        int OH, int OW, int C, catb_stream_t s);
+/* adjoint of the 2x nearest up-sampling: dx[n,h,w] = sum of the 2x2 block of dy ([N,2H,2W]). */
+int catb_upsample2x_bwd(const void* dy, int ldy, int y_coff, void* dx, int ldx, int x_coff, int N, int H, int W,
+                        int C, catb_stream_t s);
+/* InceptionSPADE.forward (inception_modules.py:746-762) fused with the activation that follows it (:555-556):
+ * y = act((x*scale[c] + shift[c]) * (1 + gamma) + beta); scale/shift = the parameter-free BatchNorm as
+ * produced by catb_norm_finalize without gamma/beta. */
+int catb_spade_modulate(const void* x, int ldx, int x_coff, const void* gamma, int ldg, int g_coff,
+                        const void* beta, int ldb, int b_coff, void* y, int ldy, int y_coff, long long pixels,
+                        int C, const float* scale, const float* shift, int act, catb_stream_t s);
+/* its backward: dz = dy*act'(y); dgamma = dz*xhat; dbeta = dz; dn = dz*(1+gamma) (dn then goes through
+ * catb_norm_bwd_reduce / catb_norm_bwd_apply of the parameter-free norm). */
+int catb_spade_modulate_bwd(const void* dy, int ldd, int d_coff, const void* y, int ldy, int y_coff, const void* x,
+                            int ldx, int x_coff, const void* gamma, int ldg, int g_coff, void* dgamma, int ldo,
+                            int o_coff, void* dbeta, int ldp, int p_coff, void* dn, int ldn, int n_coff,
+                            long long pixels, int C, const float* scale, const float* shift, int act,
+                            catb_stream_t s);
+/* y = act(x) (F.leaky_relu before conv_img, inception_spade_generator.py:115). */
+int catb_act_fwd(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, long long pixels, int C, int act,
+                 catb_stream_t s);
+/* MultiscaleDiscriminator.downsample (discriminators.py:205-210): avg_pool2d(3, stride 2, padding 1,
+ * count_include_pad=False), OH = (H+1)/2; backward writes dx = add (nullable) + adjoint(dy). */
+int catb_avgpool3s2(const void* x, int ldx, int x_coff, int H, int W, void* y, int ldy, int y_coff, int N, int C,
+                    catb_stream_t s);
+int catb_avgpool3s2_bwd(const void* dy, int ldy, int y_coff, const void* add, int lda, int a_coff, void* dx, int ldx,
+                        int x_coff, int N, int H, int W, int C, catb_stream_t s);
+/* VGG19 max_pool2d(2,2) (models/modules/loss.py:151-184) and its backward (gradient to the first maximum of
+ * each window in row-major order, like ATen). */
+int catb_maxpool2(const void* x, int ldx, int x_coff, int H, int W, void* y, int ldy, int y_coff, int N, int C,
+                  catb_stream_t s);
+int catb_maxpool2_bwd(const void* dy, int ldy, int y_coff, const void* x, int ldx, int x_coff, void* dx, int ldg,
+                      int g_coff, int N, int H, int W, int C, catb_stream_t s);
+/* SPADEModel.preprocess_input / get_edges (models/spade_model.py:142-179): y[..., label] = 1 for
+ * label < n_label, y[..., n_label] = 4-neighbour instance boundary (instance nullable: no edge channel),
+ * every other channel of the slice 0.  label / instance: int32 [N,H,W]. */
+int catb_onehot_edges(const int32_t* label, const int32_t* instance, int N, int H, int W, int n_label, void* y,
+                      int ldy, int y_coff, int C, catb_stream_t s);
+/* out[i] = sum_k arena[idx[k*n+i]] (negative index: skipped) -- the summed biases of K-concatenated convs in
+ * the padded channel order of their output slice; scatter_add is its adjoint (bias gradients);
+ * fma_vec: shift[i] += bias[i]*scale[i] (a conv bias in front of an eval-mode BatchNorm). */
+int catb_gather_sum_f32(const float* arena, const int32_t* idx, int K, int n, float* out, catb_stream_t s);
+int catb_scatter_add_f32(const float* src, const int32_t* idx, int K, int n, float* arena, catb_stream_t s);
+int catb_fma_vec(float* shift, const float* bias, const float* scale, int n, catb_stream_t s);
+/* torch.nn.utils.spectral_norm as applied by get_nonspade_norm_layer (spade_architecture/normalization.py:
+ * 17-50): per weight [rows, cols] one power iteration on (u, v) when training (in place in `bufs`),
+ * sigma = u^T W v, w_eff = W / sigma.  Backward turns the gradient w.r.t. w_eff (in `grad`, in place) into
+ * the gradient w.r.t. weight_orig: (g - <g, w_eff> u v^T) / sigma.  tmp: n*max(max_rows,max_cols) floats. */
+typedef struct {
+  int32_t w_off;        /* element offset of weight_orig in the parameter arena (same offset in w_eff / grad) */
+  int32_t rows, cols;   /* Cout, Cin*kh*kw */
+  int32_t u_off, v_off; /* element offsets of weight_u / weight_v in the buffer arena */
+  int32_t reserved;
+} catb_sn_desc;
+int catb_sn_forward(const catb_sn_desc* table /*device*/, int n, int max_rows, int max_cols, const float* arena,
+                    float* bufs, int training, float* tmp, float* sigma /*[n]*/, float* w_eff, catb_stream_t s);
+int catb_sn_backward(const catb_sn_desc* table /*device*/, int n, int max_rows, int max_cols, float* grad,
+                     const float* w_eff, const float* bufs, const float* sigma, float* cdot /*[n]*/, catb_stream_t s);
 
 #ifdef __cplusplus
 }

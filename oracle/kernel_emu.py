@@ -20,7 +20,7 @@ from cat_b200 import igemm_plan as P
 from cat_b200 import ops, _C
 from cat_b200.igemm_plan import cpad
 
-BF16 = torch.bfloat16
+BF16 = torch.bfloat16      # storage dtype of the emulated device buffers; float32 in `exact` mode
 
 
 def _get(a):
@@ -28,7 +28,7 @@ def _get(a):
 
 
 def _put(a, val):
-    a.t[..., a.coff:a.coff + a.C] = val.to(BF16)
+    a.t[..., a.coff:a.coff + a.C] = val.to(a.t.dtype)
 
 
 def _act(v, act):
@@ -62,24 +62,25 @@ def _gemm_init(orig):
 
 def _gemm_pack(self, arena):
     # the device packs a bf16 image of the weights: a snapshot, re-taken only by the next pack()
-    self._emu_w = arena.detach().to(BF16).float()
+    self._emu_w = arena.detach().to(ops.BF16).float()
 
 
 def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
     assert self._emu_w is not None, 'fprop before pack()'
-    assert y.dtype == (torch.float32 if y_is_f32 else BF16)
+    assert y.dtype == (torch.float32 if y_is_f32 else ops.BF16)
     geo = self.geo
     xf, yf = x.float(), y.float()
     n, oh, ow = P._lattice_rows(geo)
     if self._emu_segments is None:
         P.emulate_fprop(geo, self.units, self.n_rows, xf, self._emu_w, yf, bias, accumulate)
     else:
-        assert bias is None
         for (row0, span, nreal, su) in self._emu_segments:
             g2 = dataclasses.replace(geo, y_coff=geo.y_coff + row0)
             P.emulate_fprop(g2, su, nreal, xf, self._emu_w, yf, None, accumulate)
             if not accumulate:
                 yf[n, oh, ow, g2.y_coff + nreal:g2.y_coff + span] = 0
+        if bias is not None:   # the device epilogue indexes the bias by image row
+            yf[n, oh, ow, geo.y_coff:geo.y_coff + self.n_rows] += bias[:self.n_rows]
     c0 = geo.y_coff
     yf[n, oh, ow, c0:c0 + self.n_rows] = _act(yf[n, oh, ow, c0:c0 + self.n_rows], act)
     if not accumulate and self._emu_segments is None:
@@ -237,12 +238,12 @@ def _dw_weights(arena, w_off, c0, c1, k):
 
 def _dw_run(x, w, k, pad_mode):
     p = (k - 1) // 2
-    if p and pad_mode == 'reflect':
+    if p and pad_mode in ('reflect', _C.PAD_REFLECT):
         return F.conv2d(F.pad(x, (p,) * 4, mode='reflect'), w, groups=w.shape[0])
     return F.conv2d(x, w, padding=p, groups=w.shape[0])
 
 
-def dwconv_fwd(x, y, ksize, w_off, arena, pad_mode='reflect'):
+def dwconv_fwd(x, y, ksize, w_off, arena, pad_mode=_C.PAD_REFLECT):
     xv = _get(x).permute(0, 3, 1, 2)
     out = torch.zeros_like(xv)
     for (c0, c1, k) in _dw_groups(ksize, w_off):
@@ -250,7 +251,7 @@ def dwconv_fwd(x, y, ksize, w_off, arena, pad_mode='reflect'):
     _put(y, out.permute(0, 2, 3, 1))
 
 
-def dwconv_bwd_data(dy, dx, ksize, w_off, arena, pad_mode='reflect'):
+def dwconv_bwd_data(dy, dx, ksize, w_off, arena, pad_mode=_C.PAD_REFLECT):
     dyv = _get(dy).permute(0, 3, 1, 2)
     out = torch.zeros_like(dyv)
     for (c0, c1, k) in _dw_groups(ksize, w_off):
@@ -260,7 +261,7 @@ def dwconv_bwd_data(dy, dx, ksize, w_off, arena, pad_mode='reflect'):
     _put(dx, out.permute(0, 2, 3, 1))
 
 
-def dwconv_bwd_weight(x, dy, ksize, w_off, grad_arena, pad_mode='reflect'):
+def dwconv_bwd_weight(x, dy, ksize, w_off, grad_arena, pad_mode=_C.PAD_REFLECT):
     xv, dyv = _get(x).permute(0, 3, 1, 2), _get(dy).permute(0, 3, 1, 2)
     for (c0, c1, k) in _dw_groups(ksize, w_off):
         w = torch.zeros(c1 - c0, 1, k, k, requires_grad=True)
@@ -292,7 +293,7 @@ def gan_loss(pred, n, ld, mode, target_is_real, for_discriminator, grad_scale, l
     if dpred is not None:
         rows = dpred.t.view(-1, dpred.ld)
         rows[:n, dpred.coff:dpred.coff + 8] = 0
-        rows[:n, dpred.coff] = (g / n * grad_scale).to(BF16)
+        rows[:n, dpred.coff] = (g / n * grad_scale).to(rows.dtype)
 
 
 def recon_loss(a, b, Creal, kind, grad_scale, loss, da=None, extra=None):
@@ -352,15 +353,138 @@ def adam(param, grad, m, v, lr, beta1, beta2, eps, grad_scale, step_count):
     param.sub_(float(lr) / bc1 * m / (v.sqrt() / (bc2 ** 0.5) + eps))
 
 
-_PATCHED = ['nchw_to_nhwc', 'nhwc_to_nchw', 'copy_channels', 'act_bwd', 'channel_sum', 'reflect_fold', 'add',
+# ---- SPADE path ----------------------------------------------------------------------------------
+def resize_nearest(x, y):
+    v = _get(x)
+    ih = torch.clamp(torch.floor(torch.arange(y.H, dtype=torch.float32) * (float(x.H) / y.H)).long(), max=x.H - 1)
+    iw = torch.clamp(torch.floor(torch.arange(y.W, dtype=torch.float32) * (float(x.W) / y.W)).long(), max=x.W - 1)
+    _put(y, v[:, ih][:, :, iw])
+
+
+def upsample2x_bwd(dy, dx):
+    g = _get(dy)
+    _put(dx, g[:, 0::2, 0::2] + g[:, 0::2, 1::2] + g[:, 1::2, 0::2] + g[:, 1::2, 1::2])
+
+
+def spade_modulate(x, gamma, beta, y, scale, shift, act):
+    C = x.C
+    xh = _get(x) * scale[:C].view(1, 1, 1, C) + shift[:C].view(1, 1, 1, C)
+    _put(y, _act(xh * (1 + _get(gamma)) + _get(beta), act))
+
+
+def spade_modulate_bwd(dy, y, x, gamma, dgamma, dbeta, dn, scale, shift, act):
+    C = x.C
+    dz = _get(dy) * _act_grad_from_out(_get(y), act)
+    xh = _get(x) * scale[:C].view(1, 1, 1, C) + shift[:C].view(1, 1, 1, C)
+    _put(dgamma, dz * xh)
+    _put(dbeta, dz)
+    _put(dn, dz * (1 + _get(gamma)))
+
+
+def act_fwd(x, y, act):
+    _put(y, _act(_get(x), act))
+
+
+def avgpool3s2(x, y):
+    v = _get(x).permute(0, 3, 1, 2)
+    _put(y, F.avg_pool2d(v, 3, 2, padding=1, count_include_pad=False).permute(0, 2, 3, 1))
+
+
+def avgpool3s2_bwd(dy, dx, add=None):
+    g = _get(dy).permute(0, 3, 1, 2)
+    xx = torch.zeros(dx.N, dx.C, dx.H, dx.W, requires_grad=True)
+    F.avg_pool2d(xx, 3, 2, padding=1, count_include_pad=False).backward(g)
+    v = xx.grad.permute(0, 2, 3, 1)
+    if add is not None:
+        v = v + _get(add)
+    _put(dx, v)
+
+
+def maxpool2(x, y):
+    _put(y, F.max_pool2d(_get(x).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1))
+
+
+def maxpool2_bwd(dy, x, dx):
+    xx = _get(x).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.max_pool2d(xx, 2, 2).backward(_get(dy).permute(0, 3, 1, 2))
+    _put(dx, xx.grad.permute(0, 2, 3, 1))
+
+
+def onehot_edges(label, instance, n_label, y):
+    N, H, W = label.shape
+    v = torch.zeros(N, H, W, y.C)
+    lab = label.long()
+    ok = lab < n_label
+    v.scatter_(3, lab.clamp(max=y.C - 1).unsqueeze(-1), ok.float().unsqueeze(-1))
+    if instance is not None:
+        t = instance
+        e = torch.zeros(N, H, W, dtype=torch.bool)
+        dx_, dy_ = t[:, :, 1:] != t[:, :, :-1], t[:, 1:, :] != t[:, :-1, :]
+        e[:, :, 1:] |= dx_
+        e[:, :, :-1] |= dx_
+        e[:, 1:, :] |= dy_
+        e[:, :-1, :] |= dy_
+        v[..., n_label] = e.float()
+    _put(y, v)
+
+
+def gather_sum(arena, idx, out):
+    K, n = idx.shape
+    ii = idx.long()
+    vals = torch.where(ii >= 0, arena[ii.clamp(min=0)], torch.zeros(()))
+    out[:n] = vals.sum(0)
+
+
+def scatter_add(src, idx, grad_arena):
+    K, n = idx.shape
+    for k in range(K):
+        ii = idx[k].long()
+        m = ii >= 0
+        grad_arena.index_add_(0, ii[m], src[:n][m])
+
+
+def fma_vec(shift, bias, scale):
+    shift += bias.view_as(shift) * scale.view_as(shift)
+
+
+def sn_forward(table, n, max_rows, max_cols, arena, bufs, training, tmp, sigma, w_eff):
+    for d, (w_off, rows, cols, u_off, v_off, _r) in enumerate(table.tolist()):
+        W = arena[w_off:w_off + rows * cols].view(rows, cols)
+        u, v = bufs[u_off:u_off + rows], bufs[v_off:v_off + cols]
+        if training:
+            v.copy_(F.normalize(torch.mv(W.t(), u), dim=0, eps=1e-12))
+            u.copy_(F.normalize(torch.mv(W, v), dim=0, eps=1e-12))
+        sigma[d] = torch.dot(u, torch.mv(W, v))
+        w_eff[w_off:w_off + rows * cols] = (W / sigma[d]).reshape(-1)
+
+
+def sn_backward(table, n, max_rows, max_cols, grad, w_eff, bufs, sigma, cdot):
+    for d, (w_off, rows, cols, u_off, v_off, _r) in enumerate(table.tolist()):
+        g = grad[w_off:w_off + rows * cols].view(rows, cols)
+        we = w_eff[w_off:w_off + rows * cols].view(rows, cols)
+        u, v = bufs[u_off:u_off + rows], bufs[v_off:v_off + cols]
+        c = (g * we).sum()
+        cdot[d] = c
+        g.copy_((g - c * torch.outer(u, v)) / sigma[d])
+
+
+_PATCHED = ['resize_nearest', 'upsample2x_bwd', 'spade_modulate', 'spade_modulate_bwd', 'act_fwd', 'avgpool3s2',
+            'avgpool3s2_bwd', 'maxpool2', 'maxpool2_bwd', 'onehot_edges', 'gather_sum', 'scatter_add', 'fma_vec',
+            'sn_forward', 'sn_backward', 'nchw_to_nhwc', 'nhwc_to_nchw', 'copy_channels', 'act_bwd', 'channel_sum', 'reflect_fold', 'add',
             'norm_stats', 'norm_finalize', 'norm_apply', 'norm_bwd_reduce', 'norm_bwd_apply', 'dwconv_fwd',
             'dwconv_bwd_data', 'dwconv_bwd_weight', 'gan_loss', 'recon_loss', 'gram', 'ka_finish', 'ka_bwd', 'adam']
 
 
 @contextlib.contextmanager
-def emulated_kernels():
-    """Swap the kernel wrappers of cat_b200.ops for the CPU restatements above (tests only)."""
+def emulated_kernels(exact=False):
+    """Swap the kernel wrappers of cat_b200.ops for the CPU restatements above (tests only).
+    exact=True additionally keeps every activation buffer and GEMM weight image in fp32 instead of bf16, so that
+    the host logic (launch order, hand-derived backward, buffer plumbing) can be compared with the fp32 oracle
+    at rounding-free tolerances."""
     saved = {n: getattr(ops, n) for n in _PATCHED if hasattr(ops, n)}
+    saved_dtype = ops.BF16
+    if exact:
+        ops.BF16 = torch.float32
     saved_gemm = {n: getattr(ops.Gemm, n) for n in ('__init__', 'pack', 'fprop', 'wgrad')}
     saved_req = ops.require_cuda
     try:
@@ -380,3 +504,4 @@ def emulated_kernels():
         for n, f in saved_gemm.items():
             setattr(ops.Gemm, n, f)
         ops.require_cuda = saved_req
+        ops.BF16 = saved_dtype

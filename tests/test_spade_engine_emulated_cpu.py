@@ -1,0 +1,103 @@
+"""Host logic of the SPADE distillation engine on CPU: cat_b200.spade_distill_engine.SpadeDistillStep is executed
+with every kernel wrapper swapped for its torch restatement (oracle/kernel_emu.py, test infrastructure) and
+compared with the oracle (which is pinned to the real reference by tests/test_spade_oracle_golden.py).
+
+exact mode keeps the emulated buffers in fp32, so launch order, hand-derived backward passes (SPADE modulation,
+six-branch bodies, learned shortcuts, up-sampling, spectral norm, feature matching, VGG, KA) and buffer plumbing
+must reproduce the fp32 oracle to rounding; bf16 mode mirrors the device storage and is compared with the
+bf16-emulating oracle at the tolerances of the GPU suite."""
+import os
+
+import pytest
+import torch
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def run_case(golden_dir, exact):
+    from oracle import cat_oracle as O
+    from oracle import spade_oracle as SO
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    s, hp = fix['steps'][0], fix['hp']
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+              vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+              adam_G={}, adam_D={})
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    if exact:
+        ref = SO.spade_distill_step(st, seg, s['image'], hp)
+    else:
+        with O.emulate_bf16():
+            ref = SO.spade_distill_step(st, seg, s['image'], hp)
+    B, _, H, W = s['image'].shape
+    out = {}
+    with emulated_kernels(exact=exact):
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], vgg)
+        eng.set_input(s['label'], s['instance'], s['image'])
+        eng.step()
+        out['seg'] = ops.nhwc_to_nchw(eng.seg, eng.snc)
+        out['T'] = ops.nhwc_to_nchw(eng.T.out, 3)
+        out['S_D'] = ops.nhwc_to_nchw(eng.S.out, 3)
+        out['Tacts'] = {n: ops.nhwc_to_nchw(eng.T.acts[n], ref['Tacts'][n].shape[1]) for n in ref['Tacts']}
+        out['losses'] = eng.get_losses()
+        out['grads'] = {}
+        for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
+            assert all(net.arena.has(k) for k in grads), [k for k in grads if not net.arena.has(k)]
+            out['grads'][tag] = {k: net.arena.view(k, 'g').clone() for k in grads}
+        out['S_sd'], out['D_sd'] = eng.S.state_dict(), eng.D.state_dict()
+    return fix, st, seg, ref, out
+
+
+LOSSES = (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'), ('loss_G_feat', 'G_feat'),
+          ('loss_G_vgg', 'G_vgg'), ('loss_G_distill', 'G_distill'))
+
+
+@pytest.mark.timeout(900)
+def test_spade_step_host_logic_exact(golden_dir):
+    fix, st, seg, ref, out = run_case(golden_dir, exact=True)
+    assert torch.equal(out['seg'], seg)                              # one-hot + edges: bit exact
+    assert rel_l2(out['T'], ref['Tfake_B']) < 1e-5
+    assert rel_l2(out['S_D'], ref['Sfake_B_D']) < 1e-4
+    for n, t in ref['Tacts'].items():
+        assert rel_l2(out['Tacts'][n], t) < 1e-5, n
+    for k_ref, k in LOSSES:
+        r = float(ref[k_ref])
+        assert abs(out['losses'][k] - r) <= 1e-5 * max(1.0, abs(r)), (k, out['losses'][k], r)
+    for i in range(3):
+        assert abs(out['losses']['G_distill%d' % i] - float(ref['loss_G_distill_terms'][i])) < 1e-5
+    for tag, key in (('S', 'S_grads'), ('D', 'D_grads')):
+        scale = max(float(g.abs().max()) for g in ref[key].values())
+        for k, g in ref[key].items():
+            err = float((out['grads'][tag][k] - g).abs().max())
+            # biases in front of a BatchNorm: analytically zero, noise in the oracle, exactly zero here
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
+    # running statistics after the two student forwards of the step, spectral-norm vectors after two iterations
+    for k, v in st['student_sd'].items():
+        if 'running_' in k:
+            assert float((out['S_sd'][k] - v).abs().max()) < 1e-4, k
+    for k, v in st['D_sd'].items():
+        if k.endswith('weight_u') or k.endswith('weight_v'):
+            assert float((out['D_sd'][k] - v).abs().max()) < 1e-5, k
+
+
+@pytest.mark.timeout(900)
+def test_spade_step_host_logic_bf16(golden_dir):
+    fix, st, seg, ref, out = run_case(golden_dir, exact=False)
+    assert torch.equal(out['seg'], seg)
+    assert rel_l2(out['T'], ref['Tfake_B']) < 3e-2
+    assert rel_l2(out['S_D'], ref['Sfake_B_D']) < 5e-2
+    for k_ref, k in LOSSES:
+        r = float(ref[k_ref])
+        assert abs(out['losses'][k] - r) <= 2e-2 * max(1.0, abs(r)), (k, out['losses'][k], r)
+    for tag, key in (('S', 'S_grads'), ('D', 'D_grads')):
+        ks = list(ref[key])
+        mine = torch.cat([out['grads'][tag][k].flatten() for k in ks])
+        theirs = torch.cat([ref[key][k].flatten() for k in ks])
+        assert rel_l2(mine, theirs) < 0.35, tag
