@@ -484,7 +484,7 @@ def maxpool2_bwd(dy: Act, x: Act, dx: Act):
 def onehot_edges(label, instance, n_label, y: Act):
     """label / instance: int32 [N,H,W] device tensors (instance may be None)."""
     assert label.dtype == torch.int32 and label.is_contiguous() and (instance is None or instance.dtype == torch.int32)
-    _C.call('catb_onehot_edges', _p(label), _p(instance), y.N, y.H, y.W, int(n_label), *y.args(), _stream())
+    _C.call('catb_onehot_edges', _p(label), _p(instance), y.N, y.H, y.W, int(n_label), *y.args(), y.C, _stream())
 
 
 def gather_sum(arena, idx, out):
