@@ -30,14 +30,23 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cat_b200', choices=['cat_b200', 'reference'])
     ap.add_argument('--workload', default='pix2pix_5p6B')
-    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
-    ap.add_argument('--height', type=int, default=256)
-    ap.add_argument('--width', type=int, default=256)
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default: 16; gaugan_5p6B: 4)')
+    ap.add_argument('--height', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
+    ap.add_argument('--width', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='images per step of the bounded CPU sample')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-gemms', action='store_true', help='print the per-GEMM timing table to stderr')
-    return ap.parse_args()
+    args = ap.parse_args()
+    spade = is_spade(args.workload)
+    args.batch = args.batch or (4 if spade else 16)
+    args.height = args.height or (512 if spade else 256)
+    args.width = args.width or (512 if spade else 256)
+    return args
+
+
+def is_spade(workload):
+    return workload.startswith('gaugan')
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -121,6 +130,28 @@ def cpu_reference_steps(arch, hp, B, H, W, steps, warmup):
     return B / dt, dt, torch.get_num_threads()
 
 
+def cpu_reference_spade_steps(arch, hp, B, H, W, steps, warmup):
+    """Times oracle.spade_oracle.spade_distill_step (CPU restatement of BaseSPADEDistiller.optimize_parameters) on a
+    bounded sample of the workload: same networks and resolution, `B` images per step."""
+    from cat_b200 import workload as WL
+    from oracle import spade_oracle as SO
+    torch.set_num_threads(_best_thread_count())
+    arch = WL.spade_arch_for(arch, H, W)
+    state = dict(teacher_sd=WL.init_spade_reference_sd(arch['teacher_arch'], 0), student_sd=WL.init_spade_reference_sd(arch['student_arch'], 1),
+                 D_sd=WL.init_multiscale_D_sd(arch['D_arch'], 2), vgg_sd=WL.init_vgg(3), teacher_arch=arch['teacher_arch'],
+                 student_arch=arch['student_arch'], D_arch=arch['D_arch'], adam_G={}, adam_D={})
+    lab, inst, img = WL.synthetic_spade_batch(B, H, W, hp['n_label'], 233)
+    seg = SO.preprocess_input(lab, inst, hp['n_label'])
+    for _ in range(warmup):
+        SO.spade_distill_step(state, seg, img, hp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        seg = SO.preprocess_input(lab, inst, hp['n_label'])
+        SO.spade_distill_step(state, seg, img, hp)
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt, torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -129,7 +160,8 @@ def run_reference(args):
     arch = WL.load_arch(args.workload)
     hp = dict(arch['hp'])
     B = args.cpu_batch
-    ips, dt, cores = cpu_reference_steps(arch, hp, B, args.height, args.width, args.steps, args.warmup)
+    fn = cpu_reference_spade_steps if is_spade(args.workload) else cpu_reference_steps
+    ips, dt, cores = fn(arch, hp, B, args.height, args.width, args.steps, args.warmup)
     sample = f'{B} images/step at {args.height}x{args.width}, same networks; CPU oracle port of optimize_parameters'
     print(json.dumps({
         'impl': 'reference', 'metric': 'distill-step images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
@@ -142,6 +174,13 @@ def run_reference(args):
 
 
 def workload_config(args, arch, B, world):
+    if is_spade(args.workload):
+        return {'workload': f'{args.workload}: GauGAN/SPADE inception student distill step (spade_distiller: teacher ngf64 '
+                            f'{arch["teacher_macs"] / 1e9:.1f} GMAC + pruned student {arch["student_macs"] / 1e9:.2f} GMAC @256x512, '
+                            f'multi-scale spectral D ndf{arch["D_arch"]["ndf"]}, VGG19 loss, KA), {args.height}x{args.width}, '
+                            f'batch {B}/GPU',
+                'global_batch': B * world, 'height': args.height, 'width': args.width, 'parallelism': f'dp{world}',
+                'l2': 'per-step working set (~GBs of activations) exceeds the 126 MB L2; no explicit flush'}
     return {'workload': f'{args.workload}: pix2pix inception student distill step (teacher ngf64 + pruned student '
                         f'{arch["student_macs"] / 1e9:.2f} GMAC + PatchGAN ndf{arch["D_arch"]["ndf"]}), '
                         f'{args.height}x{args.width}, batch {B}/GPU',
@@ -217,8 +256,39 @@ def main():
 
     arch = WL.load_arch(args.workload)
     hp = dict(arch['hp'])
-    hp['ka_scale'] = float(world)   # the reference sums the per-replica KA terms (inception_distiller.py:145-148)
     B, H, W = args.batch, args.height, args.width
+    spade = is_spade(args.workload)
+    if spade:
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        from cat_b200.spade_engine import SpadeGenNet
+        sarch = WL.spade_arch_for(arch, H, W)
+        hp['ka_scale'] = 1.0        # the SPADE distiller averages the per-replica losses (spade_model.py:191)
+        eng = SpadeDistillStep(sarch['teacher_arch'], sarch['student_arch'], sarch['D_arch'], hp, B, H, W, device=dev,
+                               world_size=world, use_cuda_graph=not args.no_graph)
+        host = WL.synthetic_spade_batch(B, H, W, hp['n_label'], 233 + rank, pin=True)
+        # synthetic "trained" teacher: running statistics calibrated on one synthetic batch (momentum 1)
+        eng.set_input(*host)
+        eng._preprocess()
+        cal = SpadeGenNet(dict(sarch['teacher_arch'], momentum=1.0), eng.seg, dev, training=True, need_grad=False)
+        cal.load_state_dict(WL.init_from_entries(cal, 0, 'uniform'))
+        cal.forward()
+        torch.cuda.synchronize()
+        t_sd = cal.state_dict()
+        del cal
+        eng.load(t_sd, WL.init_from_entries(eng.S, 1), WL.init_from_entries(eng.D, 2), WL.init_vgg(3))
+        h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+        macs = WL.spade_macs_per_image(arch, H, W)
+    else:
+        hp['ka_scale'] = float(world)   # the reference sums the per-replica KA terms (inception_distiller.py:145-148)
+        eng, host, h2d_bytes, macs = build_pix2pix(args, arch, hp, B, H, W, dev, world, rank)
+    return run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local)
+
+
+def build_pix2pix(args, arch, hp, B, H, W, dev, world, rank):
+    from cat_b200 import ops
+    from cat_b200 import workload as WL
+    from cat_b200.distill_engine import DistillStep
+    from cat_b200.engine import GenNet
     eng = DistillStep(arch['teacher_arch'], arch['student_arch'], arch['D_arch'], hp, B, H, W, device=dev,
                       world_size=world, use_cuda_graph=not args.no_graph)
     t_sd = WL.init_generator(arch['teacher_arch'], 0, 'uniform')
@@ -235,6 +305,13 @@ def main():
         t_sd = cal.state_dict()
         del cal
     eng.load(t_sd, WL.init_generator(arch['student_arch'], 1), WL.init_discriminator(arch['D_arch'], 2))
+    return eng, (a_host, b_host), 2 * B * 3 * H * W * 4, WL.macs_per_image(arch, H, W)
+
+
+def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local):
+    from cat_b200 import _C
+    if world > 1:
+        import torch.distributed as dist
     torch.cuda.synchronize()
 
     def barrier():
@@ -243,7 +320,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    eng.set_input(a_host, b_host)
+    eng.set_input(*host)
     for _ in range(args.warmup):
         eng.step()
     launches0 = _C.LAUNCH_COUNT[0]
@@ -268,7 +345,7 @@ def main():
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        eng.set_input(a_host, b_host)
+        eng.set_input(*host)
         eng.step()
         losses = eng.get_losses()
     t1.record()
@@ -320,14 +397,14 @@ def main():
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, dt, cores = cpu_reference_steps(arch, dict(arch['hp']), args.cpu_batch, H, W, 1, 1)
+        fn = cpu_reference_spade_steps if is_spade(args.workload) else cpu_reference_steps
+        ips, dt, cores = fn(arch, dict(arch['hp']), args.cpu_batch, H, W, 1, 1)
         cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                'sample': f'{args.cpu_batch} images/step at {H}x{W}, 1 warm-up + 1 timed step of the CPU oracle '
                          f'(same networks), {dt:.2f} s/step'}
 
     if rank == 0:
         imgs = B * world * args.steps
-        macs = WL.macs_per_image(arch, H, W)
         value = imgs / (ms * 1e-3)
         print(json.dumps({
             'metric': 'distill-step images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
@@ -335,7 +412,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(args, arch, B, world),
             'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
-                    'h2d_bytes_per_step': 2 * B * 3 * H * W * 4, 'd2h_bytes_per_step': (16 + 4) * 4},
+                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': (16 + 4) * 4},
             'gpu_launches': launches_per_step * args.steps * 2 + launches_per_step,
             'launches_per_step': launches_per_step,
             'algorithmic_gflop_per_image': 2 * macs['step'] / 1e9,

@@ -155,7 +155,7 @@ class _Net:
                 kw['dbeta'] = a.span(first + '.bias', last + '.bias', 'g')
         kw['rmean'] = b.span(first + '.running_mean', last + '.running_mean')
         kw['rvar'] = b.span(first + '.running_var', last + '.running_var')
-        n = BNorm(self.dev, self.B, HW, Cp, 'batch', 1e-5, 0.1, self.training, True, **kw)
+        n = BNorm(self.dev, self.B, HW, Cp, 'batch', 1e-5, getattr(self, 'bn_momentum', 0.1), self.training, True, **kw)
         n._bias_slot = bias_slot
         self.norms.append(n)
         return n
@@ -421,14 +421,16 @@ class SpadeGenNet(_Net):
 
     UPSAMPLED = ('G_middle_0', 'up_0', 'up_1', 'up_2', 'up_3', 'up_4')
 
-    def __init__(self, arch, seg: Act, device, training, need_grad):
+    def __init__(self, arch, seg: Act, device, training, need_grad, alloc_only=False):
         """seg: the persistent NHWC bf16 input buffer [B,H,W,cpad(semantic_nc)] (one-hot labels + edge map) every
-        forward pass reads; teacher and student are compiled against the same buffer."""
-        B, H, W = seg.N, seg.H, seg.W
+        forward pass reads; teacher and student are compiled against the same buffer.
+        alloc_only: only lay out the parameter / buffer tables (names and shapes of the reference state_dict)."""
+        B, H, W = (seg.N, seg.H, seg.W) if seg is not None else (1, 0, 0)
         self._init_common(B, device, training, need_grad)
+        self.bn_momentum = arch.get('momentum', 0.1)
         self.arch, self.H, self.W = arch, H, W
         self.snc = arch['semantic_nc']
-        assert seg.C == cpad(self.snc)
+        assert alloc_only or seg.C == cpad(self.snc)
         self.seg_in = seg
         ks = arch['kernel_sizes']
         ar = self.arena
@@ -453,6 +455,8 @@ class SpadeGenNet(_Net):
             self.blocks.append(b)
         ar.alloc('conv_img.weight', (3, arch['final_nc'], 3, 3))
         ar.alloc('conv_img.bias', (3,))
+        if alloc_only:
+            return
         ar.finalize(device)
         self.bufs.finalize(device)
         self._build()
@@ -657,7 +661,7 @@ class MultiScaleDis:
     parameter arena (one Adam launch, one all-reduce); spectrally normalised weights are materialised in `w_eff`
     and the GEMM images are packed from there."""
 
-    def __init__(self, arch, N, H, W, device):
+    def __init__(self, arch, N, H, W, device, alloc_only=False):
         assert arch['norm_D'] == 'spectralinstance', arch['norm_D']
         self.arch, self.N, self.H, self.W, self.dev = arch, N, H, W, device
         self.arena, self.bufs = Arena(True), Arena(False)
@@ -683,6 +687,8 @@ class MultiScaleDis:
                     self.bufs.alloc(base + '.weight_u', (L.cout,))
                     self.bufs.alloc(base + '.weight_v', (L.cin * 16,))
                     sn_rows.append((L.wn, L.cout, L.cin * 16, base + '.weight_u', base + '.weight_v'))
+        if alloc_only:
+            return
         self.arena.finalize(device)
         self.bufs.finalize(device)
         self.w_eff = torch.zeros_like(self.arena.p)
@@ -776,7 +782,7 @@ class VggNet(_Net):
     with bias + ReLU fused into the GEMM epilogue, 2x2 max pools, and the input gradient (no weight gradients:
     the network is frozen)."""
 
-    def __init__(self, B, H, W, device, need_grad=True):
+    def __init__(self, B, H, W, device, need_grad=True, alloc_only=False):
         self._init_common(B, device, False, False)
         self.need_input_grad = need_grad
         self.layers = []
@@ -795,6 +801,8 @@ class VggNet(_Net):
                 cin = c
                 idx += 2
             self.layers.append(L)
+        if alloc_only:
+            return
         self.arena.finalize(device)
         self.bufs.finalize(device)
         ar = self.arena
