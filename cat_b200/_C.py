@@ -35,7 +35,7 @@ class HaloDesc(C.Structure):
                 ('plane_pa', C.c_int32 * 4), ('plane_pb', C.c_int32 * 4), ('plane_y0', C.c_int32 * 4),
                 ('plane_x0', C.c_int32 * 4), ('mul', C.c_int32), ('TW', C.c_int32), ('n_strips', C.c_int32),
                 ('Wf', C.c_int32), ('Lh', C.c_int32),
-                ('Ymax', C.c_int32), ('Xmax', C.c_int32), ('m_sub', C.c_int32)]
+                ('Ymax', C.c_int32), ('Xmax', C.c_int32), ('m_sub', C.c_int32), ('b_budget', C.c_int32)]
 
 
 class CatbError(RuntimeError):
@@ -48,6 +48,7 @@ _DP = C.POINTER(IgemmDesc)
 # name -> argtypes (all return int unless listed in _SPECIAL)
 _PROTOS = {
     'catb_init': [_I],
+    'catb_debug_timeline': [_P],
     'catb_pack_weights': [_DP, _P, _P, _P, _P],
     'catb_pack_weights_rows': [_DP, _P, _P, _P, _I, _I, _I, _P],
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],

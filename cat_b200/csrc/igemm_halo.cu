@@ -37,7 +37,20 @@ struct HaloParams {
   void* y;
   int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, bo_mode;
   uint32_t idesc;
+  unsigned long long* dbg;  // optional per-CTA phase timestamps (catb_debug_timeline), null in production
 };
+
+static unsigned long long* g_halo_dbg = nullptr;
+constexpr int kDbgSlots = 8, kDbgCtas = 4096;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_STAMP(slot)                                                                              \
+  do {                                                                                               \
+    if (p.dbg != nullptr && blockIdx.y == 0 && blockIdx.x < kDbgCtas) p.dbg[blockIdx.x * kDbgSlots + (slot)] = gtimer(); \
+  } while (0)
 
 __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                        int bo_mode) {
@@ -98,6 +111,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(0);   // prologue done (barriers, TMEM)
 
   if (warp < 4) {
     // ---------------------------------------------------------------- halo producer
@@ -144,11 +158,13 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
+      if (threadIdx.x == 0 && c == 0) DBG_STAMP(1);   // first halo chunk filled
     }
 
     // ---------------------------------------------------------------- epilogue
     mbar_wait(accum, 0);
     tcgen05_fence_after();
+    if (threadIdx.x == 0) DBG_STAMP(4);   // accumulators complete
     for (int sub = 0; sub < h.m_sub; ++sub) {
       const int m = m0 + sub * 128 + warp * 32 + lane;
       const int i = m / h.Wf, j = m - i * h.Wf;
@@ -199,18 +215,22 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int sg = 0;  // global step counter (ring position of the weight tiles)
+      long long dbg_wait = 0;
       for (int c = 0; c < h.n_chunks; ++c) {
         const int buf = c % p.a_bufs;
         const uint32_t ph = (c / p.a_bufs) & 1;
         const catb_halo_chunk ch = p.chunks[c];
         mbar_wait(&a_full[buf], ph);
         tcgen05_fence_after();
+        if (c == 0) DBG_STAMP(2);   // MMA thread sees the first chunk
         const uint32_t a_addr = smem_u32(a_base + static_cast<size_t>(buf) * p.halo_bytes);
         for (int s = ch.first_step; s < ch.first_step + ch.n_steps; ++s, ++sg) {
           const int st = sg % p.b_stages;
           const uint32_t phb = (sg / p.b_stages) & 1;
           const int a_row = p.steps[s].a_row;
+          const long long tw0 = p.dbg != nullptr ? clock64() : 0;
           mbar_wait(&b_full[st], phb);
+          if (p.dbg != nullptr) dbg_wait += clock64() - tw0;
           tcgen05_fence_after();
           const uint32_t b_addr = smem_u32(b_base + static_cast<size_t>(st) * b_bytes);
           for (int sub = 0; sub < h.m_sub; ++sub) {
@@ -227,6 +247,8 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
         umma_commit(&a_empty[buf]);
       }
       umma_commit(accum);
+      DBG_STAMP(3);   // last MMA issued
+      if (p.dbg != nullptr && blockIdx.y == 0 && blockIdx.x < kDbgCtas) p.dbg[blockIdx.x * kDbgSlots + 7] = dbg_wait;
     }
     __syncwarp();
   } else {
@@ -244,9 +266,11 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     __syncwarp();
   }
 
+  if (threadIdx.x == 0) DBG_STAMP(5);   // epilogue of warp 0 done
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) DBG_STAMP(6);
 }
 
 int init_halo_attributes() {
@@ -306,6 +330,7 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   p.wpk = static_cast<const uint8_t*>(packed_w);
   p.bias = bias;
   p.y = y;
+  p.dbg = g_halo_dbg;
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
   {
     const char* e = getenv("CATB_HALO_BO");  // experiment switch for the descriptor base-offset convention
@@ -321,8 +346,9 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   {
     // keep >= ~64 KB of weight tiles in flight (bulk-copy latency ~1.5 us), but not more stages than that needs
     const int b_bytes = d->n_tile * 128;
-    int want = (64 * 1024 + b_bytes - 1) / b_bytes;
-    if (want < 4) want = 4;
+    const int budget = h->b_budget > 0 ? h->b_budget : 64 * 1024;
+    int want = (budget + b_bytes - 1) / b_bytes;
+    if (want < (h->b_budget > 0 ? 2 : 4)) want = h->b_budget > 0 ? 2 : 4;
     if (p.b_stages > want) p.b_stages = want;
   }
   smem = 1024 + kHHeader + static_cast<size_t>(p.a_bufs) * p.halo_bytes + static_cast<size_t>(p.b_stages) * d->n_tile * 128;
@@ -337,4 +363,11 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   dim3 grid(p.tiles_per_image * h->n_strips * d->N, n_tiles, 1);
   igemm_halo_fprop_kernel<<<grid, kHThreads, smem, static_cast<cudaStream_t>(s)>>>(p);
   return check_launch("igemm_halo_fprop");
+}
+
+// Development aid (tools/profile_gemm.py --timeline): when a device buffer of 4096 x 8 uint64 is registered, every
+// halo-fprop CTA with blockIdx.x < 4096 records %globaltimer at its phase boundaries.  Pass NULL to switch it off.
+extern "C" int catb_debug_timeline(void* device_buffer) {
+  g_halo_dbg = static_cast<unsigned long long*>(device_buffer);
+  return CATB_OK;
 }

@@ -130,22 +130,27 @@ class Gemm:
                     widths = [geo.OWs] + [t for t in (64, 32, 16) if t < geo.OWs]
                     cands = [(tw, ms) for tw in widths for ms in (2, 1)]
                 n_strip_widths = 0
+                # short weight tiles (thin GEMMs): a second variant with a small weight ring, so that 2-4 CTAs share
+                # an SM and the fill / MMA / epilogue phases of neighbouring tiles overlap
+                budgets = (0, 16 * 1024) if (force_tile is None and self.n_tile <= 128) else (0,)
                 for tw, ms in cands:
                     plan.TW, plan.m_sub = tw, ms
                     if not lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms):
                         continue
                     if force_tile is None and tw not in [t[0] for t in self.tilings]:
                         n_strip_widths += 1
-                        if n_strip_widths > 2:
+                        if n_strip_widths > (3 if self.n_tile <= 128 else 2):
                             break
-                    hd = _C.HaloDesc()
-                    hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
-                    for i, (pa, pb, y0, x0) in enumerate(plan.planes):
-                        hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
-                    hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
-                    hd.Ymax, hd.Xmax, hd.m_sub = plan.Ymax, plan.Xmax, plan.m_sub
                     st = np.array([[pl * plan.Lh + dy * plan.Wf + dx, ci] for (ci, pl, dy, dx) in plan.steps], dtype=np.int32)
-                    self.tilings.append((tw, ms, hd, torch.from_numpy(st).to(device)))
+                    st = torch.from_numpy(st).to(device)
+                    for budget in budgets:
+                        hd = _C.HaloDesc()
+                        hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
+                        for i, (pa, pb, y0, x0) in enumerate(plan.planes):
+                            hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
+                        hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
+                        hd.Ymax, hd.Xmax, hd.m_sub, hd.b_budget = plan.Ymax, plan.Xmax, plan.m_sub, budget
+                        self.tilings.append((tw, ms, hd, st))
                 if not self.tilings:
                     plan = None
             if plan is not None:

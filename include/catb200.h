@@ -126,6 +126,8 @@ typedef struct {
   int32_t Wf, Lh;                   /* frame pitch TW+Xmax; halo rows per plane 128*m_sub+Ymax*Wf+Xmax  */
   int32_t Ymax, Xmax;               /* tap extent in frame rows / columns                               */
   int32_t m_sub;                    /* 128-row sub-tiles per CTA (1 or 2) sharing every weight tile     */
+  int32_t b_budget;                 /* bytes of weight tiles kept in flight (0: 64 KB); a smaller ring lets
+                                       several CTAs share an SM when the tiles are short (thin GEMMs)    */
 } catb_halo_desc;
 /* 1 when the halo tile + weight ring fit in shared memory / TMEM for these parameters, else 0. */
 int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub);
@@ -145,6 +147,11 @@ int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, con
                           const catb_halo_chunk* chunks /*device*/, const catb_halo_wgroup* groups /*device*/,
                           int n_groups, const catb_weight_unit* wunits /*device*/, const void* x, const void* y,
                           float* arena_grad, catb_stream_t s);
+
+/* Development aid: with a device buffer of 4096 x 8 uint64 registered, every catb_igemm_halo_fprop CTA with
+ * blockIdx.x < 4096 records %globaltimer (ns) at its phase boundaries: 0 prologue done, 1 first halo chunk filled,
+ * 2 MMA thread released, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit.  NULL: off. */
+int catb_debug_timeline(void* device_buffer);
 
 /* Slow SIMT restatements of the two kernels above (same descriptors); kept for on-device bisection
  * in tests.  Not used by the product path. */

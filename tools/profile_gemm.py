@@ -30,10 +30,20 @@ CASES = {
     'd4w': ('wgrad', 512, 1024, 4, 1, 1, False, 16, 32, 32),
     'd2w': ('wgrad', 256, 512, 4, 2, 1, False, 16, 64, 64),
     's5w': ('wgrad', 90, 16, 5, 1, 2, True, 16, 64, 64),        # student-sized wgrad
+    # thin GEMMs (HBM bound by rights): student / SPADE full-resolution layers
+    'shead': ('fprop', 17, 3, 7, 1, 3, True, 16, 256, 256),     # student head 7x7
+    'sstem': ('fprop', 3, 25, 7, 1, 3, True, 16, 256, 256),
+    'thin3': ('fprop', 8, 64, 3, 1, 1, False, 4, 512, 512),     # SPADE: 3x3, 8 -> 64 at full resolution
+    'thin1': ('fprop', 36, 21, 1, 1, 0, False, 4, 512, 512),    # SPADE gamma/beta first 1x1 on the label map
+    'thin5': ('fprop', 36, 21, 5, 1, 2, False, 4, 512, 512),
+    's1x1': ('fprop', 62, 90, 1, 1, 0, False, 16, 64, 64),      # student block, fused 1x1 first convs
+    's3x3': ('fprop', 62, 15, 3, 1, 1, True, 16, 64, 64),
+    'vgg1': ('fprop', 64, 64, 3, 1, 1, False, 4, 512, 512),     # VGG conv1_2
+    'vgg3': ('fprop', 256, 256, 3, 1, 1, False, 4, 128, 128),   # VGG conv3_x
 }
 
 
-def run(name, iters):
+def run(name, iters, variants=False, tiling=None, timeline=False):
     kind, Cin, Cout, k, stride, pad, reflect, N, H, W = CASES[name]
     dev = 'cuda:0'
     OH = (H + 2 * pad - k) // stride + 1
@@ -52,27 +62,78 @@ def run(name, iters):
         fn = lambda: g.fprop(x, y)  # noqa: E731
     else:
         fn = lambda: g.wgrad(x, y, grad)  # noqa: E731
-    for _ in range(2):
+    if tiling is not None and kind != 'wgrad':      # pin one v2 variant (for ncu): 'TW,m_sub,budgetK'
+        tw, ms_, bk = (int(v) for v in tiling.split(','))
+        ops.AUTOTUNE = False
+        pick = [t for t in g.tilings if (t[0], t[1], t[2].b_budget // 1024) == (tw, ms_, bk)]
+        assert pick, [(t[0], t[1], t[2].b_budget // 1024) for t in g.tilings]
+        g._use_tiling(pick[0])
+
+    def timed(f):
+        for _ in range(2):
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    if timeline and kind != 'wgrad':
+        import ctypes as C
+        from cat_b200 import _C
+        buf = torch.zeros(4096 * 8, dtype=torch.int64, device=dev)
         fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
+        torch.cuda.synchronize()
+        _C.load().catb_debug_timeline(C.c_void_p(buf.data_ptr()))
         fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+        torch.cuda.synchronize()
+        _C.load().catb_debug_timeline(None)
+        t = buf.view(4096, 8).cpu()
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        rel = (t[:, :7] - t[:, 0:1]).float() / 1e3
+        names = ['fill done', 'mma start', 'last mma issued', 'accum complete', 'epilogue done', 'exit']
+        print(f'{name}: {t.shape[0]} CTAs recorded; kernel span {(t[:, 6].max() - t0).item() / 1e3:.1f} us; per-CTA phase times (us after prologue) median / p90:')
+        for i, nme in enumerate(names):
+            col = rel[:, i + 1]
+            print(f'    {nme:18s} {col.median().item():8.2f} {col.quantile(0.9).item():8.2f}')
+        print(f'    MMA thread: cycles waiting for weight tiles (median) {t[:, 7].float().median().item():.0f} '
+              f'= {t[:, 7].float().median().item() / 1.965e3:.2f} us')
+        start = (t[:, 0] - t0).float() / 1e3
+        print('    CTA start times (us): first 8', [round(v, 1) for v in start[:8].tolist()], ' median', round(start.median().item(), 1))
+        return
+
     flops = 2.0 * N * OH * OW * Cout * Cin * k * k
+    hbm_us = (x.numel() + y.numel()) * 2 / 6.5e12 * 1e6          # read x once, write y once at ~6.5 TB/s
+    if variants and kind != 'wgrad':
+        ops.AUTOTUNE = False
+        rows = [('v1', timed(lambda: g.fprop(x, y, force_v1=True)))]
+        for t in (g.tilings if g.halo is not None else []):
+            g._use_tiling(t)
+            rows.append((f'v2 TW{t[0]} m{t[1]} b{t[2].b_budget // 1024}K', timed(lambda: g.fprop(x, y))))
+        best = min(r[1] for r in rows)
+        print(f'{name:6s} M={N * OH * OW} N={Cout} K={Cin * k * k} n_tile {g.n_tile}  HBM floor {hbm_us:6.1f} us  best {best * 1e3:7.1f} us '
+              f'({flops / best / 1e9:6.1f} TF/s, {hbm_us / (best * 1e3) * 100:4.1f}% of the HBM floor rate)')
+        for nme, ms in rows:
+            print(f'        {nme:22s} {ms * 1e3:9.1f} us')
+        return
+    ms = timed(fn)
     gathered = N * OH * OW * len(units) * 16
     print(f'{name:6s} {kind:6s} M={N * OH * OW} N={Cout} K={Cin * k * k}: {ms * 1e3:9.1f} us  {flops / ms / 1e9:8.1f} TFLOP/s  '
-          f'gather {gathered / ms / 1e9:7.2f} TB/s (n_tile {g.n_tile})')
+          f'gather {gathered / ms / 1e9:7.2f} TB/s (n_tile {g.n_tile})  HBM floor {hbm_us:6.1f} us')
 
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('cases', nargs='*', default=list(CASES))
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--tiling', default=None, help="pin a v2 variant: 'TW,m_sub,budgetK'")
+    ap.add_argument('--timeline', action='store_true', help='per-CTA phase timestamps of the halo kernel')
+    ap.add_argument('--variants', action='store_true', help='time v1 and every v2 tiling / weight-ring variant')
     a = ap.parse_args()
     ops.require_cuda()
     for c in a.cases:
-        run(c, a.iters)
+        run(c, a.iters, a.variants, a.tiling, a.timeline)
