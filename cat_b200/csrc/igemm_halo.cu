@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       const uint32_t ph = (c / p.a_bufs) & 1;
       const catb_halo_chunk ch = p.chunks[c];
       const bool uvalid = ul < ch.n_units;
+      const bool ufill = ul < ((ch.n_units + 1) & ~1);   // columns the MMAs of this chunk read (K = 16 granularity)
       const __nv_bfloat16* xc = p.x + d.x_coff + (ch.cu0 + ul) * 8;
       uint8_t* abuf = a_base + static_cast<size_t>(buf) * p.halo_bytes;
       mbar_wait(&a_empty[buf], ph ^ 1);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
           }
           const __nv_bfloat16* src = ok ? xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx : p.x;
           const int row = plane * h.Lh + hr;  // swizzle phase follows the absolute row in the buffer
-          cp_async16_zfill(prow + static_cast<size_t>(hr) * 128 + ((ul ^ (row & 7)) << 4), src, ok);
+          if (ufill) cp_async16_zfill(prow + static_cast<size_t>(hr) * 128 + ((ul ^ (row & 7)) << 4), src, ok);
           fx += 16;
           while (fx >= h.Wf) {
             fx -= h.Wf;
@@ -233,13 +234,18 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
           if (p.dbg != nullptr) dbg_wait += clock64() - tw0;
           tcgen05_fence_after();
           const uint32_t b_addr = smem_u32(b_base + static_cast<size_t>(st) * b_bytes);
+          // a chunk that uses only n_units of its 8 channel units needs only ceil(n_units / 2) of the four K=16
+          // MMAs (the remaining columns of the halo rows and of the weight tile are zero)
+          const int kmax = (ch.n_units + 1) >> 1;
           for (int sub = 0; sub < h.m_sub; ++sub) {
             const uint32_t wa = a_addr + static_cast<uint32_t>(a_row + sub * 128) * 128u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024, p.bo_mode);
-              const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(tmem_base + sub * d.n_tile, adesc, bdesc, p.idesc, (sg | k) != 0 ? 1u : 0u);
+              if (k < kmax) {
+                const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024, p.bo_mode);
+                const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+                umma_bf16(tmem_base + sub * d.n_tile, adesc, bdesc, p.idesc, (sg | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&b_empty[st]);
