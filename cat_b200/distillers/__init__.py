@@ -5,7 +5,10 @@ def find_distiller_using_name(distiller_name):
     if distiller_name == 'inception':
         from .inception_distiller import InceptionDistiller
         return InceptionDistiller
-    raise NotImplementedError('distiller [%s] is not available in cat_b200 yet (spade is the next section-8 row)' % distiller_name)
+    if distiller_name == 'spade':
+        from .spade_distiller import SPADEDistiller
+        return SPADEDistiller
+    raise NotImplementedError('distiller [%s] is not a CAT distiller (inception | spade)' % distiller_name)
 
 
 def get_option_setter(distiller_name):

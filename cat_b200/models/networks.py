@@ -358,9 +358,11 @@ def define_G(input_nc, output_nc, ngf, netG, norm='batch', dropout_rate=0, init_
     """models/networks.py:167-202.  `opt.arch_G` (optional) carries a pruned architecture."""
     norm_layer = get_norm_layer(norm_type=norm, affine=getattr(opt, 'norm_affine', False),
                                 track_running_stats=getattr(opt, 'norm_track_running_stats', False))
+    if netG == 'inception_spade':
+        from .spade_networks import define_spade_G
+        return init_net(define_spade_G(opt), init_type, init_gain, gpu_ids)
     if netG != 'inception_9blocks':
-        raise NotImplementedError('Generator model name [%s] is not available in cat_b200 yet '
-                                  '(inception_spade is the next SURVEY section-8 row)' % netG)
+        raise NotImplementedError('Generator model name [%s] is not on the CAT distillation path' % netG)
     net = InceptionGenerator(input_nc, output_nc, ngf=ngf, channels=opt.channels,
                              channels_reduction_factor=opt.channels_reduction_factor, kernel_sizes=opt.kernel_sizes,
                              norm_layer=norm_layer, norm_momentum=opt.norm_momentum, norm_epsilon=opt.norm_epsilon,
@@ -372,7 +374,10 @@ def define_D(input_nc, ndf, netD, n_layers_D=3, norm='batch', init_type='normal'
     """models/networks.py:205-266."""
     norm_layer = get_norm_layer(norm_type=norm, affine=getattr(opt, 'norm_affine_D', False),
                                 track_running_stats=getattr(opt, 'norm_track_running_stats', False))
+    if netD == 'multi_scale':
+        from .spade_networks import define_spade_D
+        return init_net(define_spade_D(opt), init_type, init_gain, gpu_ids)
     if netD != 'n_layers':
-        raise NotImplementedError('Discriminator model name [%s] is not available in cat_b200 yet' % netD)
+        raise NotImplementedError('Discriminator model name [%s] is not on the CAT distillation path' % netD)
     net = NLayerDiscriminator(input_nc, ndf, n_layers_D, norm_layer=norm_layer, active_fn=opt.active_fn_D)
     return init_net(net, init_type, init_gain, gpu_ids)

@@ -82,3 +82,48 @@ def test_product_path_does_not_import_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in re.sub(r'"""[\s\S]*?"""', '', src), f'{f} must not reference the test oracle'
+
+
+def test_spade_module_trees_match_reference_state_dicts(golden_dir):
+    """The SPADE mirrors (InceptionSPADEGenerator, MultiscaleDiscriminator) keep the reference's state_dict keys, order
+    and shapes -- teacher, pruned student (from_arch) and spectral-norm discriminator -- and describe the same
+    architecture to the engine."""
+    from cat_b200.models.spade_networks import InceptionSPADEGenerator
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    Ta, Sa, Da = fix['teacher_arch'], fix['student_arch'], fix['D_arch']
+    opt = argparse.Namespace(ngf=Ta['fc_out'] // 16, norm_G='spadesyncbatch3x3', semantic_nc=Ta['semantic_nc'],
+                             num_upsampling_layers=Ta['num_upsampling_layers'], crop_size=128, aspect_ratio=2.0, channels=None,
+                             channels_reduction_factor=6, kernel_sizes=[1, 3, 5], active_fn='nn.ReLU', norm_D=Da['norm_D'],
+                             ndf=Da['ndf'], n_layers_D=Da['n_layers'], num_D=Da['num_D'], output_nc=3)
+    T = networks.define_G(opt.semantic_nc - 1, 3, opt.ngf, 'inception_spade', 'instance', 0, 'xavier', 0.02, [], opt=opt)
+    S = InceptionSPADEGenerator.from_arch(Sa, opt)
+    D = networks.define_D(Da['input_nc'], Da['ndf'], 'multi_scale', Da['n_layers'], 'instance', 'xavier', 0.02, [], opt=opt)
+    for net, sd, arch in ((T, fix['teacher_sd'], Ta), (S, fix['student_sd0'], Sa), (D, fix['D_sd0'], Da)):
+        mine = net.state_dict()
+        assert list(mine.keys()) == list(sd.keys())
+        assert all(mine[k].shape == v.shape for k, v in sd.items())
+        net.load_state_dict(sd)
+        assert net.arch() == arch
+    assert list(S.get_named_block_list().keys()) == Sa['block_names']
+    assert list(S.head_0.get_named_first_bn().keys())[0] == 'res_ops.0.0.norm'
+
+
+def test_spade_engine_compiles_on_cpu_and_round_trips_state(golden_dir):
+    """Table building / arena layout of the SPADE networks for the fixture architecture, and state_dict round trip
+    (every reference key is stored, nothing else)."""
+    from cat_b200.ops import Act
+    from cat_b200.spade_engine import MultiScaleDis, SpadeGenNet, VggNet
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    B, _, H, W = fix['steps'][0]['image'].shape
+    seg = Act.empty(B, H, W, fix['teacher_arch']['semantic_nc'], 'cpu', zero=True)
+    for arch, sd, need_grad in ((fix['teacher_arch'], fix['teacher_sd'], False), (fix['student_arch'], fix['student_sd0'], True)):
+        net = SpadeGenNet(arch, seg, 'cpu', training=need_grad, need_grad=need_grad, alloc_only=True)
+        keys = set(net.arena.entries) | set(net.bufs.entries)
+        assert keys == set(sd.keys()), (sorted(keys - set(sd))[:3], sorted(set(sd) - keys)[:3])
+        for k, v in sd.items():
+            ent = (net.arena.entries.get(k) or net.bufs.entries.get(k))
+            assert tuple(ent[1]) == (tuple(v.shape) or (1,)), k
+    D = MultiScaleDis(fix['D_arch'], 2 * B, H, W, 'cpu', alloc_only=True)
+    assert set(D.arena.entries) | set(D.bufs.entries) == set(fix['D_sd0'].keys())
+    V = VggNet(B, H, W, 'cpu', alloc_only=True)
+    assert len(V.arena.entries) == 26
