@@ -266,28 +266,65 @@ __global__ void norm_finalize_kernel(const float* __restrict__ sums, int G, int 
   }
 }
 
+// Element-wise normalisation kernels: a thread owns ONE 8-channel unit (its per-channel constants live in
+// registers for the whole kernel) and walks over pixels, `lanes` = blockDim / U pixels per block iteration, two
+// pixels in flight per thread; blockIdx.y = sample when the statistics are per sample.  No per-element
+// divisions, no per-element constant loads: the loop is 16-byte loads, FMAs and one 16-byte store.
+struct UnitMap {
+  int u, pl, lanes;
+  bool active;
+};
+__device__ __forceinline__ UnitMap unit_map(int U) {
+  UnitMap m;
+  m.lanes = U >= static_cast<int>(blockDim.x) ? 1 : static_cast<int>(blockDim.x) / U;
+  m.u = threadIdx.x % U;
+  m.pl = threadIdx.x / U;
+  m.active = (U >= static_cast<int>(blockDim.x)) || m.pl < m.lanes;
+  if (U >= static_cast<int>(blockDim.x)) m.pl = 0;
+  return m;
+}
+
 __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, __nv_bfloat16* __restrict__ y,
                                   int ldy, int y_coff, const __nv_bfloat16* __restrict__ res, int ldr, int r_coff, int HW,
                                   int C, int per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
                                   int act, long long pixels) {
   const int U = C / 8;
-  const long long total = pixels * U;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(idx % U);
-    const size_t pix = static_cast<size_t>(idx / U);
-    const int g = per_sample ? static_cast<int>(pix / HW) : 0;
-    f8 v = unpack8(ldg16(x + pix * ldx + x_coff + u * 8));
-    const float* sc = scale + static_cast<size_t>(g) * C + u * 8;
-    const float* sh = shift + static_cast<size_t>(g) * C + u * 8;
+  const UnitMap m = unit_map(U);
+  if (!m.active) return;
+  const int g = per_sample ? blockIdx.y : 0;
+  const long long pix0 = per_sample ? static_cast<long long>(g) * HW : 0;
+  const long long npix = per_sample ? HW : pixels;
+  const long long stride = static_cast<long long>(gridDim.x) * m.lanes;
+  for (int u = m.u; u < U; u += blockDim.x) {  // only loops when U > blockDim.x
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + static_cast<size_t>(g) * C + u * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + static_cast<size_t>(g) * C + u * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8 + 4));
+    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += 2 * stride) {
+      const size_t p0 = static_cast<size_t>(pix0 + pp), p1 = p0 + stride;
+      const bool two = pp + stride < npix;
+      f8 v0 = unpack8(ldg16(x + p0 * ldx + x_coff + u * 8)), v1, r0, r1;
+      if (two) v1 = unpack8(ldg16(x + p1 * ldx + x_coff + u * 8));
+      if (res != nullptr) {
+        r0 = unpack8(ldg16(res + p0 * ldr + r_coff + u * 8));
+        if (two) r1 = unpack8(ldg16(res + p1 * ldr + r_coff + u * 8));
+      }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v.v[q] = apply_act(v.v[q] * __ldg(sc + q) + __ldg(sh + q), act);
-    if (res != nullptr) {
-      const f8 r = unpack8(ldg16(res + pix * ldr + r_coff + u * 8));
+      for (int q = 0; q < 8; ++q) {
+        v0.v[q] = apply_act(v0.v[q] * sc[q] + sh[q], act);
+        if (res != nullptr) v0.v[q] += r0.v[q];
+      }
+      st16(y + p0 * ldy + y_coff + u * 8, pack8(v0));
+      if (two) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v.v[q] += r.v[q];
+        for (int q = 0; q < 8; ++q) {
+          v1.v[q] = apply_act(v1.v[q] * sc[q] + sh[q], act);
+          if (res != nullptr) v1.v[q] += r1.v[q];
+        }
+        st16(y + p1 * ldy + y_coff + u * 8, pack8(v1));
+      }
     }
-    st16(y + pix * ldy + y_coff + u * 8, pack8(v));
   }
 }
 
@@ -299,8 +336,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, in
                                       const float* __restrict__ red, float count, int act, float* dgamma, float* dbeta,
                                       int G, long long pixels) {
   const int U = C / 8;
-  const long long total = pixels * U;
-  if (blockIdx.x == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float sb = 0.f, sg = 0.f;
       for (int g = 0; g < G; ++g) {
@@ -311,30 +347,43 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, in
       if (dgamma) atomicAdd(dgamma + c, sg);
     }
   }
+  const UnitMap m = unit_map(U);
+  if (!m.active) return;
+  const int g = per_sample ? blockIdx.y : 0;
+  const long long pix0 = per_sample ? static_cast<long long>(g) * HW : 0;
+  const long long npix = per_sample ? HW : pixels;
+  const long long stride = static_cast<long long>(gridDim.x) * m.lanes;
   const float inv_count = 1.f / count;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(idx % U);
-    const size_t pix = static_cast<size_t>(idx / U);
-    const int g = per_sample ? static_cast<int>(pix / HW) : 0;
-    const f8 dv = unpack8(ldg16(dout + pix * ldd + d_coff + u * 8));
-    const f8 xv = unpack8(ldg16(x + pix * ldx + x_coff + u * 8));
-    f8 ov;
-    if (act != CATB_ACT_NONE) ov = unpack8(ldg16(out + pix * ldo + o_coff + u * 8));
-    f8 r;
+  for (int u = m.u; u < U; u += blockDim.x) {
+    // dx = k1 * dz + k2 * x + k3 with per-channel constants (xhat = (x - mu) * rs):
+    //   k1 = ga*rs,  k2 = -ga*rs*rs*s2/count,  k3 = -ga*rs*s1/count + ga*rs*rs*mu*s2/count
+    float k1[8], k2[8], k3[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int c = u * 8 + q;
       const float mu = __ldg(mean_rstd + (static_cast<size_t>(g) * 2 + 0) * C + c);
       const float rs = __ldg(mean_rstd + (static_cast<size_t>(g) * 2 + 1) * C + c);
       const float ga = gamma ? __ldg(gamma + c) : 1.f;
-      const float s1 = __ldg(red + (static_cast<size_t>(g) * 2 + 0) * C + c);
-      const float s2 = __ldg(red + (static_cast<size_t>(g) * 2 + 1) * C + c);
-      const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
-      const float xh = (xv.v[q] - mu) * rs;
-      r.v[q] = ga * rs * (dz - s1 * inv_count - xh * s2 * inv_count);
+      const float s1 = __ldg(red + (static_cast<size_t>(g) * 2 + 0) * C + c) * inv_count;
+      const float s2 = __ldg(red + (static_cast<size_t>(g) * 2 + 1) * C + c) * inv_count;
+      k1[q] = ga * rs;
+      k2[q] = -ga * rs * rs * s2;
+      k3[q] = -ga * rs * s1 + ga * rs * rs * mu * s2;
     }
-    st16(dx + pix * ldg + g_coff + u * 8, pack8(r));
+    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += stride) {
+      const size_t pix = static_cast<size_t>(pix0 + pp);
+      const f8 dv = unpack8(ldg16(dout + pix * ldd + d_coff + u * 8));
+      const f8 xv = unpack8(ldg16(x + pix * ldx + x_coff + u * 8));
+      f8 ov;
+      if (act != CATB_ACT_NONE) ov = unpack8(ldg16(out + pix * ldo + o_coff + u * 8));
+      f8 r;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
+        r.v[q] = k1[q] * dz + k2[q] * xv.v[q] + k3[q];
+      }
+      st16(dx + pix * ldg + g_coff + u * 8, pack8(r));
+    }
   }
 }
 
@@ -784,6 +833,17 @@ static dim3 reduce_grid(long long pixels_per_group, int C, int groups) {
   return dim3(static_cast<unsigned>(gx), groups, 1);
 }
 
+// grid of the unit-mapped element-wise kernels: x = pixel blocks (two pixels per thread iteration), y = groups
+static dim3 elementwise_grid(long long pixels_per_group, int C, int groups) {
+  const int U = C / 8;
+  const int lanes = U >= 256 ? 1 : 256 / U;
+  long long gx = (pixels_per_group + static_cast<long long>(lanes) * 2 - 1) / (static_cast<long long>(lanes) * 2);
+  const long long cap = std::max(1, 148 * 8 / groups);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3(static_cast<unsigned>(gx), groups, 1);
+}
+
 extern "C" int catb_norm_stats(const void* x, int ldx, int x_coff, int N, int HW, int C, int per_sample, float* sums,
                                catb_stream_t s) {
   CHK_SLICE(ldx, x_coff, C);
@@ -812,7 +872,7 @@ extern "C" int catb_norm_apply(const void* x, int ldx, int x_coff, void* y, int 
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long pixels = static_cast<long long>(N) * HW;
-  norm_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, S(s)>>>(
+  norm_apply_kernel<<<elementwise_grid(per_sample ? HW : pixels, C, per_sample ? N : 1), 256, 0, S(s)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<__nv_bfloat16*>(y), ldy, y_coff,
       static_cast<const __nv_bfloat16*>(residual), ldr, r_coff, HW, C, per_sample, scale, shift, act, pixels);
   return check_launch("norm_apply");
@@ -839,7 +899,7 @@ extern "C" int catb_norm_bwd_apply(const void* dout, int ldd, int d_coff, const 
   CHK_SLICE(ldd, d_coff, C);
   CHK_SLICE(ldg, g_coff, C);
   const long long pixels = static_cast<long long>(N) * HW;
-  norm_bwd_apply_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, S(s)>>>(
+  norm_bwd_apply_kernel<<<elementwise_grid(per_sample ? HW : pixels, C, per_sample ? N : 1), 256, 0, S(s)>>>(
       static_cast<const __nv_bfloat16*>(dout), ldd, d_coff, static_cast<const __nv_bfloat16*>(out), ldo, o_coff,
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<__nv_bfloat16*>(dx), ldg, g_coff, HW, C,
       per_sample, mean_rstd, gamma, red, count, act, dgamma, dbeta, per_sample ? N : 1, pixels);

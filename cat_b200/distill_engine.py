@@ -9,6 +9,8 @@ bf16 activations / weights with fp32 accumulation, the two discriminator passes 
 back-propagated one after the other instead of jointly (same gradients), conv biases that feed a
 normalisation layer are not updated (their gradient is analytically zero).
 """
+import os
+
 import torch
 
 from . import ops, parallel
@@ -53,6 +55,8 @@ class DistillStep:
         self.step_D = torch.zeros(1, dtype=torch.int32, device=device)
         self._graphs = None
         self.use_cuda_graph = use_cuda_graph
+        self.overlap_teacher = os.environ.get('CATB_NO_OVERLAP', '0') != '1'
+        self._side = None
 
     LOSS_SLOTS = {'D_fake': 0, 'D_real': 1, 'G_gan': 2, 'G_recon': 3, 'G_distill': 4}
 
@@ -74,10 +78,24 @@ class DistillStep:
 
     # ---- phases --------------------------------------------------------------------------------
     def _forward_generators(self):
+        """The frozen teacher's forward pass is independent of everything until backward_G needs its output and mapped
+        activations, so it runs on a side stream (a parallel branch of the captured graph) next to the student forward
+        and the discriminator phase; _join_teacher() closes the branch at the end of the first segment."""
         ops.nchw_to_nhwc(self.real_A, self.xA)
         ops.nchw_to_nhwc(self.real_B, self.xB)
-        self.T.forward(self.xA)
+        if self.overlap_teacher and self.dev != 'cpu':
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self.T.forward(self.xA)
+        else:
+            self.T.forward(self.xA)
         self.S.forward(self.xA)
+
+    def _join_teacher(self):
+        if self.overlap_teacher and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     def _d_inputs(self):
         if self.aligned:
@@ -138,6 +156,7 @@ class DistillStep:
         self.losses.zero_()
         self._forward_generators()
         self._phase_D()
+        self._join_teacher()
 
     def _part2(self):
         self._adam(self.D, self.lr_D, self.step_D)

@@ -11,6 +11,8 @@ Deviations from the reference, stated in DESIGN.md: bf16 activations / GEMM oper
 conv biases that feed a BatchNorm are not updated (analytically zero gradient); per-rank BatchNorm statistics
 under data parallelism (= the reference's single-GPU semantics on every rank).
 """
+import os
+
 import torch
 
 from . import ops, parallel
@@ -60,6 +62,8 @@ class SpadeDistillStep:
         self.step_D = torch.zeros(1, dtype=torch.int32, device=device)
         self._graphs = None
         self.use_cuda_graph = use_cuda_graph
+        self.overlap = os.environ.get('CATB_NO_OVERLAP', '0') != '1'
+        self._side = None
 
     # ---- state ---------------------------------------------------------------------------------
     def load(self, teacher_sd, student_sd, D_sd, vgg_sd):
@@ -103,7 +107,18 @@ class SpadeDistillStep:
     def _phase_G(self):
         hp, D, S, T, V, B = self.hp, self.D, self.S, self.T, self.V, self.B
         S.arena.g.zero_()
-        T.forward()
+        # two independent branches next to the student / discriminator work (parallel branches of the captured graph):
+        # the frozen teacher (needed by the KA terms) and the VGG features of the real image (needed by the VGG loss)
+        main = torch.cuda.current_stream() if self.overlap and self.dev != 'cpu' else None
+        if main is not None:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
+            for st, fn in ((self._side[0], T.forward), (self._side[1], lambda: V.forward(self.xB, save_ref=True))):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    fn()
+        else:
+            T.forward()
         S.forward()
         nets = D.forward(self._d_input(S.out))
         num_D = len(nets)
@@ -124,11 +139,16 @@ class SpadeDistillStep:
         d_in = D.backward(self.dpreds, param_grads=False, input_grad=True, act_grad_hook=feat_hook)
         ops.copy_channels(_chan_view(Act(d_in.t[:B]), self.snc), self.dS_gan, 3)
         # VGG loss: features of the real image first (kept at the five taps), then the fake image with backward
-        V.forward(self.xB, save_ref=True)
+        if main is not None:
+            main.wait_stream(self._side[1])
+        else:
+            V.forward(self.xB, save_ref=True)
         V.forward(S.out)
         d_vgg = V.loss_and_backward(self.losses[self.S_VGG0:self.S_VGG0 + 5], hp['lambda_vgg'])
         ops.add(self.dS_gan, d_vgg, self.dS)
         act_grads = {}
+        if main is not None:
+            main.wait_stream(self._side[0])
         if hp['lambda_distill'] > 0:
             self.Gx.zero_()
             self.Gy.zero_()
