@@ -96,6 +96,9 @@ _PROTOS = {
     'catb_fma_vec': [_P, _P, _P, _I, _P],
     'catb_sn_forward': [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     'catb_sn_backward': [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    'catb_expand_x': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'catb_shift_sum': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    'catb_shift_expand': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 _SPECIAL = {
     'catb_version': ([], C.c_char_p),

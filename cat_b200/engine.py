@@ -12,6 +12,7 @@ Networks restated here (same maths as the reference modules, different execution
   DisNet  -- NLayerDiscriminator (models/modules/discriminators.py:14-79)
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -242,9 +243,12 @@ class GenNet:
         self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
         self.training, self.need_grad = training, need_grad
         self.use_bias = arch['use_bias']
+        # x-packed 7x7 stem / head (cat_b200/csrc/packx.cu): the seven horizontal taps become channels of a 7x1 conv
+        self.packx = os.environ.get('CATB_NO_PACKX', '0') != '1' and 7 * arch['input_nc'] <= 24 and arch['output_nc'] <= 8
         if share is not None:
             assert share.arch == arch and (share.arena.with_grad or not need_grad)
-            self.arena, self.bufs = share.arena, share.bufs
+            self.arena, self.bufs, self.aux = share.arena, share.bufs, share.aux
+            self.aux_idx = share.aux_idx
             self.ns = _NormSpec(self.arena, self.bufs, arch)
         else:
             self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
@@ -252,6 +256,7 @@ class GenNet:
             self._alloc_params()
             self.arena.finalize(device)
             self.bufs.finalize(device)
+            self._alloc_aux(device)
         self._build()
         self.pool_sums, self.pool_red = pool_norm_buffers(self.ns.created, device)
 
@@ -298,6 +303,31 @@ class GenNet:
         self.ns.alloc_group([('up_sampling.4', c4)])
         self._conv_alloc('up_sampling.7', (A['output_nc'], c4, 7, 7), True)
 
+    def _alloc_aux(self, device):
+        """Derived weight tensors of the x-packed stem / head, refreshed from the parameters before every packing:
+        stem.wx[co, dx*cin + ci, dy] = W[co, ci, dy, dx];  head.wx[co*8 + dx, ci, dy] = W[co, ci, dy, dx].  Their
+        gradients accumulate in aux.g and are scattered back through the same index table."""
+        import numpy as np
+        A = self.arch
+        self.aux = Arena(with_grad=self.need_grad)
+        self.aux_idx = None
+        if not self.packx:
+            return
+        c0, c4, cin, cout = A['widths'][0], A['widths'][4], A['input_nc'], A['output_nc']
+        Cx = cpad(7 * cin)
+        o_stem = self.aux.alloc('stem.wx', (c0, Cx, 7, 1))
+        o_head = self.aux.alloc('head.wx', (cout * 8, c4, 7, 1))
+        self.aux.finalize(device)
+        idx = -np.ones(self.aux.p.numel(), dtype=np.int32)
+        w = self.arena.off('down_sampling.1.weight')
+        co, ch, dy = np.meshgrid(np.arange(c0), np.arange(7 * cin), np.arange(7), indexing='ij')
+        dx, ci = ch // cin, ch % cin
+        idx[o_stem + (co * Cx + ch) * 7 + dy] = w + ((co * cin + ci) * 7 + dy) * 7 + dx
+        w = self.arena.off('up_sampling.7.weight')
+        co, dx, ci, dy = np.meshgrid(np.arange(cout), np.arange(7), np.arange(c4), np.arange(7), indexing='ij')
+        idx[o_head + ((co * 8 + dx) * c4 + ci) * 7 + dy] = w + ((co * c4 + ci) * 7 + dy) * 7 + dx
+        self.aux_idx = torch.from_numpy(idx).view(1, -1).to(device)
+
     def load_state_dict(self, sd):
         self.arena.load_state_dict(sd)
         self.bufs.load_state_dict(sd)
@@ -329,8 +359,16 @@ class GenNet:
         # ---- stem / down-sampling
         self.x_in = None  # set per forward (shared NHWC input)
         self.y0, self.a0 = self._act(H, W, c0), self._act(H, W, c0)
-        self.g_stem = G(P.Geometry(B, H, W, cpad(cin), 0, H, W, cpad(c0), 0, pad_mode=P.PAD_REFLECT),
-                        P.conv_fprop_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 3), c0)
+        self.aux_gemms = []
+        if self.packx:
+            Cx = cpad(7 * cin)
+            self.x_stem = self._act(H, W, Cx)
+            self.g_stem = Gemm(P.Geometry(B, H, W, Cx, 0, H, W, cpad(c0), 0, pad_mode=P.PAD_REFLECT),
+                               P.conv_fprop_units(self.aux.off('stem.wx'), c0, Cx, 7, 1, 3, pad_s=0), c0, dev)
+            self.aux_gemms.append(self.g_stem)
+        else:
+            self.g_stem = G(P.Geometry(B, H, W, cpad(cin), 0, H, W, cpad(c0), 0, pad_mode=P.PAD_REFLECT),
+                            P.conv_fprop_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 3), c0)
         self.n_stem = self.ns.make(dev, B, H * W, [('down_sampling.2', c0)], tr)
         self.y1, self.a1 = self._act(H2, W2, c1), self._act(H2, W2, c1)
         self.g_d1 = G(P.Geometry(B, H, W, cpad(c0), 0, H2, W2, cpad(c1), 0, sn=2),
@@ -472,8 +510,14 @@ class GenNet:
         self.yu1, self.au1, self.g_u1, self.n_u1, self.gb_u1 = up('up_sampling.0', 'up_sampling.1', c2, c3, H4, W4)
         self.yu2, self.au2, self.g_u2, self.n_u2, self.gb_u2 = up('up_sampling.3', 'up_sampling.4', c3, c4, H2, W2)
         self.out = self._act(H, W, cout)
-        self.g_head = G(P.Geometry(B, H, W, cpad(c4), 0, H, W, cpad(cout), 0, pad_mode=P.PAD_REFLECT),
-                        P.conv_fprop_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 3), cout)
+        if self.packx:
+            self.head_P = Act.empty(B, H, W + 6, cout * 8, dev)
+            self.g_head = Gemm(P.Geometry(B, H, W, cpad(c4), 0, H, W + 6, cout * 8, 0, pad_mode=P.PAD_REFLECT),
+                               P.conv_fprop_units(self.aux.off('head.wx'), cout * 8, c4, 7, 1, 3, pad_s=3), cout * 8, dev)
+            self.aux_gemms.append(self.g_head)
+        else:
+            self.g_head = G(P.Geometry(B, H, W, cpad(c4), 0, H, W, cpad(cout), 0, pad_mode=P.PAD_REFLECT),
+                            P.conv_fprop_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 3), cout)
         self.head_bias = ar.view('up_sampling.7.bias')
 
         self.acts = {'down_sampling.9': self.a2}
@@ -492,8 +536,14 @@ class GenNet:
             # head / up / down gradient buffers
             self.d_head_z = self._act(H, W, cout)
             self.d_head_frame = Act.empty(B, H + 6, W + 6, c4, dev)
-            self.gb_head = G(P.Geometry(B, H, W, cpad(cout), 0, H + 6, W + 6, cpad(c4), 0),
-                             P.conv_dgrad_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 0), c4, bwd=True)
+            if self.packx:
+                self.d_head_P = Act.empty(B, H, W + 6, cout * 8, dev, zero=True)
+                self.gb_head = Gemm(P.Geometry(B, H, W + 6, cout * 8, 0, H + 6, W + 6, cpad(c4), 0),
+                                    P.conv_dgrad_units(self.aux.off('head.wx'), cout * 8, c4, 7, 1, 0, q_s=0), c4, dev)
+                self.aux_gemms.append(self.gb_head)
+            else:
+                self.gb_head = G(P.Geometry(B, H, W, cpad(cout), 0, H + 6, W + 6, cpad(c4), 0),
+                                 P.conv_dgrad_units(ar.off('up_sampling.7.weight'), cout, c4, 7, 7, 0), c4, bwd=True)
             self.d_au2, self.d_yu2 = self._act(H, W, c4), self._act(H, W, c4)
             self.d_au1, self.d_yu1 = self._act(H2, W2, c3), self._act(H2, W2, c3)
             self.d_y2, self.d_a1, self.d_y1, self.d_a0, self.d_y0 = (self._act(H4, W4, c2), self._act(H2, W2, c1),
@@ -511,6 +561,10 @@ class GenNet:
     def pack_weights(self):
         for g in self.fprop_gemms + self.bwd_gemms:
             g.pack(self.arena.p)
+        if self.aux_gemms:
+            ops.gather_sum(self.arena.p, self.aux_idx, self.aux.p)
+            for g in self.aux_gemms:
+                g.pack(self.aux.p)
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, x_in: Act):
@@ -518,7 +572,11 @@ class GenNet:
         self.x_in = x_in
         relu, none = ACT['relu'], ACT['none']
         self.pool_sums.zero_()
-        self.g_stem.fprop(x_in.t, self.y0.t)
+        if self.packx:
+            ops.expand_x(x_in, self.x_stem, self.arch['input_nc'], 7)
+            self.g_stem.fprop(self.x_stem.t, self.y0.t)
+        else:
+            self.g_stem.fprop(x_in.t, self.y0.t)
         self.n_stem.forward(self.y0, self.a0, relu)
         self.g_d1.fprop(self.a0.t, self.y1.t)
         self.n_d1.forward(self.y1, self.a1, relu)
@@ -542,7 +600,11 @@ class GenNet:
         for g in self.g_u2:
             g.fprop(self.au1.t, self.yu2.t)
         self.n_u2.forward(self.yu2, self.au2, relu)
-        self.g_head.fprop(self.au2.t, self.out.t, bias=self.head_bias, act=ACT['tanh'])
+        if self.packx:
+            self.g_head.fprop(self.au2.t, self.head_P.t)
+            ops.shift_sum(self.head_P, self.out, self.arch['output_nc'], 7, self.head_bias, ACT['tanh'])
+        else:
+            self.g_head.fprop(self.au2.t, self.out.t, bias=self.head_bias, act=ACT['tanh'])
         return self.out
 
     # ---- backward ------------------------------------------------------------------------------
@@ -559,9 +621,15 @@ class GenNet:
         Cp = cpad(c2)
         # head: tanh, 7x7 reflect conv
         ops.act_bwd(d_out, self.out, self.d_head_z, ACT['tanh'])
-        self.g_head.wgrad(self.au2.t, self.d_head_z.t, ar.g)
         ops.channel_sum(self.d_head_z, ar.view('up_sampling.7.bias', 'g'))
-        self.gb_head.fprop(self.d_head_z.t, self.d_head_frame.t)
+        if self.packx:
+            self.aux.g.zero_()
+            ops.shift_expand(self.d_head_z, self.d_head_P, self.arch['output_nc'], 7)
+            self.g_head.wgrad(self.au2.t, self.d_head_P.t, self.aux.g)
+            self.gb_head.fprop(self.d_head_P.t, self.d_head_frame.t)
+        else:
+            self.g_head.wgrad(self.au2.t, self.d_head_z.t, ar.g)
+            self.gb_head.fprop(self.d_head_z.t, self.d_head_frame.t)
         ops.reflect_fold(self.d_head_frame, self.d_au2, 3)
         # up 2
         self.n_u2.backward(self.d_au2, self.au2, self.yu2, self.d_yu2, relu)
@@ -623,7 +691,11 @@ class GenNet:
         for g in self.gb_d1:
             g.fprop(self.d_y1.t, self.d_a0.t)
         self.n_stem.backward(self.d_a0, self.a0, self.y0, self.d_y0, relu)
-        self.g_stem.wgrad(self.x_in.t, self.d_y0.t, ar.g)
+        if self.packx:
+            self.g_stem.wgrad(self.x_stem.t, self.d_y0.t, self.aux.g)
+            ops.scatter_add(self.aux.g, self.aux_idx, ar.g)     # d(stem.wx), d(head.wx) -> the 7x7 parameter gradients
+        else:
+            self.g_stem.wgrad(self.x_in.t, self.d_y0.t, ar.g)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -50,14 +50,16 @@ class Units:
         return out
 
 
-def conv_fprop_units(w_off, Cout, Cin, R, S, pad, cu0=0) -> Units:
+def conv_fprop_units(w_off, Cout, Cin, R, S, pad, cu0=0, pad_s=None) -> Units:
     """nn.Conv2d weight [Cout, Cin, R, S] at arena offset w_off; input channels start at unit cu0 of
-    the gathered buffer.  GEMM rows = output channels.  Used for fprop and (same tables) wgrad."""
+    the gathered buffer.  GEMM rows = output channels.  Used for fprop and (same tables) wgrad.
+    pad_s: horizontal padding when it differs from the vertical one (x-packed 7x1 convs)."""
+    pad_s = pad if pad_s is None else pad_s
     u = Units()
     for r in range(R):
         for s in range(S):
             for cu in range(cpad(Cin) // 8):
-                u.g.append((r - pad, s - pad, cu0 + cu))
+                u.g.append((r - pad, s - pad_s, cu0 + cu))
                 u.w.append((w_off + cu * 8 * R * S + r * S + s, Cin * R * S, R * S, max(0, min(8, Cin - cu * 8))))
     return u
 
@@ -84,15 +86,16 @@ def conv_embedded_units(w_off, Cout, Cin, k, Kmax, cu0=0) -> Units:
     return u
 
 
-def conv_dgrad_units(w_off, Cout, Cin, R, S, q, cu0=0) -> Units:
+def conv_dgrad_units(w_off, Cout, Cin, R, S, q, cu0=0, q_s=None) -> Units:
     """Input gradient of the same convolution: gather dY with offset dr = q - r (q = pad for a direct
     zero-padded gradient, q = 0 when the result is the gradient w.r.t. the *padded* frame of a reflect
     padded conv, folded afterwards by catb_reflect_fold).  GEMM rows = input channels."""
+    q_s = q if q_s is None else q_s
     u = Units()
     for r in range(R):
         for s in range(S):
             for nu in range(cpad(Cout) // 8):
-                u.g.append((q - r, q - s, cu0 + nu))
+                u.g.append((q - r, q_s - s, cu0 + nu))
                 u.w.append((w_off + nu * 8 * Cin * R * S + r * S + s, R * S, Cin * R * S, max(0, min(8, Cout - nu * 8))))
     return u
 

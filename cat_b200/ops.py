@@ -516,3 +516,21 @@ def sn_forward(table, n, max_rows, max_cols, arena, bufs, training, tmp, sigma, 
 def sn_backward(table, n, max_rows, max_cols, grad, w_eff, bufs, sigma, cdot):
     _C.call('catb_sn_backward', _p(table), n, max_rows, max_cols, _p(grad), _p(w_eff), _p(bufs), _p(sigma), _p(cdot),
             _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# x-packed 7x7 stem / head helpers
+# ------------------------------------------------------------------------------------------------
+def expand_x(x: Act, y: Act, Cin, taps):
+    assert (x.N, x.H, x.W) == (y.N, y.H, y.W)
+    _C.call('catb_expand_x', *x.args(), *y.args(), x.N, x.H, x.W, int(Cin), int(taps), y.C, _stream())
+
+
+def shift_sum(P: Act, out: Act, Cout, taps, bias, act):
+    assert P.W == out.W + taps - 1 and (P.N, P.H) == (out.N, out.H)
+    _C.call('catb_shift_sum', *P.args(), *out.args(), out.N, out.H, out.W, int(Cout), int(taps), _p(bias), int(act), _stream())
+
+
+def shift_expand(dz: Act, dP: Act, Cout, taps):
+    assert dP.W == dz.W + taps - 1 and (dP.N, dP.H) == (dz.N, dz.H)
+    _C.call('catb_shift_expand', *dz.args(), *dP.args(), dz.N, dz.H, dz.W, int(Cout), int(taps), _stream())

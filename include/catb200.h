@@ -311,6 +311,19 @@ int catb_sn_forward(const catb_sn_desc* table /*device*/, int n, int max_rows, i
 int catb_sn_backward(const catb_sn_desc* table /*device*/, int n, int max_rows, int max_cols, float* grad,
                      const float* w_eff, const float* bufs, const float* sigma, float* cdot /*[n]*/, catb_stream_t s);
 
+/* ---- x-packed 7x7 stem / head convolutions (inception_generator.py:37-56,130-134) -------------------
+ * Packing the horizontal taps into the channel dimension turns a 7x7 conv with 3 input (stem) or 3 output (head)
+ * channels into a 7x1 implicit GEMM with 24 channels on that side (7x fewer GEMM steps):
+ *   expand_x:     y[n,h,w, dx*Cin + ci] = x[n,h, reflect(w + dx - taps/2), ci]   (channels >= taps*Cin: 0)
+ *   shift_sum:    out[n,h,w,co] = act(bias[co] + sum_dx P[n,h,w+dx, co*8+dx]),  P is [N,H,W+taps-1,.]
+ *   shift_expand: dP[n,h,c', co*8+dx] = dz[n,h,c'-dx,co] (0 outside [0,W)): the adjoint of shift_sum. */
+int catb_expand_x(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int N, int H, int W, int Cin,
+                  int taps, int Cy, catb_stream_t s);
+int catb_shift_sum(const void* P, int ldp, int p_coff, void* out, int ldo, int o_coff, int N, int H, int W, int Cout,
+                   int taps, const float* bias /*nullable*/, int act, catb_stream_t s);
+int catb_shift_expand(const void* dz, int ldz, int z_coff, void* dP, int ldp, int p_coff, int N, int H, int W, int Cout,
+                      int taps, catb_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

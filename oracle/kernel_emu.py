@@ -468,7 +468,43 @@ def sn_backward(table, n, max_rows, max_cols, grad, w_eff, bufs, sigma, cdot):
         g.copy_((g - c * torch.outer(u, v)) / sigma[d])
 
 
-_PATCHED = ['resize_nearest', 'upsample2x_bwd', 'spade_modulate', 'spade_modulate_bwd', 'act_fwd', 'avgpool3s2',
+def expand_x(x, y, Cin, taps):
+    v = _get(x)[..., :Cin]
+    W, p = x.W, (taps - 1) // 2
+    out = torch.zeros(x.N, x.H, x.W, y.C)
+    cols = torch.arange(W)
+    for dx in range(taps):
+        i = (cols + dx - p).abs()
+        i = torch.where(i >= W, 2 * (W - 1) - i, i)
+        out[..., dx * Cin:(dx + 1) * Cin] = v[:, :, i]
+    _put(y, out)
+
+
+def shift_sum(P, out, Cout, taps, bias, act):
+    v = _get(P)
+    W = out.W
+    res = torch.zeros(out.N, out.H, W, out.C)
+    for co in range(Cout):
+        acc = torch.zeros(out.N, out.H, W) + (bias[co] if bias is not None else 0.0)
+        for dx in range(taps):
+            acc = acc + v[:, :, dx:dx + W, co * 8 + dx]
+        res[..., co] = _act(acc, act)
+    _put(out, res)
+
+
+def shift_expand(dz, dP, Cout, taps):
+    v = _get(dz)
+    W = dz.W
+    res = _get(dP).clone()
+    for co in range(Cout):
+        blk = torch.zeros(dz.N, dz.H, dP.W, 8)
+        for dx in range(taps):
+            blk[:, :, dx:dx + W, dx] = v[..., co]
+        res[..., co * 8:co * 8 + 8] = blk
+    _put(dP, res)
+
+
+_PATCHED = ['expand_x', 'shift_sum', 'shift_expand', 'resize_nearest', 'upsample2x_bwd', 'spade_modulate', 'spade_modulate_bwd', 'act_fwd', 'avgpool3s2',
             'avgpool3s2_bwd', 'maxpool2', 'maxpool2_bwd', 'onehot_edges', 'gather_sum', 'scatter_add', 'fma_vec',
             'sn_forward', 'sn_backward', 'nchw_to_nhwc', 'nhwc_to_nchw', 'copy_channels', 'act_bwd', 'channel_sum', 'reflect_fold', 'add',
             'norm_stats', 'norm_finalize', 'norm_apply', 'norm_bwd_reduce', 'norm_bwd_apply', 'dwconv_fwd',

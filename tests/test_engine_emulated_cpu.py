@@ -58,3 +58,43 @@ def test_product_path_still_requires_cuda():
         pytest.skip('GPU present')
     with pytest.raises(_C.CatbError):
         ops.require_cuda()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('name', ['pix2pix_bn_lsgan_l2', 'cyclegan_in_lsgan'])
+@pytest.mark.parametrize('packx', ['1', '0'])
+def test_distill_step_host_logic_exact(golden_dir, name, packx, monkeypatch):
+    """Exact mode (fp32 emulated buffers): launch order, table construction (incl. the x-packed 7x7 stem / head and their
+    derived weight tensors), hand-derived backward and buffer plumbing must reproduce the fp32 oracle to rounding."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    monkeypatch.setenv('CATB_NO_PACKX', '0' if packx == '1' else '1')
+    fix = torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+    step = fix['steps'][0]
+    B, _, H, W = step['real_A'].shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
+              D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
+              D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    ref = O.distill_step(st, step['real_A'], step['real_B'], fix['hp'])
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device='cpu')
+        assert eng.S.packx == (packx == '1')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(step['real_A'], step['real_B'])
+        eng.step()
+        assert rel_l2(ops.nhwc_to_nchw(eng.T.out, 3), ref['Tfake_B']) < 1e-5
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), ref['Sfake_B']) < 1e-5
+        L = eng.get_losses()
+        for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'),
+                         ('loss_G_recon', 'G_recon'), ('loss_G_distill', 'G_distill')):
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+        for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
+            scale = max(float(g.abs().max()) for g in grads.values())
+            for k, g in grads.items():
+                if not net.arena.has(k):
+                    continue
+                err = float((net.arena.view(k, 'g') - g).abs().max())
+                assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))

@@ -201,3 +201,26 @@ def test_dwconv_zero_padding(k):
     ops.dwconv_bwd_weight(xg, yg, ksz.to(DEV), wof.to(DEV), ga_g, _C.PAD_ZERO)
     E.dwconv_bwd_weight(xc, yc, ksz, wof, ga_c, _C.PAD_ZERO)
     assert float((ga_g.cpu() - ga_c).abs().max()) <= 2e-3 * max(1.0, float(ga_c.abs().max()))
+
+
+def test_xpack_helpers():
+    """catb_expand_x / catb_shift_sum / catb_shift_expand (x-packed 7x7 stem / head) against their restatements."""
+    from cat_b200 import ops, _C
+    from oracle import kernel_emu as E
+    N, H, W = 2, 9, 13
+    xg, xc = mk(N, H, W, 8, seed=1)
+    yg, yc = mk(N, H, W, 24, seed=2)
+    ops.expand_x(xg, yg, 3, 7)
+    E.expand_x(xc, yc, 3, 7)
+    same(yg, yc, exact=True)
+    Pg, Pc = mk(N, H, W + 6, 24, seed=3)
+    og, oc = mk(N, H, W, 8, seed=4)
+    bias = torch.tensor([0.1, -0.2, 0.3])
+    ops.shift_sum(Pg, og, 3, 7, bias.to(DEV), _C.ACT_TANH)
+    E.shift_sum(Pc, oc, 3, 7, bias, _C.ACT_TANH)
+    same(og, oc)
+    assert float(og.t[..., 3:].float().abs().max()) == 0.0
+    dPg, dPc = mk(N, H, W + 6, 24, seed=5)
+    ops.shift_expand(og, dPg, 3, 7)
+    E.shift_expand(oc, dPc, 3, 7)
+    same(dPg, dPc)
