@@ -367,7 +367,13 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         prof.install()
         eng.use_cuda_graph = False
         ws, eng.world_size = eng.world_size, 1   # rank 0 only: this extra step must not enter a collective
+        # per-kernel timing needs the kernels alone on the GPU: no side-stream branches in this step
+        saved = {k: getattr(eng, k) for k in ('overlap', 'overlap_teacher') if hasattr(eng, k)}
+        for k in saved:
+            setattr(eng, k, False)
         eng.step()
+        for k, v in saved.items():
+            setattr(eng, k, v)
         eng.world_size = ws
         agg, per = prof.summary()
         prof.remove()
