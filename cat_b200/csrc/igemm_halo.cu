@@ -61,12 +61,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint3
   return d;
 }
 
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
