@@ -38,6 +38,11 @@ class HaloDesc(C.Structure):
                 ('Ymax', C.c_int32), ('Xmax', C.c_int32), ('m_sub', C.c_int32), ('b_budget', C.c_int32)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [('wunits', C.c_void_p), ('packed', C.c_void_p), ('n_tile', C.c_int32), ('n_units', C.c_int32),
+                ('n_chunks', C.c_int32), ('row0', C.c_int32), ('span', C.c_int32), ('nreal', C.c_int32)]
+
+
 class CatbError(RuntimeError):
     pass
 
@@ -51,6 +56,7 @@ _PROTOS = {
     'catb_debug_timeline': [_P],
     'catb_pack_weights': [_DP, _P, _P, _P, _P],
     'catb_pack_weights_rows': [_DP, _P, _P, _P, _I, _I, _I, _P],
+    'catb_pack_weights_batch': [_P, _I, _I, _P, _P],
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],

@@ -425,6 +425,36 @@ __global__ void pack_weights_kernel(catb_igemm_desc d, const catb_weight_unit* _
   }
 }
 
+// Batched form: blockIdx.y selects a job of a device-resident table, so that all GEMM images of a network are
+// re-packed by ONE launch after an optimiser step (instead of one launch per GEMM).
+__global__ void pack_weights_batch_kernel(const catb_pack_job* __restrict__ jobs, const float* __restrict__ arena) {
+  const catb_pack_job j = jobs[blockIdx.y];
+  const long long total = static_cast<long long>(j.span) * j.n_chunks * 8;
+  const catb_weight_unit* wunits = reinterpret_cast<const catb_weight_unit*>(j.wunits);
+  uint8_t* packed = reinterpret_cast<uint8_t*>(j.packed);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ul = static_cast<int>(idx & 7);
+    long long t = idx >> 3;
+    const int r = static_cast<int>(t % j.span);
+    const int chunk = static_cast<int>(t / j.span);
+    const int n = j.row0 + r;
+    const int tile = n / j.n_tile, row = n - tile * j.n_tile;
+    const int u = chunk * 8 + ul;
+    f8 o;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o.v[q] = 0.f;
+    if (r < j.nreal && u < j.n_units) {
+      const catb_weight_unit wu = wunits[u];
+      const float* base = arena + wu.w_off + static_cast<long long>(r) * wu.sn_w;
+      for (int q = 0; q < wu.nvalid; ++q) o.v[q] = base[q * wu.sc_w];
+    }
+    uint8_t* dst = packed + (static_cast<size_t>(tile) * j.n_chunks + chunk) * j.n_tile * 128 + row * 128 +
+                   ((ul ^ (row & 7)) << 4);
+    st16(dst, pack8(o));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT restatements (tests only)
 // ------------------------------------------------------------------------------------------------
@@ -542,6 +572,13 @@ extern "C" int catb_pack_weights_rows(const catb_igemm_desc* d, const catb_weigh
   pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(*d, wunits, arena, static_cast<uint8_t*>(packed),
                                                                          n_chunks, row0, span, nreal);
   return check_launch("pack_weights");
+}
+
+extern "C" int catb_pack_weights_batch(const catb_pack_job* jobs, int n_jobs, int blocks_per_job, const float* arena,
+                                       catb_stream_t s) {
+  CATB_REQUIRE(jobs != nullptr && n_jobs > 0 && n_jobs <= 65535 && blocks_per_job > 0, "bad pack job table (%d jobs)", n_jobs);
+  pack_weights_batch_kernel<<<dim3(blocks_per_job, n_jobs), 256, 0, static_cast<cudaStream_t>(s)>>>(jobs, arena);
+  return check_launch("pack_weights_batch");
 }
 
 extern "C" int catb_pack_weights(const catb_igemm_desc* d, const catb_weight_unit* wunits, const float* arena,

@@ -559,12 +559,14 @@ class GenNet:
         return Act(flat[:self.B * H * W * C].view(self.B, H, W, C))
 
     def pack_weights(self):
-        for g in self.fprop_gemms + self.bwd_gemms:
-            g.pack(self.arena.p)
+        """Re-pack every GEMM weight image from the parameters: one launch (+ one for the x-packed stem / head)."""
+        if getattr(self, '_packer', None) is None:
+            self._packer = ops.PackBatch(self.fprop_gemms + self.bwd_gemms, self.dev)
+            self._packer_aux = ops.PackBatch(self.aux_gemms, self.dev)
+        self._packer.run(self.arena.p)
         if self.aux_gemms:
             ops.gather_sum(self.arena.p, self.aux_idx, self.aux.p)
-            for g in self.aux_gemms:
-                g.pack(self.aux.p)
+            self._packer_aux.run(self.aux.p)
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, x_in: Act):
@@ -808,8 +810,9 @@ class DisNet:
 
     def pack_weights(self):
         src = self.arena.p if self.w_src is None else self.w_src
-        for g in self.fprop_gemms + self.bwd_gemms:
-            g.pack(src)
+        if getattr(self, '_packer', None) is None:
+            self._packer = ops.PackBatch(self.fprop_gemms + self.bwd_gemms, self.dev)
+        self._packer.run(src)
 
     def forward(self, x: Act):
         self.x = x

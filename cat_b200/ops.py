@@ -198,6 +198,25 @@ class Gemm:
         d.act, d.accumulate, d.y_is_f32 = int(act), int(bool(accumulate)), int(bool(y_is_f32))
         return d
 
+    def pack_jobs(self):
+        """The (wunits, packed image, n_tile, n_units, row0, span, nreal) tuples pack() would launch one by one."""
+        do1 = self.halo is None or self.choice != 'v2'
+        do2 = self.halo is not None and self.choice != 'v1'
+        n_img = ((self.n_rows + self.n_tile - 1) // self.n_tile) * self.n_tile
+        jobs = []
+        if self.segments is None:
+            if do1:
+                jobs.append((self.wt, self.packed_v1, self.n_tile, self.n_units, 0, n_img, self.n_rows))
+            if do2:
+                jobs.append((self.f_wt, self.packed, self.n_tile, len(self.f_units), 0, n_img, self.n_rows))
+            return jobs
+        for (row0, span, nreal, wt1, wt2) in self.segments:
+            if do1:
+                jobs.append((wt1, self.packed_v1, self.n_tile, self.n_units, row0, span, nreal))
+            if do2:
+                jobs.append((wt2, self.packed, self.n_tile, len(self.f_units), row0, span, nreal))
+        return jobs
+
     def pack(self, arena):
         do1 = self.halo is None or self.choice != 'v2'
         do2 = self.halo is not None and self.choice != 'v1'
@@ -534,3 +553,42 @@ def shift_sum(P: Act, out: Act, Cout, taps, bias, act):
 def shift_expand(dz: Act, dP: Act, Cout, taps):
     assert dP.W == dz.W + taps - 1 and (dP.N, dP.H) == (dz.N, dz.H)
     _C.call('catb_shift_expand', *dz.args(), *dP.args(), dz.N, dz.H, dz.W, int(Cout), int(taps), _stream())
+
+
+class PackBatch:
+    """One-launch re-packing of the GEMM weight images of a network (catb_pack_weights_batch).  The job table is
+    built from the Gemm objects once their kernel choice is final (after autotuning the unused image of a GEMM is
+    dropped), and rebuilt whenever that set changes."""
+
+    def __init__(self, gemms, device):
+        self.gemms, self.dev = list(gemms), device
+        self.key, self.table, self.n = None, None, 0
+
+    def _signature(self):
+        return tuple((id(g), g.choice) for g in self.gemms)
+
+    def _build(self):
+        jobs = [j for g in self.gemms for j in g.pack_jobs()]
+        arr = (_C.PackJob * max(len(jobs), 1))()
+        big = 1
+        for i, (wt, packed, n_tile, n_units, row0, span, nreal) in enumerate(jobs):
+            n_chunks = (n_units + 7) // 8
+            arr[i] = _C.PackJob(wt.data_ptr(), packed.data_ptr(), n_tile, n_units, n_chunks, row0, span, nreal)
+            big = max(big, span * n_chunks * 8)
+        raw = np.frombuffer(arr, dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(self.dev)
+        self.n = len(jobs)
+        self.blocks = max(1, min(16, (big + 255) // 256))
+        self.key = self._signature()
+
+    def run(self, arena):
+        if not arena.is_cuda:            # host tensors only exist under the test emulation, which patches Gemm.pack
+            for g in self.gemms:
+                g.pack(arena)
+            return
+        if torch.cuda.is_current_stream_capturing():
+            assert self.key == self._signature(), 'pack table must be built before graph capture'
+        elif self.key != self._signature():
+            self._build()
+        if self.n:
+            _C.call('catb_pack_weights_batch', _p(self.table), self.n, self.blocks, _p(arena), _stream())

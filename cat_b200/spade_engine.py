@@ -169,8 +169,9 @@ class _Net:
         self.pool_sums, self.pool_red = pool_norm_buffers(self.norms, self.dev)
 
     def pack_weights(self):
-        for g in self.fprop_gemms + self.bwd_gemms:
-            g.pack(self.arena.p)
+        if getattr(self, '_packer', None) is None:
+            self._packer = ops.PackBatch(self.fprop_gemms + self.bwd_gemms, self.dev)
+        self._packer.run(self.arena.p)
 
     def load_state_dict(self, sd):
         self.arena.load_state_dict(sd)

@@ -153,6 +153,17 @@ int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, con
  * 2 MMA thread released, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit.  NULL: off. */
 int catb_debug_timeline(void* device_buffer);
 
+/* All GEMM images of a network in ONE launch: a device-resident job table (one entry per packed image or row
+ * segment, same meaning as the arguments of catb_pack_weights_rows; n_chunks = ceil(n_units / 8)). */
+typedef struct {
+  const void* wunits;   /* const catb_weight_unit* (device) */
+  void* packed;         /* packed image (device) */
+  int32_t n_tile, n_units, n_chunks;
+  int32_t row0, span, nreal;
+} catb_pack_job;
+int catb_pack_weights_batch(const catb_pack_job* jobs /*device*/, int n_jobs, int blocks_per_job, const float* arena,
+                            catb_stream_t s);
+
 /* Slow SIMT restatements of the two kernels above (same descriptors); kept for on-device bisection
  * in tests.  Not used by the product path. */
 int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
