@@ -33,7 +33,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default: 16; gaugan_5p6B: 4)')
     ap.add_argument('--height', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
     ap.add_argument('--width', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
-    ap.add_argument('--cpu-batch', type=int, default=1, help='images per step of the bounded CPU sample')
+    ap.add_argument('--cpu-batch', type=int, default=None,
+                    help='images per step of the bounded CPU sample (default 4; gaugan_5p6B: 2 -- KA is degenerate at 1)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-gemms', action='store_true', help='print the per-GEMM timing table to stderr')
@@ -42,6 +43,7 @@ def parse():
     args.batch = args.batch or (4 if spade else 16)
     args.height = args.height or (512 if spade else 256)
     args.width = args.width or (512 if spade else 256)
+    args.cpu_batch = args.cpu_batch or (2 if spade else 4)
     return args
 
 
@@ -415,9 +417,10 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fn = cpu_reference_spade_steps if is_spade(args.workload) else cpu_reference_steps
-        ips, dt, cores = fn(arch, dict(arch['hp']), args.cpu_batch, H, W, 1, 1)
+        cpu_steps = 2 if is_spade(args.workload) else 3
+        ips, dt, cores = fn(arch, dict(arch['hp']), args.cpu_batch, H, W, cpu_steps, 1)
         cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'{args.cpu_batch} images/step at {H}x{W}, 1 warm-up + 1 timed step of the CPU oracle '
+               'sample': f'{args.cpu_batch} images/step at {H}x{W}, 1 warm-up + {cpu_steps} timed steps of the CPU oracle '
                          f'(same networks), {dt:.2f} s/step'}
 
     if rank == 0:
