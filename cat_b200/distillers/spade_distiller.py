@@ -130,8 +130,9 @@ class SPADEDistiller:
         eng = SpadeDistillStep(t_arch, s_arch, mm.netD.arch(), self._hp(), B, H, W, device=str(self.device),
                                world_size=int(getattr(self.opt, 'world_size', 1)),
                                use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
-        for module, net in ((mm.netG_teacher, eng.T), (mm.netG_student, eng.S), (mm.netD, eng.D)):
-            module._alias_into(net)        # copies the module's weights in, then re-points them at the arena
+        mm.netG_teacher.bind(eng.T)        # copies the module's weights in, then re-points them at the arena
+        mm.netG_student.bind(eng.S)
+        mm.netD._alias_into(eng.D)
         vgg = getattr(self.opt, 'vgg_state_dict', None)
         if vgg is None:
             raise RuntimeError('opt.vgg_state_dict (torchvision vgg19().features state_dict) is required: the pretrained '
@@ -152,6 +153,19 @@ class SPADEDistiller:
 
     def optimize_parameters(self, steps):
         self.engine.step()
+
+    def forward(self, on_one_gpu=False):
+        """generate_fake (base_spade_distiller_modules.py:107-112): teacher and student images for the current input."""
+        from .. import ops
+        eng = self.engine
+        eng._preprocess()
+        self.input_semantics = ops.nhwc_to_nchw(eng.seg, eng.snc)
+        self.real_B = eng.image
+        self.Tfake_B = ops.nhwc_to_nchw(eng.T.forward(), 3)
+        self.Sfake_B = ops.nhwc_to_nchw(eng.S.forward(), 3)
+
+    def test(self):
+        self.forward(on_one_gpu=True)
 
     def get_current_losses(self):
         L = self.engine.get_losses()

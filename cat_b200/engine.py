@@ -41,6 +41,9 @@ class Arena:
     def alloc(self, name, shape, pad_to=None, pad_value=0.0):
         n = int(math.prod(shape))
         L = max(n, pad_to or n)
+        if self.p is not None:   # finalised arena shared by a second compilation of the same network: look up
+            assert name in self.entries and self.entries[name][1] == tuple(shape), name
+            return self.entries[name][0]
         assert name not in self.entries, name
         self.entries[name] = (self.size, tuple(shape), L, pad_value)
         self.size += L

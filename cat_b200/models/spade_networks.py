@@ -250,8 +250,38 @@ class InceptionSPADEGenerator(BaseNetwork, _EngineBacked):
         pass   # the generators of the CAT scripts carry no spectral norm
 
     def _compile(self, B, H, W, device, training, need_grad, share):
-        raise NotImplementedError('compiled by SpadeDistillStep (the generator reads the step\'s label-map buffer); '
-                                  'use SPADEDistiller / InceptionSPADEGenerator.bind')
+        from .. import ops
+        from ..spade_engine import SpadeGenNet
+        seg = ops.Act.empty(B, H, W, int(self.opt.semantic_nc), device, zero=True)
+        arch = dict(self.arch(), sh=H >> self._n_up(), sw=W >> self._n_up())
+        return SpadeGenNet(arch, seg, device, training=training, need_grad=need_grad, share=share)
+
+    def _n_up(self):
+        return {'normal': 5, 'more': 6, 'most': 7}[self.opt.num_upsampling_layers]
+
+    def bind(self, net):
+        """Adopt an already compiled engine network (the distiller's) as the owner of this module's storage."""
+        self._alias_into(net)
+        self.__dict__['_primary'] = net
+        self.__dict__['_engines'] = {(net.B, net.H, net.W, str(net.dev), bool(net.training)): net}
+
+    def forward(self, input, mapping_layers=()):
+        """Inference on the CUDA engine: `input` = one-hot label map (+ edge channel) NCHW fp32 [B, semantic_nc, H, W]
+        (what SPADEModel.preprocess_input returns) -> image NCHW fp32; with `mapping_layers` also the requested block
+        outputs, like the reference forward (inception_spade_generator.py:63-124)."""
+        from .. import ops
+        B, C, H, W = input.shape
+        net = self.engine(B, H, W, input.device, self.training, False)
+        ops.nchw_to_nhwc(input.float().contiguous(), net.seg_in)
+        net.pack_weights()
+        out = ops.nhwc_to_nchw(net.forward(), 3)
+        if not mapping_layers:
+            return out
+        acts = {}
+        for b in net.blocks:
+            if b.name in mapping_layers:
+                acts[b.name] = ops.nhwc_to_nchw(b.out, b.fout)
+        return out, acts
 
 
 class SPADENLayerDiscriminator(BaseNetwork):

@@ -114,9 +114,13 @@ class BNorm(Norm):
 class _Net:
     """Arena / norm / bias bookkeeping shared by the networks below."""
 
-    def _init_common(self, B, device, training, need_grad):
+    def _init_common(self, B, device, training, need_grad, share=None):
         self.B, self.dev, self.training, self.need_grad = B, device, training, need_grad
-        self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
+        if share is not None:      # another compilation (shape / mode) of the same weights: reuse its finalised arenas
+            assert share.arena.with_grad or not need_grad
+            self.arena, self.bufs = share.arena, share.bufs
+        else:
+            self.arena, self.bufs = Arena(with_grad=need_grad), Arena(with_grad=False)
         self.biases = BiasPool()
         self.norms = []
         self.fprop_gemms, self.bwd_gemms = [], []
@@ -422,12 +426,12 @@ class SpadeGenNet(_Net):
 
     UPSAMPLED = ('G_middle_0', 'up_0', 'up_1', 'up_2', 'up_3', 'up_4')
 
-    def __init__(self, arch, seg: Act, device, training, need_grad, alloc_only=False):
+    def __init__(self, arch, seg: Act, device, training, need_grad, alloc_only=False, share=None):
         """seg: the persistent NHWC bf16 input buffer [B,H,W,cpad(semantic_nc)] (one-hot labels + edge map) every
         forward pass reads; teacher and student are compiled against the same buffer.
         alloc_only: only lay out the parameter / buffer tables (names and shapes of the reference state_dict)."""
         B, H, W = (seg.N, seg.H, seg.W) if seg is not None else (1, 0, 0)
-        self._init_common(B, device, training, need_grad)
+        self._init_common(B, device, training, need_grad, share=share)
         self.bn_momentum = arch.get('momentum', 0.1)
         self.arch, self.H, self.W = arch, H, W
         self.snc = arch['semantic_nc']
@@ -458,8 +462,9 @@ class SpadeGenNet(_Net):
         ar.alloc('conv_img.bias', (3,))
         if alloc_only:
             return
-        ar.finalize(device)
-        self.bufs.finalize(device)
+        if share is None:
+            ar.finalize(device)
+            self.bufs.finalize(device)
         self._build()
         self._finish_build()
 

@@ -74,3 +74,35 @@ def test_spade_trainer_style_loop(golden_dir, tmp_path):
         assert os.path.exists(os.path.join(str(tmp_path), 'checkpoints', f))
     model.update_learning_rate()
     assert abs(float(model.engine.lr_D) - model.optimizer_D.param_groups[0]['lr']) < 1e-9      # device copy is fp32
+
+
+def test_spade_inference_paths(golden_dir, tmp_path):
+    """SPADEDistiller.test() (generate_fake) and InceptionSPADEGenerator.forward (the generator inference of
+    evaluate_model) on the GPU against the oracle's eval-mode teacher."""
+    from cat_b200.distillers import create_distiller
+    from oracle import spade_oracle as SO
+    from oracle.cat_oracle import clone_sd
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    model = create_distiller(_opt(fix, str(tmp_path), vgg), verbose=False)
+    mm = model.modules_on_one_gpu
+    mm.netG_teacher.load_state_dict(fix['teacher_sd'])
+    mm.netG_student.load_state_dict(fix['student_sd0'])
+    mm.netD.load_state_dict(fix['D_sd0'])
+    s = fix['steps'][0]
+    B = s['image'].shape[0]
+    model.set_input({'label': s['label'], 'instance': s['instance'], 'image': s['image'], 'path': ['x'] * B})
+    model.test()
+    seg = SO.preprocess_input(s['label'], s['instance'], fix['hp']['n_label'])
+    ref = SO.spade_generator_forward(clone_sd(fix['teacher_sd']), fix['teacher_arch'], seg, training=False)
+    assert torch.equal(model.input_semantics.cpu(), seg)
+    err = float((model.Tfake_B.cpu() - ref).norm() / ref.norm())
+    assert err < 3e-2, err
+    assert model.Sfake_B.shape == ref.shape and bool(torch.isfinite(model.Sfake_B).all())
+    # the module mirror runs the same compiled network (bound to the distiller's arenas) ...
+    mm.netG_teacher.eval()
+    out = mm.netG_teacher(seg.cuda())
+    assert float((out - model.Tfake_B).abs().max()) < 1e-6
+    # ... and compiles a second shape against the same weights
+    out1 = mm.netG_teacher(seg[:1].cuda())
+    assert float((out1.cpu() - ref[:1]).norm() / ref[:1].norm()) < 3e-2

@@ -101,3 +101,37 @@ def test_spade_step_host_logic_bf16(golden_dir):
         mine = torch.cat([out['grads'][tag][k].flatten() for k in ks])
         theirs = torch.cat([ref[key][k].flatten() for k in ks])
         assert rel_l2(mine, theirs) < 0.35, tag
+
+
+@pytest.mark.timeout(900)
+def test_spade_generator_inference_through_the_module_mirror(golden_dir):
+    """InceptionSPADEGenerator.forward (evaluate_model's generator inference) in exact emulation: reference
+    checkpoints loaded into the module tree, eval-mode forward for two batch shapes (the second compilation shares the
+    first one's arenas), mapped activations returned like the reference forward."""
+    import argparse
+    from oracle import spade_oracle as SO
+    from oracle.cat_oracle import clone_sd
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200.models.spade_networks import InceptionSPADEGenerator
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    Sa, hp, s = fix['student_arch'], fix['hp'], fix['steps'][0]
+    opt = argparse.Namespace(ngf=Sa['fc_out'] // 16, norm_G='spadesyncbatch3x3', semantic_nc=Sa['semantic_nc'],
+                             num_upsampling_layers=Sa['num_upsampling_layers'], crop_size=128, aspect_ratio=2.0, channels=None,
+                             channels_reduction_factor=6, kernel_sizes=[1, 3, 5], active_fn='nn.ReLU')
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    caps = {}
+    ref = SO.spade_generator_forward(clone_sd(fix['student_sd0']), Sa, seg, training=False, capture=caps)
+    with emulated_kernels(exact=True):
+        net = InceptionSPADEGenerator.from_arch(Sa, opt)
+        net.load_state_dict(fix['student_sd0'])
+        net.eval()
+        out, acts = net(seg, mapping_layers=['head_0', 'up_1'])
+        assert rel_l2(out, ref) < 1e-5
+        assert rel_l2(acts['up_1'], caps['up_1']) < 1e-5 and rel_l2(acts['head_0'], caps['head_0']) < 1e-5
+        out1 = net(seg[:1])                      # second shape: compiled against the same arenas
+        assert rel_l2(out1, ref[:1]) < 1e-5
+        assert len(net.__dict__['_engines']) == 2
+        e = list(net.__dict__['_engines'].values())
+        assert e[0].arena is e[1].arena
+        # parameters of the module tree alias the engine arena
+        assert net.conv_img.weight.data_ptr() == e[0].arena.view('conv_img.weight').data_ptr()
