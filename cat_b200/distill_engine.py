@@ -192,10 +192,14 @@ class DistillStep:
             state += [t for t in (net.arena.p, net.arena.g, net.arena.m, net.arena.v, net.bufs.p) if t is not None]
         state += [self.step_G, self.step_D, self.losses, self.ka_vals]
         snap = [t.clone() for t in state]
+        # kernels are timed one at a time: no side-stream branches during the tuning step
+        saved = (self.overlap_teacher, self.S.overlap_wgrad)
+        self.overlap_teacher = self.S.overlap_wgrad = False
         self._part1()
         self._part2()
         self._part3()
         torch.cuda.synchronize()
+        self.overlap_teacher, self.S.overlap_wgrad = saved
         for t, c in zip(state, snap):
             t.copy_(c)
         self.S.pack_weights()

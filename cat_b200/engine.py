@@ -248,6 +248,9 @@ class GenNet:
         self.use_bias = arch['use_bias']
         # x-packed 7x7 stem / head (cat_b200/csrc/packx.cu): the seven horizontal taps become channels of a 7x1 conv
         self.packx = os.environ.get('CATB_NO_PACKX', '0') != '1' and 7 * arch['input_nc'] <= 24 and arch['output_nc'] <= 8
+        # weight-gradient GEMMs of the residual blocks run on a side stream next to the input-gradient chain
+        self.overlap_wgrad = os.environ.get('CATB_NO_WOVERLAP', '0') != '1' and str(device) != 'cpu'
+        self._wside = None
         if share is not None:
             assert share.arch == arch and (share.arena.with_grad or not need_grad)
             self.arena, self.bufs, self.aux = share.arena, share.bufs, share.aux
@@ -646,6 +649,32 @@ class GenNet:
         cur = self.dfeat[0]
         self.gb_u1.fprop(self.d_yu1.t, cur.t)
         nxt_i = 1
+        # Weight gradients only feed the optimiser, so inside the residual blocks they are issued on a side stream
+        # (parallel branches of the captured graph) while the main stream carries the input-gradient chain.  The side
+        # stream reads two workspaces shared by all blocks: `ws_dtmp` (stage-2 weight gradient) and `dmid_raw`
+        # (depthwise / stage-1 weight gradients); the main stream waits for those readers right before the next block
+        # overwrites the respective buffer (ev_tmp / ev_raw), and joins the side stream after the last block.
+        ov = self.overlap_wgrad
+        main = torch.cuda.current_stream() if ov else None
+        if ov and self._wside is None:
+            self._wside = torch.cuda.Stream(device=self.dev)
+        side = self._wside
+        ev_tmp = ev_raw = None
+
+        def on_side(fn):
+            if not ov:
+                return fn()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn()
+
+        def mark():
+            if not ov:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return ev
+
         for i in range(len(self.blocks) - 1, -1, -1):
             b = self.blocks[i]
             name = f'features.{i}'
@@ -656,8 +685,11 @@ class GenNet:
             dmid_act = self._ws(self.ws_dmid_act, H4, W4, b.L)
             dmid_raw = self._ws(self.ws_dmid_raw, H4, W4, b.L)
             # x + pw_bn(tmp): norm backward without activation
+            if ev_tmp is not None:
+                main.wait_event(ev_tmp)          # the previous block's stage-2 weight gradient has read ws_dtmp
             b.npw.backward(cur, None, b.tmp, self.ws_dtmp, none)
-            b.g2.wgrad(b.mid_act.t, self.ws_dtmp.t, ar.g)
+            on_side(lambda: b.g2.wgrad(b.mid_act.t, self.ws_dtmp.t, ar.g))
+            ev_tmp = mark()
             for (g, sl, m, p) in b.d2:
                 if p > 0:
                     fr = self._ws(self.ws_frame, H4 + 2 * p, W4 + 2 * p, cpad(m))
@@ -665,16 +697,23 @@ class GenNet:
                     ops.reflect_fold(fr, dmid_act.slice(sl, cpad(m)), p)
                 else:
                     g.fprop(self.ws_dtmp.t, dmid_act.t)
+            if ev_raw is not None:
+                main.wait_event(ev_raw)          # the previous block's depthwise / stage-1 weight gradients have read dmid_raw
             if b.dw:
                 nB = b.L - b.LA
                 b.nB.backward(dmid_act.slice(b.LA, nB), b.mid_act.slice(b.LA, nB), b.mid_raw.slice(b.LA, nB),
                               dmid_raw.slice(b.LA, nB), relu)
-                ops.dwconv_bwd_weight(b.mid_act.slice(b.D0, b.D1 - b.D0), dmid_raw.slice(b.LA, nB), b.dw_k, b.dw_w, ar.g)
+                on_side(lambda: ops.dwconv_bwd_weight(b.mid_act.slice(b.D0, b.D1 - b.D0), dmid_raw.slice(b.LA, nB), b.dw_k,
+                                                      b.dw_w, ar.g))
                 ops.dwconv_bwd_data(dmid_raw.slice(b.LA, nB), dmid_act.slice(b.D0, b.D1 - b.D0), b.dw_k, b.dw_w, ar.p)
             b.nA.backward(dmid_act.slice(0, b.LA), b.mid_act.slice(0, b.LA), b.mid_raw.slice(0, b.LA),
                           dmid_raw.slice(0, b.LA), relu)
-            for (g, sl, m, k, wn) in b.s1:
-                g.wgrad(b.x.t, dmid_raw.t, ar.g)
+
+            def s1_wgrads(b=b, dmid_raw=dmid_raw):
+                for (g, sl, m, k, wn) in b.s1:
+                    g.wgrad(b.x.t, dmid_raw.t, ar.g)
+            on_side(s1_wgrads)
+            ev_raw = mark()
             nxt = self.dfeat[nxt_i]
             if b.P1 > 0:
                 fr = self._ws(self.ws_dxp, H4 + 2 * b.P1, W4 + 2 * b.P1, Cp)
@@ -684,6 +723,8 @@ class GenNet:
                 b.g1d.fprop(dmid_raw.t, nxt.t)
                 ops.add(nxt, cur, nxt)
             cur, nxt_i = nxt, 1 - nxt_i
+        if ov:
+            main.wait_stream(side)               # join: every block weight gradient is in the arena
         if 'down_sampling.9' in act_grads:
             act_grads['down_sampling.9'](cur)
         # down 2, down 1, stem (no input gradient needed for the image)

@@ -151,3 +151,30 @@ def test_distill_step_matches_oracle(golden_dir, name, use_graph, kernels):
             assert v <= 0.25 * (int(k[-1]) + 1), ('emu', k, v)
         else:
             assert v <= 3e-2, ('emu', k, v)
+
+
+def test_side_stream_branches_do_not_change_the_gradients(golden_dir):
+    """The weight-gradient side stream of GenNet.backward and the teacher branch only re-order independent work.  fp32
+    atomics make every run of the step slightly different (summation order -> a few flipped bf16 roundings), so the
+    yardstick is the run-to-run difference of the step WITHOUT side streams: the step with side streams must not differ
+    from it by more than a small multiple of that (a missing dependency corrupts whole tensors, i.e. O(1))."""
+    from cat_b200.distill_engine import DistillStep
+    fix = torch.load(os.path.join(golden_dir, 'pix2pix_bn_lsgan_l2.pt'), weights_only=False)
+    s0 = fix['steps'][0]
+    B, _, H, W = s0['real_A'].shape
+
+    def run(overlap):
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, use_cuda_graph=True)
+        eng.overlap_teacher = overlap
+        eng.S.overlap_wgrad = overlap
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(s0['real_A'], s0['real_B'])
+        eng.step()
+        torch.cuda.synchronize()
+        return eng.S.arena.g.clone().cpu(), eng.get_losses()
+    (ga, la), (gb, lb), (g1, l1) = run(False), run(False), run(True)
+    noise, diff = rel_l2(gb, ga), rel_l2(g1, ga)
+    print('student gradient: run-to-run', noise, 'side streams vs none', diff)
+    assert diff <= 3 * noise + 2e-3, (diff, noise)
+    for k in la:
+        assert abs(l1[k] - la[k]) <= 3 * abs(lb[k] - la[k]) + 1e-3 * max(1.0, abs(la[k])), (k, l1[k], la[k], lb[k])
