@@ -371,11 +371,14 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         ws, eng.world_size = eng.world_size, 1   # rank 0 only: this extra step must not enter a collective
         # per-kernel timing needs the kernels alone on the GPU: no side-stream branches in this step
         saved = {k: getattr(eng, k) for k in ('overlap', 'overlap_teacher') if hasattr(eng, k)}
+        saved_w = eng.S.overlap_wgrad
         for k in saved:
             setattr(eng, k, False)
+        eng.S.overlap_wgrad = False
         eng.step()
         for k, v in saved.items():
             setattr(eng, k, v)
+        eng.S.overlap_wgrad = saved_w
         eng.world_size = ws
         agg, per = prof.summary()
         prof.remove()

@@ -221,12 +221,13 @@ class SpadeDistillStep:
         state is restored so that the captured graphs start from exactly the loaded weights."""
         state = self._mutable_state()
         snap = [t.clone() for t in state]
-        saved, self.overlap = self.overlap, False     # kernels are timed one at a time during the tuning step
+        saved, self.overlap = (self.overlap, self.S.overlap_wgrad), False     # kernels are timed one at a time while tuning
+        self.S.overlap_wgrad = False
         self._part1()
         self._part2()
         self._part3()
         torch.cuda.synchronize()
-        self.overlap = saved
+        self.overlap, self.S.overlap_wgrad = saved
         for t, c in zip(state, snap):
             t.copy_(c)
         self.S.pack_weights()

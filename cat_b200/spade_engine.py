@@ -11,6 +11,8 @@ Networks restated here (same maths as the reference modules, different execution
                    torch.nn.utils.spectral_norm + InstanceNorm2d(affine=False) (spade_architecture/normalization.py:17-50)
   VggNet        -- VGG19 slices 1-5 of VGGLoss (models/modules/loss.py:151-203), forward + input gradient
 """
+import os
+
 import numpy as np
 import torch
 
@@ -124,6 +126,38 @@ class _Net:
         self.biases = BiasPool()
         self.norms = []
         self.fprop_gemms, self.bwd_gemms = [], []
+
+    # ---- weight gradients on a side stream (parallel branches of the captured graph) ------------------------------
+    def _side_begin(self):
+        """Called at the start of a backward pass.  Weight-gradient launches only feed the optimiser, so they run on a
+        side stream while the main stream carries the input-gradient chain; the side stream reads one workspace shared
+        by all six-branch bodies (`dmid_raw`), which the main stream re-writes only after waiting for `_ev_raw`."""
+        self._ov = getattr(self, 'overlap_wgrad', False) and str(self.dev) != 'cpu'
+        self._ev_raw = None
+        if self._ov:
+            self._main = torch.cuda.current_stream()
+            if getattr(self, '_wside', None) is None:
+                self._wside = torch.cuda.Stream(device=self.dev)
+
+    def _on_side(self, fn):
+        if not self._ov:
+            return fn()
+        self._wside.wait_stream(self._main)
+        with torch.cuda.stream(self._wside):
+            fn()
+
+    def _mark_raw(self):
+        if self._ov:
+            self._ev_raw = torch.cuda.Event()
+            self._ev_raw.record(self._wside)
+
+    def _wait_raw(self):
+        if self._ov and self._ev_raw is not None:
+            self._main.wait_event(self._ev_raw)
+
+    def _side_end(self):
+        if self._ov:
+            self._main.wait_stream(self._wside)
 
     def G(self, geo, units, n_rows, bwd=False, **kw):
         g = Gemm(geo, units, n_rows, self.dev, **kw)
@@ -394,22 +428,30 @@ class SixBranch:
         net, ar, relu = self.net, self.net.arena, ACT['relu']
         assert d_out.ld == self.out_span.ld and d_out.coff == self.out_span.coff
         ops.channel_sum(Act(d_out.t, d_out.coff, self.out_span.C), net.biases.slot(self.s2_bias_slot, 'dvec'))
-        for (gw, seg) in self.s2_w:
-            gw.wgrad(self.mid_act.t, d_out.t, ar.g)
+
+        def s2_wgrads():
+            for (gw, seg) in self.s2_w:
+                gw.wgrad(self.mid_act.t, d_out.t, ar.g)
+        net._on_side(s2_wgrads)                 # reads d_out (owned by the caller's block) and this body's mid_act
         for g in self.d2:
             g.fprop(d_out.t, dmid_act.t)
+        net._wait_raw()                         # the previous body's weight gradients have read the shared dmid_raw
         if self.dw:
             nB = self.L - self.LA
             self.nB.backward(dmid_act.slice(self.LA, nB), self.mid_act.slice(self.LA, nB), self.mid_raw.slice(self.LA, nB),
                              dmid_raw.slice(self.LA, nB), relu)
-            ops.dwconv_bwd_weight(self.mid_act.slice(self.D0, self.D1 - self.D0), dmid_raw.slice(self.LA, nB), self.dw_k,
-                                  self.dw_w, ar.g, PAD_ZERO)
+            net._on_side(lambda: ops.dwconv_bwd_weight(self.mid_act.slice(self.D0, self.D1 - self.D0), dmid_raw.slice(self.LA, nB),
+                                                       self.dw_k, self.dw_w, ar.g, PAD_ZERO))
             ops.dwconv_bwd_data(dmid_raw.slice(self.LA, nB), dmid_act.slice(self.D0, self.D1 - self.D0), self.dw_k, self.dw_w,
                                 ar.p, PAD_ZERO)
         self.nA.backward(dmid_act.slice(0, self.LA), self.mid_act.slice(0, self.LA), self.mid_raw.slice(0, self.LA),
                          dmid_raw.slice(0, self.LA), relu)
-        for (g, sl, m, k, wn) in self.s1:
-            g.wgrad(self.x.t, dmid_raw.t, ar.g)
+
+        def s1_wgrads():
+            for (g, sl, m, k, wn) in self.s1:
+                g.wgrad(self.x.t, dmid_raw.t, ar.g)
+        net._on_side(s1_wgrads)
+        net._mark_raw()
         if self.g1d is not None:
             self.g1d.fprop(dmid_raw.t, self.dx.t)
 
@@ -433,6 +475,7 @@ class SpadeGenNet(_Net):
         B, H, W = (seg.N, seg.H, seg.W) if seg is not None else (1, 0, 0)
         self._init_common(B, device, training, need_grad, share=share)
         self.bn_momentum = arch.get('momentum', 0.1)
+        self.overlap_wgrad = os.environ.get('CATB_NO_WOVERLAP', '0') != '1'
         self.arch, self.H, self.W = arch, H, W
         self.snc = arch['semantic_nc']
         assert alloc_only or seg.C == cpad(self.snc)
@@ -610,6 +653,7 @@ class SpadeGenNet(_Net):
         self.pool_red.zero_()
         if self.biases.used:
             self.biases.dvec.zero_()
+        self._side_begin()
         ops.act_bwd(d_out, self.out, self.d_img_z, ACT['tanh'])
         self.g_img.wgrad(self.l_img.t, self.d_img_z.t, ar.g)
         ops.channel_sum(self.d_img_z, ar.view('conv_img.bias', 'g'))
@@ -644,6 +688,7 @@ class SpadeGenNet(_Net):
                 cur = b.d_up_in
         self.n_fc.backward(cur, None, self.y_fc, self.d_y_fc, none)
         self.g_fc.wgrad(self._seg(self.fc_res).t, self.d_y_fc.t, ar.g)
+        self._side_end()
         self.biases.scatter(ar.g)
 
 
