@@ -544,8 +544,10 @@ class SpadeGenNet(_Net):
             b.h, b.w, b.x = h, w, x
             b.seg_res = seg_at(h, w)
             b.empty = b.main.empty
-            if b.empty and not b.learned:
+            if b.empty and not b.learned:     # forward returns its input (inception_modules.py:550-553)
                 b.out = x
+                if ng and b.up_in is not None:
+                    b.d_up_in = self._act(h // 2, w // 2, b.fin)
                 continue
             b.out = self._act(h, w, b.fout)
             if b.learned:

@@ -135,3 +135,78 @@ def test_spade_generator_inference_through_the_module_mirror(golden_dir):
         assert e[0].arena is e[1].arena
         # parameters of the module tree alias the engine arena
         assert net.conv_img.weight.data_ptr() == e[0].arena.view('conv_img.weight').data_ptr()
+
+
+def _toy_spade_arch(mode, blocks):
+    names = ['head_0', 'G_middle_0', 'G_middle_1', 'up_0', 'up_1', 'up_2', 'up_3'] + (['up_4'] if mode == 'most' else [])
+    n_up = {'normal': 5, 'more': 6, 'most': 7}[mode]
+    return {'semantic_nc': 5, 'fc_out': blocks['head_0']['fin'], 'sh': 1, 'sw': 2, 'num_upsampling_layers': mode,
+            'kernel_sizes': [1, 3, 5], 'final_nc': blocks[names[-1]]['fout'], 'block_names': names,
+            'blocks': {n: blocks[n] for n in names}, 'eps': 1e-5, 'momentum': 0.1}, (1 << n_up, 2 << n_up)
+
+
+def _blk(fin, fout, res, dw, sres, sdw):
+    return {'fin': fin, 'fout': fout, 'res': res, 'dw': dw, 'spade_res': sres, 'spade_dw': sdw, 'learned_shortcut': fin != fout}
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('mode,seed', [('normal', 3), ('most', 5)])
+def test_spade_generator_edge_architectures_exact(mode, seed):
+    """Generator-only forward + backward in exact emulation on hand-made pruned architectures that exercise the corner
+    cases of shrink_spade_model's output: 'normal' / 'most' up-sampling, a block without any branch (identity and learned
+    shortcut), a block whose SPADE body lost every branch (gamma = beta = 0), zero-width branches in the middle of the
+    kernel-size list, widths that are not multiples of 8.  (The seeds are ones for which no LeakyReLU / ReLU input sits
+    within rounding distance of zero at a pixel with a large gradient: one such sign flip is a 1e-2 gradient difference
+    between ANY two fp32 evaluations of these tiny, badly conditioned networks.)"""
+    from oracle import spade_oracle as SO
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    from cat_b200 import workload as WL
+    from cat_b200.ops import Act
+    from cat_b200.spade_engine import SpadeGenNet
+    blocks = {
+        'head_0': _blk(24, 24, [3, 0, 2], [0, 4, 0], [2, 0, 3], [0, 0, 2]),
+        'G_middle_0': _blk(24, 24, [0, 0, 0], [0, 0, 0], [2, 2, 2], [2, 2, 2]),      # no branch, identity shortcut
+        'G_middle_1': _blk(24, 24, [2, 2, 0], [3, 0, 0], [0, 0, 0], [0, 0, 0]),      # SPADE body empty
+        'up_0': _blk(24, 12, [0, 0, 0], [0, 0, 0], [1, 1, 1], [1, 1, 1]),            # no branch, learned shortcut
+        'up_1': _blk(12, 9, [1, 2, 3], [2, 1, 1], [3, 3, 3], [2, 2, 2]),
+        'up_2': _blk(9, 7, [0, 3, 0], [0, 0, 5], [4, 0, 0], [0, 3, 0]),
+        'up_3': _blk(7, 5, [2, 0, 0], [0, 2, 0], [0, 2, 0], [2, 0, 0]),
+        'up_4': _blk(5, 3, [1, 1, 1], [1, 1, 1], [2, 2, 2], [1, 1, 1]),
+    }
+    arch, (H, W) = _toy_spade_arch(mode, blocks)
+    B = 2
+    sd = WL.init_spade_reference_sd(arch, 11, 'uniform')
+    g = torch.Generator().manual_seed(seed)
+    for k in sd:
+        if k.endswith('.bias'):
+            sd[k] = 0.1 * torch.randn(sd[k].shape, generator=g)
+    lab = torch.randint(0, 4, (B, 1, H // 4, W // 4), generator=g).repeat_interleave(4, 2).repeat_interleave(4, 3)
+    inst = torch.randint(0, 3, (B, 1, H // 2, W // 2), generator=g).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    seg = SO.preprocess_input(lab, inst, 4)
+    R = torch.randn(B, 3, H, W, generator=g)
+    # oracle: training-mode forward, gradient of <out, R>
+    osd = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in osd.items() if SO._is_param(k)}
+    out_ref = SO.spade_generator_forward(osd, arch, seg, training=True)
+    (out_ref * R).sum().backward()
+    with emulated_kernels(exact=True):
+        seg_act = Act.empty(B, H, W, arch['semantic_nc'], 'cpu', zero=True)
+        ops.nchw_to_nhwc(seg, seg_act)
+        net = SpadeGenNet(arch, seg_act, 'cpu', training=True, need_grad=True)
+        net.load_state_dict(sd)
+        out = ops.nhwc_to_nchw(net.forward(), 3)
+        assert rel_l2(out, out_ref.detach()) < 1e-5
+        dS = Act.empty(B, H, W, 3, 'cpu', zero=True)
+        ops.nchw_to_nhwc(R, dS)
+        net.arena.g.zero_()
+        net.backward(dS)
+        scale = max(float(p.grad.abs().max()) for p in params.values() if p.grad is not None)
+        for k, p in params.items():
+            if p.grad is None:
+                continue
+            err = float((net.arena.view(k, 'g') - p.grad).abs().max())
+            assert err <= 2e-3 * float(p.grad.abs().max()) + 2e-5 * scale, (k, err, float(p.grad.abs().max()))
+        for k, v in osd.items():
+            if 'running_' in k:
+                assert float((net.state_dict()[k] - v.detach()).abs().max()) < 1e-4, k
