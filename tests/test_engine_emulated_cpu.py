@@ -98,3 +98,49 @@ def test_distill_step_host_logic_exact(golden_dir, name, packx, monkeypatch):
                     continue
                 err = float((net.arena.view(k, 'g') - g).abs().max())
                 assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('norm', ['instance', 'batch'])
+def test_generator_edge_architectures_exact(norm):
+    """Generator-only forward + backward in exact emulation on a hand-made pruned InceptionGenerator: a block without
+    any branch (forward returns its input), zero-width branches in the middle of the kernel-size list, widths that
+    are not multiples of 8, non-square input."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    from cat_b200 import workload as WL
+    from cat_b200.engine import GenNet
+    from cat_b200.ops import Act
+    track = norm == 'batch'
+    arch = {'input_nc': 3, 'output_nc': 3, 'widths': [9, 13, 21, 11, 7], 'kernel_sizes': [1, 3, 5], 'norm': norm, 'affine': True,
+            'track_running_stats': track, 'eps': 1e-5, 'momentum': 0.1, 'use_bias': norm == 'instance',
+            'blocks': [{'res': [3, 0, 2], 'dw': [0, 4, 0]}, {'res': [0, 0, 0], 'dw': [0, 0, 0]}, {'res': [0, 5, 0], 'dw': [2, 0, 3]},
+                       {'res': [1, 1, 1], 'dw': [1, 1, 1]}, {'res': [0, 0, 0], 'dw': [0, 0, 6]}, {'res': [4, 0, 0], 'dw': [0, 0, 0]},
+                       {'res': [0, 0, 0], 'dw': [0, 0, 0]}, {'res': [2, 3, 0], 'dw': [0, 2, 2]}, {'res': [0, 0, 7], 'dw': [5, 0, 0]}]}
+    B, H, W = 2, 24, 40
+    sd = WL.init_generator(arch, 5, 'uniform', gain=0.3)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    R = torch.randn(B, 3, H, W, generator=g)
+    osd = O.clone_sd(sd)
+    params = {k: v.requires_grad_(True) for k, v in osd.items() if k.endswith(('.weight', '.bias'))}
+    out_ref = O.generator_forward(osd, arch, x, training=True)
+    (out_ref * R).sum().backward()
+    with emulated_kernels(exact=True):
+        net = GenNet(arch, B, H, W, 'cpu', training=True, need_grad=True)
+        net.load_state_dict(sd)
+        xa = Act.empty(B, H, W, 3, 'cpu', zero=True)
+        ops.nchw_to_nhwc(x, xa)
+        out = ops.nhwc_to_nchw(net.forward(xa), 3)
+        assert rel_l2(out, out_ref.detach()) < 1e-5
+        dS = Act.empty(B, H, W, 3, 'cpu', zero=True)
+        ops.nchw_to_nhwc(R, dS)
+        net.arena.g.zero_()
+        net.backward(dS)
+        scale = max(float(p.grad.abs().max()) for p in params.values() if p.grad is not None)
+        for k, p in params.items():
+            if p.grad is None or not net.arena.has(k):
+                continue
+            err = float((net.arena.view(k, 'g') - p.grad).abs().max())
+            assert err <= 2e-3 * float(p.grad.abs().max()) + 2e-5 * scale, (k, err, float(p.grad.abs().max()))
