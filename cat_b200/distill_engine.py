@@ -15,7 +15,6 @@ import torch
 
 from . import ops, parallel
 from .engine import MAPPING_LAYERS, DisNet, GenNet
-from .igemm_plan import cpad
 from .ops import Act
 
 LOSS_NAMES = ['G_gan', 'G_distill', 'G_recon', 'D_fake', 'D_real', 'G_distill0', 'G_distill1', 'G_distill2',

@@ -15,7 +15,6 @@ import functools
 import torch
 from torch import nn
 
-from ..igemm_plan import cpad
 
 
 # --------------------------------------------------------------------------------------------------

@@ -12,7 +12,6 @@ import collections
 import functools
 import re
 
-import torch
 from torch import nn
 
 from .networks import BaseNetwork, _EngineBacked, get_active_fn, _pre

@@ -16,7 +16,6 @@ import os
 import torch
 
 from . import ops, parallel
-from .igemm_plan import cpad
 from .ops import Act
 from .spade_engine import MAPPING_LAYERS, VGG_WEIGHTS, MultiScaleDis, SpadeGenNet, VggNet, dis_feature
 

@@ -17,7 +17,6 @@ import tempfile
 import numpy as np
 import torch
 import torchvision
-import torch.nn as nn
 
 from oracle.ref_harness import REF_ROOT, _install_shims
 
