@@ -1,0 +1,116 @@
+"""world_size-2 gloo test of the data-parallel path of the ENGINES (not just the recipe): two processes run
+cat_b200.distill_engine.DistillStep / cat_b200.spade_distill_engine.SpadeDistillStep with world_size=2 on their shard of a
+global batch, with every kernel wrapper swapped for its torch restatement in exact (fp32) mode (oracle/kernel_emu.py, test
+infrastructure).  Checked: the all-reduced gradient arenas equal the reference's nn.DataParallel semantics evaluated in one
+process by the oracle (Inception distiller: tests/test_data_parallel_cpu._data_parallel_reference; SPADE distiller: the
+average of the per-shard gradients), and both ranks hold bit-identical weights after the step."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for _p in (HERE, os.path.dirname(HERE)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORLD = 2
+PER_RANK = 2
+
+
+def _worker_inception(rank, port, path, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=WORLD)
+    torch.set_num_threads(2)
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import parallel
+    from test_data_parallel_cpu import _batch
+    fix = torch.load(path, weights_only=False)
+    a, b = _batch(fix)
+    sl = slice(rank * PER_RANK, (rank + 1) * PER_RANK)
+    hp = dict(fix['hp'], ka_scale=parallel.ka_scale(WORLD))
+    _, _, H, W = a.shape
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, PER_RANK, H, W, device='cpu', world_size=WORLD)
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(a[sl].float(), b[sl].float())
+        eng.step()
+        scale = parallel.grad_scale(WORLD)
+        out = {'S_g': {k: eng.S.arena.view(k, 'g').clone() * scale for k in eng.S.arena.entries},
+               'D_g': {k: eng.D.arena.view(k, 'g').clone() * scale for k in eng.D.arena.entries},
+               'S_p': eng.S.arena.p.clone(), 'D_p': eng.D.arena.p.clone()}
+    torch.save(out, os.path.join(out_dir, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_engine_two_ranks_inception(golden_dir, tmp_path):
+    from test_data_parallel_cpu import _data_parallel_reference
+    path = os.path.join(golden_dir, 'cyclegan_in_lsgan.pt')
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_worker_inception, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    fix = torch.load(path, weights_only=False)
+    S_ref, D_ref, _ = _data_parallel_reference(fix)       # fp64, single process, reference DataParallel semantics
+    ranks = [torch.load(os.path.join(tmp_path, f'rank{r}.pt'), weights_only=False) for r in range(WORLD)]
+    assert torch.equal(ranks[0]['S_p'], ranks[1]['S_p']) and torch.equal(ranks[0]['D_p'], ranks[1]['D_p'])
+    for tag, ref in (('S_g', S_ref), ('D_g', D_ref)):
+        scale = max(float(g.abs().max()) for g in ref.values())
+        for k, g in ref.items():
+            if k not in ranks[0][tag]:
+                continue
+            err = float((ranks[0][tag][k].double() - g).abs().max())
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
+
+
+def _worker_spade(rank, port, path, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=WORLD)
+    torch.set_num_threads(2)
+    from oracle import spade_oracle as SO
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import parallel
+    fix = torch.load(path, weights_only=False)
+    s = fix['steps']
+    lab, inst, img = (torch.cat([s[0][k], s[1][k]]) for k in ('label', 'instance', 'image'))
+    sl = slice(rank * PER_RANK, (rank + 1) * PER_RANK)
+    H, W = img.shape[2:]
+    with emulated_kernels(exact=True):
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], dict(fix['hp'], ka_scale=1.0), PER_RANK, H, W,
+                               device='cpu', world_size=WORLD)
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], SO.make_vgg_sd(fix['vgg_seed']))
+        eng.set_input(lab[sl], inst[sl], img[sl])
+        eng.step()
+        scale = parallel.grad_scale(WORLD)
+        out = {'S_g': {k: eng.S.arena.view(k, 'g').clone() * scale for k in eng.S.arena.entries},
+               'S_p': eng.S.arena.p.clone(), 'D_p': eng.D.arena.p.clone()}
+    torch.save(out, os.path.join(out_dir, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(1200)
+def test_engine_two_ranks_spade(golden_dir, tmp_path):
+    from oracle import spade_oracle as SO
+    from test_spade_data_parallel_cpu import _batch, _state
+    path = os.path.join(golden_dir, 'spade_more.pt')
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_worker_spade, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    ranks = [torch.load(os.path.join(tmp_path, f'rank{r}.pt'), weights_only=False) for r in range(WORLD)]
+    assert torch.equal(ranks[0]['S_p'], ranks[1]['S_p']) and torch.equal(ranks[0]['D_p'], ranks[1]['D_p'])
+    fix = torch.load(path, weights_only=False)
+    seg, img = _batch(fix)
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    shard = []
+    for r in range(WORLD):
+        sl = slice(r * PER_RANK, (r + 1) * PER_RANK)
+        res = SO.spade_distill_step(_state(fix, vgg), seg[sl], img[sl], dict(fix['hp'], ka_scale=1.0, lr_G=0.0, lr_D=0.0))
+        shard.append(res['S_grads'])
+    scale = max(float(g.abs().max()) for g in shard[0].values())
+    for k in shard[0]:
+        avg = sum(s[k] for s in shard) / WORLD
+        err = float((ranks[0]['S_g'][k] - avg).abs().max())
+        assert err <= 2e-3 * float(avg.abs().max()) + 2e-5 * scale, (k, err, float(avg.abs().max()))
