@@ -131,7 +131,47 @@ def shrink_arch(teacher_sd, teacher_arch, target_flops, H, W, prune_cin_lb=1, pr
 
 
 def shrink(model, opt):
-    """Drop-in for `utils.common.shrink(model, opt)` as trainer.py:106-107 calls it on an Inception distiller: replaces
+    """Drop-in for `utils.common.shrink(model, opt)` (utils/common.py:872-878) as trainer.py:106-107 calls it."""
+    if hasattr(model, 'modules_on_one_gpu'):
+        return shrink_spade(model, opt)
+    return shrink_inception(model, opt)
+
+
+def shrink_spade(model, opt):
+    """`shrink_spade_model` on a SPADE distiller mirror: `modules_on_one_gpu.netG_student` becomes a freshly initialised
+    InceptionSPADEGenerator of the searched architecture, the adaptor convs `netAs` are re-created for the student width
+    (utils/common.py:835-843), and the compiled engine is dropped."""
+    import copy
+    from torch import nn
+    from .models import networks
+    from .models.spade_networks import InceptionSPADEGenerator
+    mm = model.modules_on_one_gpu
+    teacher = mm.netG_teacher
+    sd = {k: v.detach().float().cpu() for k, v in teacher.state_dict().items() if k.endswith('norm.weight')}
+    target = float(getattr(opt, 'target_flops', 0.0))
+    assert target > 0, 'opt.target_flops must be positive'
+    student_arch, info = shrink_spade_arch(sd, teacher.arch(), target, prune_cin_lb=int(getattr(opt, 'prune_cin_lb', 1)),
+                                           prune_cin_ub=getattr(opt, 'prune_cin_ub', float('inf')))
+    s_opt = copy.deepcopy(teacher.opt)
+    s_opt.ngf = student_arch['fc_out'] // 16
+    gpu_ids = list(getattr(model, 'gpu_ids', []))[:1]
+    mm.netG_student = networks.init_net(InceptionSPADEGenerator.from_arch(student_arch, s_opt), opt.init_type, opt.init_gain, gpu_ids)
+    mm.netG_student.n_macs = info['macs']
+    teacher.n_macs = spade_generator_macs(teacher.arch())
+    ngf_stu = student_arch['fc_out'] // 16
+    netAs = nn.ModuleList()
+    for layer in mm.mapping_layers:
+        fs, ft = (ngf_stu * 16, opt.teacher_ngf * 16) if layer != 'up_1' else (ngf_stu * 4, opt.teacher_ngf * 4)
+        netAs.append(nn.Conv2d(fs, ft, kernel_size=1))
+    mm.netAs = netAs
+    if hasattr(model, 'engine'):
+        model.engine = None
+    print('scale threshold: %g, searched flops: %d, target flops: %g' % (info['threshold'], info['macs'], target))
+    return info
+
+
+def shrink_inception(model, opt):
+    """`shrink_model` (utils/common.py:315-707) on an Inception distiller mirror: replaces
     `model.netG_student` by a freshly initialised generator of the searched architecture (the reference also copies the
     surviving teacher weights, which trainer.py overwrites with `init_net` on the next line) and drops the compiled
     engine so that the next `set_input` compiles the step for the new shapes.  Returns the search record."""
@@ -152,3 +192,94 @@ def shrink(model, opt):
         model.engine = None
     print('scale threshold: %g, searched flops: %d, target flops: %g' % (info['threshold'], info['macs'], target))
     return info
+
+
+# ----------------------------------------------------------------------------------------------------
+# SPADE generator (shrink_spade_model, utils/common.py:710-835)
+# ----------------------------------------------------------------------------------------------------
+def spade_generator_macs(arch, H=None, W=None):
+    """n_macs of an InceptionSPADEGenerator as model_profiling reports it (batch 1): every conv of the six-branch bodies,
+    of the SPADE gamma / beta bodies (evaluated on the label map at the block's resolution), the learned shortcuts, fc and
+    conv_img; SynchronizedBatchNorm (tracking running statistics), up-sampling and activations count 0."""
+    ks, snc = arch['kernel_sizes'], arch['semantic_nc']
+    h, w = arch['sh'], arch['sw']
+    more = arch['num_upsampling_layers'] in ('more', 'most')
+    m = snc * arch['fc_out'] * 9 * h * w
+
+    def body(cin, cout, res, dw, hw):
+        t = 0
+        for mid, k in zip(res, ks):
+            if mid:
+                t += cin * mid * k * k * hw + mid * cout * k * k * hw
+        for mid, k in zip(dw, ks):
+            if mid:
+                t += cin * mid * hw + mid * k * k * hw + mid * cout * hw
+        return t
+    for name in arch['block_names']:
+        if name in ('G_middle_0', 'up_0', 'up_1', 'up_2', 'up_3', 'up_4') or (name == 'G_middle_1' and more):
+            h, w = 2 * h, 2 * w
+        b = arch['blocks'][name]
+        hw = h * w
+        empty = not any(b['res']) and not any(b['dw'])
+        if b['learned_shortcut']:
+            m += b['fin'] * b['fout'] * hw
+        if not empty:     # forward returns early for a branch-less block: its SPADE body is never run (hooks do not fire)
+            m += body(b['fin'], b['fout'], b['res'], b['dw'], hw)
+            m += body(snc, 2 * b['fin'], b['spade_res'], b['spade_dw'], hw)
+    m += arch['final_nc'] * 3 * 9 * h * w
+    return int(m)
+
+
+def _spade_candidate(sd, A, thr, lb, ub):
+    ch_div = 32 if A['num_upsampling_layers'] == 'most' else 16
+    c = _count(sd['fc_norm.weight'], thr)
+    c = max(c // ch_div, lb) * ch_div
+    c = int(min(c // ch_div, ub) * ch_div)
+    blocks, cin = {}, c
+    for name in A['block_names']:
+        T = A['blocks'][name]
+        fout = cin // 2 if 'up' in name else cin
+
+        def counts(widths, fmt):
+            out, j = [], 0
+            for mid in widths:
+                if mid == 0:
+                    out.append(0)
+                    continue
+                out.append(_count(sd[fmt.format(name, j)], thr))
+                j += 1
+            return out
+        blocks[name] = {'fin': cin, 'fout': fout, 'res': counts(T['res'], '{}.res_ops.{}.0.norm.weight'),
+                        'dw': counts(T['dw'], '{}.dw_ops.{}.0.norm.weight'),
+                        'spade_res': counts(T['spade_res'], '{}.spade.res_ops.{}.0.norm.weight'),
+                        'spade_dw': counts(T['spade_dw'], '{}.spade.dw_ops.{}.0.norm.weight'), 'learned_shortcut': cin != fout}
+        cin = fout
+    return dict(A, fc_out=c, final_nc=cin, blocks=blocks)
+
+
+def shrink_spade_arch(teacher_sd, teacher_arch, target_flops, prune_cin_lb=1, prune_cin_ub=float('inf')):
+    """The pruned InceptionSPADEGenerator architecture `shrink_spade_model` would produce (the candidate of the last
+    bisection step).  `teacher_arch` carries the latent size (sh, sw) of the profiling resolution."""
+    A = teacher_arch
+    keys = ['fc_norm.weight']
+    for name in A['block_names']:
+        T = A['blocks'][name]
+        for widths, fmt in ((T['res'], '{}.res_ops.{}.0.norm.weight'), (T['dw'], '{}.dw_ops.{}.0.norm.weight'),
+                            (T['spade_res'], '{}.spade.res_ops.{}.0.norm.weight'), (T['spade_dw'], '{}.spade.dw_ops.{}.0.norm.weight')):
+            keys += [fmt.format(name, j) for j in range(sum(1 for c in widths if c > 0))]
+    allw = torch.cat([teacher_sd[k].detach().float().abs().view(-1) for k in keys])
+    lb, ub = allw.min(), allw.max()
+    searched, thr, iters, cand = float('inf'), None, 0, None
+    while bool((ub - lb).abs() > 1e-3 * lb) or searched > target_flops:
+        thr = (lb + ub) / 2
+        cand = _spade_candidate(teacher_sd, A, thr, prune_cin_lb, prune_cin_ub)
+        searched = spade_generator_macs(cand)
+        if searched > target_flops:
+            lb = thr
+        else:
+            ub = thr
+        iters += 1
+        if iters > 200:
+            raise RuntimeError('shrink_spade_arch: the target (%g MACs) cannot be reached; smallest candidate has %d MACs'
+                               % (target_flops, searched))
+    return cand, {'threshold': float(thr), 'macs': searched, 'iterations': iters}

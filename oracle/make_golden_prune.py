@@ -47,5 +47,38 @@ def main():
     print('->', OUT, os.path.getsize(OUT))
 
 
+SPADE_OUT = os.path.join(os.path.dirname(OUT), 'prune_spade_cases.pt')
+SPADE_CASES = {
+    'spade_small': dict(crop_size=128, aspect_ratio=2.0, teacher_ngf=6, student_ngf=6, ndf=8, input_nc=6, prune_cin_lb=2, frac=0.4),
+    'spade_small_b': dict(crop_size=128, aspect_ratio=1.0, teacher_ngf=8, student_ngf=8, ndf=8, input_nc=5, prune_cin_lb=1, frac=0.25, seed=4),
+    # scripts/gaugan/cityscapes/train_inception_student_5p6B.sh -> tests/golden/arch_gaugan_5p6B.json
+    'gaugan_5p6B': dict(crop_size=512, aspect_ratio=2.0, teacher_ngf=64, student_ngf=48, ndf=64, input_nc=35, prune_cin_lb=16,
+                        target_flops=5.6e9),
+}
+
+
+def main_spade():
+    from oracle.ref_harness_spade import build_reference_spade_distiller, spade_generator_arch
+    out = {}
+    for name, cfg in SPADE_CASES.items():
+        cfg = dict(cfg)
+        frac = cfg.pop('frac', None)
+        if frac is not None:
+            probe, _ = build_reference_spade_distiller(batch_size=1, do_shrink=False, **cfg)
+            cfg['target_flops'] = probe.modules_on_one_gpu.netG_teacher.n_macs * frac
+        model, opt = build_reference_spade_distiller(batch_size=1, **cfg)
+        mm = model.modules_on_one_gpu
+        keep = {k: v.detach().clone() for k, v in mm.netG_teacher.state_dict().items() if k.endswith('norm.weight')}
+        out[name] = {'gammas': keep, 'teacher_arch': spade_generator_arch(mm.netG_teacher), 'student_arch': spade_generator_arch(mm.netG_student),
+                     'teacher_macs': int(mm.netG_teacher.n_macs), 'student_macs': int(mm.netG_student.n_macs),
+                     'target_flops': float(cfg['target_flops']), 'prune_cin_lb': cfg['prune_cin_lb']}
+        print(name, out[name]['teacher_macs'], out[name]['student_macs'], out[name]['student_arch']['fc_out'])
+    torch.save(out, SPADE_OUT)
+    print('->', SPADE_OUT, os.path.getsize(SPADE_OUT))
+
+
 if __name__ == '__main__':
-    main()
+    if 'spade' in sys.argv[1:]:
+        main_spade()
+    else:
+        main()
