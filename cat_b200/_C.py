@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libcatb200.so')
 
-ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_TANH, ACT_LEAKY001 = 0, 1, 2, 3, 4
 PAD_ZERO, PAD_REFLECT = 0, 1
 GAN_MODES = {'hinge': 0, 'lsgan': 1, 'vanilla': 2}
 RECON_KINDS = {'l1': 0, 'l2': 1, 'smooth_l1': 2}

@@ -62,6 +62,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case CATB_ACT_RELU: return fmaxf(v, 0.f);
     case CATB_ACT_LEAKY02: return v > 0.f ? v : 0.2f * v;
+    case CATB_ACT_LEAKY001: return v > 0.f ? v : 0.01f * v;
     case CATB_ACT_TANH: return tanhf(v);
     default: return v;
   }
@@ -72,6 +73,7 @@ __device__ __forceinline__ float act_grad_from_out(float out, int act) {
   switch (act) {
     case CATB_ACT_RELU: return out > 0.f ? 1.f : 0.f;
     case CATB_ACT_LEAKY02: return out > 0.f ? 1.f : 0.2f;
+    case CATB_ACT_LEAKY001: return out > 0.f ? 1.f : 0.01f;
     case CATB_ACT_TANH: return 1.f - out * out;
     default: return 1.f;
   }

@@ -13,7 +13,7 @@ import torch
 from . import _C
 from .igemm_plan import Geometry, Units, choose_n_tile, cpad, make_halo_plan
 
-ACT = {'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'leaky': _C.ACT_LEAKY02, 'tanh': _C.ACT_TANH}
+ACT = {'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'leaky': _C.ACT_LEAKY02, 'tanh': _C.ACT_TANH, 'leaky001': _C.ACT_LEAKY001}
 BF16 = torch.bfloat16
 
 

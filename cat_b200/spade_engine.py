@@ -239,6 +239,9 @@ class SixBranch:
 
     def __init__(self, net, prefix, res_w, dw_w, ks, Cin, last_key, dw_affine):
         self.net, self.prefix, self.Cin, self.last_key, self.dw_affine = net, prefix, Cin, last_key, dw_affine
+        # the modulation body (InceptionSPADE, dw_affine) is always nn.ReLU (inception_modules.py:600); the main body of
+        # a block follows the generator's active_fn (:357, 442-474)
+        self.act = ACT['relu'] if dw_affine else net.act
         self.res = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(res_w, ks) if mk[0] > 0))]
         self.dw = [(j, m, k) for j, (m, k) in enumerate((mk for mk in zip(dw_w, ks) if mk[0] > 0))]
         self.empty = not self.res and not self.dw
@@ -412,7 +415,7 @@ class SixBranch:
         self.dx = dx
 
     def forward(self):
-        net, relu = self.net, ACT['relu']
+        net, relu = self.net, self.act
         for g in self.s1_fwd:
             g.fprop(self.x.t, self.mid_raw.t)
         self.nA.forward(self.mid_raw.slice(0, self.LA), self.mid_act.slice(0, self.LA), relu)
@@ -425,7 +428,7 @@ class SixBranch:
 
     def backward(self, d_out: Act, dmid_act: Act, dmid_raw: Act):
         """d_out: gradient buffer with the layout of the output buffer (same pitch / offsets as out_span)."""
-        net, ar, relu = self.net, self.net.arena, ACT['relu']
+        net, ar, relu = self.net, self.net.arena, self.act
         assert d_out.ld == self.out_span.ld and d_out.coff == self.out_span.coff
         ops.channel_sum(Act(d_out.t, d_out.coff, self.out_span.C), net.biases.slot(self.s2_bias_slot, 'dvec'))
 
@@ -475,6 +478,9 @@ class SpadeGenNet(_Net):
         B, H, W = (seg.N, seg.H, seg.W) if seg is not None else (1, 0, 0)
         self._init_common(B, device, training, need_grad, share=share)
         self.bn_momentum = arch.get('momentum', 0.1)
+        # generator activation: nn.ReLU on the distillation path (options/distill_options.py:123), nn.LeakyReLU() at its
+        # default slope 0.01 when SPADEModel trains the teacher (models/spade_model.py:92)
+        self.act = ACT[{'nn.ReLU': 'relu', 'nn.LeakyReLU': 'leaky001'}[arch.get('active_fn', 'nn.ReLU')]]
         self.overlap_wgrad = os.environ.get('CATB_NO_WOVERLAP', '0') != '1'
         self.arch, self.H, self.W = arch, H, W
         self.snc = arch['semantic_nc']
@@ -617,7 +623,7 @@ class SpadeGenNet(_Net):
     def forward(self):
         """Reads the bound segmentation buffer.  Returns the output Act (tanh applied)."""
         seg = self.seg_in
-        relu, none = ACT['relu'], ACT['none']
+        relu, none = self.act, ACT['none']
         self.pool_sums.zero_()
         self.biases.gather(self.arena.p)
         for (h, w), t in self.seg_pyr.items():
@@ -650,7 +656,7 @@ class SpadeGenNet(_Net):
         """d_out: gradient w.r.t. the tanh output; act_grads: {mapping layer: callable(Act)} accumulating the KA
         gradient into d(block output)."""
         assert self.need_grad
-        relu, none, ar = ACT['relu'], ACT['none'], self.arena
+        relu, none, ar = self.act, ACT['none'], self.arena
         act_grads = act_grads or {}
         self.pool_red.zero_()
         if self.biases.used:

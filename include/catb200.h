@@ -34,7 +34,9 @@ typedef enum {
   CATB_ERR_NO_DEVICE = -3
 } catb_status;
 
-enum { CATB_ACT_NONE = 0, CATB_ACT_RELU = 1, CATB_ACT_LEAKY02 = 2, CATB_ACT_TANH = 3 };
+/* CATB_ACT_LEAKY001 = nn.LeakyReLU() at its default slope: the generator activation of SPADE TEACHER training
+ * (models/spade_model.py:92 sets active_fn='nn.LeakyReLU'; the distillers keep nn.ReLU, options/distill_options.py:123). */
+enum { CATB_ACT_NONE = 0, CATB_ACT_RELU = 1, CATB_ACT_LEAKY02 = 2, CATB_ACT_TANH = 3, CATB_ACT_LEAKY001 = 4 };
 enum { CATB_PAD_ZERO = 0, CATB_PAD_REFLECT = 1 };
 enum { CATB_GAN_HINGE = 0, CATB_GAN_LSGAN = 1, CATB_GAN_VANILLA = 2 };
 

@@ -36,6 +36,8 @@ def _act(v, act):
         return torch.relu(v)
     if act == _C.ACT_LEAKY02:
         return F.leaky_relu(v, 0.2)
+    if act == _C.ACT_LEAKY001:
+        return F.leaky_relu(v, 0.01)
     if act == _C.ACT_TANH:
         return torch.tanh(v)
     return v
@@ -46,6 +48,8 @@ def _act_grad_from_out(o, act):
         return (o > 0).float()
     if act == _C.ACT_LEAKY02:
         return torch.where(o > 0, torch.ones_like(o), torch.full_like(o, 0.2))
+    if act == _C.ACT_LEAKY001:
+        return torch.where(o > 0, torch.ones_like(o), torch.full_like(o, 0.01))
     if act == _C.ACT_TANH:
         return 1.0 - o * o
     return torch.ones_like(o)

@@ -141,7 +141,7 @@ def spade_generator_arch(net, opt_ngf_unused=None):
         'semantic_nc': int(net.opt.semantic_nc), 'fc_out': int(net.fc.out_channels), 'sh': int(net.sh), 'sw': int(net.sw),
         'num_upsampling_layers': net.opt.num_upsampling_layers, 'kernel_sizes': [int(k) for k in net.opt.kernel_sizes],
         'final_nc': int(net.conv_img.in_channels), 'block_names': names, 'blocks': blocks,
-        'eps': 1e-5, 'momentum': 0.1,
+        'eps': 1e-5, 'momentum': 0.1, 'active_fn': getattr(net.opt, 'active_fn', 'nn.ReLU'),
     }
 
 

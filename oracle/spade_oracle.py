@@ -42,7 +42,17 @@ def _conv(x, sd, prefix, k, groups=1):
 # --------------------------------------------------------------------------------------------
 # SPADE generator
 # --------------------------------------------------------------------------------------------
-def _branches(x, sd, prefix, res, dw, ks, training, dw_affine, last_conv_key):
+# Activation of SPADEInvertedResidualChannels (block activation + its six main branches) for the pass being evaluated, set
+# by spade_generator_forward from arch['active_fn'] (inception_modules.py:357,401-402).  The InceptionSPADE modulation
+# body always uses nn.ReLU (inception_modules.py:600).
+_ACTIVE = [F.relu]
+
+
+def _active(x):
+    return _ACTIVE[0](x)
+
+
+def _branches(x, sd, prefix, res, dw, ks, training, dw_affine, last_conv_key, act=F.relu):
     """The six-branch body shared by SPADEInvertedResidualChannels._build (inception_modules.py:412-470) and
     InceptionSPADE._build (:672-722): res = ConvSyncBNReLU(k) -> Conv(k); dw = ConvSyncBNReLU(1) ->
     ConvSyncBNReLU(k, depthwise) -> Conv(1).  Zero padding (k-1)//2, every conv has a bias, branches of width 0
@@ -53,7 +63,7 @@ def _branches(x, sd, prefix, res, dw, ks, training, dw_affine, last_conv_key):
         if mid == 0:
             continue
         p = f'{prefix}.res_ops.{j}'
-        h = qa(F.relu(_bn(qa(_conv(x, sd, p + '.0.conv', k)), sd, p + '.0.norm', True, training)))
+        h = qa(act(_bn(qa(_conv(x, sd, p + '.0.conv', k)), sd, p + '.0.norm', True, training)))
         outs.append(_conv(h, sd, p + '.1' + last_conv_key, k))
         j += 1
     j = 0
@@ -61,8 +71,8 @@ def _branches(x, sd, prefix, res, dw, ks, training, dw_affine, last_conv_key):
         if mid == 0:
             continue
         p = f'{prefix}.dw_ops.{j}'
-        h = qa(F.relu(_bn(qa(_conv(x, sd, p + '.0.conv', 1)), sd, p + '.0.norm', True, training)))
-        h = qa(F.relu(_bn(qa(_conv(h, sd, p + '.1.conv', k, groups=mid)), sd, p + '.1.norm', dw_affine, training)))
+        h = qa(act(_bn(qa(_conv(x, sd, p + '.0.conv', 1)), sd, p + '.0.norm', True, training)))
+        h = qa(act(_bn(qa(_conv(h, sd, p + '.1.conv', k, groups=mid)), sd, p + '.1.norm', dw_affine, training)))
         outs.append(_conv(h, sd, p + '.2' + last_conv_key, 1))
         j += 1
     if not outs:
@@ -95,14 +105,17 @@ def spade_block(x, seg, sd, prefix, blk, ks, training):
         return F.conv2d(h, qw(sd[prefix + '.shortcut.1.conv.weight']))
     if not any(blk['res']) and not any(blk['dw']):
         return qa(shortcut(x))
-    tmp = qa(F.relu(spade_norm(x, seg, sd, prefix + '.spade', blk, ks, training)))
-    tmp = _branches(tmp, sd, prefix, blk['res'], blk['dw'], ks, training, False, '.conv')
+    tmp = qa(_active(spade_norm(x, seg, sd, prefix + '.spade', blk, ks, training)))
+    tmp = _branches(tmp, sd, prefix, blk['res'], blk['dw'], ks, training, False, '.conv', _active)
     return qa(tmp + shortcut(x))
 
 
 def spade_generator_forward(sd, arch, seg, training=False, capture=None):
-    """InceptionSPADEGenerator.forward (inception_spade_generator.py:63-124)."""
+    """InceptionSPADEGenerator.forward (inception_spade_generator.py:63-124).  arch['active_fn'] is the generator's
+    activation (get_active_fn, inception_modules.py:12-19): nn.ReLU on the distillation path (distill_options.py:123),
+    nn.LeakyReLU() -- default slope 0.01 -- when SPADEModel trains the teacher (models/spade_model.py:92)."""
     ks = arch['kernel_sizes']
+    _ACTIVE[0] = {'nn.ReLU': F.relu, 'nn.LeakyReLU': lambda t: F.leaky_relu(t, 0.01)}[arch.get('active_fn', 'nn.ReLU')]
     seg = qa(seg)
     x = F.interpolate(seg, size=(arch['sh'], arch['sw']))
     x = qa(F.conv2d(x, qw(sd['fc.weight']), sd['fc.bias'], padding=1))
