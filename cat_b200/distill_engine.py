@@ -29,7 +29,10 @@ class DistillStep:
         self.world_size = world_size
         self.aligned = bool(hp['aligned'])
         assert D_arch['input_nc'] == (6 if self.aligned else 3)
-        self.T = GenNet(teacher_arch, B, H, W, device, training=False, need_grad=False)
+        # teacher_arch None: no frozen teacher and no KA terms -- the pix2pix TEACHER-TRAINING step
+        # (cat_b200/train_engine.py, models/pix2pix_model.py:203-212) is this step without them
+        self.T = GenNet(teacher_arch, B, H, W, device, training=False, need_grad=False) if teacher_arch is not None else None
+        assert self.T is not None or (self.aligned and not hp.get('lambda_distill', 0.0))
         self.S = GenNet(student_arch, B, H, W, device, training=hp.get('student_training', True), need_grad=True)
         self.D = DisNet(D_arch, B, H, W, device)
         f32 = dict(dtype=torch.float32, device=device)
@@ -61,7 +64,8 @@ class DistillStep:
 
     # ---- state ---------------------------------------------------------------------------------
     def load(self, teacher_sd, student_sd, D_sd):
-        self.T.load_state_dict(teacher_sd)
+        if self.T is not None:
+            self.T.load_state_dict(teacher_sd)
         self.S.load_state_dict(student_sd)
         self.D.load_state_dict(D_sd)
 
@@ -82,7 +86,9 @@ class DistillStep:
         and the discriminator phase; _join_teacher() closes the branch at the end of the first segment."""
         ops.nchw_to_nhwc(self.real_A, self.xA)
         ops.nchw_to_nhwc(self.real_B, self.xB)
-        if self.overlap_teacher and self.dev != 'cpu':
+        if self.T is None:
+            pass
+        elif self.overlap_teacher and self.dev != 'cpu':
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.dev)
             self._side.wait_stream(torch.cuda.current_stream())
@@ -136,7 +142,7 @@ class DistillStep:
         ops.recon_loss(S.out, target, 3, hp.get('recon_loss_type', 'l1'), hp['lambda_recon'], self.losses[3:4],
                        self.dS, extra)
         act_grads = {}
-        if hp['lambda_distill'] > 0:
+        if hp.get('lambda_distill', 0.0) > 0:
             self.Gx.zero_()
             self.Gy.zero_()
             scale = -hp['lambda_distill'] * hp.get('ka_scale', 1.0)
@@ -188,6 +194,8 @@ class DistillStep:
         graph starts from exactly the loaded weights."""
         state = []
         for net in (self.S, self.D, self.T):
+            if net is None:
+                continue
             state += [t for t in (net.arena.p, net.arena.g, net.arena.m, net.arena.v, net.bufs.p) if t is not None]
         state += [self.step_G, self.step_D, self.losses, self.ka_vals]
         snap = [t.clone() for t in state]

@@ -239,12 +239,16 @@ def _stage1_order(res, dw):
 class GenNet:
     """InceptionGenerator compiled for a fixed (B, H, W)."""
 
-    def __init__(self, arch, B, H, W, device, training, need_grad, share=None):
+    def __init__(self, arch, B, H, W, device, training, need_grad, share=None, input_grad=False):
         """share: another GenNet of the same architecture whose parameter / buffer arenas are reused (e.g. an
-        eval-mode or different-resolution compilation of the same weights)."""
+        eval-mode or different-resolution compilation of the same weights, or a second application of the same
+        generator inside one CycleGAN step).
+        input_grad: backward() also produces the gradient w.r.t. the input image in self.d_in (CycleGAN's
+        rec_A = G_B(G_A(real_A)) back-propagates through the input of G_B, models/cycle_gan_model.py:221-226)."""
         assert H % 4 == 0 and W % 4 == 0, 'the generator down-samples twice'
         self.arch, self.B, self.H, self.W, self.dev = arch, B, H, W, device
         self.training, self.need_grad = training, need_grad
+        self.input_grad = input_grad and need_grad
         self.use_bias = arch['use_bias']
         # x-packed 7x7 stem / head (cat_b200/csrc/packx.cu): the seven horizontal taps become channels of a 7x1 conv
         self.packx = os.environ.get('CATB_NO_PACKX', '0') != '1' and 7 * arch['input_nc'] <= 24 and arch['output_nc'] <= 8
@@ -560,6 +564,13 @@ class GenNet:
             self.gb_d1 = _strided_dgrad(dict(N=B, H=H2, W=W2, ldx=cpad(c1), x_coff=0, OH=H, OW=W, ldy=cpad(c0), y_coff=0),
                                         P.conv_dgrad_units(ar.off('down_sampling.4.weight'), c1, c0, 3, 3, 1), c0, dev, 2)
             self.bwd_gemms += self.gb_d2 + self.gb_d1
+            if self.input_grad:
+                # gradient w.r.t. the reflection-padded input frame of the 7x7 stem (always from the 7x7 parameter tensor,
+                # also when the forward pass uses the x-packed image), folded by catb_reflect_fold
+                self.d_in_frame = Act.empty(B, H + 6, W + 6, cin, dev)
+                self.d_in = self._act(H, W, cin)
+                self.gb_stem = G(P.Geometry(B, H, W, cpad(c0), 0, H + 6, W + 6, cpad(cin), 0),
+                                 P.conv_dgrad_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 0), cin, bwd=True)
 
     def _ws(self, flat, H, W, C):
         return Act(flat[:self.B * H * W * C].view(self.B, H, W, C))
@@ -742,6 +753,10 @@ class GenNet:
             ops.scatter_add(self.aux.g, self.aux_idx, ar.g)     # d(stem.wx), d(head.wx) -> the 7x7 parameter gradients
         else:
             self.g_stem.wgrad(self.x_in.t, self.d_y0.t, ar.g)
+        if self.input_grad:
+            self.gb_stem.fprop(self.d_y0.t, self.d_in_frame.t)
+            ops.reflect_fold(self.d_in_frame, self.d_in, 3)
+            return self.d_in
 
 
 # ------------------------------------------------------------------------------------------------

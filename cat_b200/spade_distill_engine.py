@@ -31,7 +31,7 @@ class SpadeDistillStep:
         self.hp, self.B, self.H, self.W, self.dev = dict(hp), B, H, W, device
         self.world_size = world_size
         snc = student_arch['semantic_nc']
-        assert teacher_arch['semantic_nc'] == snc and D_arch['input_nc'] == snc + 3
+        assert (teacher_arch is None or teacher_arch['semantic_nc'] == snc) and D_arch['input_nc'] == snc + 3
         self.snc, self.n_label = snc, int(hp['n_label'])
         f32 = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
@@ -40,7 +40,10 @@ class SpadeDistillStep:
         self.image = torch.zeros(B, 3, H, W, **f32)
         self.seg = Act.empty(B, H, W, snc, device, zero=True)
         self.xB = Act.empty(B, H, W, 3, device, zero=True)
-        self.T = SpadeGenNet(teacher_arch, self.seg, device, training=False, need_grad=False)
+        # teacher_arch None: no frozen teacher and no KA terms -- SPADEModel's TEACHER-TRAINING step
+        # (cat_b200/train_engine.py, models/spade_model.py:207-215) is this step without them
+        self.T = SpadeGenNet(teacher_arch, self.seg, device, training=False, need_grad=False) if teacher_arch is not None else None
+        assert self.T is not None or not hp.get('lambda_distill', 0.0)
         self.S = SpadeGenNet(student_arch, self.seg, device, training=True, need_grad=True)
         self.D = MultiScaleDis(D_arch, 2 * B, H, W, device)
         self.V = VggNet(B, H, W, device)
@@ -66,7 +69,8 @@ class SpadeDistillStep:
 
     # ---- state ---------------------------------------------------------------------------------
     def load(self, teacher_sd, student_sd, D_sd, vgg_sd):
-        self.T.load_state_dict(teacher_sd)
+        if self.T is not None:
+            self.T.load_state_dict(teacher_sd)
         self.S.load_state_dict(student_sd)
         self.D.load_state_dict(D_sd)
         self.V.load_state_dict(vgg_sd)
@@ -112,11 +116,12 @@ class SpadeDistillStep:
         if main is not None:
             if self._side is None:
                 self._side = (torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev))
-            for st, fn in ((self._side[0], T.forward), (self._side[1], lambda: V.forward(self.xB, save_ref=True))):
+            for st, fn in ((self._side[0], T.forward if T is not None else (lambda: None)),
+                           (self._side[1], lambda: V.forward(self.xB, save_ref=True))):
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
                     fn()
-        else:
+        elif T is not None:
             T.forward()
         S.forward()
         nets = D.forward(self._d_input(S.out))
@@ -148,7 +153,7 @@ class SpadeDistillStep:
         act_grads = {}
         if main is not None:
             main.wait_stream(self._side[0])
-        if hp['lambda_distill'] > 0:
+        if hp.get('lambda_distill', 0.0) > 0:
             self.Gx.zero_()
             self.Gy.zero_()
             scale = -hp['lambda_distill'] * hp.get('ka_scale', 1.0)
@@ -212,6 +217,8 @@ class SpadeDistillStep:
     def _mutable_state(self):
         state = []
         for net in (self.S, self.D, self.T):
+            if net is None:
+                continue
             state += [t for t in (net.arena.p, net.arena.g, net.arena.m, net.arena.v, net.bufs.p) if t is not None]
         return state + [self.step_G, self.step_D, self.losses, self.ka_vals]
 

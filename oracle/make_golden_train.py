@@ -79,7 +79,7 @@ def make_pix2pix(name, norm, gan_mode, recon, B, H, W):
     return fix
 
 
-def make_cyclegan(name, norm, gan_mode, B, H, W, pool_size, n_steps):
+def make_cyclegan(name, norm, gan_mode, B, H, W, pool_size, n_steps, data_seed=233):
     model, opt = build_reference_cyclegan(norm=norm, batch_size=B, gan_mode=gan_mode, pool_size=pool_size)
     nets = (model.netG_A, model.netG_B, model.netD_A, model.netD_B)
     rescale(nets, 7, 5.0)
@@ -91,7 +91,7 @@ def make_cyclegan(name, norm, gan_mode, B, H, W, pool_size, n_steps):
            'G_A_sd0': snap(model.netG_A.state_dict()), 'G_B_sd0': snap(model.netG_B.state_dict()),
            'D_A_sd0': snap(model.netD_A.state_dict()), 'D_B_sd0': snap(model.netD_B.state_dict()), 'steps': []}
     random.seed(fix['python_random_seed'])       # ImagePool draws from Python's global generator (utils/image_pool.py:41-44)
-    gen = torch.Generator().manual_seed(233)
+    gen = torch.Generator().manual_seed(data_seed)
     for it in range(n_steps):
         A = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
         Bt = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
@@ -179,7 +179,9 @@ CASES = {
     'train_pix2pix_in_lsgan_l2': lambda n: make_pix2pix(n, 'instance', 'lsgan', 'l2', 2, 32, 48),
     # scripts/cycle_gan/horse2zebra/train_inception_teacher.sh: InstanceNorm, lsgan, identity 0.5; a pool of 3 images
     # so that the history branch (random replacement) is taken within the recorded steps
-    'train_cyclegan_in_lsgan': lambda n: make_cyclegan(n, 'instance', 'lsgan', 2, 32, 32, 3, 5),
+    # (data seed 235: with 233 one pre-activation of D_A's 3x3 layer sits 5e-6 from the LeakyReLU kink at step 0, which
+    # makes d loss / d fake_B flip by 4.5 % under 1e-6 input differences -- useless as a parity vector)
+    'train_cyclegan_in_lsgan': lambda n: make_cyclegan(n, 'instance', 'lsgan', 2, 32, 32, 3, 5, data_seed=235),
     # BatchNorm generators: running statistics move three times per generator per step, in the reference's call order
     'train_cyclegan_bn_lsgan': lambda n: make_cyclegan(n, 'batch', 'lsgan', 2, 32, 32, 0, 2),
     # scripts/gaugan/cityscapes/train_inception_teacher.sh
