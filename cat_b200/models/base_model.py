@@ -1,0 +1,163 @@
+"""Shared protocol of the teacher-training model mirrors (models/base_model.py:12-232 in the reference): what
+``trainer.py:79-175`` calls on a model -- ``setup``, ``set_input``, ``optimize_parameters``, ``get_current_losses``,
+``update_learning_rate``, ``save_networks`` / ``load_networks``, ``print_networks``, ``eval`` / ``train`` / ``test`` -- on
+top of an engine step (cat_b200/train_engine.py).  The networks are the module-tree mirrors of
+cat_b200.models.networks whose parameters alias the engine arenas, so checkpoints written here load in the reference
+(and in the distillers as ``restore_teacher_G_path`` / ``restore_D_path``) and vice versa.
+Out of scope: FID / mIoU evaluation (``evaluate_model`` raises), data loading, logging.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+
+from .. import ops
+
+
+class ArenaOptimizer:
+    """Stand-in for one torch.optim.Adam over one or several engine arenas (CycleGAN's optimizer_G owns both generators,
+    cycle_gan_model.py:165-174): exposes what the reference touches (param_groups[0]['lr'], state_dict /
+    load_state_dict for checkpoints)."""
+
+    def __init__(self, lr, betas):
+        self.param_groups = [{'lr': lr, 'betas': betas}]
+        self.nets, self.counters = [], []
+
+    def bind(self, nets, counters):
+        self.nets, self.counters = list(nets), list(counters)
+
+    def state_dict(self):
+        out = {'param_groups': self.param_groups, 'arenas': []}
+        for net, c in zip(self.nets, self.counters):
+            a = net.arena
+            out['arenas'].append({'exp_avg': a.m.detach().cpu(), 'exp_avg_sq': a.v.detach().cpu(), 'step': int(c.item()),
+                                  'layout': {k: (v[0], v[1]) for k, v in a.entries.items()}})
+        return out
+
+    def load_state_dict(self, sd):
+        for net, c, s in zip(self.nets, self.counters, sd.get('arenas', [])):
+            net.arena.m.copy_(s['exp_avg'])
+            net.arena.v.copy_(s['exp_avg_sq'])
+            c.fill_(int(s['step']))
+
+
+class BaseModel:
+    """Subclasses define ``model_names`` (net<name> attributes), ``loss_names``, ``_make_engine(B, H, W)`` and
+    ``_set_engine_input(input)``."""
+
+    def __init__(self, opt):
+        assert opt.isTrain
+        self.opt = opt
+        self.isTrain = True
+        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0])) or [0]
+        # raises without an sm_100 device and libcatb200.so: there is no CPU path.  (Only the kernel emulation of the
+        # test suite patches this check out; it then runs the host logic on CPU tensors.)
+        ops.require_cuda()
+        self.device = torch.device('cuda:%d' % self.gpu_ids[0]) if torch.cuda.is_available() else torch.device('cpu')
+        self._ids = self.gpu_ids[:1] if self.device.type == 'cuda' else []
+        self.save_dir = os.path.join(getattr(opt, 'log_dir', '.'), 'checkpoints')
+        self.model_names, self.loss_names, self.visual_names, self.image_paths = [], [], [], []
+        self.optimizers = []
+        self.engine = None
+        self.is_best = False
+        self.metric = 0
+        self._epoch = 0
+
+    @staticmethod
+    def modify_commandline_options(parser, is_train):
+        return parser
+
+    def _net(self, name):
+        return getattr(self, 'net' + name)
+
+    # ---- protocol -------------------------------------------------------------------------------
+    def setup(self, opt, verbose=True):
+        self.load_networks(verbose)
+        if verbose:
+            self.print_networks()
+
+    def _ensure_engine(self, B, H, W):
+        if self.engine is None or (self.engine.B, self.engine.H, self.engine.W) != (B, H, W):
+            self.engine = self._make_engine(B, H, W)
+
+    def optimize_parameters(self, steps):
+        self.engine.step()
+
+    def get_current_losses(self):
+        """One device synchronisation, like float(loss) in base_model.py:187; same keys and order."""
+        L = self.engine.get_losses()
+        out = OrderedDict()
+        for name in self.loss_names:
+            if name not in L:
+                continue
+            key = ('Specific_loss/' if any(ch.isdigit() for ch in name) else ('D_loss/' if name.startswith('D_') else 'G_loss/')) + name
+            out[key] = L[name]
+            setattr(self, 'loss_' + name, L[name])
+        return out
+
+    def _lr_scale(self):
+        """'linear' policy of models/networks.py:80-87, stepped once per epoch (trainer.py:175)."""
+        o = self.opt
+        if getattr(o, 'lr_policy', 'linear') != 'linear':
+            raise NotImplementedError('lr_policy [%s]: the CAT scripts use the linear policy' % o.lr_policy)
+        self._epoch += 1
+        return 1.0 - max(0, self._epoch + 1 - o.nepochs) / float(o.nepochs_decay + 1)
+
+    def update_learning_rate(self, logger=None):
+        scale = self._lr_scale()
+        lrs = [base * scale for base in self._base_lrs()]
+        for opt_, lr in zip(self.optimizers, lrs):
+            opt_.param_groups[0]['lr'] = lr
+        if self.engine is not None:
+            self.engine.set_lr(*lrs)
+        msg = 'learning rate = %.7f' % lrs[0]
+        logger.print_info(msg + '\n') if logger is not None else print(msg)
+
+    def _base_lrs(self):
+        return [self.opt.lr, self.opt.lr]
+
+    def eval(self):
+        for name in self.model_names:
+            self._net(name).eval()
+
+    def train(self):
+        for name in self.model_names:
+            self._net(name).train()
+
+    def test(self):
+        with torch.no_grad():
+            self.forward()
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def get_current_visuals(self):
+        return OrderedDict((n, getattr(self, n)) for n in self.visual_names if hasattr(self, n))
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        pass    # the engine step freezes / unfreezes the discriminators by construction
+
+    def evaluate_model(self, step):
+        raise NotImplementedError('FID / mIoU evaluation (metric/) is outside the training hot path')
+
+    def print_networks(self):
+        for name in self.model_names:
+            n = sum(p.numel() for p in self._net(name).parameters())
+            print('[Network %s] Total number of parameters : %.3f M' % (name, n / 1e6))
+
+    # ---- checkpoints (file names and key layout of base_model.py:196-219, trainer.py:146-160) -------
+    def load_networks(self, verbose=True, teacher_only=False, restore_pretrain=True):
+        for name in self.model_names:
+            path = getattr(self.opt, 'restore_%s_path' % name, None)
+            if path is not None:
+                self._net(name).load_state_dict(torch.load(path, map_location='cpu'))
+                if verbose:
+                    print('Load network at %s' % path)
+
+    def save_networks(self, epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
+        for name in self.model_names:
+            sd = OrderedDict((k, v.detach().cpu().clone()) for k, v in self._net(name).state_dict().items())
+            torch.save(sd, os.path.join(self.save_dir, '%s_net_%s.pth' % (epoch, name)))
+        for i, optimizer in enumerate(self.optimizers):
+            torch.save(optimizer.state_dict(), os.path.join(self.save_dir, '%s_optim-%d.pth' % (epoch, i)))

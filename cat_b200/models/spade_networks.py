@@ -176,8 +176,10 @@ class InceptionSPADEGenerator(BaseNetwork, _EngineBacked):
         super().__init__()
         self.opt = opt
         nf = opt.ngf
-        if getattr(opt, 'active_fn', 'nn.ReLU') != 'nn.ReLU':
-            raise NotImplementedError('cat_b200 SPADE generators use nn.ReLU (distill_options default)')
+        # nn.ReLU on the distillation path (distill_options default), nn.LeakyReLU() when SPADEModel trains the
+        # teacher (models/spade_model.py:92)
+        if getattr(opt, 'active_fn', 'nn.ReLU') not in ('nn.ReLU', 'nn.LeakyReLU'):
+            raise NotImplementedError('cat_b200 SPADE generators implement nn.ReLU and nn.LeakyReLU (the CAT scripts)')
         self.fc_norm = SynchronizedBatchNorm2d(16 * nf, affine=True)
         self.sw, self.sh = self.compute_latent_vector_size(opt)
         self.fc = nn.Conv2d(opt.semantic_nc, 16 * nf, 3, padding=1)
@@ -215,10 +217,13 @@ class InceptionSPADEGenerator(BaseNetwork, _EngineBacked):
                          'dw': [int(c) for c in b.dw_channels], 'spade_res': [int(c) for c in b.spade.res_channels],
                          'spade_dw': [int(c) for c in b.spade.dw_channels], 'learned_shortcut': b.shortcut is not None}
         ks = self.opt.kernel_sizes
-        return {'semantic_nc': int(self.opt.semantic_nc), 'fc_out': int(self.fc.out_channels), 'sh': int(self.sh), 'sw': int(self.sw),
+        arch = {'semantic_nc': int(self.opt.semantic_nc), 'fc_out': int(self.fc.out_channels), 'sh': int(self.sh), 'sw': int(self.sw),
                 'num_upsampling_layers': self.opt.num_upsampling_layers, 'kernel_sizes': [int(k) for k in ([ks] if isinstance(ks, int) else ks)],
                 'final_nc': int(self.conv_img.in_channels), 'block_names': self.block_names(), 'blocks': blocks,
                 'eps': 1e-5, 'momentum': 0.1}
+        if getattr(self.opt, 'active_fn', 'nn.ReLU') != 'nn.ReLU':      # the engines default to nn.ReLU
+            arch['active_fn'] = self.opt.active_fn
+        return arch
 
     @classmethod
     def from_arch(cls, arch, opt):

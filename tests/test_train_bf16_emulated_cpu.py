@@ -1,0 +1,41 @@
+"""The bodies of the GPU parity tests of the teacher-training steps (tests/test_train_gpu.py) re-run on CPU with the
+kernel wrappers swapped for their torch restatements in bf16-storage mode (oracle/kernel_emu.py): the stated GPU
+tolerances must hold for the same launch sequences when only the storage precision of the device path is modelled."""
+import importlib
+
+import pytest
+
+G = importlib.import_module('test_train_gpu')
+
+
+@pytest.fixture
+def on_cpu():
+    from oracle.kernel_emu import emulated_kernels
+    G.DEV[0] = 'cpu'
+    try:
+        with emulated_kernels():
+            yield
+    finally:
+        G.DEV[0] = 'cuda:0'
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('name', ['train_pix2pix_in_lsgan_l2', 'train_pix2pix_bn_hinge'])
+def test_pix2pix_bodies(golden_dir, on_cpu, name):
+    G.test_pix2pix_train_step(golden_dir, name, False)
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize('name', ['train_cyclegan_in_lsgan'])
+def test_cyclegan_bodies(golden_dir, on_cpu, name):
+    G.test_cyclegan_train_steps(golden_dir, name, False)
+
+
+@pytest.mark.timeout(1200)
+def test_spade_body(golden_dir, on_cpu):
+    G.test_spade_train_step(golden_dir, False)
+
+
+@pytest.mark.timeout(300)
+def test_leaky001_body(on_cpu):
+    G.test_leaky001_activation_kernels()

@@ -84,13 +84,14 @@ def test_cyclegan_train_steps_exact(golden_dir, name):
               D_B_sd=clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
               pool_A=TO.ImagePool(hp['pool_size']), pool_B=TO.ImagePool(hp['pool_size']))
     random.seed(fix['python_random_seed'])
-    refs = [TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp) for s in fix['steps']]
+    steps = fix['steps'][:4]      # pool of 3, batch 2: filled during steps 0-1, history decisions from step 1 on
+    refs = [TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp) for s in steps]
     with emulated_kernels(exact=True):
         from cat_b200.train_engine import CycleGANTrainStep
         eng = CycleGANTrainStep(fix['G_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
         eng.load(fix['G_A_sd0'], fix['G_B_sd0'], fix['D_A_sd0'], fix['D_B_sd0'])
         random.seed(fix['python_random_seed'])      # the pools draw from Python's global generator, like the reference
-        for it, (s, ref) in enumerate(zip(fix['steps'], refs)):
+        for it, (s, ref) in enumerate(zip(steps, refs)):
             eng.set_input(s['real_A'], s['real_B'])
             eng.step()
             L = eng.get_losses()

@@ -1,0 +1,248 @@
+"""Teacher-training steps (cat_b200/train_engine.py) through libcatb200.so on the GPU against the
+CPU oracle (oracle/train_oracle.py, pinned to the real reference models by tests/test_train_oracle_golden.py), on the
+committed fixtures.  Same two comparisons and the same stated tolerances as tests/test_distill_gpu.py:
+
+(1) fp32 oracle (the reference algorithm): images rel-L2 <= 3e-2 (0.3 after two chained generators: with 5x-scaled
+    weights the second generator amplifies the first one's bf16 rounding; 0.14 in the bf16 kernel emulation on CPU), losses
+    |delta| <= 5e-2 * max(1, |loss|) on the first step (8e-2 later; these fixtures scale the N(0, 0.02) weights by 5, so
+    the lsgan losses sit at 5-10 and the bf16-emulating oracle itself is 2.3 % away from the fp32 one on D_fake),
+    parameter gradients rel-L2 <= 0.5;
+(2) the same oracle with bf16 storage emulated where cat_b200 keeps bf16 in HBM: same bounds (the loose gradient bound
+    only excludes real defects, which are O(1); the conditioning argument is in tests/test_distill_gpu.py).
+The host logic of these steps is verified to rounding in exact emulation on CPU (tests/test_train_engine_emulated_cpu.py),
+so what this file establishes is that the same launch sequences run on the device kernels."""
+import os
+import random
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+DEV = ['cuda:0']      # tests/test_train_bf16_emulated_cpu.py re-runs these bodies on 'cpu' under the bf16 kernel emulation
+
+
+def _sync():
+    if DEV[0] != 'cpu':
+        torch.cuda.synchronize()
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+
+
+def _grad_err(net, grads):
+    mine, theirs = [], []
+    for k, g in grads.items():
+        if net.arena.has(k):
+            mine.append(net.arena.view(k, 'g').flatten().cpu())
+            theirs.append(g.flatten())
+    return rel_l2(torch.cat(mine), torch.cat(theirs))
+
+
+def _check_losses(L, refs, it, what, tols=(5e-2, 8e-2)):
+    tol = tols[min(it, len(tols) - 1)]
+    for k, v in L.items():
+        assert v == v, (what, it, k)
+        for ref in refs:
+            r = float(ref['loss_' + k])
+            assert abs(v - r) <= tol * max(1.0, abs(r)), (what, it, k, v, r)
+
+
+@pytest.mark.parametrize('name', ['train_pix2pix_in_lsgan_l2', 'train_pix2pix_bn_hinge'])
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_pix2pix_train_step(golden_dir, name, use_graph):
+    from cat_b200 import ops
+    from cat_b200.train_engine import Pix2PixTrainStep
+    from oracle import cat_oracle as O
+    from oracle import train_oracle as TO
+    fix = _load(golden_dir, name)
+    B, _, H, W = fix['steps'][0]['real_A'].shape
+    eng = Pix2PixTrainStep(fix['G_arch'], fix['D_arch'], fix['hp'], B, H, W, device=DEV[0], use_cuda_graph=use_graph)
+    eng.load(fix['G_sd0'], fix['D_sd0'])
+    mk = lambda: dict(G_sd=O.clone_sd(fix['G_sd0']), D_sd=O.clone_sd(fix['D_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'],
+                      adam_G={}, adam_D={})
+    st32, stq = mk(), mk()
+    for it, s in enumerate(fix['steps']):
+        ref32 = TO.pix2pix_train_step(st32, s['real_A'], s['real_B'], fix['hp'])
+        with O.emulate_bf16():
+            refq = TO.pix2pix_train_step(stq, s['real_A'], s['real_B'], fix['hp'])
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        _sync()
+        _check_losses(eng.get_losses(), (ref32, refq), it, name)
+        if it == 0:
+            fake = ops.nhwc_to_nchw(eng.G.out, 3).cpu()
+            for ref in (ref32, refq):
+                assert rel_l2(fake, ref['fake_B']) <= 3e-2
+                assert _grad_err(eng.G, ref['G_grads']) <= 0.5
+                assert _grad_err(eng.D, ref['D_grads']) <= 0.5
+    lr = fix['hp']['lr']
+    mine = eng.G.state_dict()
+    worst = max(float((mine[k].double() - v.double()).abs().max()) for k, v in stq['G_sd'].items()
+                if v.is_floating_point() and k in mine and k.endswith('.weight') and v.dim() == 4)
+    assert worst <= 2.1 * lr * len(fix['steps'])
+
+
+@pytest.mark.parametrize('name,use_graph', [('train_cyclegan_in_lsgan', False), ('train_cyclegan_in_lsgan', True),
+                                            ('train_cyclegan_bn_lsgan', True)])
+def test_cyclegan_train_steps(golden_dir, name, use_graph):
+    """Three steps on the pool-of-3 fixture: from the second step on the discriminators read images chosen by the pools'
+    history decisions.  The bf16 trajectories of this GAN separate quickly (the fp32 ones already do: 1e-6 -> 7e-5 ->
+    6e-4 over steps 2-4, tests/test_train_oracle_golden.py), so later steps carry wider loss bands; the images handed
+    to the discriminators pin the pools (a wrong image is O(1) away; the pool logic itself is verified exactly on CPU,
+    tests/test_train_engine_emulated_cpu.py)."""
+    from cat_b200 import ops
+    from cat_b200.train_engine import CycleGANTrainStep
+    from oracle import cat_oracle as O
+    from oracle import train_oracle as TO
+    fix = _load(golden_dir, name)
+    hp = fix['hp']
+    B, _, H, W = fix['steps'][0]['real_A'].shape
+    eng = CycleGANTrainStep(fix['G_arch'], fix['D_arch'], hp, B, H, W, device=DEV[0], use_cuda_graph=use_graph)
+    eng.load(fix['G_A_sd0'], fix['G_B_sd0'], fix['D_A_sd0'], fix['D_B_sd0'])
+
+    def oracle_run(emulate):
+        st = dict(G_A_sd=O.clone_sd(fix['G_A_sd0']), G_B_sd=O.clone_sd(fix['G_B_sd0']), D_A_sd=O.clone_sd(fix['D_A_sd0']),
+                  D_B_sd=O.clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
+                  pool_A=TO.ImagePool(hp['pool_size']), pool_B=TO.ImagePool(hp['pool_size']))
+        random.seed(fix['python_random_seed'])
+        if emulate:
+            with O.emulate_bf16():
+                return [TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp) for s in steps]
+        return [TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp) for s in steps]
+    steps = fix['steps'][:3]
+    refs32, refsq = oracle_run(False), oracle_run(True)
+    random.seed(fix['python_random_seed'])        # the device pools draw from Python's global generator, like the reference
+    for it, s in enumerate(steps):
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        _sync()
+        _check_losses(eng.get_losses(), (refs32[it], refsq[it]), it, name, tols=(5e-2, 8e-2, 0.15))
+        assert rel_l2(ops.nhwc_to_nchw(eng.d_in_fake_B, 3).cpu(), refsq[it]['pooled_B']) <= (3e-2 if it == 0 else 0.2), it
+        assert rel_l2(ops.nhwc_to_nchw(eng.d_in_fake_A, 3).cpu(), refsq[it]['pooled_A']) <= (3e-2 if it == 0 else 0.2), it
+        if it:
+            continue
+        for ref in (refs32[0], refsq[0]):
+            for mine, theirs, tol in ((eng.GA_real.out, 'fake_B', 3e-2), (eng.GB_real.out, 'fake_A', 3e-2),
+                                      (eng.GB_cyc.out, 'rec_A', 0.3), (eng.GA_cyc.out, 'rec_B', 0.3)):
+                assert rel_l2(ops.nhwc_to_nchw(mine, 3).cpu(), ref[theirs]) <= tol, theirs
+            # gradient w.r.t. the first generator's output = GAN term through the frozen D + cycle term through the
+            # INPUT of the second generator (stem input-gradient GEMM + reflect fold)
+            assert rel_l2(ops.nhwc_to_nchw(eng.d_fake_B, 3).cpu(), ref['fake_B_grad']) <= 0.5
+            assert rel_l2(ops.nhwc_to_nchw(eng.d_fake_A, 3).cpu(), ref['fake_A_grad']) <= 0.5
+            for tag, net in (('G_A', eng.G_A), ('G_B', eng.G_B), ('D_A', eng.D_A), ('D_B', eng.D_B)):
+                assert _grad_err(net, ref[tag + '_grads']) <= 0.5, tag
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_spade_train_step(golden_dir, use_graph):
+    from cat_b200 import ops
+    from cat_b200.train_engine import SpadeTrainStep
+    from oracle import cat_oracle as O
+    from oracle import spade_oracle as SO
+    from oracle import train_oracle as TO
+    fix = _load(golden_dir, 'train_spade_more')
+    assert fix['G_arch']['active_fn'] == 'nn.LeakyReLU'        # CATB_ACT_LEAKY001 on the device
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    hp = fix['hp']
+    B, _, H, W = fix['steps'][0]['image'].shape
+    eng = SpadeTrainStep(fix['G_arch'], fix['D_arch'], hp, B, H, W, device=DEV[0], use_cuda_graph=use_graph)
+    eng.load(fix['G_sd0'], fix['D_sd0'], vgg)
+    mk = lambda: dict(G_sd=O.clone_sd(fix['G_sd0']), D_sd=O.clone_sd(fix['D_sd0']), vgg_sd=vgg, G_arch=fix['G_arch'],
+                      D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    st32, stq = mk(), mk()
+    for it, s in enumerate(fix['steps']):
+        seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+        ref32 = TO.spade_train_step(st32, seg, s['image'], hp)
+        with O.emulate_bf16():
+            refq = TO.spade_train_step(stq, seg, s['image'], hp)
+        eng.set_input(s['label'], s['instance'], s['image'])
+        eng.step()
+        _sync()
+        assert torch.equal(ops.nhwc_to_nchw(eng.seg, eng.snc).cpu(), seg)
+        L = eng.get_losses()
+        tol = 6e-2 if it else 3e-2
+        for k, v in L.items():
+            for ref in (ref32, refq):
+                r = float(ref['loss_' + k])
+                assert abs(v - r) <= tol * max(1.0, abs(r)), (it, k, v, r)
+        if it == 0:
+            for ref in (ref32, refq):
+                for net, key in ((eng.G, 'G_grads'), (eng.D, 'D_grads')):
+                    ks = {k: g for k, g in ref[key].items() if float(ref32[key][k].abs().max()) > 1e-6}
+                    assert _grad_err(net, ks) <= 0.5, key
+
+
+def test_leaky001_activation_kernels():
+    """CATB_ACT_LEAKY001 (nn.LeakyReLU() at its default slope, the generator activation of SPADE teacher training) through
+    the three kernel families that take an activation code: GEMM epilogue, norm apply / backward, act_fwd / act_bwd."""
+    import torch.nn.functional as F
+    from cat_b200 import ops
+    from cat_b200.ops import ACT, Act
+    dev = DEV[0]
+    torch.manual_seed(0)
+    B, H, W, C = 2, 16, 24, 16
+    x = torch.randn(B, C, H, W)
+    xa, ya = Act.empty(B, H, W, C, dev, zero=True), Act.empty(B, H, W, C, dev, zero=True)
+    ops.nchw_to_nhwc(x.to(dev), xa)
+    ops.act_fwd(xa, ya, ACT['leaky001'])
+    xq = ops.nhwc_to_nchw(xa, C).cpu()
+    y = ops.nhwc_to_nchw(ya, C).cpu()
+    assert rel_l2(y, F.leaky_relu(xq, 0.01)) <= 1e-2
+    d = torch.randn(B, C, H, W)
+    da, dz = Act.empty(B, H, W, C, dev, zero=True), Act.empty(B, H, W, C, dev, zero=True)
+    ops.nchw_to_nhwc(d.to(dev), da)
+    ops.act_bwd(da, ya, dz, ACT['leaky001'])
+    dq = ops.nhwc_to_nchw(da, C).cpu()
+    want = dq * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.01))
+    assert rel_l2(ops.nhwc_to_nchw(dz, C).cpu(), want) <= 1e-2
+
+
+def test_pix2pix_model_trainer_loop(golden_dir, tmp_path):
+    """create_model -> setup -> set_input -> optimize_parameters -> get_current_losses -> save_networks on the device."""
+    import argparse
+    from cat_b200.models import create_model
+    from oracle import cat_oracle as O
+    from oracle import train_oracle as TO
+    fix = _load(golden_dir, 'train_pix2pix_in_lsgan_l2')
+    hp, Ga, Da = fix['hp'], fix['G_arch'], fix['D_arch']
+    opt = argparse.Namespace(
+        isTrain=True, gpu_ids=[0], log_dir=str(tmp_path), model='pix2pix', input_nc=3, output_nc=3, netG='inception_9blocks',
+        dropout_rate=0, norm=Ga['norm'], norm_affine=Ga['affine'], norm_affine_D=Da['affine'],
+        norm_track_running_stats=Ga['track_running_stats'], norm_momentum=0.1, norm_epsilon=1e-5, channels=None,
+        channels_reduction_factor=6, kernel_sizes=[1, 3, 5], active_fn='nn.ReLU', active_fn_D='nn.LeakyReLU', init_type='normal',
+        init_gain=0.02, netD='n_layers', ngf=Ga['widths'][0], ndf=Da['ndf'], n_layers_D=3, direction='AtoB', nepochs=5,
+        nepochs_decay=15, lr_policy='linear', cuda_graph=True, dataset_mode='aligned', gan_mode=hp['gan_mode'],
+        recon_loss_type=hp['recon_loss_type'], lambda_recon=hp['lambda_recon'], lambda_gan=hp['lambda_gan'], lr=hp['lr'],
+        beta1=hp['beta1'], restore_G_path=None, restore_D_path=None)
+    model = create_model(opt, verbose=False)
+    model.setup(opt, verbose=False)
+    model.netG.load_state_dict(fix['G_sd0'])
+    model.netD.load_state_dict(fix['D_sd0'])
+    st = dict(G_sd=O.clone_sd(fix['G_sd0']), D_sd=O.clone_sd(fix['D_sd0']), G_arch=Ga, D_arch=Da, adam_G={}, adam_D={})
+    for it, s in enumerate(fix['steps']):
+        ref = TO.pix2pix_train_step(st, s['real_A'], s['real_B'], hp)
+        B = s['real_A'].shape[0]
+        model.set_input({'A': s['real_A'], 'B': s['real_B'], 'A_paths': ['x'] * B, 'B_paths': ['x'] * B})
+        model.optimize_parameters(it)
+        L = model.get_current_losses()
+        assert list(L.keys()) == ['G_loss/G_gan', 'G_loss/G_recon', 'D_loss/D_real', 'D_loss/D_fake']
+        for key, v in L.items():
+            r = float(ref['loss_' + key.split('/')[-1]])
+            assert abs(v - r) <= 5e-2 * max(1.0, abs(r)), (it, key, v, r)
+    sd = model.netG.state_dict()
+    eng_sd = model.engine.G.state_dict()
+    for k, v in sd.items():
+        if v.is_floating_point():
+            assert torch.equal(v.detach().cpu().reshape(-1), eng_sd[k].reshape(-1)), k
+    model.test()
+    assert model.fake_B.shape == s['real_A'].shape and torch.isfinite(model.fake_B).all()
+    model.save_networks('latest')
+    g = torch.load(os.path.join(str(tmp_path), 'checkpoints', 'latest_net_G.pth'), weights_only=False)
+    assert list(g.keys()) == list(fix['G_sd0'].keys())
