@@ -114,3 +114,62 @@ def test_engine_two_ranks_spade(golden_dir, tmp_path):
         avg = sum(s[k] for s in shard) / WORLD
         err = float((ranks[0]['S_g'][k] - avg).abs().max())
         assert err <= 2e-3 * float(avg.abs().max()) + 2e-5 * scale, (k, err, float(avg.abs().max()))
+
+
+def _worker_cyclegan(rank, port, path, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=WORLD)
+    torch.set_num_threads(2)
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import parallel
+    fix = torch.load(path, weights_only=False)
+    s = fix['steps'][0]
+    _, _, H, W = s['real_A'].shape
+    with emulated_kernels(exact=True):
+        from cat_b200.train_engine import CycleGANTrainStep
+        eng = CycleGANTrainStep(fix['G_arch'], fix['D_arch'], fix['hp'], 1, H, W, device='cpu', world_size=WORLD)
+        eng.load(fix['G_A_sd0'], fix['G_B_sd0'], fix['D_A_sd0'], fix['D_B_sd0'])
+        eng.set_input(s['real_A'][rank:rank + 1], s['real_B'][rank:rank + 1])
+        eng.step()
+        scale = parallel.grad_scale(WORLD)
+        out = {}
+        for tag, net in (('G_A', eng.G_A), ('G_B', eng.G_B), ('D_A', eng.D_A), ('D_B', eng.D_B)):
+            out[tag + '_g'] = {k: net.arena.view(k, 'g').clone() * scale for k in net.arena.entries}
+            out[tag + '_p'] = net.arena.p.clone()
+    torch.save(out, os.path.join(out_dir, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_engine_two_ranks_cyclegan_training(golden_dir, tmp_path):
+    """Teacher training under data parallelism: CycleGANTrainStep with one image per rank.  With
+    InstanceNorm and per-sample-mean losses the reference's nn.DataParallel step on the global batch of two
+    (models/networks.py:160-161: replicas' outputs are gathered, the losses are means over the gathered batch) has exactly
+    the averaged per-shard gradients, so the all-reduced arenas must equal the single-process oracle step on both images;
+    four all-reduces per step (two generators, two discriminators), bit-identical weights on both ranks afterwards."""
+    import random
+    from oracle import train_oracle as TO
+    from oracle.cat_oracle import clone_sd
+    path = os.path.join(golden_dir, 'train_cyclegan_in_lsgan.pt')
+    port = 37500 + os.getpid() % 2000
+    mp.spawn(_worker_cyclegan, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    ranks = [torch.load(os.path.join(tmp_path, f'rank{r}.pt'), weights_only=False) for r in range(WORLD)]
+    fix = torch.load(path, weights_only=False)
+    hp, s = fix['hp'], fix['steps'][0]
+    st = dict(G_A_sd=clone_sd(fix['G_A_sd0']), G_B_sd=clone_sd(fix['G_B_sd0']), D_A_sd=clone_sd(fix['D_A_sd0']),
+              D_B_sd=clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
+              pool_A=TO.ImagePool(hp['pool_size']), pool_B=TO.ImagePool(hp['pool_size']))
+    random.seed(0)
+    ref = TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp)
+    for tag in ('G_A', 'G_B', 'D_A', 'D_B'):
+        assert torch.equal(ranks[0][tag + '_p'], ranks[1][tag + '_p']), tag
+        grads = ref[tag + '_grads']
+        scale = max(float(g.abs().max()) for g in grads.values())
+        n = 0
+        for k, g in grads.items():
+            if k not in ranks[0][tag + '_g']:
+                continue
+            n += 1
+            err = float((ranks[0][tag + '_g'][k] - g).abs().max())
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
+        assert n > 5, tag
