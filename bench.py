@@ -40,7 +40,7 @@ def parse():
     ap.add_argument('--profile-gemms', action='store_true', help='print the per-GEMM timing table to stderr')
     args = ap.parse_args()
     spade = is_spade(args.workload)
-    args.batch = args.batch or (4 if spade else 16)
+    args.batch = args.batch or (4 if spade else (8 if args.workload.startswith('cyclegan') else 16))
     args.height = args.height or (512 if spade else 256)
     args.width = args.width or (512 if spade else 256)
     args.cpu_batch = args.cpu_batch or (2 if spade else 4)
@@ -49,6 +49,38 @@ def parse():
 
 def is_spade(workload):
     return workload.startswith('gaugan')
+
+
+# Teacher-training workloads: the unpruned generator of the same published configuration trained by
+# Pix2PixModel / CycleGANModel / SPADEModel.optimize_parameters.  Not the headline metric -- the default workload stays
+# the distillation step of BASELINE.json configs[1].
+TEACHER = {'pix2pix_teacher': 'pix2pix_5p6B', 'cyclegan_teacher': 'cyclegan_2p6B', 'gaugan_teacher': 'gaugan_5p6B'}
+
+
+def arch_name(workload):
+    return TEACHER.get(workload, workload)
+
+
+def teacher_hp(workload, arch):
+    hp = dict(arch['hp'])
+    if workload == 'cyclegan_teacher':      # scripts/cycle_gan/horse2zebra/train_inception_teacher.sh + CycleGANModel defaults
+        return dict(gan_mode='lsgan', lambda_A=10.0, lambda_B=10.0, lambda_identity=0.5, lr=hp['lr'], beta1=hp['beta1'], pool_size=50)
+    return hp
+
+
+def teacher_macs(workload, arch, H, W):
+    """Algorithmic MACs per image of one teacher-training step (G = the unpruned generator, MAC = 2 FLOP):
+    pix2pix 3 G + 8 D (as the distillation step without T and with S = G); CycleGAN 2 generators x 3 applications x
+    (fwd + dgrad + wgrad) = 18 G, 2 discriminators x (G phase: fwd + dgrad; D phase: 2 fwd + 2 full bwd) = 16 D;
+    SPADE 4 G + 10 D + 3 V (as the distillation step without T and with S = G)."""
+    from cat_b200 import workload as WL
+    if workload == 'gaugan_teacher':
+        m = WL.spade_macs_per_image(arch, H, W)
+        return dict(m, step=4 * m['T'] + 10 * m['D'] + 3 * m['V'])
+    m = WL.macs_per_image(arch, H, W)
+    if workload == 'cyclegan_teacher':
+        return dict(m, step=18 * m['T'] + 16 * m['D'])
+    return dict(m, step=3 * m['T'] + 8 * m['D'])
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -154,19 +186,59 @@ def cpu_reference_spade_steps(arch, hp, B, H, W, steps, warmup):
     return B / dt, dt, torch.get_num_threads()
 
 
+def cpu_teacher_steps(workload, arch, hp, B, H, W, steps, warmup):
+    """Times oracle.train_oracle (CPU restatement of the reference's teacher-training optimize_parameters) on a bounded
+    sample of the workload: same networks and resolution, `B` images per step."""
+    from cat_b200 import workload as WL
+    from oracle import train_oracle as TO
+    torch.set_num_threads(_best_thread_count())
+    G_arch, D_arch = arch['teacher_arch'], arch['D_arch']
+    if workload == 'gaugan_teacher':
+        from oracle import spade_oracle as SO
+        G_arch = dict(WL.spade_arch_for(arch, H, W)['teacher_arch'], active_fn='nn.LeakyReLU')
+        state = dict(G_sd=WL.init_spade_reference_sd(G_arch, 1), D_sd=WL.init_multiscale_D_sd(D_arch, 2), vgg_sd=WL.init_vgg(3),
+                     G_arch=G_arch, D_arch=D_arch, adam_G={}, adam_D={})
+        lab, inst, img = WL.synthetic_spade_batch(B, H, W, hp['n_label'], 233)
+        one = lambda: TO.spade_train_step(state, SO.preprocess_input(lab, inst, hp['n_label']), img, hp)
+    elif workload == 'cyclegan_teacher':
+        state = dict(G_A_sd=WL.init_generator(G_arch, 1), G_B_sd=WL.init_generator(G_arch, 4),
+                     D_A_sd=WL.init_discriminator(D_arch, 2), D_B_sd=WL.init_discriminator(D_arch, 5), G_arch=G_arch, D_arch=D_arch,
+                     adam_G={}, adam_D={}, pool_A=TO.ImagePool(hp['pool_size']), pool_B=TO.ImagePool(hp['pool_size']))
+        a, b = WL.synthetic_batch(B, H, W, 233)
+        one = lambda: TO.cyclegan_train_step(state, a, b, hp)
+    else:
+        state = dict(G_sd=WL.init_generator(G_arch, 1), D_sd=WL.init_discriminator(D_arch, 2), G_arch=G_arch, D_arch=D_arch,
+                     adam_G={}, adam_D={})
+        a, b = WL.synthetic_batch(B, H, W, 233)
+        one = lambda: TO.pix2pix_train_step(state, a, b, hp)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt, torch.get_num_threads()
+
+
+def cpu_steps_fn(workload):
+    if workload in TEACHER:
+        return lambda arch, hp, B, H, W, steps, warmup: cpu_teacher_steps(workload, arch, teacher_hp(workload, arch), B, H, W, steps, warmup)
+    return cpu_reference_spade_steps if is_spade(workload) else cpu_reference_steps
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from cat_b200 import workload as WL
-    arch = WL.load_arch(args.workload)
+    arch = WL.load_arch(arch_name(args.workload))
     hp = dict(arch['hp'])
     B = args.cpu_batch
-    fn = cpu_reference_spade_steps if is_spade(args.workload) else cpu_reference_steps
+    fn = cpu_steps_fn(args.workload)
     ips, dt, cores = fn(arch, hp, B, args.height, args.width, args.steps, args.warmup)
     sample = f'{B} images/step at {args.height}x{args.width}, same networks; CPU oracle port of optimize_parameters'
     print(json.dumps({
-        'impl': 'reference', 'metric': 'distill-step images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': metric_name(args.workload), 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, arch, B, 1),
@@ -175,7 +247,20 @@ def run_reference(args):
     }))
 
 
+def metric_name(workload):
+    return 'teacher-train-step images/sec' if workload in TEACHER else 'distill-step images/sec'
+
+
 def workload_config(args, arch, B, world):
+    if args.workload in TEACHER:
+        what = {'pix2pix_teacher': 'Pix2PixModel.optimize_parameters (generator ngf64 + PatchGAN ndf%d, hinge + L1)' % arch['D_arch']['ndf'],
+                'cyclegan_teacher': 'CycleGANModel.optimize_parameters (2 generators ngf64 x 3 applications, 2 PatchGANs ndf%d, '
+                                    'lsgan + cycle + identity, image pools of 50)' % arch['D_arch']['ndf'],
+                'gaugan_teacher': 'SPADEModel.optimize_parameters (SPADE generator ngf64 with LeakyReLU, multi-scale spectral D, '
+                                  'feature matching, VGG19 loss)'}[args.workload]
+        return {'workload': f'{args.workload}: teacher training step, {what}, {args.height}x{args.width}, batch {B}/GPU',
+                'global_batch': B * world, 'height': args.height, 'width': args.width, 'parallelism': f'dp{world}',
+                'l2': 'per-step working set (~GBs of activations) exceeds the 126 MB L2; no explicit flush'}
     if is_spade(args.workload):
         return {'workload': f'{args.workload}: GauGAN/SPADE inception student distill step (spade_distiller: teacher ngf64 '
                             f'{arch["teacher_macs"] / 1e9:.1f} GMAC + pruned student {arch["student_macs"] / 1e9:.2f} GMAC @256x512, '
@@ -256,11 +341,14 @@ def main():
     from cat_b200.distill_engine import DistillStep
     from cat_b200.engine import GenNet
 
-    arch = WL.load_arch(args.workload)
+    arch = WL.load_arch(arch_name(args.workload))
     hp = dict(arch['hp'])
     B, H, W = args.batch, args.height, args.width
     spade = is_spade(args.workload)
-    if spade:
+    if args.workload in TEACHER:
+        eng, host, h2d_bytes = build_teacher(args, arch, teacher_hp(args.workload, arch), B, H, W, dev, world, rank)
+        macs = teacher_macs(args.workload, arch, H, W)
+    elif spade:
         from cat_b200.spade_distill_engine import SpadeDistillStep
         from cat_b200.spade_engine import SpadeGenNet
         sarch = WL.spade_arch_for(arch, H, W)
@@ -284,6 +372,29 @@ def main():
         hp['ka_scale'] = float(world)   # the reference sums the per-replica KA terms (inception_distiller.py:145-148)
         eng, host, h2d_bytes, macs = build_pix2pix(args, arch, hp, B, H, W, dev, world, rank)
     return run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local)
+
+
+def build_teacher(args, arch, hp, B, H, W, dev, world, rank):
+    """Engines of the teacher-training workloads (cat_b200/train_engine.py) with reference-style random initialisation."""
+    from cat_b200 import workload as WL
+    from cat_b200.train_engine import CycleGANTrainStep, Pix2PixTrainStep, SpadeTrainStep
+    kw = dict(device=dev, world_size=world, use_cuda_graph=not args.no_graph)
+    G_arch, D_arch = arch['teacher_arch'], arch['D_arch']
+    if args.workload == 'gaugan_teacher':
+        G_arch = dict(WL.spade_arch_for(arch, H, W)['teacher_arch'], active_fn='nn.LeakyReLU')    # models/spade_model.py:92
+        eng = SpadeTrainStep(G_arch, D_arch, hp, B, H, W, **kw)
+        host = WL.synthetic_spade_batch(B, H, W, hp['n_label'], 233 + rank, pin=True)
+        eng.load(WL.init_from_entries(eng.G, 1), WL.init_from_entries(eng.D, 2), WL.init_vgg(3))
+    elif args.workload == 'cyclegan_teacher':
+        eng = CycleGANTrainStep(G_arch, D_arch, hp, B, H, W, **kw)
+        host = WL.synthetic_batch(B, H, W, 233 + rank, pin=True)
+        eng.load(WL.init_generator(G_arch, 1), WL.init_generator(G_arch, 4), WL.init_discriminator(D_arch, 2),
+                 WL.init_discriminator(D_arch, 5))
+    else:
+        eng = Pix2PixTrainStep(G_arch, D_arch, hp, B, H, W, **kw)
+        host = WL.synthetic_batch(B, H, W, 233 + rank, pin=True)
+        eng.load(WL.init_generator(G_arch, 1), WL.init_discriminator(D_arch, 2))
+    return eng, host, sum(t.numel() * t.element_size() for t in host)
 
 
 def build_pix2pix(args, arch, hp, B, H, W, dev, world, rank):
@@ -371,14 +482,18 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         ws, eng.world_size = eng.world_size, 1   # rank 0 only: this extra step must not enter a collective
         # per-kernel timing needs the kernels alone on the GPU: no side-stream branches in this step
         saved = {k: getattr(eng, k) for k in ('overlap', 'overlap_teacher') if hasattr(eng, k)}
-        saved_w = eng.S.overlap_wgrad
+        gens = [g for g in (getattr(eng, n, None) for n in ('S', 'GA_real', 'GA_cyc', 'GA_idt', 'GB_real', 'GB_cyc', 'GB_idt'))
+                if g is not None]
+        saved_w = [g.overlap_wgrad for g in gens]
         for k in saved:
             setattr(eng, k, False)
-        eng.S.overlap_wgrad = False
+        for g in gens:
+            g.overlap_wgrad = False
         eng.step()
         for k, v in saved.items():
             setattr(eng, k, v)
-        eng.S.overlap_wgrad = saved_w
+        for g, v in zip(gens, saved_w):
+            g.overlap_wgrad = v
         eng.world_size = ws
         agg, per = prof.summary()
         prof.remove()
@@ -419,7 +534,7 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fn = cpu_reference_spade_steps if is_spade(args.workload) else cpu_reference_steps
+        fn = cpu_steps_fn(args.workload)
         cpu_steps = 2 if is_spade(args.workload) else 3
         ips, dt, cores = fn(arch, dict(arch['hp']), args.cpu_batch, H, W, cpu_steps, 1)
         cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
@@ -430,7 +545,7 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         imgs = B * world * args.steps
         value = imgs / (ms * 1e-3)
         print(json.dumps({
-            'metric': 'distill-step images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world,
+            'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(args, arch, B, world),
