@@ -14,6 +14,7 @@ import os
 import torch
 
 from . import ops, parallel
+from .adaptors import Adaptors
 from .engine import MAPPING_LAYERS, DisNet, GenNet
 from .ops import Act
 
@@ -35,6 +36,13 @@ class DistillStep:
         assert self.T is not None or (self.aligned and not hp.get('lambda_distill', 0.0))
         self.S = GenNet(student_arch, B, H, W, device, training=hp.get('student_training', True), need_grad=True)
         self.D = DisNet(D_arch, B, H, W, device)
+        # --distill_G_loss_type mse (inception_distiller.py:111-133): MSE(netA_i(Sact_i), Tact_i) through the adaptor convs
+        self.mse = hp.get('distill_loss_type', 'ka') == 'mse'
+        assert hp.get('distill_loss_type', 'ka') in ('ka', 'mse')
+        self.A = None
+        if self.mse and hp.get('lambda_distill', 0.0) > 0:
+            cS, cT = student_arch['widths'][2], teacher_arch['widths'][2]
+            self.A = Adaptors([(self.S.acts[n], cS, self.T.acts[n], cT) for n in MAPPING_LAYERS], device)
         f32 = dict(dtype=torch.float32, device=device)
         self.real_A = torch.zeros(B, 3, H, W, **f32)
         self.real_B = torch.zeros(B, 3, H, W, **f32)
@@ -55,6 +63,7 @@ class DistillStep:
         self.lr_D = torch.full((1,), float(hp['lr']), **f32)
         self.step_G = torch.zeros(1, dtype=torch.int32, device=device)
         self.step_D = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step_A = torch.zeros(1, dtype=torch.int32, device=device)
         self._graphs = None
         self.use_cuda_graph = use_cuda_graph
         self.overlap_teacher = os.environ.get('CATB_NO_OVERLAP', '0') != '1'
@@ -63,11 +72,13 @@ class DistillStep:
     LOSS_SLOTS = {'D_fake': 0, 'D_real': 1, 'G_gan': 2, 'G_recon': 3, 'G_distill': 4}
 
     # ---- state ---------------------------------------------------------------------------------
-    def load(self, teacher_sd, student_sd, D_sd):
+    def load(self, teacher_sd, student_sd, D_sd, netA_sds=None):
         if self.T is not None:
             self.T.load_state_dict(teacher_sd)
         self.S.load_state_dict(student_sd)
         self.D.load_state_dict(D_sd)
+        if self.A is not None:
+            self.A.load_state_dicts(netA_sds)
 
     def set_input(self, real_A, real_B):
         """Host or device NCHW fp32 tensors -> the persistent device buffers (the H2D copy of
@@ -142,7 +153,14 @@ class DistillStep:
         ops.recon_loss(S.out, target, 3, hp.get('recon_loss_type', 'l1'), hp['lambda_recon'], self.losses[3:4],
                        self.dS, extra)
         act_grads = {}
-        if hp.get('lambda_distill', 0.0) > 0:
+        if self.A is not None:
+            self.A.arena.g.zero_()
+            self.ka_vals.zero_()
+            scale = hp['lambda_distill'] * hp.get('ka_scale', 1.0)
+            for i, n in enumerate(MAPPING_LAYERS):
+                self.A.loss(i, scale, self.ka_vals[i:i + 1])
+                act_grads[n] = (lambda dact, i=i: self.A.backward_into(i, dact))
+        elif hp.get('lambda_distill', 0.0) > 0:
             self.Gx.zero_()
             self.Gy.zero_()
             scale = -hp['lambda_distill'] * hp.get('ka_scale', 1.0)
@@ -152,9 +170,6 @@ class DistillStep:
                 ops.ka_finish(self.Gx[i], self.Gy[i], self.B, scale, self.losses[4:5], self.ka_vals[i:i + 1], self.coef[i])
                 act_grads[n] = (lambda dact, i=i, n=n: ops.ka_bwd(S.acts[n], self.coef[i], dact, True))
         S.backward(self.dS, act_grads)
-
-    def _allreduce(self, net):
-        parallel.reduce_gradients(net.arena.g, self.world_size)
 
     # ---- the step ------------------------------------------------------------------------------
     def _part1(self):
@@ -169,6 +184,8 @@ class DistillStep:
 
     def _part3(self):
         self._adam(self.S, self.lr_G, self.step_G)
+        if self.A is not None:          # the adaptors are the second parameter group of optimizer_G
+            self._adam(self.A, self.lr_G, self.step_A)
 
     def step(self):
         """optimize_parameters(): three launch segments separated by the two gradient all-reduces."""
@@ -188,16 +205,21 @@ class DistillStep:
             self._allreduce(self.S)
             self._part3()
 
+    def _allreduce(self, net):
+        parallel.reduce_gradients(net.arena.g, self.world_size)
+        if net is self.S and self.A is not None:
+            parallel.reduce_gradients(self.A.arena.g, self.world_size)
+
     def _tune_pass(self):
         """One eager step on a snapshot of every mutable tensor: each Gemm times its two forward kernels on
         its real operands (ops.Gemm.fprop) and keeps the faster; the state is then restored, so the captured
         graph starts from exactly the loaded weights."""
         state = []
-        for net in (self.S, self.D, self.T):
+        for net in (self.S, self.D, self.T, self.A):
             if net is None:
                 continue
             state += [t for t in (net.arena.p, net.arena.g, net.arena.m, net.arena.v, net.bufs.p) if t is not None]
-        state += [self.step_G, self.step_D, self.losses, self.ka_vals]
+        state += [self.step_G, self.step_D, self.step_A, self.losses, self.ka_vals]
         snap = [t.clone() for t in state]
         # kernels are timed one at a time: no side-stream branches during the tuning step
         saved = (self.overlap_teacher, self.S.overlap_wgrad)
@@ -211,6 +233,8 @@ class DistillStep:
             t.copy_(c)
         self.S.pack_weights()
         self.D.pack_weights()
+        if self.A is not None:
+            self.A.pack_weights()
         torch.cuda.synchronize()
 
     def _capture(self):
@@ -238,8 +262,10 @@ class DistillStep:
         hp = self.hp
         scale = hp.get('ka_scale', 1.0)
         out = {'D_fake': l[0], 'D_real': l[1], 'G_gan': l[2] * hp['lambda_gan'], 'G_recon': l[3] * hp['lambda_recon'], 'G_distill': l[4]}
+        if self.A is not None:          # 'mse': the slots hold the four unscaled MSE terms
+            out['G_distill'] = hp['lambda_distill'] * scale * sum(k[:4])
         for i in range(4):
-            out['G_distill%d' % i] = -k[i] * scale
+            out['G_distill%d' % i] = (k[i] if self.A is not None else -k[i]) * scale
         return out
 
 

@@ -59,7 +59,7 @@ class InceptionDistiller:
         parser.add_argument('--restore_D_path', type=str, default=None)
         parser.add_argument('--restore_O_path', type=str, default=None)
         parser.add_argument('--recon_loss_type', type=str, default='l1', choices=['l1', 'l2', 'smooth_l1'])
-        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka'])
+        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka', 'mse'])
         parser.add_argument('--lambda_distill', type=float, default=1)
         parser.add_argument('--lambda_recon', type=float, default=100)
         parser.add_argument('--lambda_gan', type=float, default=1)
@@ -76,8 +76,8 @@ class InceptionDistiller:
             raise RuntimeError('cat_b200.InceptionDistiller needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda:%d' % self.gpu_ids[0])
         self.save_dir = os.path.join(getattr(opt, 'log_dir', '.'), 'checkpoints')
-        if getattr(opt, 'distill_G_loss_type', 'ka') != 'ka':
-            raise NotImplementedError("only --distill_G_loss_type ka (the CAT kernel-alignment loss) is implemented")
+        if getattr(opt, 'distill_G_loss_type', 'ka') not in ('ka', 'mse'):
+            raise NotImplementedError('--distill_G_loss_type [%s]: ka | mse' % opt.distill_G_loss_type)
         if opt.recon_loss_type == 'vgg':
             raise NotImplementedError('VGG reconstruction loss is not on the inception distillation scripts')
         self.loss_names = ['G_gan', 'G_distill', 'G_recon', 'D_fake', 'D_real'] + ['G_distill%d' % i for i in range(4)]
@@ -99,8 +99,10 @@ class InceptionDistiller:
                                       ids, opt=opt)
         self.netG_teacher.eval()
         self.mapping_layers = list(MAPPING_LAYERS)
-        # adaptor convs: parameters of optimizer_G in the reference, unused under the 'ka' loss
-        self.netAs = [nn.Conv2d(opt.student_ngf * 4, opt.teacher_ngf * 4, kernel_size=1).to(self.device) for _ in range(4)]
+        # adaptor convs (base_inception_distiller.py:195-202): parameters of optimizer_G, used by the 'mse' loss only; their
+        # input width follows the (pruned) student like utils/common.py:154-161
+        c_s = self.netG_student.arch()['widths'][2]
+        self.netAs = [nn.Conv2d(c_s, opt.teacher_ngf * 4, kernel_size=1).to(self.device) for _ in range(4)]
         self.optimizer_G = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
         self.optimizer_D = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
         self.optimizers = [self.optimizer_G, self.optimizer_D]
@@ -120,7 +122,7 @@ class InceptionDistiller:
         return dict(gan_mode=o.gan_mode, aligned=o.dataset_mode in ('aligned', 'cityscapes'), lambda_recon=o.lambda_recon,
                     lambda_gan=o.lambda_gan, lambda_distill=o.lambda_distill, lr=o.lr, beta1=o.beta1,
                     student_training=self.netG_student.training, recon_loss_type=o.recon_loss_type,
-                    ka_scale=float(getattr(o, 'world_size', 1)))
+                    ka_scale=float(getattr(o, 'world_size', 1)), distill_loss_type=getattr(o, 'distill_G_loss_type', 'ka'))
 
     def _ensure_engine(self, B, H, W):
         if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
@@ -131,6 +133,11 @@ class InceptionDistiller:
         for module, net in ((self.netG_teacher, eng.T), (self.netG_student, eng.S), (self.netD, eng.D)):
             module.bind(net)               # copies the module's weights in, then re-points them at the arena
             net.pack_weights()
+        if eng.A is not None:              # 'mse': the adaptor modules alias the engine's adaptor arena
+            eng.A.load_state_dicts([net.state_dict() for net in self.netAs])
+            for i, net in enumerate(self.netAs):
+                net.weight.data = eng.A.arena.view('%d.weight' % i)
+                net.bias.data = eng.A.arena.view('%d.bias' % i)
         self.optimizer_G.bind(eng.S, eng.step_G)
         self.optimizer_D.bind(eng.D, eng.step_D)
         self.engine = eng

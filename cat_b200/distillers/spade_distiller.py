@@ -46,7 +46,7 @@ class SPADEDistillerModules(nn.Module):
         self.netD = networks.define_D(opt.input_nc + opt.output_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm,
                                       opt.init_type, opt.init_gain, self.gpu_ids, opt=opt)
         self.mapping_layers = list(MAPPING_LAYERS)
-        self.netAs = nn.ModuleList()     # adaptor convs: optimiser parameters in the reference, unused under 'ka'
+        self.netAs = nn.ModuleList()     # adaptor convs: parameters of optimizer_G, used by the 'mse' loss only
         for layer in self.mapping_layers:
             fs, ft = (opt.student_ngf * 16, opt.teacher_ngf * 16) if layer != 'up_1' else (opt.student_ngf * 4, opt.teacher_ngf * 4)
             self.netAs.append(nn.Conv2d(fs, ft, kernel_size=1))
@@ -73,7 +73,7 @@ class SPADEDistiller:
         parser.add_argument('--lambda_feat', type=float, default=10)
         parser.add_argument('--lambda_vgg', type=float, default=10)
         parser.add_argument('--lambda_distill', type=float, default=10)
-        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka'])
+        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka', 'mse'])
         parser.add_argument('--beta2', type=float, default=0.999)
         parser.add_argument('--no_TTUR', action='store_true')
         parser.add_argument('--num_D', type=int, default=2)
@@ -88,8 +88,8 @@ class SPADEDistiller:
         self.gpu_ids = list(getattr(opt, 'gpu_ids', [0]))
         if not self.gpu_ids or not torch.cuda.is_available():
             raise RuntimeError('cat_b200.SPADEDistiller needs a CUDA device (sm_100a); there is no CPU path')
-        if getattr(opt, 'distill_G_loss_type', 'ka') != 'ka':
-            raise NotImplementedError("only --distill_G_loss_type ka (the CAT kernel-alignment loss) is implemented")
+        if getattr(opt, 'distill_G_loss_type', 'ka') not in ('ka', 'mse'):
+            raise NotImplementedError('--distill_G_loss_type [%s]: ka | mse' % opt.distill_G_loss_type)
         if getattr(opt, 'gan_mode', 'hinge') != 'hinge':
             raise NotImplementedError('the SPADE distiller uses the hinge GAN loss (spade_model.py default)')
         self.device = torch.device('cuda:%d' % self.gpu_ids[0])
@@ -120,7 +120,8 @@ class SPADEDistiller:
     def _hp(self):
         o = self.opt
         return dict(lambda_gan=o.lambda_gan, lambda_feat=o.lambda_feat, lambda_vgg=o.lambda_vgg, lambda_distill=o.lambda_distill,
-                    lr_G=self.lr_G, lr_D=self.lr_D, beta1=self.betas[0], beta2=self.betas[1], n_label=int(o.input_nc), ka_scale=1.0)
+                    lr_G=self.lr_G, lr_D=self.lr_D, beta1=self.betas[0], beta2=self.betas[1], n_label=int(o.input_nc), ka_scale=1.0,
+                    distill_loss_type=getattr(o, 'distill_G_loss_type', 'ka'))
 
     def _ensure_engine(self, B, H, W):
         if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
@@ -138,6 +139,11 @@ class SPADEDistiller:
             raise RuntimeError('opt.vgg_state_dict (torchvision vgg19().features state_dict) is required: the pretrained '
                                'VGG19 of models/modules/loss.py:154 cannot be downloaded here')
         eng.V.load_state_dict(vgg)
+        if eng.A is not None:              # 'mse': the adaptor modules alias the engine's adaptor arena
+            eng.A.load_state_dicts([net.state_dict() for net in mm.netAs])
+            for i, net in enumerate(mm.netAs):
+                net.weight.data = eng.A.arena.view('%d.weight' % i)
+                net.bias.data = eng.A.arena.view('%d.bias' % i)
         self.optimizer_G.bind(eng.S, eng.step_G)
         self.optimizer_D.bind(eng.D, eng.step_D)
         self.engine = eng

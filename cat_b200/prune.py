@@ -188,6 +188,10 @@ def shrink_inception(model, opt):
     model.netG_student = networks.init_net(networks.InceptionGenerator.from_arch(student_arch), opt.init_type, opt.init_gain, gpu_ids)
     model.netG_student.n_macs = info['macs']
     teacher.n_macs = generator_macs(teacher.arch(), int(opt.data_height), int(opt.data_width))
+    if getattr(model, 'netAs', None):       # adaptor convs follow the pruned width (utils/common.py:154-161)
+        from torch import nn
+        dev = model.netAs[0].weight.device
+        model.netAs = [nn.Conv2d(student_arch['widths'][2], a.out_channels, kernel_size=1).to(dev) for a in model.netAs]
     if hasattr(model, 'engine'):
         model.engine = None
     print('scale threshold: %g, searched flops: %d, target flops: %g' % (info['threshold'], info['macs'], target))

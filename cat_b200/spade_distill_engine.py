@@ -16,6 +16,7 @@ import os
 import torch
 
 from . import ops, parallel
+from .adaptors import Adaptors
 from .ops import Act
 from .spade_engine import MAPPING_LAYERS, VGG_WEIGHTS, MultiScaleDis, SpadeGenNet, VggNet, dis_feature
 
@@ -46,6 +47,13 @@ class SpadeDistillStep:
         assert self.T is not None or not hp.get('lambda_distill', 0.0)
         self.S = SpadeGenNet(student_arch, self.seg, device, training=True, need_grad=True)
         self.D = MultiScaleDis(D_arch, 2 * B, H, W, device)
+        # --distill_G_loss_type mse (spade_distiller_modules.py:23-25): MSE(netA_i(Sact_i), Tact_i) through the adaptor convs
+        assert hp.get('distill_loss_type', 'ka') in ('ka', 'mse')
+        self.A = None
+        if hp.get('distill_loss_type', 'ka') == 'mse' and hp.get('lambda_distill', 0.0) > 0:
+            self.A = Adaptors([(self.S.acts[n], student_arch['blocks'][n]['fout'], self.T.acts[n], teacher_arch['blocks'][n]['fout'])
+                               for n in MAPPING_LAYERS], device)
+        self.step_A = torch.zeros(1, dtype=torch.int32, device=device)
         self.V = VggNet(B, H, W, device)
         cin = D_arch['input_nc']
         self.d_in = Act.empty(2 * B, H, W, cin, device, zero=True)       # [seg | fake ; seg | real]
@@ -68,12 +76,14 @@ class SpadeDistillStep:
         self._side = None
 
     # ---- state ---------------------------------------------------------------------------------
-    def load(self, teacher_sd, student_sd, D_sd, vgg_sd):
+    def load(self, teacher_sd, student_sd, D_sd, vgg_sd, netA_sds=None):
         if self.T is not None:
             self.T.load_state_dict(teacher_sd)
         self.S.load_state_dict(student_sd)
         self.D.load_state_dict(D_sd)
         self.V.load_state_dict(vgg_sd)
+        if self.A is not None:
+            self.A.load_state_dicts(netA_sds)
 
     def set_input(self, label, instance, image):
         """label / instance: [B,1,H,W] (any integer or float dtype, host or device), image: [B,3,H,W] fp32 in
@@ -153,7 +163,14 @@ class SpadeDistillStep:
         act_grads = {}
         if main is not None:
             main.wait_stream(self._side[0])
-        if hp.get('lambda_distill', 0.0) > 0:
+        if self.A is not None:
+            self.A.arena.g.zero_()
+            self.ka_vals.zero_()
+            scale = hp['lambda_distill'] * hp.get('ka_scale', 1.0)
+            for i, n in enumerate(MAPPING_LAYERS):
+                self.A.loss(i, scale, self.ka_vals[i:i + 1])
+                act_grads[n] = (lambda dact, i=i: self.A.backward_into(i, dact))
+        elif hp.get('lambda_distill', 0.0) > 0:
             self.Gx.zero_()
             self.Gy.zero_()
             scale = -hp['lambda_distill'] * hp.get('ka_scale', 1.0)
@@ -182,6 +199,8 @@ class SpadeDistillStep:
 
     def _allreduce(self, net):
         parallel.reduce_gradients(net.arena.g, self.world_size)
+        if net is self.S and self.A is not None:
+            parallel.reduce_gradients(self.A.arena.g, self.world_size)
 
     # ---- the step ------------------------------------------------------------------------------
     def _part1(self):
@@ -191,6 +210,8 @@ class SpadeDistillStep:
 
     def _part2(self):
         self._adam(self.S, self.lr_G, self.step_G)
+        if self.A is not None:          # the adaptors are parameters of optimizer_G
+            self._adam(self.A, self.lr_G, self.step_A)
         self._phase_D()
 
     def _part3(self):
@@ -216,11 +237,11 @@ class SpadeDistillStep:
 
     def _mutable_state(self):
         state = []
-        for net in (self.S, self.D, self.T):
+        for net in (self.S, self.D, self.T, self.A):
             if net is None:
                 continue
             state += [t for t in (net.arena.p, net.arena.g, net.arena.m, net.arena.v, net.bufs.p) if t is not None]
-        return state + [self.step_G, self.step_D, self.losses, self.ka_vals]
+        return state + [self.step_G, self.step_D, self.step_A, self.losses, self.ka_vals]
 
     def _tune_pass(self):
         """One eager step on a snapshot of every mutable tensor (each Gemm autotunes on its real operands), then the
@@ -237,6 +258,8 @@ class SpadeDistillStep:
         for t, c in zip(state, snap):
             t.copy_(c)
         self.S.pack_weights()
+        if self.A is not None:
+            self.A.pack_weights()
         self.D.spectral_forward(training=False)
         torch.cuda.synchronize()
 
@@ -266,8 +289,10 @@ class SpadeDistillStep:
                'G_vgg': sum(w * v for w, v in zip(VGG_WEIGHTS, l[self.S_VGG0:self.S_VGG0 + 5])) * hp['lambda_vgg'],
                'G_distill': l[self.S_DISTILL], 'D_fake': l[self.S_DFAKE] / num_D, 'D_real': l[self.S_DREAL] / num_D}
         scale = hp.get('ka_scale', 1.0)
+        if self.A is not None:          # 'mse': the slots hold the unscaled MSE terms
+            out['G_distill'] = hp['lambda_distill'] * scale * sum(k[:len(MAPPING_LAYERS)])
         for i in range(len(MAPPING_LAYERS)):
-            out['G_distill%d' % i] = -k[i] * scale
+            out['G_distill%d' % i] = (k[i] if self.A is not None else -k[i]) * scale
         return out
 
 

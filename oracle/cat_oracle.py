@@ -268,6 +268,9 @@ def distill_step(state, real_A, real_B, hp, grad_hook=None):
     hp:    dict(gan_mode, aligned, lambda_recon, lambda_gan, lambda_distill, lr, beta1,
                 student_training, ka_scale) -- ka_scale is the DataParallel replica-sum factor of
            inception_distiller.py:145-148 (1 on a single device).
+           hp['distill_loss_type'] == 'mse' (--distill_G_loss_type mse, inception_distiller.py:111-133): the four terms
+           are F.mse_loss(netA_i(Sact_i), Tact_i) through the 1x1 adaptor convs state['netA_sds'][i] ('weight', 'bias';
+           base_inception_distiller.py:195-202), which are parameters of optimizer_G (:204-210).
     Returns dict of losses, outputs, activations and gradients."""
     T_sd, S_sd, D_sd = state['teacher_sd'], state['student_sd'], state['D_sd']
     T_arch, S_arch, D_arch = state['teacher_arch'], state['student_arch'], state['D_arch']
@@ -329,8 +332,19 @@ def distill_step(state, real_A, real_B, hp, grad_hook=None):
     pred_fake = discriminator_forward(D_sd, D_arch, fake, training=True)
     loss_G_gan = gan_loss(hp['gan_mode'], pred_fake, True, False) * hp['lambda_gan']
     distill_terms = []
-    for n in MAPPING_LAYERS:
-        distill_terms.append(-ka(Sacts[n], Tacts[n]) * hp.get('ka_scale', 1.0))
+    mse = hp.get('distill_loss_type', 'ka') == 'mse'
+    A_params = {}
+    if mse:
+        A_params = {f'A{i}.{k}': v for i, sd in enumerate(state['netA_sds']) for k, v in sd.items()}
+        for p in A_params.values():
+            p.requires_grad_(True)
+            p.grad = None
+    for i, n in enumerate(MAPPING_LAYERS):
+        if mse:
+            mapped = qa(F.conv2d(Sacts[n], qw(A_params[f'A{i}.weight']), A_params[f'A{i}.bias']))
+            distill_terms.append(F.mse_loss(mapped, Tacts[n]) * hp.get('ka_scale', 1.0))
+        else:
+            distill_terms.append(-ka(Sacts[n], Tacts[n]) * hp.get('ka_scale', 1.0))
     loss_G_distill = sum(distill_terms) * hp['lambda_distill']
     loss_G = loss_G_gan + loss_G_recon + loss_G_distill
     loss_G.backward()
@@ -340,12 +354,17 @@ def distill_step(state, real_A, real_B, hp, grad_hook=None):
     out['Sact_grads'] = {k: v.grad.detach().clone() for k, v in Sacts.items()}
     out['Sfake_grad'] = Sfake.grad.detach().clone()
     out['S_grads'] = {k: p.grad.detach().clone() for k, p in S_params.items()}
+    out['A_grads'] = {k: p.grad.detach().clone() for k, p in A_params.items()}
     with torch.no_grad():
         if grad_hook is not None:
             out['S_grads'] = grad_hook('S', out['S_grads'])
+            if mse:
+                out['A_grads'] = grad_hook('A', out['A_grads'])
         adam_update(S_params, out['S_grads'], state['adam_G'], hp['lr'], hp['beta1'])
-    for p in S_params.values():
+        adam_update(A_params, out['A_grads'], state['adam_G'], hp['lr'], hp['beta1'])     # same optimizer_G, second group
+    for p in list(S_params.values()) + list(A_params.values()):
         p.requires_grad_(False)
+        p.grad = None
     return out
 
 

@@ -33,6 +33,10 @@ CASES = {
     'pix2pix_bn_lsgan_l2': dict(norm='batch', gan_mode='lsgan', dataset_mode='aligned', lambda_distill=0.5,
                                 lambda_recon=100.0, batch_size=4, height=32, width=32, frac=0.2,
                                 recon_loss_type='l2'),
+    # --distill_G_loss_type mse (inception_distiller.py:111-133): MSE(netA_i(Sact_i), Tact_i) through the 1x1 adaptor convs
+    # netAs, which are parameters of optimizer_G; smooth losses so that the backward pass is pinned tightly.
+    'pix2pix_bn_mse': dict(norm='batch', gan_mode='lsgan', dataset_mode='aligned', lambda_distill=2.0, lambda_recon=100.0,
+                           batch_size=3, height=32, width=32, frac=0.2, recon_loss_type='l2', distill_G_loss_type='mse'),
 }
 
 
@@ -52,7 +56,8 @@ def make_case(name, cfg):
                                            dataset_mode=cfg['dataset_mode'],
                                            lambda_distill=cfg['lambda_distill'],
                                            lambda_recon=cfg['lambda_recon'],
-                                           recon_loss_type=cfg.get('recon_loss_type', 'l1'))
+                                           recon_loss_type=cfg.get('recon_loss_type', 'l1'),
+                                           distill_G_loss_type=cfg.get('distill_G_loss_type', 'ka'))
     # after the first evaluate_model the reference puts the student back in train mode
     # (inception_distiller.py:280); the golden steps are recorded in that steady state.
     model.netG_student.train()
@@ -74,12 +79,17 @@ def make_case(name, cfg):
         'hp': dict(gan_mode=opt.gan_mode, aligned=opt.dataset_mode == 'aligned',
                    lambda_recon=float(opt.lambda_recon), lambda_gan=float(opt.lambda_gan),
                    lambda_distill=float(opt.lambda_distill), lr=float(opt.lr),
-                   beta1=float(opt.beta1), student_training=True, recon_loss_type=opt.recon_loss_type),
+                   beta1=float(opt.beta1), student_training=True, recon_loss_type=opt.recon_loss_type,
+                   distill_loss_type=opt.distill_G_loss_type),
         'teacher_sd': snap(model.netG_teacher.state_dict()),
         'student_sd0': snap(model.netG_student.state_dict()),
         'D_sd0': snap(model.netD.state_dict()),
         'steps': [],
     }
+    if opt.distill_G_loss_type == 'mse':
+        for net in model.netAs:      # default Conv2d init is U(+-1/sqrt(fan_in)): keep, add a spread to the biases
+            net.bias.data = 0.05 * torch.randn(net.bias.shape, generator=g)
+        fix['netA_sd0'] = [snap(net.state_dict()) for net in model.netAs]
     gen = torch.Generator().manual_seed(233)
     for it in range(2):
         A = torch.rand(B, 3, H, W, generator=gen) * 2 - 1
@@ -100,6 +110,7 @@ def make_case(name, cfg):
             v.retain_grad()
         model.backward_G(it)
         S_grads = {k: p.grad.detach().clone() for k, p in model.netG_student.named_parameters()}
+        A_grads = [{k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None} for net in model.netAs]
         Sact_grads = {k: v.grad.detach().clone() for k, v in Sacts.items()}
         model.optimizer_G.step()
         step = {
@@ -115,6 +126,8 @@ def make_case(name, cfg):
                 'Sacts': {k: v.detach().clone() for k, v in Sacts.items()},
                 'Sact_grads': Sact_grads, 'S_grads': S_grads, 'D_grads': D_grads,
             })
+            if opt.distill_G_loss_type == 'mse':
+                step.update(netA_grads=A_grads, netA_sd_after=[snap(net.state_dict()) for net in model.netAs])
         fix['steps'].append(step)
     return fix
 

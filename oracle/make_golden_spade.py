@@ -110,9 +110,62 @@ def make_case(name, cfg):
     return fix
 
 
+def make_mse_addon(base_name, cfg):
+    """--distill_G_loss_type mse on the SAME seeded networks as `base_name` (the adaptor convs are created in both modes,
+    so the random streams agree): a small add-on fixture with the adaptors, the first-step losses and the gradients the
+    'mse' terms reach (adaptors + student); the networks themselves are taken from the base fixture."""
+    kw = {k: v for k, v in cfg.items() if k != 'frac'}
+    probe, _ = build_reference_spade_distiller(do_shrink=False, **kw)
+    target = probe.modules_on_one_gpu.netG_teacher.n_macs * cfg['frac']
+    model, opt = build_reference_spade_distiller(target_flops=target, distill_G_loss_type='mse', lambda_distill=2.0, **kw)
+    from models import networks
+    mm = model.modules_on_one_gpu
+    mm.netG_student = networks.init_net(mm.netG_student, opt.init_type, opt.init_gain, []).to(model.device)
+    mm.netG_student.train()
+    g = torch.Generator().manual_seed(7)
+    for net in (mm.netG_student, mm.netD):
+        for k, p in net.named_parameters():
+            if p.dim() == 4:
+                p.data = p.data * 2.0
+            elif k.endswith('bias'):
+                p.data = 0.05 * torch.randn(p.shape, generator=g)
+    for m in mm.netG_student.modules():
+        if hasattr(m, 'running_mean') and getattr(m, 'weight', None) is not None:
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+    base = torch.load(os.path.join(OUT_DIR, base_name + '.pt'), weights_only=False)
+    for k, v in mm.netG_student.state_dict().items():
+        assert torch.equal(v, base['student_sd0'][k]), ('student differs from the base fixture', k)
+    for k, v in mm.netD.state_dict().items():
+        assert torch.equal(v, base['D_sd0'][k]), ('D differs from the base fixture', k)
+    s0 = base['steps'][0]
+    B = cfg['batch_size']
+    fix = {'name': base_name + '_mse', 'base': base_name, 'lambda_distill': float(opt.lambda_distill),
+           'netA_sd0': [snap(net.state_dict()) for net in mm.netAs]}
+    model.set_input({'label': s0['label'].clone(), 'instance': s0['instance'].clone(), 'image': s0['image'].clone(), 'path': ['x'] * B})
+    model.set_requires_grad(mm.netD, False)
+    model.optimizer_G.zero_grad()
+    model.backward_G()
+    fix['netA_grads'] = [{k: p.grad.detach().clone() for k, p in net.named_parameters()} for net in mm.netAs]
+    fix['S_grads'] = {k: p.grad.detach().clone() for k, p in mm.netG_student.named_parameters() if p.grad is not None}
+    model.optimizer_G.step()
+    fix['netA_sd_after'] = [snap(net.state_dict()) for net in mm.netAs]
+    model.set_requires_grad(mm.netD, True)
+    model.optimizer_D.zero_grad()
+    model.backward_D()
+    model.optimizer_D.step()
+    fix['losses'] = {k: float(v) for k, v in model.get_current_losses().items()}
+    return fix
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     only = sys.argv[1:]
+    if only == ['spade_more_mse']:
+        fix = make_mse_addon('spade_more', dict(CASES['spade_more']))
+        path = os.path.join(OUT_DIR, 'spade_more_mse.pt')
+        torch.save(fix, path)
+        print('spade_more_mse', fix['losses'], '-> %.2f MB' % (os.path.getsize(path) / 1e6))
+        return
     for name, cfg in CASES.items():
         if only and name not in only:
             continue

@@ -57,7 +57,8 @@ def _install_shims():
 def build_reference_distiller(norm='instance', batch_size=2, height=32, width=32, teacher_ngf=16,
                               student_ngf=8, ndf=8, target_flops=None, gan_mode='hinge',
                               dataset_mode='aligned', lambda_distill=1.0, lambda_recon=100.0,
-                              prune_cin_lb=4, seed=0, workdir=None, do_shrink=True, recon_loss_type='l1'):
+                              prune_cin_lb=4, seed=0, workdir=None, do_shrink=True, recon_loss_type='l1',
+                              distill_G_loss_type='ka'):
     """Build the real InceptionDistiller with a seeded synthetic teacher, run the reference's
     shrink() + init_net() exactly as trainer.py:106-107 does, and return (model, opt)."""
     _install_shims()
@@ -98,7 +99,7 @@ def build_reference_distiller(norm='instance', batch_size=2, height=32, width=32
             '6', '--kernel_sizes', '1', '3', '5', '--lambda_distill', str(lambda_distill),
             '--lambda_recon', str(lambda_recon), '--prune_cin_lb', str(prune_cin_lb),
             '--gan_mode', gan_mode, '--dataset_mode', dataset_mode,
-            '--distill_G_loss_type', 'ka', '--batch_size', str(batch_size), '--recon_loss_type', recon_loss_type]
+            '--distill_G_loss_type', distill_G_loss_type, '--batch_size', str(batch_size), '--recon_loss_type', recon_loss_type]
     if target_flops is not None:
         argv += ['--target_flops', str(target_flops)]
     if track:

@@ -66,7 +66,8 @@ def _install_spade_shims():
 
 def build_reference_spade_distiller(batch_size=2, crop_size=64, aspect_ratio=2.0, teacher_ngf=12, student_ngf=12,
                                     ndf=8, input_nc=6, target_flops=None, prune_cin_lb=4, lambda_distill=0.5,
-                                    seed=0, workdir=None, do_shrink=True, num_upsampling_layers='more'):
+                                    seed=0, workdir=None, do_shrink=True, num_upsampling_layers='more',
+                                    distill_G_loss_type='ka'):
     """Real SPADEDistiller with a seeded synthetic teacher; shrink() as trainer.py:106-107 when target_flops."""
     _install_spade_shims()
     from models import networks
@@ -100,7 +101,7 @@ def build_reference_spade_distiller(batch_size=2, crop_size=64, aspect_ratio=2.0
             '--teacher_norm_G', 'spadesyncbatch3x3', '--student_norm_G', 'spadesyncbatch3x3',
             '--channels_reduction_factor', '6', '--kernel_sizes', '1', '3', '5',
             '--lambda_distill', str(lambda_distill), '--prune_cin_lb', str(prune_cin_lb),
-            '--distill_G_loss_type', 'ka', '--batch_size', str(batch_size), '--input_nc', str(input_nc),
+            '--distill_G_loss_type', distill_G_loss_type, '--batch_size', str(batch_size), '--input_nc', str(input_nc),
             '--crop_size', str(crop_size), '--load_size', str(crop_size), '--aspect_ratio', str(aspect_ratio),
             '--num_upsampling_layers', num_upsampling_layers]
     if target_flops is not None:

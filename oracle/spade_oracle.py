@@ -279,7 +279,9 @@ def spade_distill_step(state, seg, real_B, hp, grad_hook=None):
     updated weights), optimizer_D.step.
 
     state: 'teacher_sd','student_sd','D_sd','vgg_sd' + 'teacher_arch','student_arch','D_arch' + 'adam_G','adam_D'.
-    hp: lambda_gan, lambda_feat, lambda_vgg, lambda_distill, lr_G, lr_D, beta1, beta2, ka_scale."""
+    hp: lambda_gan, lambda_feat, lambda_vgg, lambda_distill, lr_G, lr_D, beta1, beta2, ka_scale.
+    hp['distill_loss_type'] == 'mse' (spade_distiller_modules.py:23-25): the terms are F.mse_loss(netA_i(Sact_i), Tact_i)
+    through the 1x1 adaptor convs state['netA_sds'][i], parameters of optimizer_G (base_spade_distiller_modules.py:91-105)."""
     T_sd, S_sd, D_sd, V_sd = state['teacher_sd'], state['student_sd'], state['D_sd'], state['vgg_sd']
     T_arch, S_arch, D_arch = state['teacher_arch'], state['student_arch'], state['D_arch']
     out = {}
@@ -295,7 +297,17 @@ def spade_distill_step(state, seg, real_B, hp, grad_hook=None):
     for a in Sacts.values():
         a.retain_grad()
     Sfake.retain_grad()
-    terms = [-ka(Sacts[n], Tacts[n]) * hp.get('ka_scale', 1.0) for n in MAPPING_LAYERS]
+    mse = hp.get('distill_loss_type', 'ka') == 'mse'
+    A_params = {}
+    if mse:
+        A_params = {f'A{i}.{k}': v for i, sd in enumerate(state['netA_sds']) for k, v in sd.items()}
+        for p in A_params.values():
+            p.requires_grad_(True)
+            p.grad = None
+        terms = [F.mse_loss(qa(F.conv2d(Sacts[n], qw(A_params[f'A{i}.weight']), A_params[f'A{i}.bias'])), Tacts[n])
+                 * hp.get('ka_scale', 1.0) for i, n in enumerate(MAPPING_LAYERS)]
+    else:
+        terms = [-ka(Sacts[n], Tacts[n]) * hp.get('ka_scale', 1.0) for n in MAPPING_LAYERS]
     loss_distill = sum(terms) * hp['lambda_distill']
     pred_fake, pred_real = _discriminate(D_sd, D_arch, seg, Sfake, real_B)
     loss_gan = hinge_multiscale(pred_fake, True, False) * hp['lambda_gan']
@@ -313,12 +325,16 @@ def spade_distill_step(state, seg, real_B, hp, grad_hook=None):
                Sfake_grad=Sfake.grad.detach().clone(),
                loss_G_gan=loss_gan.detach(), loss_G_distill=loss_distill.detach(), loss_G_feat=loss_feat.detach(),
                loss_G_vgg=loss_vgg.detach(), loss_G_distill_terms=[t.detach() for t in terms],
-               S_grads={k: p.grad.detach().clone() for k, p in S_params.items() if p.grad is not None})
+               S_grads={k: p.grad.detach().clone() for k, p in S_params.items() if p.grad is not None},
+               A_grads={k: p.grad.detach().clone() for k, p in A_params.items()})
     with torch.no_grad():
         if grad_hook is not None:
             out['S_grads'] = grad_hook('S', out['S_grads'])
+            if mse:
+                out['A_grads'] = grad_hook('A', out['A_grads'])
         adam_update(S_params, out['S_grads'], state['adam_G'], hp['lr_G'], hp['beta1'], hp['beta2'])
-    for p in S_params.values():
+        adam_update(A_params, out['A_grads'], state['adam_G'], hp['lr_G'], hp['beta1'], hp['beta2'])
+    for p in list(S_params.values()) + list(A_params.values()):
         p.requires_grad_(False)
         p.grad = None
     # ---- D phase

@@ -7,7 +7,7 @@ import os
 import pytest
 import torch
 
-CASES = ['pix2pix_bn_lsgan_l2', 'pix2pix_bn_hinge', 'cyclegan_in_lsgan']
+CASES = ['pix2pix_bn_lsgan_l2', 'pix2pix_bn_hinge', 'cyclegan_in_lsgan', 'pix2pix_bn_mse']
 
 
 def rel_l2(a, b):
@@ -27,12 +27,14 @@ def test_distill_step_host_logic(golden_dir, name):
     st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
               D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
               D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    if 'netA_sd0' in fix:
+        st['netA_sds'] = [O.clone_sd(sd) for sd in fix['netA_sd0']]
     with O.emulate_bf16():
         ref = O.distill_step(st, step['real_A'], step['real_B'], fix['hp'])
     with emulated_kernels():
         from cat_b200.distill_engine import DistillStep
         eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device='cpu')
-        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], fix.get('netA_sd0'))
         eng.set_input(step['real_A'], step['real_B'])
         eng.step()
         assert rel_l2(ops.nhwc_to_nchw(eng.T.out, 3), ref['Tfake_B']) < 3e-2
@@ -61,7 +63,7 @@ def test_product_path_still_requires_cuda():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('name', ['pix2pix_bn_lsgan_l2', 'cyclegan_in_lsgan'])
+@pytest.mark.parametrize('name', ['pix2pix_bn_lsgan_l2', 'cyclegan_in_lsgan', 'pix2pix_bn_mse'])
 @pytest.mark.parametrize('packx', ['1', '0'])
 def test_distill_step_host_logic_exact(golden_dir, name, packx, monkeypatch):
     """Exact mode (fp32 emulated buffers): launch order, table construction (incl. the x-packed 7x7 stem / head and their
@@ -76,12 +78,14 @@ def test_distill_step_host_logic_exact(golden_dir, name, packx, monkeypatch):
     st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
               D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
               D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    if 'netA_sd0' in fix:           # --distill_G_loss_type mse
+        st['netA_sds'] = [O.clone_sd(sd) for sd in fix['netA_sd0']]
     ref = O.distill_step(st, step['real_A'], step['real_B'], fix['hp'])
     with emulated_kernels(exact=True):
         from cat_b200.distill_engine import DistillStep
         eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device='cpu')
         assert eng.S.packx == (packx == '1')
-        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], fix.get('netA_sd0'))
         eng.set_input(step['real_A'], step['real_B'])
         eng.step()
         assert rel_l2(ops.nhwc_to_nchw(eng.T.out, 3), ref['Tfake_B']) < 1e-5
@@ -98,6 +102,17 @@ def test_distill_step_host_logic_exact(golden_dir, name, packx, monkeypatch):
                     continue
                 err = float((net.arena.view(k, 'g') - g).abs().max())
                 assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
+        if 'netA_sd0' in fix:
+            assert eng.A is not None
+            for i in range(4):
+                r = float(ref['loss_G_distill_terms'][i])
+                assert abs(L['G_distill%d' % i] - r) <= 1e-5 * max(1.0, abs(r)), (i, L['G_distill%d' % i], r)
+            for k, g in ref['A_grads'].items():          # 'A<i>.weight' / 'A<i>.bias'
+                mine = eng.A.arena.view(k[1:], 'g')
+                assert float((mine - g).abs().max()) <= 2e-3 * float(g.abs().max()) + 1e-7, k
+            for i, sd in enumerate(eng.A.state_dicts()):    # after the Adam step of optimizer_G's second parameter group
+                for k, v in sd.items():
+                    assert float((v - st['netA_sds'][i][k]).abs().max()) <= 1e-5, (i, k)
 
 
 @pytest.mark.timeout(600)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import cat_oracle as O
 
-CASES = ['pix2pix_bn_hinge', 'cyclegan_in_lsgan', 'pix2pix_bn_lsgan_l2']
+CASES = ['pix2pix_bn_hinge', 'cyclegan_in_lsgan', 'pix2pix_bn_lsgan_l2', 'pix2pix_bn_mse']
 
 
 def _close(a, b, rtol=2e-4, atol=2e-5, what=''):
@@ -43,6 +43,8 @@ def test_two_distill_steps_match_reference(golden_dir, name):
     state = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
                  D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'],
                  student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    if 'netA_sd0' in fix:       # --distill_G_loss_type mse: the adaptor convs netAs
+        state['netA_sds'] = [O.clone_sd(sd) for sd in fix['netA_sd0']]
     for it, step in enumerate(fix['steps']):
         out = O.distill_step(state, step['real_A'], step['real_B'], fix['hp'])
         L = step['losses']
@@ -69,6 +71,11 @@ def test_two_distill_steps_match_reference(golden_dir, name):
             noise_S = {k: g.abs() < 1e-5 * sscale for k, g in step['S_grads'].items()}
             for k, g in step['Sact_grads'].items():
                 _close(out['Sact_grads'][k], g, rtol=1e-3, atol=1e-7)
+            for i, grads in enumerate(step.get('netA_grads', [])):
+                for k, g in grads.items():
+                    _close(out['A_grads'][f'A{i}.{k}'], g, rtol=1e-3, atol=1e-7, what=f'netA{i}.{k}')
+                for k, v in step['netA_sd_after'][i].items():
+                    _close(state['netA_sds'][i][k], v, rtol=1e-3, atol=1e-5, what=f'netA{i}.{k} after Adam')
         lr = fix['hp']['lr']
         for sd_key, noise, mine in (('student_sd_after', noise_S, state['student_sd']),
                                    ('D_sd_after', noise_D, state['D_sd'])):

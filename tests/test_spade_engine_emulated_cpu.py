@@ -210,3 +210,46 @@ def test_spade_generator_edge_architectures_exact(mode, seed):
         for k, v in osd.items():
             if 'running_' in k:
                 assert float((net.state_dict()[k] - v.detach()).abs().max()) < 1e-4, k
+
+
+@pytest.mark.timeout(900)
+def test_spade_mse_distill_step_exact(golden_dir):
+    """--distill_G_loss_type mse through cat_b200.adaptors.Adaptors in exact emulation: the three MSE terms, the gradients of
+    the adaptor convs and of the student (the 1x1 input-gradient GEMM accumulated into d(activation) at the mapping layers)
+    and the adaptors after the Adam step of optimizer_G."""
+    from oracle import cat_oracle as O
+    from oracle import spade_oracle as SO
+    from oracle.kernel_emu import emulated_kernels
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    add = torch.load(os.path.join(golden_dir, 'spade_more_mse.pt'), weights_only=False)
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    s = fix['steps'][0]
+    hp = dict(fix['hp'], distill_loss_type='mse', lambda_distill=add['lambda_distill'])
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+              vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+              adam_G={}, adam_D={}, netA_sds=[O.clone_sd(sd) for sd in add['netA_sd0']])
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    ref = SO.spade_distill_step(st, seg, s['image'], hp)
+    B, _, H, W = s['image'].shape
+    with emulated_kernels(exact=True):
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], vgg, add['netA_sd0'])
+        eng.set_input(s['label'], s['instance'], s['image'])
+        eng.step()
+        L = eng.get_losses()
+        for k_ref, k in LOSSES:
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+            assert abs(L[k] - add['losses'][('D_loss/' if k.startswith('D_') else 'G_loss/') + k]) <= 1e-4 * max(1.0, abs(r)), k
+        for i in range(3):
+            assert abs(L['G_distill%d' % i] - float(ref['loss_G_distill_terms'][i])) < 1e-5
+        for k, g in ref['A_grads'].items():
+            assert float((eng.A.arena.view(k[1:], 'g') - g).abs().max()) <= 2e-3 * float(g.abs().max()) + 1e-8, k
+        scale = max(float(g.abs().max()) for g in ref['S_grads'].values())
+        for k, g in ref['S_grads'].items():
+            err = float((eng.S.arena.view(k, 'g') - g).abs().max())
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
+        for i, sd in enumerate(eng.A.state_dicts()):
+            for k, v in sd.items():
+                assert float((v - st['netA_sds'][i][k]).abs().max()) <= 1e-5, (i, k)

@@ -53,3 +53,32 @@ def test_two_spade_steps_match_reference(golden_dir):
         assert abs(cs - s['D_param_checksum_after']) < 1e-3
         cs = float(sum(v.double().abs().sum() for k, v in state['student_sd'].items() if SO._is_param(k)))
         assert abs(cs - s['student_param_checksum_after']) < 1e-2
+
+
+def test_spade_mse_distill_step_matches_reference(golden_dir):
+    """--distill_G_loss_type mse (spade_distiller_modules.py:23-25) on the networks of spade_more.pt: losses, the gradients
+    of the adaptor convs netAs and of the student, and the adaptors after optimizer_G.step, against the real SPADEDistiller
+    (oracle/make_golden_spade.py spade_more_mse)."""
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    add = torch.load(os.path.join(golden_dir, 'spade_more_mse.pt'), weights_only=False)
+    state = spade_state(fix)
+    state['netA_sds'] = [clone_sd(sd) for sd in add['netA_sd0']]
+    hp = dict(fix['hp'], distill_loss_type='mse', lambda_distill=add['lambda_distill'])
+    s = fix['steps'][0]
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    out = SO.spade_distill_step(state, seg, s['image'], hp)
+    for mine, theirs in LOSS_KEYS:
+        r = add['losses'][theirs]
+        assert abs(float(out[mine]) - r) < 1e-4 * max(1.0, abs(r)), (mine, float(out[mine]), r)
+    for i in range(3):
+        assert abs(float(out['loss_G_distill_terms'][i]) - add['losses']['Specific_loss/G_distill%d' % i]) < 1e-5
+    for i, grads in enumerate(add['netA_grads']):
+        for k, g in grads.items():
+            err = float((out['A_grads'][f'A{i}.{k}'] - g).abs().max())
+            assert err <= 1e-3 * float(g.abs().max()) + 1e-8, (i, k, err)
+        for k, v in add['netA_sd_after'][i].items():
+            assert float((state['netA_sds'][i][k] - v).abs().max()) < 1e-5, (i, k)
+    scale = max(float(g.abs().max()) for g in add['S_grads'].values())
+    for k, g in add['S_grads'].items():
+        err = float((out['S_grads'][k] - g).abs().max())
+        assert err <= 1e-3 * float(g.abs().max()) + 1e-5 * scale, (k, err)

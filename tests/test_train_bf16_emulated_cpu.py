@@ -39,3 +39,17 @@ def test_spade_body(golden_dir, on_cpu):
 @pytest.mark.timeout(300)
 def test_leaky001_body(on_cpu):
     G.test_leaky001_activation_kernels()
+
+
+@pytest.mark.timeout(900)
+def test_mse_distill_body(golden_dir, on_cpu, monkeypatch):
+    from cat_b200 import distill_engine, spade_distill_engine
+    # the GPU body asks for CUDA graphs; on CPU the same launch sequence runs eagerly
+    for cls in (distill_engine.DistillStep, spade_distill_engine.SpadeDistillStep):
+        orig = cls.__init__
+
+        def init(self, *a, _orig=orig, **k):
+            k['use_cuda_graph'] = False
+            _orig(self, *a, **k)
+        monkeypatch.setattr(cls, '__init__', init)
+    G.test_mse_distill_steps(golden_dir)

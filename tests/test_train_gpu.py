@@ -246,3 +246,54 @@ def test_pix2pix_model_trainer_loop(golden_dir, tmp_path):
     model.save_networks('latest')
     g = torch.load(os.path.join(str(tmp_path), 'checkpoints', 'latest_net_G.pth'), weights_only=False)
     assert list(g.keys()) == list(fix['G_sd0'].keys())
+
+
+def test_mse_distill_steps(golden_dir):
+    """--distill_G_loss_type mse (cat_b200/adaptors.py) on the device for both distillers: losses within the
+    distillation suites' bounds of the fp32 oracle, adaptor gradients within the loose gradient bound."""
+    from cat_b200.distill_engine import DistillStep
+    from cat_b200.spade_distill_engine import SpadeDistillStep
+    from oracle import cat_oracle as O
+    from oracle import spade_oracle as SO
+    fix = _load(golden_dir, 'pix2pix_bn_mse')
+    s = fix['steps'][0]
+    B, _, H, W = s['real_A'].shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+              teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
+              netA_sds=[O.clone_sd(sd) for sd in fix['netA_sd0']])
+    ref = O.distill_step(st, s['real_A'], s['real_B'], fix['hp'])
+    eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device=DEV[0], use_cuda_graph=True)
+    eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], fix['netA_sd0'])
+    eng.set_input(s['real_A'], s['real_B'])
+    eng.step()
+    _sync()
+    L = eng.get_losses()
+    for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'), ('loss_G_recon', 'G_recon'),
+                     ('loss_G_distill', 'G_distill')):
+        r = float(ref[k_ref])
+        assert abs(L[k] - r) <= 3e-2 * max(1.0, abs(r)), (k, L[k], r)
+    mine = torch.cat([eng.A.arena.view(k[1:], 'g').flatten().cpu() for k in ref['A_grads']])
+    assert rel_l2(mine, torch.cat([g.flatten() for g in ref['A_grads'].values()])) <= 0.5
+    assert _grad_err(eng.S, ref['S_grads']) <= 0.5
+
+    fix = _load(golden_dir, 'spade_more')
+    add = _load(golden_dir, 'spade_more_mse')
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    s = fix['steps'][0]
+    hp = dict(fix['hp'], distill_loss_type='mse', lambda_distill=add['lambda_distill'])
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+              vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+              adam_G={}, adam_D={}, netA_sds=[O.clone_sd(sd) for sd in add['netA_sd0']])
+    ref = SO.spade_distill_step(st, SO.preprocess_input(s['label'], s['instance'], hp['n_label']), s['image'], hp)
+    B, _, H, W = s['image'].shape
+    eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device=DEV[0], use_cuda_graph=True)
+    eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], vgg, add['netA_sd0'])
+    eng.set_input(s['label'], s['instance'], s['image'])
+    eng.step()
+    _sync()
+    L = eng.get_losses()
+    for k in ('G_gan', 'G_feat', 'G_vgg', 'G_distill', 'D_fake', 'D_real'):
+        r = float(ref['loss_' + k])
+        assert abs(L[k] - r) <= 3e-2 * max(1.0, abs(r)), (k, L[k], r)
+    mine = torch.cat([eng.A.arena.view(k[1:], 'g').flatten().cpu() for k in ref['A_grads']])
+    assert rel_l2(mine, torch.cat([g.flatten() for g in ref['A_grads'].values()])) <= 0.5
