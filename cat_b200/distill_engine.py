@@ -86,6 +86,15 @@ class DistillStep:
         self.real_A.copy_(real_A, non_blocking=True)
         self.real_B.copy_(real_B, non_blocking=True)
 
+    def set_student_training(self, training):
+        """netG_student.train() / .eval(): the reference runs its first step of a run with the pruned student still in
+        eval() and switches it to train() at the end of the first evaluate_model (inception_distiller.py:280).  The
+        captured graphs are dropped (the launch sequence of the normalisation layers changes)."""
+        if bool(training) != bool(self.S.training):
+            self.S.set_training(bool(training))
+            self.hp['student_training'] = bool(training)
+            self._graphs = None
+
     def set_lr(self, lr_G, lr_D=None):
         self.lr_G.fill_(float(lr_G))
         self.lr_D.fill_(float(lr_G if lr_D is None else lr_D))

@@ -152,6 +152,7 @@ class InceptionDistiller:
         self.engine.set_input(self.real_A, self.real_B)
 
     def optimize_parameters(self, steps):
+        self.engine.set_student_training(self.netG_student.training)     # follows netG_student.train() / .eval()
         self.engine.step()
         self._losses = None
 

@@ -118,6 +118,12 @@ class Norm:
         self._frozen = False
         self.pooled = False   # True once sums / red live in a per-network pool that is zeroed once per pass
 
+    def set_training(self, training):
+        """nn.Module.train() / eval() on the layer this object stands for."""
+        self.training = training
+        self.batch_stats = self.per_sample or training or not self.track
+        self._frozen = False
+
     def forward(self, x: Act, y: Act, act, residual=None):
         if self.batch_stats:
             if not self.pooled:
@@ -130,17 +136,22 @@ class Norm:
         elif not self._frozen:
             ops.norm_finalize(None, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
                               self.rmean, self.rvar, self.scale, self.shift, self.mean_rstd)
-            self._frozen = not self.training  # eval-mode affine of a frozen net is computed once
+            # eval-mode affine of a frozen net is computed once; a net that is being optimised in eval mode (the
+            # reference's first distillation step, see backward) recomputes it from the current gamma / beta
+            self._frozen = not self.training and self.dgamma is None
         ops.norm_apply(x, y, self.scale, self.shift, self.per_sample, act, residual)
 
     def backward(self, dout: Act, out, x: Act, dx: Act, act, param_grads=True):
-        if not self.batch_stats:
-            raise NotImplementedError('backward through eval-mode BatchNorm (the reference\'s first-step quirk, '
-                                      'SURVEY.md section 7) is not supported')
         if not self.pooled:
             self.red.zero_()
         ops.norm_bwd_reduce(dout, out, x, self.per_sample, self.mean_rstd, act, self.red)
-        ops.norm_bwd_apply(dout, out, x, dx, self.per_sample, self.mean_rstd, self.gamma, self.red, self.count, act,
+        # Eval-mode BatchNorm (the student until the first evaluate_model: model_profiling leaves it in eval(),
+        # utils/model_profiling.py:299, inception_distiller.py:280 -- the reference's FIRST step back-propagates through
+        # running statistics): mean / rstd are constants, so dx = gamma * rstd * dz and the batch-mean terms of the
+        # training-mode formula drop out -- the same kernel with an infinite element count; d gamma / d beta are the
+        # same reductions against the running statistics saved by the forward pass.
+        count = self.count if self.batch_stats else float('inf')
+        ops.norm_bwd_apply(dout, out, x, dx, self.per_sample, self.mean_rstd, self.gamma, self.red, count, act,
                            self.dgamma if param_grads else None, self.dbeta if param_grads else None)
 
 
@@ -347,6 +358,13 @@ class GenNet:
         sd = self.arena.state_dict()
         sd.update(self.bufs.state_dict())
         return sd
+
+    def set_training(self, training):
+        """train() / eval() of the generator: only the normalisation layers depend on it (dropout_rate is 0).  The launch
+        sequence changes (statistics kernels), so a captured CUDA graph of this network must be re-captured."""
+        self.training = training
+        for n in self.ns.created:
+            n.set_training(training)
 
     # ---- graph construction --------------------------------------------------------------------
     def _act(self, H, W, C, zero=False):

@@ -132,9 +132,71 @@ def make_case(name, cfg):
     return fix
 
 
+def make_first_step_addon(base_name):
+    """The reference's FIRST optimize_parameters of a run: model_profiling leaves the pruned student in eval()
+    (utils/model_profiling.py:299) and it only returns to train() at the end of the first evaluate_model
+    (inception_distiller.py:280, trainer.py:141), so that one step normalises with the BatchNorm running statistics and
+    back-propagates through them.  Same seeded networks as `base_name` (asserted), without the .train() call of make_case:
+    a small add-on fixture with the losses and gradients of that step."""
+    cfg = copy.deepcopy(CASES[base_name])
+    probe, _ = build_reference_distiller(norm=cfg['norm'], teacher_ngf=12, student_ngf=8, ndf=8, height=cfg['height'],
+                                         width=cfg['width'], batch_size=cfg['batch_size'], do_shrink=False)
+    target = probe.netG_teacher.n_macs * cfg['frac']
+    model, opt = build_reference_distiller(norm=cfg['norm'], teacher_ngf=12, student_ngf=8, ndf=8, height=cfg['height'],
+                                           width=cfg['width'], batch_size=cfg['batch_size'], target_flops=target,
+                                           gan_mode=cfg['gan_mode'], dataset_mode=cfg['dataset_mode'],
+                                           lambda_distill=cfg['lambda_distill'], lambda_recon=cfg['lambda_recon'],
+                                           recon_loss_type=cfg.get('recon_loss_type', 'l1'))
+    assert not model.netG_student.training, 'the reference is expected to leave the pruned student in eval mode'
+    g = torch.Generator().manual_seed(7)
+    for net in (model.netG_student, model.netD):
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                m.weight.data = m.weight.data * 5.0
+                if m.bias is not None:
+                    m.bias.data = 0.05 * torch.randn(m.bias.shape, generator=g)
+    base = torch.load(os.path.join(OUT_DIR, base_name + '.pt'), weights_only=False)
+    for k, v in model.netG_student.state_dict().items():
+        assert torch.equal(v, base['student_sd0'][k]), ('student differs from the base fixture', k)
+    # non-trivial running statistics (a freshly initialised student has mean 0 / var 1)
+    gs = torch.Generator().manual_seed(11)
+    stats = {}
+    for k, v in model.netG_student.state_dict().items():
+        if k.endswith('running_mean'):
+            stats[k] = 0.1 * torch.randn(v.shape, generator=gs)
+        elif k.endswith('running_var'):
+            stats[k] = 0.5 + torch.rand(v.shape, generator=gs)
+    model.netG_student.load_state_dict(stats, strict=False)
+    s0 = base['steps'][0]
+    B = cfg['batch_size']
+    model.set_input({'A': s0['real_A'].clone(), 'B': s0['real_B'].clone(), 'A_paths': ['x'] * B, 'B_paths': ['x'] * B})
+    model.forward()
+    model.set_requires_grad(model.netD, True)
+    model.optimizer_D.zero_grad()
+    model.backward_D()
+    model.optimizer_D.step()
+    model.set_requires_grad(model.netD, False)
+    model.optimizer_G.zero_grad()
+    model.backward_G(0)
+    fix = {'name': base_name + '_first_step', 'base': base_name, 'running_stats': stats,
+           'Sfake_B': model.Sfake_B.detach().clone(),
+           'S_grads': {k: p.grad.detach().clone() for k, p in model.netG_student.named_parameters()},
+           'losses': None}
+    model.optimizer_G.step()
+    fix['losses'] = {k: float(v) for k, v in model.get_current_losses().items()}
+    fix['running_stats_after'] = {k: v.detach().clone() for k, v in model.netG_student.state_dict().items() if 'running_' in k}
+    return fix
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     only = sys.argv[1:]
+    if only and only[0].endswith('_first_step'):
+        fix = make_first_step_addon(only[0][:-len('_first_step')])
+        path = os.path.join(OUT_DIR, only[0] + '.pt')
+        torch.save(fix, path)
+        print(only[0], fix['losses'], '-> %.2f MB' % (os.path.getsize(path) / 1e6))
+        return
     for name, cfg in CASES.items():
         if only and name not in only:
             continue

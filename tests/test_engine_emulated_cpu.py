@@ -159,3 +159,57 @@ def test_generator_edge_architectures_exact(norm):
                 continue
             err = float((net.arena.view(k, 'g') - p.grad).abs().max())
             assert err <= 2e-3 * float(p.grad.abs().max()) + 2e-5 * scale, (k, err, float(p.grad.abs().max()))
+
+
+@pytest.mark.timeout(600)
+def test_first_step_with_the_student_in_eval_mode_exact(golden_dir):
+    """hp['student_training'] = False: the reference's first step of a run (student still in eval(), BatchNorm running
+    statistics used and differentiated through).  Norm.backward runs the training-mode kernels with an infinite element
+    count; the affine of an eval-mode net that is being optimised is recomputed every forward pass."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    from test_oracle_golden import _first_step_state
+    fix, add, st, hp = _first_step_state(golden_dir)
+    student0 = O.clone_sd(st['student_sd'])
+    s = fix['steps'][0]
+    B, _, H, W = s['real_A'].shape
+    ref = O.distill_step(st, s['real_A'], s['real_B'], hp)
+    s1 = fix['steps'][1]
+    ref1 = O.distill_step(st, s1['real_A'], s1['real_B'], hp)        # second eval-mode step: gamma / beta have moved
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], student0, fix['D_sd0'])
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), ref['Sfake_B']) < 1e-5
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), add['Sfake_B']) < 1e-5          # the real reference's image
+        L = eng.get_losses()
+        for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'),
+                         ('loss_G_recon', 'G_recon'), ('loss_G_distill', 'G_distill')):
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+        scale = max(float(g.abs().max()) for g in ref['S_grads'].values())
+        for k, g in ref['S_grads'].items():
+            if eng.S.arena.has(k):
+                err = float((eng.S.arena.view(k, 'g') - g).abs().max())
+                assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
+        sd = eng.S.state_dict()
+        for k, v in add['running_stats'].items():
+            assert torch.equal(sd[k], v), k                       # eval mode: running statistics untouched
+        eng.set_input(s1['real_A'], s1['real_B'])
+        eng.step()
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), ref1['Sfake_B']) < 1e-4
+        # netG_student.train() after the first evaluate_model: the same engine continues in training mode
+        ref2 = O.distill_step(st, s['real_A'], s['real_B'], dict(hp, student_training=True))
+        eng.set_student_training(True)
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3), ref2['Sfake_B']) < 2e-4
+        L = eng.get_losses()
+        assert abs(L['G_recon'] - float(ref2['loss_G_recon'])) <= 2e-4 * float(ref2['loss_G_recon'])
+        sd = eng.S.state_dict()
+        for k, v in st['student_sd'].items():                     # now the running statistics move
+            if 'running_' in k:
+                assert float((sd[k] - v).abs().max()) <= 1e-4 * max(1.0, float(v.abs().max())), k

@@ -103,3 +103,32 @@ def test_ka_analytic_gradient_matches_autograd():
     X1 = torch.randn(1, 3, 4, 4, dtype=torch.float64)
     assert abs(float(O.ka(X1, torch.randn(1, 5, 4, 4, dtype=torch.float64))) - 1) < 1e-12
     assert O.ka_grad_x(X1, torch.randn(1, 5, 4, 4, dtype=torch.float64)).abs().max() < 1e-12
+
+
+def _first_step_state(golden_dir):
+    fix = _load(golden_dir, 'pix2pix_bn_lsgan_l2')
+    add = _load(golden_dir, 'pix2pix_bn_lsgan_l2_first_step')
+    student = O.clone_sd(fix['student_sd0'])
+    student.update({k: v.clone() for k, v in add['running_stats'].items()})
+    state = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=student, D_sd=O.clone_sd(fix['D_sd0']),
+                 teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    return fix, add, state, dict(fix['hp'], student_training=False)
+
+
+def test_first_step_with_the_student_in_eval_mode_matches_reference(golden_dir):
+    """The reference's first optimize_parameters of a run: the pruned student is still in eval() (left there by
+    model_profiling, utils/model_profiling.py:299; back to train() only at the end of the first evaluate_model,
+    inception_distiller.py:280), so BatchNorm uses -- and is differentiated through -- its running statistics."""
+    fix, add, state, hp = _first_step_state(golden_dir)
+    s = fix['steps'][0]
+    out = O.distill_step(state, s['real_A'], s['real_B'], hp)
+    _close(out['Sfake_B'], add['Sfake_B'])
+    for k_ref, k in (('loss_G_gan', 'G_loss/G_gan'), ('loss_G_recon', 'G_loss/G_recon'), ('loss_G_distill', 'G_loss/G_distill'),
+                     ('loss_D_fake', 'D_loss/D_fake'), ('loss_D_real', 'D_loss/D_real')):
+        r = add['losses'][k]
+        assert abs(float(out[k_ref]) - r) < 1e-4 * max(1.0, abs(r)), (k, float(out[k_ref]), r)
+    scale = max(float(g.abs().max()) for g in add['S_grads'].values())
+    for k, g in add['S_grads'].items():
+        _close(out['S_grads'][k], g, rtol=1e-3, atol=1e-5 * scale, what=k)
+    for k, v in add['running_stats_after'].items():          # eval mode: the running statistics do not move
+        assert torch.equal(state['student_sd'][k], add['running_stats'][k]) and torch.equal(v, add['running_stats'][k]), k

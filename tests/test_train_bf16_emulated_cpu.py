@@ -53,3 +53,8 @@ def test_mse_distill_body(golden_dir, on_cpu, monkeypatch):
             _orig(self, *a, **k)
         monkeypatch.setattr(cls, '__init__', init)
     G.test_mse_distill_steps(golden_dir)
+
+
+@pytest.mark.timeout(600)
+def test_first_step_eval_mode_body(golden_dir, on_cpu):
+    G.test_first_step_with_the_student_in_eval_mode(golden_dir)

@@ -297,3 +297,45 @@ def test_mse_distill_steps(golden_dir):
         assert abs(L[k] - r) <= 3e-2 * max(1.0, abs(r)), (k, L[k], r)
     mine = torch.cat([eng.A.arena.view(k[1:], 'g').flatten().cpu() for k in ref['A_grads']])
     assert rel_l2(mine, torch.cat([g.flatten() for g in ref['A_grads'].values()])) <= 0.5
+
+
+def test_first_step_with_the_student_in_eval_mode(golden_dir):
+    """The reference's first step of a run (student still in eval(): BatchNorm running statistics used and differentiated
+    through, Norm.backward with an infinite element count), then netG_student.train() on the same engine (graphs re-captured)."""
+    from cat_b200 import ops
+    from cat_b200.distill_engine import DistillStep
+    from oracle import cat_oracle as O
+    fix = _load(golden_dir, 'pix2pix_bn_lsgan_l2')
+    add = _load(golden_dir, 'pix2pix_bn_lsgan_l2_first_step')
+    student0 = O.clone_sd(fix['student_sd0'])
+    student0.update({k: v.clone() for k, v in add['running_stats'].items()})
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(student0), D_sd=O.clone_sd(fix['D_sd0']),
+              teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    hp = dict(fix['hp'], student_training=False)
+    s = fix['steps'][0]
+    B, _, H, W = s['real_A'].shape
+    ref = O.distill_step(st, s['real_A'], s['real_B'], hp)
+    eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device=DEV[0],
+                      use_cuda_graph=DEV[0] != 'cpu')
+    eng.load(fix['teacher_sd'], student0, fix['D_sd0'])
+    eng.set_input(s['real_A'], s['real_B'])
+    eng.step()
+    _sync()
+    assert rel_l2(ops.nhwc_to_nchw(eng.S.out, 3).cpu(), add['Sfake_B']) <= 3e-2       # the real reference's image
+    L = eng.get_losses()
+    for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'), ('loss_G_recon', 'G_recon'),
+                     ('loss_G_distill', 'G_distill')):
+        r = float(ref[k_ref])
+        assert abs(L[k] - r) <= 3e-2 * max(1.0, abs(r)), (k, L[k], r)
+    assert _grad_err(eng.S, ref['S_grads']) <= 0.5
+    sd = eng.S.state_dict()
+    for k, v in add['running_stats'].items():
+        assert torch.equal(sd[k], v), k                          # eval mode: running statistics untouched
+    ref2 = O.distill_step(st, s['real_A'], s['real_B'], dict(hp, student_training=True))
+    eng.set_student_training(True)
+    eng.step()
+    _sync()
+    L = eng.get_losses()
+    assert abs(L['G_recon'] - float(ref2['loss_G_recon'])) <= 5e-2 * float(ref2['loss_G_recon'])
+    sd = eng.S.state_dict()
+    assert any(not torch.equal(sd[k], v) for k, v in add['running_stats'].items())   # training mode: they move
