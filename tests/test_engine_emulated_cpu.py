@@ -213,3 +213,38 @@ def test_first_step_with_the_student_in_eval_mode_exact(golden_dir):
         for k, v in st['student_sd'].items():                     # now the running statistics move
             if 'running_' in k:
                 assert float((sd[k] - v).abs().max()) <= 1e-4 * max(1.0, float(v.abs().max())), k
+
+
+@pytest.mark.timeout(600)
+def test_batch_of_one_exact(golden_dir):
+    """BASELINE configs[0] shape: one image per step.  KA is degenerate there (K is 1x1: KA == 1 and its gradient vanishes,
+    SURVEY.md section 7), so the four distillation terms are exactly -1 and the student gradient is the GAN + reconstruction
+    gradient alone."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    fix = torch.load(os.path.join(golden_dir, 'cyclegan_in_lsgan.pt'), weights_only=False)
+    s = fix['steps'][0]
+    a, b = s['real_A'][:1], s['real_B'][:1]
+    _, _, H, W = a.shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+              teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    ref = O.distill_step(st, a, b, fix['hp'])
+    no_ka = O.distill_step(dict(st, student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']), adam_G={}, adam_D={}),
+                           a, b, dict(fix['hp'], lambda_distill=0.0))
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], 1, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(a, b)
+        eng.step()
+        L = eng.get_losses()
+        for i in range(4):
+            assert abs(L['G_distill%d' % i] + 1.0) < 1e-6 and abs(float(ref['loss_G_distill_terms'][i]) + 1.0) < 1e-6
+        for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'), ('loss_G_recon', 'G_recon')):
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+        scale = max(float(g.abs().max()) for g in ref['S_grads'].values())
+        for k, g in no_ka['S_grads'].items():          # identical to the step without the distillation term
+            if eng.S.arena.has(k):
+                err = float((eng.S.arena.view(k, 'g') - g).abs().max())
+                assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))

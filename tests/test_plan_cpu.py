@@ -235,3 +235,69 @@ def test_halo_plan_k_concat():
     y = torch.zeros(N, H, W, P.cpad(C), dtype=torch.float64)
     P.emulate_halo_fprop(g, plan, C, buf, arena, y)
     assert torch.allclose(from_nhwc(y, C), ref, atol=1e-10)
+
+
+@pytest.mark.parametrize('Cin,Cout,H,W', [(3, 17, 9, 11), (3, 64, 12, 8)])
+def test_stem_input_gradient_frame(Cin, Cout, H, W):
+    """GenNet(input_grad=True) (CycleGAN's cycle term back-propagates through a generator's input): gradient of the 7x7
+    reflect-padded stem w.r.t. its PADDED input frame, as one GEMM with q = 0 over a (H+6) x (W+6) output lattice and
+    n_rows = 3; both the gather-per-tap table and the halo plan, then the real ops.Gemm object (halo tilings must fit)."""
+    torch.manual_seed(3)
+    N, k, p = 2, 7, 3
+    x = torch.randn(N, Cin, H, W, dtype=torch.float64)
+    xp = F.pad(x, (p,) * 4, mode='reflect').requires_grad_(True)
+    w = torch.randn(Cout, Cin, k, k, dtype=torch.float64)
+    y = F.conv2d(xp, w)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    arena, (w_off,) = make_arena(w)
+    units = P.conv_dgrad_units(w_off, Cout, Cin, k, k, 0)
+    geo = P.Geometry(N, H, W, P.cpad(Cout), 0, H + 2 * p, W + 2 * p, P.cpad(Cin), 0)
+    fr = torch.zeros(N, H + 2 * p, W + 2 * p, P.cpad(Cin), dtype=torch.float64)
+    P.emulate_fprop(geo, units, Cin, to_nhwc(dy), arena, fr)
+    assert torch.allclose(from_nhwc(fr, Cin), xp.grad, atol=1e-9)
+    assert float(fr[..., Cin:].abs().max()) == 0.0           # padding channels stay exactly zero
+    plan = P.make_halo_plan(geo, units)
+    assert plan is not None
+    for m_sub in (1, 2):
+        plan.m_sub = m_sub
+        fr2 = torch.zeros_like(fr)
+        P.emulate_halo_fprop(geo, plan, Cin, to_nhwc(dy), arena, fr2)
+        assert torch.allclose(from_nhwc(fr2, Cin), xp.grad, atol=1e-9), m_sub
+    from cat_b200 import ops
+    g = ops.Gemm(geo, units, Cin, 'cpu')
+    assert g.halo is not None and len(g.tilings) > 0
+
+
+def test_adaptor_gemms():
+    """cat_b200/adaptors.py ('mse' distillation loss): netA_i as a biased 1x1 GEMM C_S -> C_T over the mapped student
+    activation, and its input gradient C_T -> C_S accumulated into an existing d(activation) buffer."""
+    torch.manual_seed(4)
+    N, H, W, Cs, Ct = 2, 6, 5, 18, 48
+    x = torch.randn(N, Cs, H, W, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Ct, Cs, 1, 1, dtype=torch.float64)
+    b = torch.randn(Ct, dtype=torch.float64)
+    y_ref = F.conv2d(x, w, b)
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    arena, (w_off,) = make_arena(w)
+    fu = P.conv_fprop_units(w_off, Ct, Cs, 1, 1, 0)
+    gf = P.Geometry(N, H, W, P.cpad(Cs), 0, H, W, P.cpad(Ct), 0)
+    y = torch.zeros(N, H, W, P.cpad(Ct), dtype=torch.float64)
+    P.emulate_fprop(gf, fu, Ct, to_nhwc(x.detach()), arena, y, bias=b)
+    assert torch.allclose(from_nhwc(y, Ct), y_ref.detach(), atol=1e-10)
+    du = P.conv_dgrad_units(w_off, Ct, Cs, 1, 1, 0)
+    gb = P.Geometry(N, H, W, P.cpad(Ct), 0, H, W, P.cpad(Cs), 0)
+    prev = torch.randn(N, Cs, H, W, dtype=torch.float64)
+    for plan in (None, P.make_halo_plan(gb, du)):
+        dx = to_nhwc(prev).clone()
+        if plan is None:
+            P.emulate_fprop(gb, du, Cs, to_nhwc(dy), arena, dx, None, True)
+        else:       # the halo emulator has no accumulate flag (the device epilogue has): add the product to the buffer
+            tmp = torch.zeros_like(dx)
+            P.emulate_halo_fprop(gb, plan, Cs, to_nhwc(dy), arena, tmp)
+            dx = dx + tmp
+        assert torch.allclose(from_nhwc(dx, Cs), prev + x.grad, atol=1e-9)
+    from cat_b200 import ops
+    for geo, units, rows in ((gf, fu, Ct), (gb, du, Cs)):
+        assert ops.Gemm(geo, units, rows, 'cpu').n_units == len(units)
