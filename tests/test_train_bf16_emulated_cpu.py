@@ -2,10 +2,14 @@
 kernel wrappers swapped for their torch restatements in bf16-storage mode (oracle/kernel_emu.py): the stated GPU
 tolerances must hold for the same launch sequences when only the storage precision of the device path is modelled."""
 import importlib
+import os
 
 import pytest
 
 G = importlib.import_module('test_train_gpu')
+# the bodies below repeat what the exact-mode tests establish and only calibrate the GPU tolerances: the longer ones run
+# with CATB_SLOW_TESTS=1 (they were run when the tolerances were set; the default CPU suite keeps one per engine family)
+slow = pytest.mark.skipif(os.environ.get('CATB_SLOW_TESTS', '0') != '1', reason='set CATB_SLOW_TESTS=1')
 
 
 @pytest.fixture
@@ -20,7 +24,7 @@ def on_cpu():
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize('name', ['train_pix2pix_in_lsgan_l2', 'train_pix2pix_bn_hinge'])
+@pytest.mark.parametrize('name', [pytest.param('train_pix2pix_in_lsgan_l2', marks=slow), 'train_pix2pix_bn_hinge'])
 def test_pix2pix_bodies(golden_dir, on_cpu, name):
     G.test_pix2pix_train_step(golden_dir, name, False)
 
@@ -31,6 +35,7 @@ def test_cyclegan_bodies(golden_dir, on_cpu, name):
     G.test_cyclegan_train_steps(golden_dir, name, False)
 
 
+@slow
 @pytest.mark.timeout(1200)
 def test_spade_body(golden_dir, on_cpu):
     G.test_spade_train_step(golden_dir, False)
@@ -41,6 +46,7 @@ def test_leaky001_body(on_cpu):
     G.test_leaky001_activation_kernels()
 
 
+@slow
 @pytest.mark.timeout(900)
 def test_mse_distill_body(golden_dir, on_cpu, monkeypatch):
     from cat_b200 import distill_engine, spade_distill_engine
