@@ -6,7 +6,10 @@ What ``trainer.py:79-175`` calls is kept name for name: ``InceptionDistiller(opt
 ``print_networks``, ``test``; attributes ``netG_teacher / netG_student / netD / netAs``, ``optimizers``,
 ``Tfake_B / Sfake_B``, ``loss_*``.  The networks are the module-tree mirrors of cat_b200.models.networks whose
 parameters alias the engine arenas, so checkpoints written here load in the reference and vice versa.
-Out of scope: FID / mIoU evaluation (``evaluate_model`` raises), data loading, logging.
+``evaluate_model`` runs the generator inference over ``self.eval_dataloader`` through the module mirrors and keeps the
+reference's best / mean bookkeeping; the metric networks themselves (FID InceptionV3, DRN mIoU; SURVEY.md section 2: out of
+scope) are supplied by the caller as ``self.metric_fns = {'fid': f(fakes), 'mIoU': f(fakes, names)}``.  Data loading and
+logging are out of scope.
 """
 import os
 from collections import OrderedDict
@@ -14,6 +17,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
+from .. import ops
 from ..distill_engine import DistillStep
 from ..engine import MAPPING_LAYERS
 from ..models import networks
@@ -71,10 +75,11 @@ class InceptionDistiller:
     def __init__(self, opt):
         assert opt.isTrain
         self.opt = opt
-        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0]))
-        if not self.gpu_ids or not torch.cuda.is_available():
-            raise RuntimeError('cat_b200.InceptionDistiller needs a CUDA device (sm_100a); there is no CPU path')
-        self.device = torch.device('cuda:%d' % self.gpu_ids[0])
+        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0])) or [0]
+        # raises without an sm_100 device and libcatb200.so: there is no CPU path.  (Only the kernel emulation of the test
+        # suite patches this check out; it then runs the host logic on CPU tensors.)
+        ops.require_cuda()
+        self.device = torch.device('cuda:%d' % self.gpu_ids[0]) if torch.cuda.is_available() else torch.device('cpu')
         self.save_dir = os.path.join(getattr(opt, 'log_dir', '.'), 'checkpoints')
         if getattr(opt, 'distill_G_loss_type', 'ka') not in ('ka', 'mse'):
             raise NotImplementedError('--distill_G_loss_type [%s]: ka | mse' % opt.distill_G_loss_type)
@@ -84,7 +89,7 @@ class InceptionDistiller:
         self.model_names = ['netG_student', 'netG_teacher', 'netD']
         self.visual_names = ['real_A', 'Sfake_B', 'Tfake_B', 'real_B']
         self.image_paths = []
-        ids = self.gpu_ids[:1]
+        ids = self.gpu_ids[:1] if self.device.type == 'cuda' else []
         self.netG_teacher = networks.define_G(opt.input_nc, opt.output_nc, opt.teacher_ngf, opt.teacher_netG, opt.norm,
                                               0, opt.init_type, opt.init_gain, ids, opt=opt)
         arch_S = getattr(opt, 'student_arch', None)  # pruned architecture (what shrink_model produces)
@@ -110,10 +115,18 @@ class InceptionDistiller:
         self.engine = None
         self.is_best = False
         self._epoch = 0
+        self.eval_dataloader = []          # set by the caller (data/ is outside the hot path)
+        self.metric_fns = {}               # {'fid': f(fakes) -> float, 'mIoU': f(fakes, names) -> float}
+        self.best_fid, self.best_mIoU = 1e9, -1e9
+        self.fids, self.mIoUs = [], []
 
     # ---- protocol -------------------------------------------------------------------------------
     def setup(self, opt, verbose=True):
         self.load_networks(verbose)
+        # The reference profiles both generators here (inception_distiller.py:85-97) and model_profiling leaves them in
+        # eval() (utils/model_profiling.py:299): the student only returns to train() at the end of the first
+        # evaluate_model (:280), so the FIRST optimize_parameters of a run uses the BatchNorm running statistics.
+        self.netG_student.eval()
         if verbose:
             self.print_networks()
 
@@ -188,8 +201,37 @@ class InceptionDistiller:
         msg = 'learning rate = %.7f' % lr
         logger.print_info(msg + '\n') if logger is not None else print(msg)
 
-    def evaluate_model(self, step):
-        raise NotImplementedError('FID / mIoU evaluation (metric/) is outside the distillation hot path')
+    def evaluate_model(self, step, save_image=False):
+        """inception_distiller.py:204-281: student (and teacher) inference over the evaluation set in eval mode, metric
+        bookkeeping, and the student back in train() -- the module forward compiles its own inference network per batch
+        shape against the same parameter arena, so the training engine and its optimiser state are untouched."""
+        self.is_best = False
+        self.netG_student.eval()
+        AtoB = getattr(self.opt, 'direction', 'AtoB') == 'AtoB'
+        fakes, names = [], []
+        for data_i in self.eval_dataloader:
+            real_A = data_i['A' if AtoB else 'B'].to(self.device)
+            with torch.no_grad():
+                self.Tfake_B = self.netG_teacher(real_A)
+                self.Sfake_B = self.netG_student(real_A)
+            fakes.append(self.Sfake_B.cpu())
+            names += [os.path.splitext(os.path.basename(p))[0] for p in data_i.get('A_paths' if AtoB else 'B_paths', [])]
+        ret = {}
+        if 'fid' in self.metric_fns:
+            fid = float(self.metric_fns['fid'](fakes))
+            if fid < self.best_fid:
+                self.is_best, self.best_fid = True, fid
+            self.fids = (self.fids + [fid])[-3:]
+            ret.update({'metric/fid': fid, 'metric/fid-mean': sum(self.fids) / len(self.fids), 'metric/fid-best': self.best_fid})
+        if 'mIoU' in self.metric_fns:
+            mIoU = float(self.metric_fns['mIoU'](fakes, names))
+            if mIoU > self.best_mIoU:
+                self.is_best, self.best_mIoU = True, mIoU
+            self.mIoUs = (self.mIoUs + [mIoU])[-3:]
+            ret.update({'metric/mIoU': mIoU, 'metric/mIoU-mean': sum(self.mIoUs) / len(self.mIoUs),
+                        'metric/mIoU-best': self.best_mIoU})
+        self.netG_student.train()
+        return ret
 
     def add_mapping_hook(self):
         pass   # the engine exposes the four mapped activations natively (engine.S.acts / engine.T.acts)

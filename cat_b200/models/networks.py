@@ -200,7 +200,10 @@ class _EngineBacked(nn.Module):
     def engine(self, B, H, W, device, training, need_grad):
         cache = self.__dict__.setdefault('_engines', {})
         key = (B, H, W, str(device), bool(training))
-        if key not in cache:
+        hit = cache.get(key)
+        if hit is not None and bool(getattr(hit, 'training', training)) != bool(training):
+            hit = None        # the distiller's network was switched between train() and eval() since it was registered
+        if hit is None:
             primary = self.__dict__.get('_primary')
             net = self._compile(B, H, W, device, training, need_grad, primary)
             if primary is None:

@@ -187,6 +187,7 @@ def shrink_inception(model, opt):
     gpu_ids = list(getattr(model, 'gpu_ids', []))[:1]
     model.netG_student = networks.init_net(networks.InceptionGenerator.from_arch(student_arch), opt.init_type, opt.init_gain, gpu_ids)
     model.netG_student.n_macs = info['macs']
+    model.netG_student.eval()      # shrink_model profiles the new student, which leaves it in eval() (utils/common.py:148)
     teacher.n_macs = generator_macs(teacher.arch(), int(opt.data_height), int(opt.data_width))
     if getattr(model, 'netAs', None):       # adaptor convs follow the pruned width (utils/common.py:154-161)
         from torch import nn
