@@ -21,6 +21,7 @@ from .. import ops
 from ..distill_engine import DistillStep
 from ..engine import MAPPING_LAYERS
 from ..models import networks
+from ..models.base_model import MetricBook, image_names
 
 
 class _ArenaOptimizer:
@@ -117,8 +118,7 @@ class InceptionDistiller:
         self._epoch = 0
         self.eval_dataloader = []          # set by the caller (data/ is outside the hot path)
         self.metric_fns = {}               # {'fid': f(fakes) -> float, 'mIoU': f(fakes, names) -> float}
-        self.best_fid, self.best_mIoU = 1e9, -1e9
-        self.fids, self.mIoUs = [], []
+        self.metrics = MetricBook()
 
     # ---- protocol -------------------------------------------------------------------------------
     def setup(self, opt, verbose=True):
@@ -215,21 +215,8 @@ class InceptionDistiller:
                 self.Tfake_B = self.netG_teacher(real_A)
                 self.Sfake_B = self.netG_student(real_A)
             fakes.append(self.Sfake_B.cpu())
-            names += [os.path.splitext(os.path.basename(p))[0] for p in data_i.get('A_paths' if AtoB else 'B_paths', [])]
-        ret = {}
-        if 'fid' in self.metric_fns:
-            fid = float(self.metric_fns['fid'](fakes))
-            if fid < self.best_fid:
-                self.is_best, self.best_fid = True, fid
-            self.fids = (self.fids + [fid])[-3:]
-            ret.update({'metric/fid': fid, 'metric/fid-mean': sum(self.fids) / len(self.fids), 'metric/fid-best': self.best_fid})
-        if 'mIoU' in self.metric_fns:
-            mIoU = float(self.metric_fns['mIoU'](fakes, names))
-            if mIoU > self.best_mIoU:
-                self.is_best, self.best_mIoU = True, mIoU
-            self.mIoUs = (self.mIoUs + [mIoU])[-3:]
-            ret.update({'metric/mIoU': mIoU, 'metric/mIoU-mean': sum(self.mIoUs) / len(self.mIoUs),
-                        'metric/mIoU-best': self.best_mIoU})
+            names += image_names(data_i.get('A_paths' if AtoB else 'B_paths', []))
+        ret, self.is_best = self.metrics.update(self.metric_fns, fakes, names)
         self.netG_student.train()
         return ret
 

@@ -6,7 +6,9 @@ What ``trainer.py:79-175`` touches is kept name for name: ``SPADEDistiller(opt)`
 ``label`` / ``instance`` / ``image`` / ``path``), ``optimize_parameters``, ``get_current_losses``, ``save_networks`` /
 ``load_networks``, ``update_learning_rate``, ``print_networks``; ``modules_on_one_gpu`` with ``netG_student /
 netG_teacher / netD / netAs / mapping_layers``, ``optimizer_G / optimizer_D / optimizers``, ``loss_*``.
-Out of scope: FID / mIoU evaluation (``evaluate_model`` raises), data loading, logging.
+``evaluate_model`` runs the student inference over ``self.eval_dataloader`` in eval mode with the reference's metric bookkeeping;
+the metric networks come from the caller as ``self.metric_fns`` (see cat_b200/models/base_model.py).  Data loading and logging are
+out of scope.
 The VGG19 weights come from ``opt.vgg_state_dict`` (torchvision ``vgg19().features`` keys) -- the pretrained checkpoint
 the reference downloads (models/modules/loss.py:154) has to be supplied by the caller.
 """
@@ -17,6 +19,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
+from .. import ops
 from ..models import networks
 from ..spade_distill_engine import SpadeDistillStep
 from ..spade_engine import MAPPING_LAYERS
@@ -29,7 +32,7 @@ class SPADEDistillerModules(nn.Module):
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
-        self.gpu_ids = list(opt.gpu_ids[:1])
+        self.gpu_ids = list(opt.gpu_ids[:1]) if torch.cuda.is_available() else []
         t_opt, s_opt = copy.deepcopy(opt), copy.deepcopy(opt)
         t_opt.norm_G, t_opt.ngf = opt.teacher_norm_G, opt.teacher_ngf
         s_opt.norm_G, s_opt.ngf = opt.student_norm_G, opt.student_ngf
@@ -85,14 +88,15 @@ class SPADEDistiller:
     def __init__(self, opt):
         assert opt.isTrain
         self.opt = opt
-        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0]))
-        if not self.gpu_ids or not torch.cuda.is_available():
-            raise RuntimeError('cat_b200.SPADEDistiller needs a CUDA device (sm_100a); there is no CPU path')
+        self.gpu_ids = list(getattr(opt, 'gpu_ids', [0])) or [0]
+        # raises without an sm_100 device and libcatb200.so: there is no CPU path.  (Only the kernel emulation of the test
+        # suite patches this check out; it then runs the host logic on CPU tensors.)
+        ops.require_cuda()
         if getattr(opt, 'distill_G_loss_type', 'ka') not in ('ka', 'mse'):
             raise NotImplementedError('--distill_G_loss_type [%s]: ka | mse' % opt.distill_G_loss_type)
         if getattr(opt, 'gan_mode', 'hinge') != 'hinge':
             raise NotImplementedError('the SPADE distiller uses the hinge GAN loss (spade_model.py default)')
-        self.device = torch.device('cuda:%d' % self.gpu_ids[0])
+        self.device = torch.device('cuda:%d' % self.gpu_ids[0]) if torch.cuda.is_available() else torch.device('cpu')
         self.save_dir = os.path.join(getattr(opt, 'log_dir', '.'), 'checkpoints')
         self.model_names = ['G_student', 'G_teacher', 'D']
         self.visual_names = ['labels', 'Tfake_B', 'Sfake_B', 'real_B']
@@ -194,8 +198,25 @@ class SPADEDistiller:
         msg = 'learning rate = %.7f' % (self.lr_G * scale)
         logger.print_info(msg + '\n') if logger is not None else print(msg)
 
-    def evaluate_model(self, step):
-        raise NotImplementedError('FID / mIoU evaluation (metric/) is outside the distillation hot path')
+    def evaluate_model(self, step, save_image=False):
+        """spade_distiller.py:96-171: student inference over the evaluation set in eval mode (module forward = its own
+        inference network per batch shape on the shared arena), metric bookkeeping, student back in train()."""
+        from ..models.base_model import MetricBook, image_names
+        from ..models.spade_model import input_semantics
+        if not hasattr(self, 'metrics'):
+            self.metrics = MetricBook()
+        mm, o = self.modules_on_one_gpu, self.opt
+        self.is_best = False
+        mm.netG_student.eval()
+        fakes, names = [], []
+        for data_i in getattr(self, 'eval_dataloader', []):
+            with torch.no_grad():
+                self.Sfake_B = mm.netG_student(input_semantics(data_i, int(o.input_nc), int(mm.netG_student.opt.semantic_nc), self.device))
+            fakes.append(self.Sfake_B.cpu())
+            names += image_names(data_i.get('path', []))
+        ret, self.is_best = self.metrics.update(getattr(self, 'metric_fns', {}), fakes, names)
+        mm.netG_student.train()
+        return ret
 
     def print_networks(self):
         mm = self.modules_on_one_gpu

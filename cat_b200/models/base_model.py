@@ -4,7 +4,10 @@
 top of an engine step (cat_b200/train_engine.py).  The networks are the module-tree mirrors of
 cat_b200.models.networks whose parameters alias the engine arenas, so checkpoints written here load in the reference
 (and in the distillers as ``restore_teacher_G_path`` / ``restore_D_path``) and vice versa.
-Out of scope: FID / mIoU evaluation (``evaluate_model`` raises), data loading, logging.
+``evaluate_model`` runs the generator inference over ``self.eval_dataloader`` (an iterable of dataset dicts set by the caller)
+in eval mode and keeps the reference's best / mean-of-three bookkeeping; the metric networks (FID InceptionV3, DRN mIoU;
+SURVEY.md section 2: out of scope) come from the caller as ``self.metric_fns = {'fid': f(fakes), 'mIoU': f(fakes, names)}``.
+Data loading and logging are out of scope.
 """
 import os
 from collections import OrderedDict
@@ -41,6 +44,36 @@ class ArenaOptimizer:
             c.fill_(int(s['step']))
 
 
+class MetricBook:
+    """Best / mean-of-the-last-three bookkeeping of the reference's evaluate_model (e.g. models/pix2pix_model.py:252-281)."""
+
+    def __init__(self):
+        self.best_fid, self.best_mIoU, self.fids, self.mIoUs = 1e9, -1e9, [], []
+
+    def update(self, fns, fakes, names, suffix=''):
+        """-> (metrics dict, is_best)"""
+        ret, best = {}, False
+        if 'fid' in fns:
+            fid = float(fns['fid'](fakes))
+            if fid < self.best_fid:
+                best, self.best_fid = True, fid
+            self.fids = (self.fids + [fid])[-3:]
+            ret.update({'metric/fid' + suffix: fid, 'metric/fid%s-mean' % suffix: sum(self.fids) / len(self.fids),
+                        'metric/fid%s-best' % suffix: self.best_fid})
+        if 'mIoU' in fns:
+            mIoU = float(fns['mIoU'](fakes, names))
+            if mIoU > self.best_mIoU:
+                best, self.best_mIoU = True, mIoU
+            self.mIoUs = (self.mIoUs + [mIoU])[-3:]
+            ret.update({'metric/mIoU' + suffix: mIoU, 'metric/mIoU%s-mean' % suffix: sum(self.mIoUs) / len(self.mIoUs),
+                        'metric/mIoU%s-best' % suffix: self.best_mIoU})
+        return ret, best
+
+
+def image_names(paths):
+    return [os.path.splitext(os.path.basename(p))[0] for p in paths]
+
+
 class BaseModel:
     """Subclasses define ``model_names`` (net<name> attributes), ``loss_names``, ``_make_engine(B, H, W)`` and
     ``_set_engine_input(input)``."""
@@ -62,6 +95,7 @@ class BaseModel:
         self.is_best = False
         self.metric = 0
         self._epoch = 0
+        self.eval_dataloader, self.metric_fns, self.metrics = [], {}, MetricBook()
 
     @staticmethod
     def modify_commandline_options(parser, is_train):
@@ -137,8 +171,18 @@ class BaseModel:
     def set_requires_grad(self, nets, requires_grad=False):
         pass    # the engine step freezes / unfreezes the discriminators by construction
 
-    def evaluate_model(self, step):
-        raise NotImplementedError('FID / mIoU evaluation (metric/) is outside the training hot path')
+    def evaluate_model(self, step, save_image=False):
+        """Generator inference over the evaluation set in eval mode + metric bookkeeping (subclasses: _eval_batch)."""
+        self.is_best = False
+        self.eval()
+        fakes, names = [], []
+        for data_i in self.eval_dataloader:
+            fake, paths = self._eval_batch(data_i)
+            fakes.append(fake.cpu())
+            names += image_names(paths)
+        ret, self.is_best = self.metrics.update(self.metric_fns, fakes, names)
+        self.train()
+        return ret
 
     def print_networks(self):
         for name in self.model_names:

@@ -6,7 +6,7 @@ import torch
 
 from ..train_engine import CycleGANTrainStep
 from . import networks
-from .base_model import ArenaOptimizer, BaseModel
+from .base_model import ArenaOptimizer, BaseModel, MetricBook, image_names
 
 
 class CycleGANModel(BaseModel):
@@ -70,3 +70,25 @@ class CycleGANModel(BaseModel):
             self.rec_A = self.netG_B(self.fake_B)
             self.fake_A = self.netG_B(self.engine.real_B)
             self.rec_B = self.netG_A(self.fake_A)
+
+    def evaluate_model(self, step, save_image=False):
+        """models/cycle_gan_model.py:310-365: both directions (`eval_dataloader_AtoB` -> G_A, `eval_dataloader_BtoA` -> G_B,
+        each an iterable of {'A', 'A_paths'} dicts set by the caller), FID per direction through `metric_fns_A` / `_B`."""
+        if not hasattr(self, 'metrics_B'):
+            self.metrics_A, self.metrics_B = MetricBook(), MetricBook()
+        self.is_best_A = self.is_best_B = False
+        self.eval()
+        ret = {}
+        for side, net in (('A', self.netG_A), ('B', self.netG_B)):
+            loader = getattr(self, 'eval_dataloader_AtoB' if side == 'A' else 'eval_dataloader_BtoA', [])
+            fakes, names = [], []
+            for data_i in loader:
+                with torch.no_grad():
+                    fakes.append(net(data_i['A'].to(self.device)).cpu())
+                names += image_names(data_i.get('A_paths', []))
+            r, best = getattr(self, 'metrics_' + side).update(getattr(self, 'metric_fns_' + side, {}), fakes, names, '_' + side)
+            setattr(self, 'is_best_' + side, best)
+            ret.update(r)
+        self.is_best = self.is_best_A or self.is_best_B
+        self.train()
+        return ret

@@ -61,3 +61,10 @@ class Pix2PixModel(BaseModel):
     def forward(self):
         with torch.no_grad():
             self.fake_B = self.netG(self.engine.real_A)
+
+    def _eval_batch(self, data):
+        """models/pix2pix_model.py:222-226: fake_B for one evaluation batch (module forward = inference engine)."""
+        AtoB = getattr(self.opt, 'direction', 'AtoB') == 'AtoB'
+        with torch.no_grad():
+            self.fake_B = self.netG(data['A' if AtoB else 'B'].to(self.device))
+        return self.fake_B, data.get('A_paths' if AtoB else 'B_paths', [])

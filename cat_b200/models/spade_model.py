@@ -4,11 +4,23 @@ cat_b200.train_engine.SpadeTrainStep.step().  ``modify_commandline_options`` set
 reference (spade_model.py:92), so teachers trained here have the reference's activations.
 The VGG19 weights come from ``opt.vgg_state_dict`` (torchvision ``vgg19().features`` keys): the pretrained checkpoint
 the reference downloads (models/modules/loss.py:154) has to be supplied by the caller."""
+import torch
 from torch import nn
 
 from ..train_engine import SpadeTrainStep
 from . import networks
 from .base_model import ArenaOptimizer, BaseModel
+
+
+def input_semantics(data, n_label, semantic_nc, device):
+    """preprocess_input / get_edges (models/spade_model.py:142-179) for one dataset dict -> NCHW fp32 one-hot + edge map."""
+    from .. import ops
+    B, _, H, W = data['label'].shape
+    label = data['label'].reshape(B, H, W).to(device=device, dtype=torch.int32).contiguous()
+    inst = data['instance'].reshape(B, H, W).to(device=device, dtype=torch.int32).contiguous()
+    seg = ops.Act.empty(B, H, W, semantic_nc, device, zero=True)
+    ops.onehot_edges(label, inst, n_label, seg)
+    return ops.nhwc_to_nchw(seg, semantic_nc)
 
 
 class SPADEModelModules(nn.Module):
@@ -103,3 +115,15 @@ class SPADEModel(BaseModel):
 
     def test(self):
         self.forward(on_one_gpu=True)
+
+    def eval(self):
+        self.modules_on_one_gpu.netG.eval()       # evaluate_model (spade_model.py:221) switches the generator only
+
+    def train(self):
+        self.modules_on_one_gpu.netG.train()
+
+    def _eval_batch(self, data):
+        o = self.opt
+        with torch.no_grad():
+            self.fake_B = self.modules_on_one_gpu.netG(input_semantics(data, int(o.input_nc), int(o.semantic_nc), self.device))
+        return self.fake_B, data.get('path', [])

@@ -86,3 +86,50 @@ def test_trainer_flow_with_the_first_step_in_eval_mode(golden_dir, tmp_path):
             assert abs(L[mine] - r) <= 2e-3 * max(1.0, abs(r)), (mine, L[mine], r)
         ret = model.evaluate_model(1)
         assert ret['metric/fid-mean'] == 12.5 and not model.is_best
+
+
+@pytest.mark.timeout(900)
+def test_spade_distiller_flow(golden_dir, tmp_path):
+    """SPADEDistiller mirror in exact emulation: one optimize_parameters against the oracle, then evaluate_model (student
+    inference in eval mode through the module mirror on a different batch shape, metric bookkeeping, back to train())."""
+    import importlib
+    from oracle import spade_oracle as SO
+    from oracle.cat_oracle import clone_sd
+    from oracle.kernel_emu import emulated_kernels
+    _spade_opt = importlib.import_module('test_spade_distiller_gpu')._opt
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    s = fix['steps'][0]
+    state = dict(teacher_sd=clone_sd(fix['teacher_sd']), student_sd=clone_sd(fix['student_sd0']), D_sd=clone_sd(fix['D_sd0']),
+                 vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+                 adam_G={}, adam_D={})
+    seg = SO.preprocess_input(s['label'], s['instance'], fix['hp']['n_label'])
+    ref = SO.spade_distill_step(state, seg, s['image'], fix['hp'])
+    with emulated_kernels(exact=True):
+        from cat_b200.distillers import create_distiller
+        opt = _spade_opt(fix, str(tmp_path), vgg)
+        opt.cuda_graph = False
+        model = create_distiller(opt, verbose=False)
+        model.setup(opt, verbose=False)
+        mm = model.modules_on_one_gpu
+        mm.netG_teacher.load_state_dict(fix['teacher_sd'])
+        mm.netG_student.load_state_dict(fix['student_sd0'])
+        mm.netD.load_state_dict(fix['D_sd0'])
+        mm.netG_student.train()
+        B = s['image'].shape[0]
+        model.set_input({'label': s['label'], 'instance': s['instance'], 'image': s['image'], 'path': ['x'] * B})
+        model.optimize_parameters(0)
+        L = model.get_current_losses()
+        for mine, theirs in (('G_loss/G_gan', 'loss_G_gan'), ('G_loss/G_feat', 'loss_G_feat'), ('G_loss/G_vgg', 'loss_G_vgg'),
+                             ('G_loss/G_distill', 'loss_G_distill'), ('D_loss/D_fake', 'loss_D_fake'), ('D_loss/D_real', 'loss_D_real')):
+            r = float(ref[theirs])
+            assert abs(L[mine] - r) <= 1e-5 * max(1.0, abs(r)), (mine, L[mine], r)
+        model.eval_dataloader = [{'label': s['label'][:1], 'instance': s['instance'][:1], 'image': s['image'][:1], 'path': ['v/munster_1.png']}]
+        got = {}
+        model.metric_fns = {'fid': lambda fakes: 5.0, 'mIoU': lambda fakes, names: got.setdefault('names', names) and 0.5}
+        ret = model.evaluate_model(0)
+        assert ret['metric/fid-best'] == 5.0 and ret['metric/mIoU'] == 0.5 and got['names'] == ['munster_1'] and model.is_best
+        assert mm.netG_student.training
+        want = SO.spade_generator_forward({k: v.detach().clone() for k, v in mm.netG_student.state_dict().items()},
+                                          fix['student_arch'], seg[:1], training=False)
+        assert float((model.Sfake_B - want).norm() / want.norm()) < 1e-5

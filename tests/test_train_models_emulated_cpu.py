@@ -76,6 +76,17 @@ def test_pix2pix_model_protocol(golden_dir, tmp_path):
         assert worst <= 2.1 * lr * len(fix['steps'])
         model.test()                                        # inference through the same arenas
         assert model.fake_B.shape == s['real_A'].shape and torch.isfinite(model.fake_B).all()
+        # evaluate_model (pix2pix_model.py:214-281): eval-mode inference over the evaluation set + metric bookkeeping
+        model.eval_dataloader = [{'A': s['real_A'][:2], 'B': s['real_B'][:2], 'A_paths': ['d/a.png', 'd/b.png']}]
+        got = {}
+        model.metric_fns = {'fid': lambda fakes: got.setdefault('n', len(fakes)) * 7.0,
+                            'mIoU': lambda fakes, names: got.setdefault('names', names) and 0.25}
+        ret = model.evaluate_model(1)
+        assert ret['metric/fid'] == 7.0 and ret['metric/mIoU-best'] == 0.25 and got['names'] == ['a', 'b'] and model.is_best
+        assert model.netG.training
+        want = TO.O.generator_forward(TO.O.clone_sd({k: v.detach().clone() for k, v in model.netG.state_dict().items()}),
+                                      fix['G_arch'], s['real_A'][:2], training=False)
+        assert float((model.fake_B - want).norm() / want.norm()) < 1e-5
         model.save_networks('latest')
         ck = os.path.join(str(tmp_path), 'checkpoints')
         g = torch.load(os.path.join(ck, 'latest_net_G.pth'), weights_only=False)
@@ -126,6 +137,13 @@ def test_cycle_gan_model_protocol(golden_dir, tmp_path):
                     assert torch.equal(v.reshape(-1), eng_sd[k].reshape(-1)), (n, k)
         model.test()
         assert model.rec_A.shape == s['real_A'].shape and torch.isfinite(model.rec_B).all()
+        model.eval_dataloader_AtoB = [{'A': s['real_A'], 'A_paths': ['x/1.jpg', 'x/2.jpg']}]
+        model.eval_dataloader_BtoA = [{'A': s['real_B'], 'A_paths': ['y/3.jpg', 'y/4.jpg']}]
+        model.metric_fns_A = {'fid': lambda fakes: 3.0}
+        model.metric_fns_B = {'fid': lambda fakes: 4.0}
+        ret = model.evaluate_model(2)
+        assert ret['metric/fid_A'] == 3.0 and ret['metric/fid_B-best'] == 4.0 and model.is_best_A and model.is_best_B
+        assert model.netG_A.training and model.netG_B.training
         model.save_networks(3)     # epoch-numbered checkpoints (trainer.py:170)
         ck = os.path.join(str(tmp_path), 'checkpoints')
         for n in ('G_A', 'G_B', 'D_A', 'D_B'):
@@ -173,6 +191,12 @@ def test_spade_model_protocol(golden_dir, tmp_path):
         _check_losses(L, ref, _prefix, lambda n: 1e-4)
         model.test()
         assert model.fake_B.shape == s['image'].shape and torch.isfinite(model.fake_B).all()
+        model.eval_dataloader = [{'label': s['label'][:1], 'instance': s['instance'][:1], 'image': s['image'][:1], 'path': ['c/frankfurt_0.png']}]
+        model.metric_fns = {'fid': lambda fakes: 9.0}
+        ret = model.evaluate_model(1)
+        assert ret == {'metric/fid': 9.0, 'metric/fid-mean': 9.0, 'metric/fid-best': 9.0} and mm.netG.training
+        want = SO.spade_generator_forward({k: v.detach().clone() for k, v in mm.netG.state_dict().items()}, Ga, seg[:1], training=False)
+        assert float((model.fake_B - want).norm() / want.norm()) < 1e-5
         model.save_networks('latest')
         ck = os.path.join(str(tmp_path), 'checkpoints')
         g = torch.load(os.path.join(ck, 'latest_net_G.pth'), weights_only=False)
