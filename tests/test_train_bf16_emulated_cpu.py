@@ -64,3 +64,24 @@ def test_mse_distill_body(golden_dir, on_cpu, monkeypatch):
 @pytest.mark.timeout(600)
 def test_first_step_eval_mode_body(golden_dir, on_cpu):
     G.test_first_step_with_the_student_in_eval_mode(golden_dir)
+
+
+@slow
+@pytest.mark.timeout(2400)
+def test_fullsize_bodies_at_reduced_resolution(monkeypatch):
+    """tests/test_zz_fullsize_gpu.py with CATB_FULLSIZE_HW=64 under the bf16 kernel emulation (the benchmark networks at a
+    quarter of the benchmark resolution)."""
+    from oracle.kernel_emu import emulated_kernels
+    Z = importlib.import_module('test_zz_fullsize_gpu')
+    monkeypatch.setenv('CATB_FULLSIZE_HW', '64')
+    Z.DEV[0] = 'cpu'
+    try:
+        with emulated_kernels():
+            Z.test_ka_invariances_at_benchmark_size()
+            Z.test_norm_statistics_at_benchmark_size(True)
+            Z.test_norm_statistics_at_benchmark_size(False)
+            Z.test_conv_linearity_on_the_widest_patchgan_layer()
+            Z.test_pix2pix_5p6B_step_at_benchmark_resolution()
+            Z.test_gaugan_5p6B_step_at_benchmark_resolution()
+    finally:
+        Z.DEV[0] = 'cuda:0'
