@@ -67,6 +67,7 @@ def _worker(rank, port, path, out_dir):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.slow      # the engine-level 2-rank test (tests/test_engine_data_parallel_cpu.py) covers the same recipe
 def test_two_rank_gloo_spade_step(golden_dir, tmp_path):
     path = os.path.join(golden_dir, 'spade_more.pt')
     port = 31500 + os.getpid() % 2000

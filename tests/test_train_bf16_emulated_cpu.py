@@ -7,9 +7,9 @@ import os
 import pytest
 
 G = importlib.import_module('test_train_gpu')
-# the bodies below repeat what the exact-mode tests establish and only calibrate the GPU tolerances: the longer ones run
-# with CATB_SLOW_TESTS=1 (they were run when the tolerances were set; the default CPU suite keeps one per engine family)
-slow = pytest.mark.skipif(os.environ.get('CATB_SLOW_TESTS', '0') != '1', reason='set CATB_SLOW_TESTS=1')
+# the bodies below repeat what the exact-mode tests establish and only calibrate the GPU tolerances: they run with
+# CATB_SLOW_TESTS=1 (as they were when the tolerances were set); the default CPU suite keeps the quick ones
+slow = pytest.mark.slow
 
 
 @pytest.fixture
@@ -29,6 +29,7 @@ def test_pix2pix_bodies(golden_dir, on_cpu, name):
     G.test_pix2pix_train_step(golden_dir, name, False)
 
 
+@slow
 @pytest.mark.timeout(1200)
 @pytest.mark.parametrize('name', ['train_cyclegan_in_lsgan'])
 def test_cyclegan_bodies(golden_dir, on_cpu, name):
@@ -61,6 +62,7 @@ def test_mse_distill_body(golden_dir, on_cpu, monkeypatch):
     G.test_mse_distill_steps(golden_dir)
 
 
+@slow
 @pytest.mark.timeout(600)
 def test_first_step_eval_mode_body(golden_dir, on_cpu):
     G.test_first_step_with_the_student_in_eval_mode(golden_dir)

@@ -110,7 +110,7 @@ def test_cycle_gan_model_protocol(golden_dir, tmp_path):
     st = dict(G_A_sd=clone_sd(fix['G_A_sd0']), G_B_sd=clone_sd(fix['G_B_sd0']), D_A_sd=clone_sd(fix['D_A_sd0']),
               D_B_sd=clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
               pool_A=TO.ImagePool(hp['pool_size']), pool_B=TO.ImagePool(hp['pool_size']))
-    steps = fix['steps'][:2]
+    steps = fix['steps'][:1]
     random.seed(fix['python_random_seed'])
     refs = [TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp) for s in steps]
     with emulated_kernels(exact=True):
