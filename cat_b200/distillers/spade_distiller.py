@@ -118,6 +118,9 @@ class SPADEDistiller:
     # ---- protocol -------------------------------------------------------------------------------
     def setup(self, opt, verbose=True):
         self.load_networks(verbose)
+        # the reference profiles both generators here (base_spade_distiller.py:178-190), which leaves them in eval()
+        # (utils/model_profiling.py:299) until the end of the first evaluate_model (spade_distiller.py:170)
+        self.modules_on_one_gpu.netG_student.eval()
         if verbose:
             self.print_networks()
 
@@ -162,6 +165,7 @@ class SPADEDistiller:
         self.engine.set_input(input['label'], input['instance'], input['image'])
 
     def optimize_parameters(self, steps):
+        self.engine.set_student_training(self.modules_on_one_gpu.netG_student.training)   # follows .train() / .eval()
         self.engine.step()
 
     def forward(self, on_one_gpu=False):

@@ -157,6 +157,7 @@ def shrink_spade(model, opt):
     gpu_ids = list(getattr(model, 'gpu_ids', []))[:1]
     mm.netG_student = networks.init_net(InceptionSPADEGenerator.from_arch(student_arch, s_opt), opt.init_type, opt.init_gain, gpu_ids)
     mm.netG_student.n_macs = info['macs']
+    mm.netG_student.eval()         # shrink_spade_model profiles the new student, which leaves it in eval() (utils/common.py:829)
     teacher.n_macs = spade_generator_macs(teacher.arch())
     ngf_stu = student_arch['fc_out'] // 16
     netAs = nn.ModuleList()

@@ -45,7 +45,7 @@ class SpadeDistillStep:
         # (cat_b200/train_engine.py, models/spade_model.py:207-215) is this step without them
         self.T = SpadeGenNet(teacher_arch, self.seg, device, training=False, need_grad=False) if teacher_arch is not None else None
         assert self.T is not None or not hp.get('lambda_distill', 0.0)
-        self.S = SpadeGenNet(student_arch, self.seg, device, training=True, need_grad=True)
+        self.S = SpadeGenNet(student_arch, self.seg, device, training=hp.get('student_training', True), need_grad=True)
         self.D = MultiScaleDis(D_arch, 2 * B, H, W, device)
         # --distill_G_loss_type mse (spade_distiller_modules.py:23-25): MSE(netA_i(Sact_i), Tact_i) through the adaptor convs
         assert hp.get('distill_loss_type', 'ka') in ('ka', 'mse')
@@ -92,6 +92,15 @@ class SpadeDistillStep:
         self.label.copy_(label.reshape(B, H, W).to(torch.int32), non_blocking=True)
         self.instance.copy_(instance.reshape(B, H, W).to(torch.int32), non_blocking=True)
         self.image.copy_(image, non_blocking=True)
+
+    def set_student_training(self, training):
+        """netG_student.train() / .eval(): like the Inception distiller, the reference runs its first step of a run with the
+        student still in eval() (model_profiling in BaseSPADEDistiller.setup, base_spade_distiller.py:178-190) and switches
+        it to train() at the end of the first evaluate_model (spade_distiller.py:170).  Captured graphs are dropped."""
+        if bool(training) != bool(self.S.training):
+            self.S.set_training(bool(training))
+            self.hp['student_training'] = bool(training)
+            self._graphs = None
 
     def set_lr(self, lr_G, lr_D):
         self.lr_G.fill_(float(lr_G))

@@ -112,6 +112,13 @@ class BNorm(Norm):
         self.prepare(x)
         ops.norm_apply(x, y, self.scale, self.shift, self.per_sample, act, residual)
 
+    def backward(self, dout: Act, out, x: Act, dx: Act, act, param_grads=True):
+        super().backward(dout, out, x, dx, act, param_grads)
+        if not self.batch_stats and param_grads and getattr(self, 'dbias', None) is not None:
+            # eval mode (the reference's first step of a run): the conv bias in front of the norm is live,
+            # d bias = gamma * rstd * sum(dz) = scale * red[0]
+            ops.fma_vec(self.dbias, self.red.view(-1)[:self.Cp], self.scale.view(-1)[:self.Cp])
+
 
 class _Net:
     """Arena / norm / bias bookkeeping shared by the networks below."""
@@ -198,12 +205,20 @@ class _Net:
         self.norms.append(n)
         return n
 
+    def set_training(self, training):
+        """train() / eval() of the network: only the BatchNorm layers depend on it.  The launch sequence changes, so captured
+        CUDA graphs of this network must be re-captured."""
+        self.training = training
+        for n in self.norms:
+            n.set_training(training)
+
     def _finish_build(self):
         self.biases.finalize(self.dev, self.need_grad)
         for n in self.norms:
             if getattr(n, '_bias_slot', None) is not None:
                 n.bias = self.biases.slot(n._bias_slot)
                 n.mom_vec = torch.full_like(n.bias, n.momentum)
+                n.dbias = self.biases.slot(n._bias_slot, 'dvec') if self.need_grad else None
         self.pool_sums, self.pool_red = pool_norm_buffers(self.norms, self.dev)
 
     def pack_weights(self):

@@ -157,9 +157,68 @@ def make_mse_addon(base_name, cfg):
     return fix
 
 
+def make_first_step_addon(base_name, cfg):
+    """The reference's FIRST optimize_parameters of a run: BaseSPADEDistiller.setup profiles the generators
+    (base_spade_distiller.py:178-190) and model_profiling leaves them in eval() (utils/model_profiling.py:299); the student
+    returns to train() only at the end of the first evaluate_model (spade_distiller.py:170).  Same seeded networks as
+    `base_name` (asserted) without make_case's .train() call: losses, student gradients (the conv biases in front of a
+    BatchNorm are live in eval mode) and the D-phase image of that step."""
+    kw = {k: v for k, v in cfg.items() if k != 'frac'}
+    probe, _ = build_reference_spade_distiller(do_shrink=False, **kw)
+    target = probe.modules_on_one_gpu.netG_teacher.n_macs * cfg['frac']
+    model, opt = build_reference_spade_distiller(target_flops=target, **kw)
+    from models import networks
+    mm = model.modules_on_one_gpu
+    mm.netG_student = networks.init_net(mm.netG_student, opt.init_type, opt.init_gain, []).to(model.device)
+    assert not mm.netG_student.training, 'the reference is expected to leave the pruned student in eval mode'
+    g = torch.Generator().manual_seed(7)
+    for net in (mm.netG_student, mm.netD):
+        for k, p in net.named_parameters():
+            if p.dim() == 4:
+                p.data = p.data * 2.0
+            elif k.endswith('bias'):
+                p.data = 0.05 * torch.randn(p.shape, generator=g)
+    for m in mm.netG_student.modules():
+        if hasattr(m, 'running_mean') and getattr(m, 'weight', None) is not None:
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+    base = torch.load(os.path.join(OUT_DIR, base_name + '.pt'), weights_only=False)
+    for k, v in mm.netG_student.state_dict().items():
+        assert torch.equal(v, base['student_sd0'][k]), ('student differs from the base fixture', k)
+    gs = torch.Generator().manual_seed(11)
+    stats = {}
+    for k, v in mm.netG_student.state_dict().items():
+        if k.endswith('running_mean'):
+            stats[k] = 0.1 * torch.randn(v.shape, generator=gs)
+        elif k.endswith('running_var'):
+            stats[k] = 0.5 + torch.rand(v.shape, generator=gs)
+    mm.netG_student.load_state_dict(stats, strict=False)
+    s0 = base['steps'][0]
+    B = cfg['batch_size']
+    model.set_input({'label': s0['label'].clone(), 'instance': s0['instance'].clone(), 'image': s0['image'].clone(), 'path': ['x'] * B})
+    model.set_requires_grad(mm.netD, False)
+    model.optimizer_G.zero_grad()
+    model.backward_G()
+    fix = {'name': base_name + '_first_step', 'base': base_name, 'running_stats': stats,
+           'S_grads': {k: p.grad.detach().clone() for k, p in mm.netG_student.named_parameters() if p.grad is not None}}
+    model.optimizer_G.step()
+    model.set_requires_grad(mm.netD, True)
+    model.optimizer_D.zero_grad()
+    model.backward_D()
+    model.optimizer_D.step()
+    fix['losses'] = {k: float(v) for k, v in model.get_current_losses().items()}
+    fix['running_stats_after'] = {k: v.detach().clone() for k, v in mm.netG_student.state_dict().items() if 'running_' in k}
+    return fix
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     only = sys.argv[1:]
+    if only == ['spade_more_first_step']:
+        fix = make_first_step_addon('spade_more', dict(CASES['spade_more']))
+        path = os.path.join(OUT_DIR, 'spade_more_first_step.pt')
+        torch.save(fix, path)
+        print('spade_more_first_step', fix['losses'], '-> %.2f MB' % (os.path.getsize(path) / 1e6))
+        return
     if only == ['spade_more_mse']:
         fix = make_mse_addon('spade_more', dict(CASES['spade_more']))
         path = os.path.join(OUT_DIR, 'spade_more_mse.pt')

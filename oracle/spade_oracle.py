@@ -293,7 +293,8 @@ def spade_distill_step(state, seg, real_B, hp, grad_hook=None):
     for p in S_params.values():
         p.requires_grad_(True)
         p.grad = None
-    Sfake = spade_generator_forward(S_sd, S_arch, seg, training=True, capture=Sacts)
+    s_train = hp.get('student_training', True)     # False: the reference's first step of a run (student still in eval())
+    Sfake = spade_generator_forward(S_sd, S_arch, seg, training=s_train, capture=Sacts)
     for a in Sacts.values():
         a.retain_grad()
     Sfake.retain_grad()
@@ -343,7 +344,7 @@ def spade_distill_step(state, seg, real_B, hp, grad_hook=None):
         p.requires_grad_(True)
         p.grad = None
     with torch.no_grad():
-        fake = spade_generator_forward(S_sd, S_arch, seg, training=True)
+        fake = spade_generator_forward(S_sd, S_arch, seg, training=s_train)
     out['Sfake_B_D'] = fake
     pred_fake, pred_real = _discriminate(D_sd, D_arch, seg, fake, real_B)
     loss_D_fake = hinge_multiscale(pred_fake, False, True)

@@ -254,3 +254,60 @@ def test_spade_mse_distill_step_exact(golden_dir):
         for i, sd in enumerate(eng.A.state_dicts()):
             for k, v in sd.items():
                 assert float((v - st['netA_sds'][i][k]).abs().max()) <= 1e-5, (i, k)
+
+
+@pytest.mark.timeout(900)
+def test_spade_first_step_with_the_student_in_eval_mode_exact(golden_dir):
+    """hp['student_training'] = False on the SPADE engine: every BatchNorm of the student on its running statistics (both
+    student forwards of the step), Norm.backward with an infinite element count, and the conv biases in front of a
+    BatchNorm -- inert in training mode -- receiving d bias = scale * sum(dz) through the bias pool."""
+    from oracle import spade_oracle as SO
+    from oracle.kernel_emu import emulated_kernels
+    from test_spade_oracle_golden import first_step_state
+    fix, add, st, hp = first_step_state(golden_dir)
+    student0 = {k: v.clone() for k, v in st['student_sd'].items()}
+    vgg = st['vgg_sd']
+    s = fix['steps'][0]
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    ref = SO.spade_distill_step(st, seg, s['image'], hp)
+    B, _, H, W = s['image'].shape
+    with emulated_kernels(exact=True):
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], student0, fix['D_sd0'], vgg)
+        eng.set_input(s['label'], s['instance'], s['image'])
+        eng.step()
+        L = eng.get_losses()
+        for k_ref, k in LOSSES:
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+        assert rel_l2(eng_out(eng), ref['Sfake_B_D']) < 1e-4
+        scale = max(float(g.abs().max()) for g in ref['S_grads'].values())
+        live_mine, live_ref = [], []
+        for k, g in ref['S_grads'].items():
+            mine = eng.S.arena.view(k, 'g')
+            err = float((mine - g).abs().max())
+            assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
+            if k.endswith('.0.conv.bias') and float(g.abs().max()) > 0:      # a conv bias in front of a BatchNorm: now live
+                live_mine.append(mine.flatten().clone())
+                live_ref.append(g.flatten())
+        # these gradients are tiny on this fixture (1e-9 ... 1e-7, far below the floor above), so they get their own
+        # relative comparison, over all of them together (the smallest are cancellation noise in fp32 on both sides)
+        assert len(live_ref) > 10
+        assert rel_l2(torch.cat(live_mine), torch.cat(live_ref)) < 2e-2
+        sd = eng.S.state_dict()
+        for k, v in add['running_stats'].items():
+            assert torch.equal(sd[k], v), k
+        # netG_student.train() after the first evaluate_model: the same engine continues in training mode
+        ref2 = SO.spade_distill_step(st, seg, s['image'], dict(hp, student_training=True))
+        eng.set_student_training(True)
+        eng.step()
+        L = eng.get_losses()
+        for k_ref, k in LOSSES:
+            r = float(ref2[k_ref])
+            assert abs(L[k] - r) <= 2e-3 * max(1.0, abs(r)), (k, L[k], r)
+
+
+def eng_out(eng):
+    from cat_b200 import ops
+    return ops.nhwc_to_nchw(eng.S.out, 3)

@@ -82,3 +82,30 @@ def test_spade_mse_distill_step_matches_reference(golden_dir):
     for k, g in add['S_grads'].items():
         err = float((out['S_grads'][k] - g).abs().max())
         assert err <= 1e-3 * float(g.abs().max()) + 1e-5 * scale, (k, err)
+
+
+def first_step_state(golden_dir):
+    fix = torch.load(os.path.join(golden_dir, 'spade_more.pt'), weights_only=False)
+    add = torch.load(os.path.join(golden_dir, 'spade_more_first_step.pt'), weights_only=False)
+    state = spade_state(fix)
+    state['student_sd'].update({k: v.clone() for k, v in add['running_stats'].items()})
+    return fix, add, state, dict(fix['hp'], student_training=False)
+
+
+def test_spade_first_step_with_the_student_in_eval_mode_matches_reference(golden_dir):
+    """The reference's first optimize_parameters of a run (student still in eval(): BaseSPADEDistiller.setup profiles it,
+    base_spade_distiller.py:178-190; back to train() at the end of the first evaluate_model, spade_distiller.py:170)."""
+    fix, add, state, hp = first_step_state(golden_dir)
+    s = fix['steps'][0]
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    out = SO.spade_distill_step(state, seg, s['image'], hp)
+    for mine, theirs in LOSS_KEYS:
+        r = add['losses'][theirs]
+        assert abs(float(out[mine]) - r) < 1e-4 * max(1.0, abs(r)), (mine, float(out[mine]), r)
+    scale = max(float(g.abs().max()) for g in add['S_grads'].values())
+    assert set(out['S_grads']) == set(add['S_grads'])
+    for k, g in add['S_grads'].items():
+        err = float((out['S_grads'][k] - g).abs().max())
+        assert err <= 1e-3 * float(g.abs().max()) + 1e-5 * scale, (k, err)
+    for k, v in add['running_stats_after'].items():           # eval mode: the running statistics do not move
+        assert torch.equal(v, add['running_stats'][k]) and torch.equal(state['student_sd'][k], v), k
