@@ -87,3 +87,9 @@ def test_fullsize_bodies_at_reduced_resolution(monkeypatch):
             Z.test_gaugan_5p6B_step_at_benchmark_resolution()
     finally:
         Z.DEV[0] = 'cuda:0'
+
+
+@slow
+@pytest.mark.timeout(900)
+def test_spade_first_step_eval_mode_body(golden_dir, on_cpu):
+    G.test_spade_first_step_with_the_student_in_eval_mode(golden_dir)

@@ -339,3 +339,46 @@ def test_first_step_with_the_student_in_eval_mode(golden_dir):
     assert abs(L['G_recon'] - float(ref2['loss_G_recon'])) <= 5e-2 * float(ref2['loss_G_recon'])
     sd = eng.S.state_dict()
     assert any(not torch.equal(sd[k], v) for k, v in add['running_stats'].items())   # training mode: they move
+
+
+def test_spade_first_step_with_the_student_in_eval_mode(golden_dir):
+    """SPADE distiller, the reference's first step of a run (student in eval()), then train() on the same engine."""
+    from cat_b200.spade_distill_engine import SpadeDistillStep
+    from oracle import cat_oracle as O
+    from oracle import spade_oracle as SO
+    fix = _load(golden_dir, 'spade_more')
+    add = _load(golden_dir, 'spade_more_first_step')
+    vgg = SO.make_vgg_sd(fix['vgg_seed'])
+    student0 = O.clone_sd(fix['student_sd0'])
+    student0.update({k: v.clone() for k, v in add['running_stats'].items()})
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(student0), D_sd=O.clone_sd(fix['D_sd0']), vgg_sd=vgg,
+              teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    hp = dict(fix['hp'], student_training=False)
+    s = fix['steps'][0]
+    seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+    ref = SO.spade_distill_step(st, seg, s['image'], hp)
+    B, _, H, W = s['image'].shape
+    eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device=DEV[0],
+                           use_cuda_graph=DEV[0] != 'cpu')
+    eng.load(fix['teacher_sd'], student0, fix['D_sd0'], vgg)
+    eng.set_input(s['label'], s['instance'], s['image'])
+    eng.step()
+    _sync()
+    L = eng.get_losses()
+    for k in ('G_gan', 'G_feat', 'G_vgg', 'G_distill', 'D_fake', 'D_real'):
+        r = float(ref['loss_' + k])
+        assert abs(L[k] - r) <= 3e-2 * max(1.0, abs(r)), (k, L[k], r)
+        assert abs(L[k] - add['losses'][('D_loss/' if k.startswith('D_') else 'G_loss/') + k]) <= 3e-2 * max(1.0, abs(r)), k
+    sd = eng.S.state_dict()
+    for k, v in add['running_stats'].items():
+        assert torch.equal(sd[k], v), k                          # eval mode: running statistics untouched
+    ref2 = SO.spade_distill_step(st, seg, s['image'], dict(hp, student_training=True))
+    eng.set_student_training(True)
+    eng.step()
+    _sync()
+    L = eng.get_losses()
+    for k in ('G_feat', 'G_vgg', 'D_fake', 'D_real'):
+        r = float(ref2['loss_' + k])
+        assert abs(L[k] - r) <= 6e-2 * max(1.0, abs(r)), (k, L[k], r)
+    sd = eng.S.state_dict()
+    assert any(not torch.equal(sd[k], v) for k, v in add['running_stats'].items())
