@@ -160,3 +160,35 @@ def test_spade_train_step_exact(golden_dir):
         for k, v in st['G_sd'].items():
             if 'running_' in k:
                 assert float((sd[k] - v).abs().max()) < 1e-4, k
+
+
+@pytest.mark.timeout(600)
+def test_cyclegan_without_identity_term_and_without_pool_exact(golden_dir):
+    """--lambda_identity 0 (no third application of the generators, cycle_gan_model.py:262-273) and --pool_size 0 (the
+    discriminators read the current fakes, utils/image_pool.py:31-32): one step against the oracle."""
+    from oracle import train_oracle as TO
+    from oracle.cat_oracle import clone_sd
+    from oracle.kernel_emu import emulated_kernels
+    fix = _load(golden_dir, 'train_cyclegan_in_lsgan')
+    hp = dict(fix['hp'], lambda_identity=0.0, pool_size=0)
+    s = fix['steps'][0]
+    B, _, H, W = s['real_A'].shape
+    st = dict(G_A_sd=clone_sd(fix['G_A_sd0']), G_B_sd=clone_sd(fix['G_B_sd0']), D_A_sd=clone_sd(fix['D_A_sd0']),
+              D_B_sd=clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
+              pool_A=TO.ImagePool(0), pool_B=TO.ImagePool(0))
+    ref = TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp)
+    with emulated_kernels(exact=True):
+        from cat_b200.train_engine import CycleGANTrainStep
+        eng = CycleGANTrainStep(fix['G_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        assert eng.GA_idt is None and eng.GB_idt is None
+        eng.load(fix['G_A_sd0'], fix['G_B_sd0'], fix['D_A_sd0'], fix['D_B_sd0'])
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        assert eng.d_in_fake_B is eng.GA_real.out and eng.d_in_fake_A is eng.GB_real.out
+        L = eng.get_losses()
+        assert L['G_idt_A'] == 0.0 and L['G_idt_B'] == 0.0
+        for k, v in L.items():
+            r = float(ref['loss_' + k])
+            assert abs(v - r) <= 1e-5 * max(1.0, abs(r)), (k, v, r)
+        for tag, net in (('G_A', eng.G_A), ('G_B', eng.G_B), ('D_A', eng.D_A), ('D_B', eng.D_B)):
+            _check_grads(net, ref[tag + '_grads'], tag)
