@@ -248,3 +248,36 @@ def test_batch_of_one_exact(golden_dir):
             if eng.S.arena.has(k):
                 err = float((eng.S.arena.view(k, 'g') - g).abs().max())
                 assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('packx', ['1', '0'])
+def test_generator_input_gradient_exact(golden_dir, packx, monkeypatch):
+    """GenNet(input_grad=True): d loss / d input image through the reflection-padded 7x7 stem (input-gradient GEMM into the
+    padded frame + reflect fold), with the x-packed and the plain stem, against autograd on the oracle."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import ops
+    from cat_b200.ops import Act
+    monkeypatch.setenv('CATB_NO_PACKX', '0' if packx == '1' else '1')
+    fix = torch.load(os.path.join(golden_dir, 'train_cyclegan_in_lsgan.pt'), weights_only=False)
+    arch, sd = fix['G_arch'], fix['G_A_sd0']
+    B, H, W = 2, 24, 32
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).requires_grad_(True)
+    R = torch.randn(B, 3, H, W, generator=g)
+    out_ref = O.generator_forward(O.clone_sd(sd), arch, x, training=True)
+    (out_ref * R).sum().backward()
+    with emulated_kernels(exact=True):
+        from cat_b200.engine import GenNet
+        net = GenNet(arch, B, H, W, 'cpu', training=True, need_grad=True, input_grad=True)
+        assert net.packx == (packx == '1')
+        net.load_state_dict(sd)
+        xa, dS = Act.empty(B, H, W, 3, 'cpu', zero=True), Act.empty(B, H, W, 3, 'cpu', zero=True)
+        ops.nchw_to_nhwc(x.detach(), xa)
+        ops.nchw_to_nhwc(R, dS)
+        assert rel_l2(ops.nhwc_to_nchw(net.forward(xa), 3), out_ref.detach()) < 1e-5
+        net.arena.g.zero_()
+        d_in = net.backward(dS)
+        assert rel_l2(ops.nhwc_to_nchw(d_in, 3), x.grad) < 1e-4
+        assert float(d_in.t[..., 3:].abs().max()) == 0.0          # padding channels of the gradient stay exactly zero
