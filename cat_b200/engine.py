@@ -587,8 +587,11 @@ class GenNet:
                 # also when the forward pass uses the x-packed image), folded by catb_reflect_fold
                 self.d_in_frame = Act.empty(B, H + 6, W + 6, cin, dev)
                 self.d_in = self._act(H, W, cin)
-                self.gb_stem = G(P.Geometry(B, H, W, cpad(c0), 0, H + 6, W + 6, cpad(cin), 0),
-                                 P.conv_dgrad_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 0), cin, bwd=True)
+                # (gather-per-tap kernel only: a 49-tap frame gradient with 3 output channels has not been timed or run on
+                # the halo kernel yet; this GEMM is a small part of the CycleGAN step)
+                self.gb_stem = Gemm(P.Geometry(B, H, W, cpad(c0), 0, H + 6, W + 6, cpad(cin), 0),
+                                    P.conv_dgrad_units(ar.off('down_sampling.1.weight'), c0, cin, 7, 7, 0), cin, dev, halo=False)
+                self.bwd_gemms.append(self.gb_stem)
 
     def _ws(self, flat, H, W, C):
         return Act(flat[:self.B * H * W * C].view(self.B, H, W, C))
