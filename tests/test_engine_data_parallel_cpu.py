@@ -173,3 +173,56 @@ def test_engine_two_ranks_cyclegan_training(golden_dir, tmp_path):
             err = float((ranks[0][tag + '_g'][k] - g).abs().max())
             assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err, float(g.abs().max()))
         assert n > 5, tag
+
+
+def _worker_pix2pix(rank, port, path, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=WORLD)
+    torch.set_num_threads(2)
+    from oracle.kernel_emu import emulated_kernels
+    from cat_b200 import parallel
+    fix = torch.load(path, weights_only=False)
+    s = fix['steps'][0]
+    _, _, H, W = s['real_A'].shape
+    with emulated_kernels(exact=True):
+        from cat_b200.train_engine import Pix2PixTrainStep
+        eng = Pix2PixTrainStep(fix['G_arch'], fix['D_arch'], fix['hp'], 1, H, W, device='cpu', world_size=WORLD)
+        eng.load(fix['G_sd0'], fix['D_sd0'])
+        eng.set_input(s['real_A'][rank:rank + 1], s['real_B'][rank:rank + 1])
+        eng.step()
+        scale = parallel.grad_scale(WORLD)
+        out = {'G_g': {k: eng.G.arena.view(k, 'g').clone() * scale for k in eng.G.arena.entries},
+               'G_p': eng.G.arena.p.clone(), 'D_p': eng.D.arena.p.clone()}
+    torch.save(out, os.path.join(out_dir, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_engine_two_ranks_pix2pix_training(golden_dir, tmp_path):
+    """Pix2PixTrainStep with one image per rank (InstanceNorm fixture, lsgan + l2): the all-reduced generator gradient equals
+    the single-process oracle step on both images (mean losses over the gathered batch, models/networks.py:160-161);
+    bit-identical weights on both ranks after the step."""
+    from oracle import train_oracle as TO
+    from oracle.cat_oracle import clone_sd
+    path = os.path.join(golden_dir, 'train_pix2pix_in_lsgan_l2.pt')
+    port = 39500 + os.getpid() % 2000
+    mp.spawn(_worker_pix2pix, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    ranks = [torch.load(os.path.join(tmp_path, f'rank{r}.pt'), weights_only=False) for r in range(WORLD)]
+    assert torch.equal(ranks[0]['G_p'], ranks[1]['G_p']) and torch.equal(ranks[0]['D_p'], ranks[1]['D_p'])
+    fix = torch.load(path, weights_only=False)
+    s = fix['steps'][0]
+    st = dict(G_sd=clone_sd(fix['G_sd0']), D_sd=clone_sd(fix['D_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'],
+              adam_G={}, adam_D={})
+    # the generator phase runs on the discriminator AFTER its update, which under DP is the all-reduced one: the oracle
+    # on the full batch takes exactly that step
+    ref = TO.pix2pix_train_step(st, s['real_A'], s['real_B'], fix['hp'])
+    grads = ref['G_grads']
+    scale = max(float(g.abs().max()) for g in grads.values())
+    n = 0
+    for k, g in grads.items():
+        if k not in ranks[0]['G_g']:
+            continue
+        n += 1
+        err = float((ranks[0]['G_g'][k] - g).abs().max())
+        assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
+    assert n > 10
