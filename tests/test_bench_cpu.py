@@ -31,7 +31,7 @@ def test_teacher_mac_models():
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('workload', ['pix2pix_5p6B', 'pix2pix_teacher'])
+@pytest.mark.parametrize('workload', ['pix2pix_5p6B', pytest.param('pix2pix_teacher', marks=pytest.mark.slow)])
 def test_reference_arm_prints_the_contract_line(workload):
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', workload, '--steps', '1',
                           '--warmup', '0', '--cpu-batch', '2', '--height', '32', '--width', '32'], capture_output=True, text=True,

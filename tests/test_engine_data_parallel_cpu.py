@@ -197,6 +197,7 @@ def _worker_pix2pix(rank, port, path, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.slow      # same recipe and engine base class as the CycleGAN / Inception two-rank tests above
 @pytest.mark.timeout(900)
 def test_engine_two_ranks_pix2pix_training(golden_dir, tmp_path):
     """Pix2PixTrainStep with one image per rank (InstanceNorm fixture, lsgan + l2): the all-reduced generator gradient equals

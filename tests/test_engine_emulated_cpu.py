@@ -251,7 +251,7 @@ def test_batch_of_one_exact(golden_dir):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('packx', ['1', '0'])
+@pytest.mark.parametrize('packx', ['1', pytest.param('0', marks=pytest.mark.slow)])
 def test_generator_input_gradient_exact(golden_dir, packx, monkeypatch):
     """GenNet(input_grad=True): d loss / d input image through the reflection-padded 7x7 stem (input-gradient GEMM into the
     padded frame + reflect fold), with the x-packed and the plain stem, against autograd on the oracle."""
