@@ -110,7 +110,7 @@ _SPECIAL = {
     'catb_version': ([], C.c_char_p),
     'catb_last_error_string': ([], C.c_char_p),
     'catb_packed_weight_bytes': ([_I, _I, _I], C.c_size_t),
-    'catb_igemm_halo_fits': ([_I, _I, _I, _I], C.c_int),
+    'catb_igemm_halo_fits': ([_I, _I, _I, _I, _I, _I], C.c_int),
     'catb_igemm_halo_wgrad_fits': ([_I, _I], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))

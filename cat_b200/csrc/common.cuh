@@ -181,6 +181,42 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same instruction with the two matrix descriptors passed as (low, high) 32-bit halves.  Inside an issue loop
+// only the 14-bit start-address field of the low word changes (tile base + row / K offset, all multiples of 16
+// bytes), so a descriptor update is ONE 32-bit add.  Measured on B200 (tools/mma_probe2.cu): a single thread
+// sustains one M=128 instruction per 39 / 48 / 64 / 128 cycles at N = 16 / 64 / 128 / 256 when nothing but the
+// instruction itself sits in the loop; every extra dependent scalar instruction of the issuing thread costs
+// 4-6 cycles, which is what bounded the round-1 kernels (~25 instructions = ~175 cycles per MMA whatever N).
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Leader election inside a converged warp.  The issue loops are walked by the WHOLE MMA warp (barrier waits, ring
+// bookkeeping) and only the tcgen05 instructions sit under this predicate: ptxas then emits uniform-predicated
+// UTCHMMA instead of the ELECT / BRA.U.ANY loop it wraps around an MMA issued under `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -213,6 +249,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
   return d;
+}
+
+// The two halves of the same descriptor: hi is constant for a kernel, lo = lbo field | (address >> 4).
+__host__ __device__ constexpr uint32_t sw128_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3ffffu) >> 4) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
 }
 
 // cute::UMMA::InstrDescriptor for kind::f16, BF16 x BF16 -> F32

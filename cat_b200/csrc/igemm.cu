@@ -179,25 +179,35 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_fprop_kernel(const FpropPar
       }
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const int s = c % p.stages;
-        const uint32_t ph = (c / p.stages) & 1;
-        mbar_wait(&full[s], ph);
-        tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
-#pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k) {
-          const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, p.idesc, (c | k) != 0 ? 1u : 0u);
-        }
+    // ------------------------------------------------------------------ MMA issuer
+    // whole warp walks the loop, one elected lane issues; per instruction one add per descriptor (common.cuh)
+    const uint32_t hi = sw128_desc_hi(1024);
+    const uint32_t lo0 = sw128_desc_lo(smem_u32(tiles), 16);
+    const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+    const uint32_t idesc = p.idesc;
+    uint32_t s = 0, ph = 0, a_lo = lo0, acc = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t b_lo = a_lo + (kATileBytes >> 4);
+        umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, acc);
+        umma_bf16_lh(tmem_base, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+        umma_bf16_lh(tmem_base, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+        umma_bf16_lh(tmem_base, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
         umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
       }
-      umma_commit(accum);
+      __syncwarp();
+      acc = 1u;
+      if (++s == static_cast<uint32_t>(p.stages)) {
+        s = 0;
+        ph ^= 1u;
+        a_lo = lo0;
+      } else {
+        a_lo += stage16;
+      }
     }
+    if (elect_one()) umma_commit(accum);
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ weight loader (one thread)
@@ -364,26 +374,37 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_wgrad_kernel(const WgradPar
       }
     }
   } else if (warp == 4) {
-    if (lane == 0 && nsteps > 0) {
+    if (nsteps > 0) {
+      // both operands MN-major: 16 rows (GEMM K) per instruction = two 8-row swizzle atoms = 2048 bytes (128 units)
+      const uint32_t hi = sw128_desc_hi(1024);
+      const uint32_t lo0 = sw128_desc_lo(smem_u32(tiles), kWChunkBytes);
+      const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t idesc = p.idesc;
+      uint32_t s = 0, ph = 0, a_lo = lo0, acc = 0;
       for (int t = 0; t < nsteps; ++t) {
-        const int s = t % p.stages;
-        const uint32_t ph = (t / p.stages) & 1;
         mbar_wait(&full[s], ph);
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * kWChunkBytes;
-#pragma unroll
-        for (int k = 0; k < kWStepRows / 16; ++k) {
-          // 16 rows (GEMM K) per instruction = two 8-row swizzle atoms = 2048 bytes
-          const uint64_t adesc = make_sw128_desc(a_addr + k * 2048, kWChunkBytes, 1024);
-          const uint64_t bdesc = make_sw128_desc(b_addr + k * 2048, kWChunkBytes, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, p.idesc, (t | k) != 0 ? 1u : 0u);
+        if (elect_one()) {
+          const uint32_t b_lo = a_lo + (2 * kWChunkBytes >> 4);
+          umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, acc);
+          umma_bf16_lh(tmem_base, a_lo + 128, hi, b_lo + 128, hi, idesc, 1u);
+          umma_bf16_lh(tmem_base, a_lo + 256, hi, b_lo + 256, hi, idesc, 1u);
+          umma_bf16_lh(tmem_base, a_lo + 384, hi, b_lo + 384, hi, idesc, 1u);
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
+        acc = 1u;
+        if (++s == static_cast<uint32_t>(p.stages)) {
+          s = 0;
+          ph ^= 1u;
+          a_lo = lo0;
+        } else {
+          a_lo += stage16;
+        }
       }
-      umma_commit(accum);
+      if (elect_one()) umma_commit(accum);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   tcgen05_fence_before();

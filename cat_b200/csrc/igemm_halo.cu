@@ -35,7 +35,7 @@ struct HaloParams {
   const uint8_t* wpk;
   const float* bias;
   void* y;
-  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, bo_mode;
+  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, tab_bytes;
   uint32_t idesc;
   unsigned long long* dbg;  // optional per-CTA phase timestamps (catb_debug_timeline), null in production
 };
@@ -52,16 +52,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.dbg != nullptr && blockIdx.y == 0 && blockIdx.x < kDbgCtas) p.dbg[blockIdx.x * kDbgSlots + (slot)] = gtimer(); \
   } while (0)
 
-__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                       int bo_mode) {
-  uint64_t d = make_sw128_desc(smem_addr, lbo_bytes, sbo_bytes);
-  const uint32_t phase = (smem_addr >> 7) & 7u;  // row phase of the window start inside the 1024-byte swizzle atom
-  const uint32_t bo = bo_mode == 1 ? phase : (bo_mode == 2 ? ((8u - phase) & 7u) : 0u);
-  d |= static_cast<uint64_t>(bo) << 49;  // matrix-descriptor base offset
-  return d;
-}
-
-
 __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -71,7 +61,10 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
   uint64_t* b_empty = b_full + kHMaxBStages;              // [kHMaxBStages]
   uint64_t* accum = b_empty + kHMaxBStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  uint8_t* a_base = smem + kHHeader;
+  // step / chunk tables in shared memory: the MMA thread must not wait for global loads between instructions
+  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(smem + kHHeader);                        // [n_steps] a_row * 8
+  int4* s_chunks = reinterpret_cast<int4*>(smem + kHHeader + ((p.h.n_steps * 4 + 15) & ~15));  // [n_chunks]
+  uint8_t* a_base = smem + kHHeader + p.tab_bytes;
   uint8_t* b_base = a_base + static_cast<size_t>(p.a_bufs) * p.halo_bytes;
 
   const catb_igemm_desc& d = p.d;
@@ -101,11 +94,13 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     tmem_alloc_dyn(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < h.n_steps; i += kHThreads) s_aoff[i] = static_cast<uint32_t>(p.steps[i].a_row) * 8u;
+  for (int i = threadIdx.x; i < h.n_chunks; i += kHThreads) s_chunks[i] = reinterpret_cast<const int4*>(p.chunks)[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) DBG_STAMP(0);   // prologue done (barriers, TMEM)
+  if (threadIdx.x == 0) DBG_STAMP(0);   // prologue done (barriers, TMEM, tables)
 
   if (warp < 4) {
     // ---------------------------------------------------------------- halo producer
@@ -115,7 +110,10 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     for (int c = 0; c < h.n_chunks; ++c) {
       const int buf = c % p.a_bufs;
       const uint32_t ph = (c / p.a_bufs) & 1;
-      const catb_halo_chunk ch = p.chunks[c];
+      const int4 chv = s_chunks[c];
+      catb_halo_chunk ch;
+      ch.cu0 = chv.x;
+      ch.n_units = chv.y;
       const bool uvalid = ul < ch.n_units;
       const bool ufill = ul < ((ch.n_units + 1) & ~1);   // columns the MMAs of this chunk read (K = 16 granularity)
       const __nv_bfloat16* xc = p.x + d.x_coff + (ch.cu0 + ul) * 8;
@@ -208,49 +206,70 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     }
   } else if (warp == 4) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int sg = 0;  // global step counter (ring position of the weight tiles)
-      long long dbg_wait = 0;
-      for (int c = 0; c < h.n_chunks; ++c) {
-        const int buf = c % p.a_bufs;
-        const uint32_t ph = (c / p.a_bufs) & 1;
-        const catb_halo_chunk ch = p.chunks[c];
-        mbar_wait(&a_full[buf], ph);
+    // The whole warp walks the loop (barrier waits, ring bookkeeping in registers), one elected lane issues.  Per
+    // instruction only the low descriptor words change, by one add each (common.cuh: umma_bf16_lh).
+    const uint32_t hi = sw128_desc_hi(1024);
+    const uint32_t b_lo0 = sw128_desc_lo(smem_u32(b_base), 16);
+    const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
+    const uint32_t a_step = static_cast<uint32_t>(p.halo_bytes) >> 4;
+    const uint32_t a_lo0 = sw128_desc_lo(smem_u32(a_base), 16);
+    const uint32_t idesc = p.idesc;
+    const uint32_t n_tile = d.n_tile;
+    const bool two = h.m_sub == 2;
+    uint32_t st = 0, phb = 0, b_lo = b_lo0;     // weight ring position
+    uint32_t buf = 0, pha = 0, a_lo = a_lo0;    // halo buffer position
+    uint32_t acc = 0;                           // 0 only for the first instruction into each accumulator
+    for (int c = 0; c < h.n_chunks; ++c) {
+      const int4 ch = s_chunks[c];              // cu0, n_units, first_step, n_steps
+      // a chunk that uses only n_units of its 8 channel units needs only ceil(n_units / 2) of the four K=16
+      // MMAs (the remaining columns of the halo rows and of the weight tile are zero)
+      const int kmax = (ch.y + 1) >> 1;
+      mbar_wait(&a_full[buf], pha);
+      tcgen05_fence_after();
+      if (c == 0 && lane == 0) DBG_STAMP(2);    // MMA warp sees the first chunk
+      const int s_end = ch.z + ch.w;
+      uint32_t aoff = s_aoff[ch.z];
+      for (int s = ch.z; s < s_end; ++s) {
+        const uint32_t a_cur = a_lo + aoff;
+        if (s + 1 < s_end) aoff = s_aoff[s + 1];   // next step's window offset is in flight during this step's wait
+        mbar_wait(&b_full[st], phb);
         tcgen05_fence_after();
-        if (c == 0) DBG_STAMP(2);   // MMA thread sees the first chunk
-        const uint32_t a_addr = smem_u32(a_base + static_cast<size_t>(buf) * p.halo_bytes);
-        for (int s = ch.first_step; s < ch.first_step + ch.n_steps; ++s, ++sg) {
-          const int st = sg % p.b_stages;
-          const uint32_t phb = (sg / p.b_stages) & 1;
-          const int a_row = p.steps[s].a_row;
-          const long long tw0 = p.dbg != nullptr ? clock64() : 0;
-          mbar_wait(&b_full[st], phb);
-          if (p.dbg != nullptr) dbg_wait += clock64() - tw0;
-          tcgen05_fence_after();
-          const uint32_t b_addr = smem_u32(b_base + static_cast<size_t>(st) * b_bytes);
-          // a chunk that uses only n_units of its 8 channel units needs only ceil(n_units / 2) of the four K=16
-          // MMAs (the remaining columns of the halo rows and of the weight tile are zero)
-          const int kmax = (ch.n_units + 1) >> 1;
-          for (int sub = 0; sub < h.m_sub; ++sub) {
-            const uint32_t wa = a_addr + static_cast<uint32_t>(a_row + sub * 128) * 128u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < kmax) {
-                const uint64_t adesc = make_sw128_desc_bo(wa + k * 32, 16, 1024, p.bo_mode);
-                const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
-                umma_bf16(tmem_base + sub * d.n_tile, adesc, bdesc, p.idesc, (sg | k) != 0 ? 1u : 0u);
-              }
-            }
+        if (elect_one()) {
+          umma_bf16_lh(tmem_base, a_cur, hi, b_lo, hi, idesc, acc);
+          if (kmax > 1) umma_bf16_lh(tmem_base, a_cur + 2, hi, b_lo + 2, hi, idesc, 1u);
+          if (kmax > 2) umma_bf16_lh(tmem_base, a_cur + 4, hi, b_lo + 4, hi, idesc, 1u);
+          if (kmax > 3) umma_bf16_lh(tmem_base, a_cur + 6, hi, b_lo + 6, hi, idesc, 1u);
+          if (two) {   // second 128-row sub-tile: halo rows + 128 (16 KB further), its own accumulator columns
+            umma_bf16_lh(tmem_base + n_tile, a_cur + 1024, hi, b_lo, hi, idesc, acc);
+            if (kmax > 1) umma_bf16_lh(tmem_base + n_tile, a_cur + 1026, hi, b_lo + 2, hi, idesc, 1u);
+            if (kmax > 2) umma_bf16_lh(tmem_base + n_tile, a_cur + 1028, hi, b_lo + 4, hi, idesc, 1u);
+            if (kmax > 3) umma_bf16_lh(tmem_base + n_tile, a_cur + 1030, hi, b_lo + 6, hi, idesc, 1u);
           }
           umma_commit(&b_empty[st]);
         }
-        umma_commit(&a_empty[buf]);
+        __syncwarp();
+        acc = 1u;
+        if (++st == static_cast<uint32_t>(p.b_stages)) {
+          st = 0;
+          phb ^= 1u;
+          b_lo = b_lo0;
+        } else {
+          b_lo += b_step;
+        }
       }
-      umma_commit(accum);
-      DBG_STAMP(3);   // last MMA issued
-      if (p.dbg != nullptr && blockIdx.y == 0 && blockIdx.x < kDbgCtas) p.dbg[blockIdx.x * kDbgSlots + 7] = dbg_wait;
+      if (elect_one()) umma_commit(&a_empty[buf]);
+      __syncwarp();
+      if (++buf == static_cast<uint32_t>(p.a_bufs)) {
+        buf = 0;
+        pha ^= 1u;
+        a_lo = a_lo0;
+      } else {
+        a_lo += a_step;
+      }
     }
+    if (elect_one()) umma_commit(accum);
     __syncwarp();
+    if (lane == 0) DBG_STAMP(3);   // last MMA issued
   } else {
     // ---------------------------------------------------------------- weight loader
     if (lane == 0) {
@@ -288,8 +307,13 @@ int init_halo_attributes() {
 using namespace catb;
 
 // Shared-memory plan: returns 0 and fills a_bufs / b_stages, or -1 when the halo does not fit.
-static int halo_smem_plan(int halo_bytes, int b_bytes, int* a_bufs, int* b_stages, size_t* total) {
-  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kHHeader;
+// step offsets (4 B) + chunk descriptors (16 B), rounded so that the tiles behind them stay 1024-byte aligned
+static int halo_table_bytes(int n_steps, int n_chunks) {
+  return (((n_steps * 4 + 15) & ~15) + n_chunks * 16 + 1023) / 1024 * 1024;
+}
+
+static int halo_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int* a_bufs, int* b_stages, size_t* total) {
+  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kHHeader - tab_bytes;
   int ab = 2;
   if (2 * halo_bytes + 3 * b_bytes > limit) ab = 1;
   int bs = (limit - ab * halo_bytes) / b_bytes;
@@ -297,16 +321,16 @@ static int halo_smem_plan(int halo_bytes, int b_bytes, int* a_bufs, int* b_stage
   if (bs < 2) return -1;
   *a_bufs = ab;
   *b_stages = bs;
-  *total = 1024 + kHHeader + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes;
+  *total = 1024 + kHHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes;
   return 0;
 }
 
-extern "C" int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub) {
+extern "C" int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub, int n_steps, int n_chunks) {
   const int halo_bytes = (n_planes * Lh * 128 + 1023) / 1024 * 1024;
   int ab, bs;
   size_t total;
   if (m_sub * n_tile > 512) return 0;
-  return halo_smem_plan(halo_bytes, n_tile * 128, &ab, &bs, &total) == 0 ? 1 : 0;
+  return halo_smem_plan(halo_bytes, n_tile * 128, halo_table_bytes(n_steps, n_chunks), &ab, &bs, &total) == 0 ? 1 : 0;
 }
 
 extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
@@ -332,12 +356,9 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   p.y = y;
   p.dbg = g_halo_dbg;
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
-  {
-    const char* e = getenv("CATB_HALO_BO");  // experiment switch for the descriptor base-offset convention
-    p.bo_mode = e ? atoi(e) : 0;
-  }
+  p.tab_bytes = halo_table_bytes(h->n_steps, h->n_chunks);
   size_t smem = 0;
-  CATB_REQUIRE(halo_smem_plan(p.halo_bytes, d->n_tile * 128, &p.a_bufs, &p.b_stages, &smem) == 0,
+  CATB_REQUIRE(halo_smem_plan(p.halo_bytes, d->n_tile * 128, p.tab_bytes, &p.a_bufs, &p.b_stages, &smem) == 0,
                "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
   // Ask only for what this launch can use, so that small problems co-schedule several CTAs per SM
   // (the kernel is not persistent: prologue / epilogue of one CTA overlap the MMAs of its neighbours).
@@ -351,7 +372,8 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
     if (want < (h->b_budget > 0 ? 2 : 4)) want = h->b_budget > 0 ? 2 : 4;
     if (p.b_stages > want) p.b_stages = want;
   }
-  smem = 1024 + kHHeader + static_cast<size_t>(p.a_bufs) * p.halo_bytes + static_cast<size_t>(p.b_stages) * d->n_tile * 128;
+  smem = 1024 + kHHeader + p.tab_bytes + static_cast<size_t>(p.a_bufs) * p.halo_bytes +
+         static_cast<size_t>(p.b_stages) * d->n_tile * 128;
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);
   uint32_t cols = 32;

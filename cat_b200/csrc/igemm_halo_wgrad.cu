@@ -168,30 +168,48 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0 && t1 > t0) {
+    // whole warp walks the loop, one elected lane issues; the taps' window offsets sit in registers, per instruction
+    // one add per descriptor (common.cuh: umma_bf16_lh)
+    if (t1 > t0) {
       const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t hi = sw128_desc_hi(1024);
+      uint32_t boff[8];   // (a_row * 128) >> 4 of the group's taps
+#pragma unroll
+      for (int s = 0; s < 8; ++s) boff[s] = s < grp.n_steps ? static_cast<uint32_t>(p.steps[grp.first_step + s].a_row) * 8u : 0u;
+      const uint32_t dy_lo0 = sw128_desc_lo(smem_u32(bufs), kWPos * 128);
+      const uint32_t hal_lo0 = sw128_desc_lo(smem_u32(bufs) + kDyBytes, 1024);
+      const uint32_t buf16 = static_cast<uint32_t>(buf_bytes) >> 4;
+      uint32_t buf = 0, ph = 0, dy_lo = dy_lo0, hal_lo = hal_lo0, acc = 0;
       for (int t = t0; t < t1; ++t) {
-        const int it = t - t0;
-        const int buf = it % p.bufs;
-        const uint32_t ph = (it / p.bufs) & 1;
         mbar_wait(&full[buf], ph);
         tcgen05_fence_after();
-        const uint32_t dy_addr = smem_u32(bufs + static_cast<size_t>(buf) * buf_bytes);
-        const uint32_t hal_addr = dy_addr + kDyBytes;
-        for (int s = 0; s < grp.n_steps; ++s) {
-          const uint32_t b0 = hal_addr + static_cast<uint32_t>(p.steps[grp.first_step + s].a_row) * 128u;
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kWPos / 16; ++k) {
-            const uint64_t adesc = make_sw128_desc(dy_addr + k * 2048, kWPos * 128, 1024);
-            const uint64_t bdesc = make_sw128_desc(b0 + k * 2048, 1024, 1024);
-            umma_bf16(tmem_base + s * 64, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int s = 0; s < 8; ++s) {
+            if (s < grp.n_steps) {
+              const uint32_t b_lo = hal_lo + boff[s];
+#pragma unroll
+              for (int k = 0; k < kWPos / 16; ++k)
+                umma_bf16_lh(tmem_base + s * 64, dy_lo + k * 128, hi, b_lo + k * 128, hi, idesc, k == 0 ? acc : 1u);
+            }
           }
+          umma_commit(&empty[buf]);
         }
-        umma_commit(&empty[buf]);
+        __syncwarp();
+        acc = 1u;
+        if (++buf == static_cast<uint32_t>(p.bufs)) {
+          buf = 0;
+          ph ^= 1u;
+          dy_lo = dy_lo0;
+          hal_lo = hal_lo0;
+        } else {
+          dy_lo += buf16;
+          hal_lo += buf16;
+        }
       }
-      umma_commit(accum);
+      if (elect_one()) umma_commit(accum);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   tcgen05_fence_before();

@@ -135,7 +135,7 @@ class Gemm:
                 budgets = (0, 16 * 1024) if (force_tile is None and self.n_tile <= 128) else (0,)
                 for tw, ms in cands:
                     plan.TW, plan.m_sub = tw, ms
-                    if not lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms):
+                    if not lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms, len(plan.steps), len(plan.chunks)):
                         continue
                     if force_tile is None and tw not in [t[0] for t in self.tilings]:
                         n_strip_widths += 1

@@ -131,8 +131,9 @@ typedef struct {
   int32_t b_budget;                 /* bytes of weight tiles kept in flight (0: 64 KB); a smaller ring lets
                                        several CTAs share an SM when the tiles are short (thin GEMMs)    */
 } catb_halo_desc;
-/* 1 when the halo tile + weight ring fit in shared memory / TMEM for these parameters, else 0. */
-int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub);
+/* 1 when the halo tile + weight ring + the step / chunk tables (kept in shared memory for the MMA-issuing warp)
+ * fit in shared memory / TMEM for these parameters, else 0. */
+int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub, int n_steps, int n_chunks);
 int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
                           const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
                           const float* bias /*nullable*/, void* y, catb_stream_t s);

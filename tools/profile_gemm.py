@@ -20,6 +20,8 @@ CASES = {
     't5x5': ('fprop', 256, 42, 5, 1, 2, True, 16, 64, 64),      # teacher block, first 5x5 conv
     't3x3': ('fprop', 256, 42, 3, 1, 1, True, 16, 64, 64),
     't1x1': ('fprop', 256, 42, 1, 1, 0, False, 16, 64, 64),
+    't1c': ('fprop', 256, 192, 1, 1, 0, False, 16, 64, 64),     # teacher block, N-concatenated 1x1 first convs
+    't5c': ('fprop', 256, 128, 5, 1, 2, True, 16, 64, 64),      # stand-in: all first convs embedded in one 5x5, N = 126 -> 128
     'ts2': ('fprop2', 252, 256, 5, 1, 2, True, 16, 64, 64),     # stand-in for the K-concatenated stage 2
     'd1': ('fprop', 128, 256, 4, 2, 1, False, 16, 128, 128),
     'd2': ('fprop', 256, 512, 4, 2, 1, False, 16, 64, 64),
