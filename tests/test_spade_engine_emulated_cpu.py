@@ -301,7 +301,7 @@ def test_spade_first_step_with_the_student_in_eval_mode_exact(golden_dir):
         if os.environ.get('CATB_SLOW_TESTS', '0') != '1':
             return
         # netG_student.train() after the first evaluate_model: the same engine continues in training mode (also exercised
-        # by the Inception flow test and by tests/test_train_gpu.py)
+        # by the Inception flow test and by tests/test_zzz_train_gpu.py)
         ref2 = SO.spade_distill_step(st, seg, s['image'], dict(hp, student_training=True))
         eng.set_student_training(True)
         eng.step()

@@ -3,7 +3,7 @@ wrapper is swapped for its torch restatement (oracle/kernel_emu.py, test infrast
 buffers), so launch order, the hand-derived backward passes (incl. the gradient through a generator's INPUT for the
 CycleGAN cycle terms), shared arenas of the three applications of each CycleGAN generator, the device image pools and
 the buffer plumbing must reproduce the fp32 oracle -- which tests/test_train_oracle_golden.py pins to the real reference
-models -- to rounding.  The GPU suite (tests/test_train_gpu.py) runs the same steps through libcatb200.so."""
+models -- to rounding.  The GPU suite (tests/test_zzz_train_gpu.py) runs the same steps through libcatb200.so."""
 import os
 import random
 

@@ -2,7 +2,7 @@
 SPADEModel) in exact kernel emulation on CPU: a trainer-style loop (setup -> set_input -> optimize_parameters ->
 get_current_losses -> save_networks, trainer.py:79-175) must reproduce the pinned oracle's losses, keep the module
 parameters aliased to the engine arenas and write checkpoints with the reference's file names and state_dict keys.
-The GPU suite repeats the loop through libcatb200.so (tests/test_train_gpu.py)."""
+The GPU suite repeats the loop through libcatb200.so (tests/test_zzz_train_gpu.py)."""
 import argparse
 import os
 import random
