@@ -58,25 +58,23 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 __device__ __forceinline__ uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// Activations.  The piecewise-linear ones are max(v, slope * v) with slope 1 (none) / 0 (ReLU) / 0.2 / 0.01: the slope
+// is a loop-invariant select that the compiler hoists, leaving two instructions per element.  (A `switch` over the
+// activation inside the element loop cost ~45 instructions per element -- tanhf is expanded inline in every arm of
+// every unrolled iteration -- and made the GEMM epilogues and the norm kernels instruction bound: ~1 us per 16
+// accumulator columns, profiles/r02_epilogue_ablation.txt.)
+__device__ __forceinline__ float act_slope(int act) {
+  return act == CATB_ACT_NONE ? 1.f : (act == CATB_ACT_LEAKY02 ? 0.2f : (act == CATB_ACT_LEAKY001 ? 0.01f : 0.f));
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case CATB_ACT_RELU: return fmaxf(v, 0.f);
-    case CATB_ACT_LEAKY02: return v > 0.f ? v : 0.2f * v;
-    case CATB_ACT_LEAKY001: return v > 0.f ? v : 0.01f * v;
-    case CATB_ACT_TANH: return tanhf(v);
-    default: return v;
-  }
+  if (act == CATB_ACT_TANH) return tanhf(v);
+  return fmaxf(v, act_slope(act) * v);
 }
 
 // derivative of the activation expressed through its *output*
 __device__ __forceinline__ float act_grad_from_out(float out, int act) {
-  switch (act) {
-    case CATB_ACT_RELU: return out > 0.f ? 1.f : 0.f;
-    case CATB_ACT_LEAKY02: return out > 0.f ? 1.f : 0.2f;
-    case CATB_ACT_LEAKY001: return out > 0.f ? 1.f : 0.01f;
-    case CATB_ACT_TANH: return 1.f - out * out;
-    default: return 1.f;
-  }
+  if (act == CATB_ACT_TANH) return 1.f - out * out;
+  return out > 0.f ? 1.f : act_slope(act);
 }
 
 // nn.ReflectionPad2d index map; requires -L < i < 2L-1
@@ -236,6 +234,87 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait, so that several can be in flight (tmem_wait_ld() before the registers are read).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue of the 32 accumulator rows a warp owns (TMEM lanes 32w .. 32w+31, thread <-> row), bf16 output, no
+// accumulation: bias, activation, then a COALESCED store.  With one thread per output pixel a direct store makes every
+// warp instruction touch 32 different pixels (16 bytes each, a pixel pitch apart): 32 partial-sector transactions per
+// instruction, measured at 7-25 us per CTA (1/4 - 1/2 of its lifetime, profiles/r02_timeline_*.txt).  Here every
+// 64-column slab is staged in this warp's private 4 KB of shared memory (rows of 128 bytes, 16-byte chunks XOR-swizzled
+// with the row so that both the row-wise writes and the chunk-wise reads are conflict free) and written out with
+// consecutive lanes on consecutive 16-byte chunks of a pixel, i.e. whole 128-byte lines whenever ldy == the slab.
+//   trow      TMEM address of the warp's lanes, first column of the tile
+//   col_base  global output column of tile column 0 (tile_n * n_tile)
+//   rvalid / ypix  of THIS thread's row (ypix = pixel index in Y, < 2^31)
+//   stg       4 KB, 128-byte aligned, private to the warp, free of any async-proxy traffic
+__device__ __forceinline__ void epilogue_rows_bf16(uint32_t trow, int n_tile, int col_base, int n_store, int n_rows,
+                                                   const float* __restrict__ bias, int act, bool rvalid, uint32_t ypix,
+                                                   __nv_bfloat16* __restrict__ y, int ldy, int y_coff, uint8_t* stg,
+                                                   int lane, int dbg_mode = 0) {
+  for (int c64 = 0; c64 < n_tile; c64 += 64) {
+    const int ncol = n_tile - c64 < 64 ? n_tile - c64 : 64;   // multiple of 16
+    const int n16 = ncol >> 4;
+    // two halves of 32 columns: 32 accumulator registers live at a time (the kernels rely on 3-4 resident CTAs per SM)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (2 * hf < n16) {
+        uint32_t acc[32];
+        if (dbg_mode & 2) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[e] = 0u;
+        } else {
+          tmem_ld16_nowait(trow + c64 + hf * 32, acc);
+          if (2 * hf + 1 < n16) tmem_ld16_nowait(trow + c64 + hf * 32 + 16, acc + 16);
+          tmem_wait_ld();
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          if (2 * hf + (q8 >> 1) < n16) {
+            const int col = col_base + c64 + hf * 32 + q8 * 8;
+            f8 o;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o.v[e] = __uint_as_float(acc[q8 * 8 + e]);
+            if (bias != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (col + e < n_rows) o.v[e] += __ldg(bias + col + e);
+            }
+            if (act == CATB_ACT_TANH) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o.v[e] = tanhf(o.v[e]);
+            } else if (act != CATB_ACT_NONE) {
+              const float slope = act_slope(act);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(o.v[e], slope * o.v[e]);
+            }
+            st16(stg + lane * 128 + (((hf * 4 + q8) ^ (lane & 7)) << 4), pack8(o));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int nch = ncol >> 3;   // 16-byte chunks per row: 2, 4, 6 or 8
+    for (int it = 0; it < nch; ++it) {
+      const int idx = it * 32 + lane;
+      const int row = idx / nch, ch = idx - row * nch;
+      const uint4 v = ld16(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+      const bool rv = __shfl_sync(0xffffffffu, static_cast<int>(rvalid), row) != 0;
+      const uint32_t pix = __shfl_sync(0xffffffffu, ypix, row);
+      const int col = col_base + c64 + ch * 8;
+      if (rv && col < n_store && !(dbg_mode & 1)) st16(y + static_cast<size_t>(pix) * ldy + y_coff + col, v);
+    }
+    __syncwarp();
+  }
+}
+
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).
 // Tiles are stored as rows of 128 bytes (64 bf16), 8-row atoms of 1024 bytes, 16-byte units XOR-swizzled
 // with (row & 7).  For a K-major operand the rows are M/N indices (SBO = 1024 between 8-row groups,
@@ -270,6 +349,63 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major
   d |= static_cast<uint32_t>(N >> 3) << 17;
   d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// halo fill shared by the v2 forward and weight-gradient kernels
+// ------------------------------------------------------------------------------------------
+// One parity plane of a halo chunk: frame rows [m0, m0 + Lh) in pitch space (row pitch Wf), 128 bytes (one <= 64
+// channel chunk) per row, 16-byte units XOR-swizzled with the absolute row inside the 1024-byte aligned buffer.
+// 128 threads: thread -> (row residue rsub = tid / 8 of 16, unit ul = tid % 8); every thread issues its 16-byte
+// cp.async copies (zero fill outside the image / frame) back to back.  All geometry arrives in registers and the
+// addresses advance incrementally: ~30 instructions per copy instead of the ~85 of the first version, whose loop
+// re-read the descriptor from constant memory and rebuilt every address from scratch (the fill of a 25 KB tile took
+// 3-6 us, as long as its MMAs: profiles/r02_timeline_*.txt).
+// Pins a kernel parameter in a register (otherwise ptxas re-reads it from the constant bank inside the loop).
+__device__ __forceinline__ int in_reg(int v) {
+  int r;
+  asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <bool REFLECT>
+__device__ __forceinline__ void halo_fill_plane(uint32_t plane_smem, int row_phase, const __nv_bfloat16* xc,
+                                                const __nv_bfloat16* xsafe, long long img_base, int m0, int rsub, int ul,
+                                                int Lh_, int Wf_, int Hf_, int mul_, int y0, int x0, int pa, int pb,
+                                                int H_, int W_, int ldx, bool uvalid) {
+  const int Lh = in_reg(Lh_), Wf = in_reg(Wf_), Hf = in_reg(Hf_), mul = in_reg(mul_), H = in_reg(H_), W = in_reg(W_);
+  const int pitch_bytes = in_reg(ldx * 2);                  // one image stays far below 4 GB: 32-bit byte offsets
+  const char* img = reinterpret_cast<const char*>(xc + img_base * ldx);
+  int fy = (m0 + rsub) / Wf;
+  int fx = (m0 + rsub) - fy * Wf;
+  int iy0 = mul * (fy + y0) + pa;                           // advanced together with (fy, fx)
+  int ix0 = mul * (fx + x0) + pb;
+  const int dix16 = mul * 16, dixw = mul * Wf;
+  uint32_t dst = plane_smem + rsub * 128 + ((ul ^ ((row_phase + rsub) & 7)) << 4);   // hr += 16 keeps the swizzle phase
+  for (int hr = rsub; hr < Lh; hr += 16) {
+    int iy = iy0, ix = ix0;
+    bool ok = uvalid & (fy < Hf);
+    if (REFLECT) {
+      ok &= (iy > -H) & (iy < 2 * H - 1) & (ix > -W) & (ix < 2 * W - 1);
+      iy = reflect_idx(iy, H);
+      ix = reflect_idx(ix, W);
+    } else {
+      ok &= (static_cast<unsigned>(iy) < static_cast<unsigned>(H)) & (static_cast<unsigned>(ix) < static_cast<unsigned>(W));
+    }
+    const uint32_t off = static_cast<uint32_t>(iy * W + ix) * static_cast<uint32_t>(pitch_bytes);
+    const void* src = ok ? static_cast<const void*>(img + off) : static_cast<const void*>(xsafe);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    dst += 2048;
+    fx += 16;
+    ix0 += dix16;
+    while (fx >= Wf) {
+      fx -= Wf;
+      ix0 -= dixw;
+      ++fy;
+      iy0 += mul;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -10,6 +10,8 @@
 // Warp roles (192 threads): warps 0-3 gather the activation tile into 128B-swizzled shared memory and
 // later run the epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 owns TMEM and issues the MMAs,
 // warp 5 streams the pre-packed, pre-swizzled weight tiles with 1-D bulk copies (TMA engine).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace catb {
@@ -140,6 +142,12 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_fprop_kernel(const FpropPar
       ypix = (static_cast<size_t>(n) * d.OH + (d.o_ph + i * d.o_step)) * d.OW + (d.o_pw + j * d.o_step);
     }
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    if (!d.y_is_f32 && !d.accumulate) {
+      // every stage has been consumed (accum barrier): stage 0's activation tile is the staging area (4 KB per warp)
+      epilogue_rows_bf16(trow, d.n_tile, tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
+                         static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff,
+                         tiles + warp * 4096, lane);
+    } else
     for (int cc = 0; cc < d.n_tile / 16; ++cc) {
       float acc[16];
       tmem_ld16(trow + cc * 16, acc);
@@ -241,6 +249,8 @@ struct WgradParams {
   const __nv_bfloat16* x;
   const __nv_bfloat16* y;
   float* grad;
+  float* ws;   // two-stage mode: partial tiles [split][n_rows][ws_k] written with plain stores (no atomics), see below
+  int ws_k;
   int M_total, steps_total, steps_per_cta, stages, nb_chunks, cy_p;
   uint32_t idesc;
 };
@@ -360,6 +370,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_wgrad_kernel(const WgradPar
       const int row = m_tile * 128 + warp * 32 + lane;  // channel of the lattice tensor
       const bool rvalid = row < d.n_rows;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+      if (p.ws != nullptr) {
+        // two-stage mode: the split's partial tile goes to the workspace in GEMM order (row = channel of the lattice
+        // tensor, column = unit * 8 + element) with 64-byte runs per thread; catb_wgrad_unpack sums the splits in a
+        // fixed order and adds the result to the arena layout.  No atomics here: every element is written once.
+        float* wrow = p.ws + (static_cast<size_t>(blockIdx.x) * d.n_rows + row) * p.ws_k + n_tile * 256;
+        for (int cc = 0; cc < p.nb_chunks * 4; ++cc) {
+          float acc[16];
+          tmem_ld16(trow + cc * 16, acc);
+          if (rvalid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(wrow + cc * 16 + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+          }
+        }
+      } else
       for (int cc = 0; cc < p.nb_chunks * 4; ++cc) {
         float acc[16];
         tmem_ld16(trow + cc * 16, acc);
@@ -552,6 +577,7 @@ static int validate_desc(const catb_igemm_desc* d) {
   CATB_REQUIRE(d->ldx % 8 == 0 && d->x_coff % 8 == 0 && d->y_coff % 8 == 0, "pitches/offsets must be multiples of 8");
   CATB_REQUIRE(d->n_units > 0 && d->n_rows > 0, "empty GEMM");
   CATB_REQUIRE(static_cast<long long>(d->N) * d->OHs * d->OWs < (1ll << 31), "too many lattice rows");
+  CATB_REQUIRE(static_cast<long long>(d->N) * d->OH * d->OW < (1ll << 31), "too many output pixels");
   return CATB_OK;
 }
 
@@ -638,8 +664,23 @@ extern "C" int catb_igemm_fprop(const catb_igemm_desc* d, const catb_gather_unit
   return check_launch("igemm_fprop");
 }
 
-extern "C" int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
-                                const void* x, const void* y, float* arena_grad, catb_stream_t s) {
+// Split plan of the v1 weight gradient: row splits, and the column pitch of the two-stage workspace.
+static void wgrad_split_plan(const catb_igemm_desc* d, int* splits, int* steps_per_cta, int* ws_k) {
+  const int M_total = d->N * d->OHs * d->OWs;
+  const int steps_total = (M_total + kWStepRows - 1) / kWStepRows;
+  const int m_tiles = (d->n_rows + 127) / 128;
+  const int n_tiles = (d->n_units + 31) / 32;
+  // aim at ~4 CTAs per SM in total, at least 4 pipeline steps per CTA
+  int sp = (148 * 4 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+  if (sp > (steps_total + 3) / 4) sp = (steps_total + 3) / 4;
+  if (sp < 1) sp = 1;
+  *steps_per_cta = (steps_total + sp - 1) / sp;
+  *splits = (steps_total + *steps_per_cta - 1) / *steps_per_cta;
+  *ws_k = n_tiles * 256;
+}
+
+static int launch_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
+                        const void* x, const void* y, float* arena_grad, float* ws, catb_stream_t s) {
   if (int e = validate_desc(d)) return e;
   CATB_REQUIRE(d->ldy % 8 == 0, "ldy must be a multiple of 8");
   WgradParams p;
@@ -649,6 +690,7 @@ extern "C" int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.y = static_cast<const __nv_bfloat16*>(y);
   p.grad = arena_grad;
+  p.ws = ws;
   p.M_total = d->N * d->OHs * d->OWs;
   p.steps_total = (p.M_total + kWStepRows - 1) / kWStepRows;
   const int n_chunks = (d->n_units + 7) / 8;
@@ -656,12 +698,8 @@ extern "C" int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit
   p.cy_p = (d->n_rows + 7) / 8 * 8;
   const int m_tiles = (d->n_rows + 127) / 128;
   const int n_tiles = (d->n_units + 31) / 32;
-  // aim at ~4 CTAs per SM in total, at least 4 pipeline steps per CTA
-  int splits = (148 * 4 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
-  if (splits > (p.steps_total + 3) / 4) splits = (p.steps_total + 3) / 4;
-  if (splits < 1) splits = 1;
-  p.steps_per_cta = (p.steps_total + splits - 1) / splits;
-  splits = (p.steps_total + p.steps_per_cta - 1) / p.steps_per_cta;
+  int splits;
+  wgrad_split_plan(d, &splits, &p.steps_per_cta, &p.ws_k);
   const int stage_bytes = (2 + p.nb_chunks) * kWChunkBytes;
   p.stages = pick_stages(stage_bytes);
   p.idesc = make_idesc_bf16(128, p.nb_chunks * 64, 1, 1);
@@ -669,6 +707,56 @@ extern "C" int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit
   const size_t smem = 1024 + kHeaderBytes + static_cast<size_t>(p.stages) * stage_bytes;
   igemm_wgrad_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(s)>>>(p);
   return check_launch("igemm_wgrad");
+}
+
+extern "C" int catb_igemm_wgrad(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
+                                const void* x, const void* y, float* arena_grad, catb_stream_t s) {
+  return launch_wgrad(d, units, wunits, x, y, arena_grad, nullptr, s);
+}
+
+extern "C" int catb_igemm_wgrad_ws_shape(const catb_igemm_desc* d, int* splits, int* ws_k) {
+  if (int e = validate_desc(d)) return e;
+  int spc;
+  wgrad_split_plan(d, splits, &spc, ws_k);
+  return CATB_OK;
+}
+
+extern "C" int catb_igemm_wgrad_ws(const catb_igemm_desc* d, const catb_gather_unit* units, const void* x, const void* y,
+                                   float* ws, catb_stream_t s) {
+  CATB_REQUIRE(ws != nullptr, "null workspace");
+  return launch_wgrad(d, units, nullptr, x, y, nullptr, ws, s);
+}
+
+// Second stage of the two-stage weight gradient: arena_grad[w(row, unit, q)] += sum over splits (in split order) of
+// ws[split][row][unit * 8 + q].  One thread per workspace column: coalesced reads, one atomic add per real element (the
+// add itself is ordered by the stream, so the result is deterministic).
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, int n_splits, int n_rows, int n_units, int ws_k,
+                                    const catb_weight_unit* __restrict__ wunits, float* __restrict__ grad) {
+  const long long total = static_cast<long long>(n_rows) * n_units * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(idx & 7);
+    const int u = static_cast<int>((idx >> 3) % n_units);
+    const int row = static_cast<int>((idx >> 3) / n_units);
+    const catb_weight_unit wu = wunits[u];
+    if (q >= wu.nvalid) continue;
+    const float* src = ws + static_cast<size_t>(row) * ws_k + u * 8 + q;
+    const size_t split_stride = static_cast<size_t>(n_rows) * ws_k;
+    float acc = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) acc += src[sp * split_stride];
+    atomicAdd(grad + wu.w_off + static_cast<long long>(row) * wu.sn_w + q * wu.sc_w, acc);
+  }
+}
+
+extern "C" int catb_wgrad_unpack(const float* ws, int n_splits, int n_rows, int n_units, int ws_k,
+                                 const catb_weight_unit* wunits, float* arena_grad, catb_stream_t s) {
+  CATB_REQUIRE(ws != nullptr && wunits != nullptr && arena_grad != nullptr, "null pointer");
+  CATB_REQUIRE(n_splits > 0 && n_rows > 0 && n_units > 0 && ws_k >= n_units * 8, "bad workspace shape");
+  const long long total = static_cast<long long>(n_rows) * n_units * 8;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  wgrad_unpack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(ws, n_splits, n_rows, n_units, ws_k, wunits,
+                                                                        arena_grad);
+  return check_launch("wgrad_unpack");
 }
 
 extern "C" int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,

@@ -14,7 +14,9 @@
 //
 // Warp roles as in v1: warps 0-3 fill the halo then run the epilogue, warp 4 issues tcgen05.mma for every
 // (chunk, tap, sub-tile), warp 5 streams the pre-swizzled weight tile of each (chunk, tap) step with one
-// bulk copy.  Up to two 128-row sub-tiles share every weight tile (halves weight traffic per FLOP).
+// bulk copy.  Up to four 128-row sub-tiles share every weight tile: a thin GEMM (N <= 64) issues an MMA every ~45
+// cycles, i.e. with one sub-tile it would pull a fresh weight tile from L2 every ~180 cycles per SM (~10 TB/s over the
+// chip); sharing the tile between sub-tiles divides that traffic.
 #include <algorithm>
 #include <cstdlib>
 
@@ -35,12 +37,13 @@ struct HaloParams {
   const uint8_t* wpk;
   const float* bias;
   void* y;
-  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, tab_bytes;
+  int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, tab_bytes, dbg_mode;
   uint32_t idesc;
   unsigned long long* dbg;  // optional per-CTA phase timestamps (catb_debug_timeline), null in production
 };
 
 static unsigned long long* g_halo_dbg = nullptr;
+static int g_halo_dbg_mode = 0;   // experiment switches of the epilogue (catb_debug_mode): 1 no global stores, 2 no TMEM loads, 4 direct stores
 constexpr int kDbgSlots = 8, kDbgCtas = 4096;
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
   const catb_igemm_desc& d = p.d;
   const catb_halo_desc& h = p.h;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DBG_STAMP(7);   // kernel entry
   const int per_img = p.tiles_per_image * h.n_strips;   // tiles_per_image = tiles per (image, strip)
   const int n_img = blockIdx.x / per_img;
   const int strip = (blockIdx.x - n_img * per_img) / p.tiles_per_image;
@@ -121,31 +125,18 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       mbar_wait(&a_empty[buf], ph ^ 1);
       // Every thread issues all of its 16-byte copies back to back with cp.async (LDGSTS, zero-fill for
       // padding / out-of-frame pixels): hundreds of loads in flight per SM, no register staging.
-      for (int plane = 0; plane < h.n_planes; ++plane) {
-        const int y0 = h.plane_y0[plane], x0 = h.plane_x0[plane] + strip_x;
-        const int pa = h.plane_pa[plane], pb = h.plane_pb[plane];
-        int fy = (m0 + rsub) / h.Wf;
-        int fx = (m0 + rsub) - fy * h.Wf;
-        uint8_t* prow = abuf + static_cast<size_t>(plane) * h.Lh * 128;
-        for (int hr = rsub; hr < h.Lh; hr += 16) {
-          int iy = h.mul * (fy + y0) + pa;
-          int ix = h.mul * (fx + x0) + pb;
-          bool ok = uvalid & (fy < Hf);
-          if (d.pad_mode == CATB_PAD_REFLECT) {
-            ok &= (iy > -d.H) & (iy < 2 * d.H - 1) & (ix > -d.W) & (ix < 2 * d.W - 1);
-            iy = reflect_idx(iy, d.H);
-            ix = reflect_idx(ix, d.W);
-          } else {
-            ok &= (iy >= 0) & (iy < d.H) & (ix >= 0) & (ix < d.W);
-          }
-          const __nv_bfloat16* src = ok ? xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx : p.x;
-          const int row = plane * h.Lh + hr;  // swizzle phase follows the absolute row in the buffer
-          if (ufill) cp_async16_zfill(prow + static_cast<size_t>(hr) * 128 + ((ul ^ (row & 7)) << 4), src, ok);
-          fx += 16;
-          while (fx >= h.Wf) {
-            fx -= h.Wf;
-            ++fy;
-          }
+      if (ufill) {
+        const uint32_t abuf_s = smem_u32(abuf);
+        for (int plane = 0; plane < h.n_planes; ++plane) {
+          const uint32_t plane_smem = abuf_s + static_cast<uint32_t>(plane) * h.Lh * 128u;
+          if (d.pad_mode == CATB_PAD_REFLECT)
+            halo_fill_plane<true>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+                                  h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
+                                  h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
+          else
+            halo_fill_plane<false>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+                                   h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
+                                   h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
         }
       }
       cp_async_wait_all();
@@ -165,14 +156,27 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       const bool rvalid = (i < d.OHs) & (j < h.TW) & (jg < d.OWs);
       const size_t ypix = (static_cast<size_t>(n_img) * d.OH + (d.o_ph + i * d.o_step)) * d.OW + (d.o_pw + jg * d.o_step);
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + sub * d.n_tile;
+      if (!d.y_is_f32 && !d.accumulate && !(p.dbg_mode & 4)) {
+        // all MMAs have completed (accum barrier), every fill of this CTA is consumed: the halo buffers are free and
+        // serve as the staging area of the coalesced store (4 KB per warp)
+        epilogue_rows_bf16(trow, d.n_tile, tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
+                           static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff,
+                           a_base + warp * 4096, lane, p.dbg_mode);
+        continue;
+      }
       for (int cc = 0; cc < d.n_tile / 16; ++cc) {
         float acc[16];
-        tmem_ld16(trow + cc * 16, acc);
+        if (p.dbg_mode & 2) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        } else {
+          tmem_ld16(trow + cc * 16, acc);
+        }
         const int col0 = tile_n * d.n_tile + cc * 16;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = col0 + g * 8;
-          if (!rvalid || col >= p.n_store) continue;
+          if (!rvalid || col >= p.n_store || (p.dbg_mode & 1)) continue;
           f8 o;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
     const uint32_t a_lo0 = sw128_desc_lo(smem_u32(a_base), 16);
     const uint32_t idesc = p.idesc;
     const uint32_t n_tile = d.n_tile;
-    const bool two = h.m_sub == 2;
+    const uint32_t m_sub = h.m_sub;
     uint32_t st = 0, phb = 0, b_lo = b_lo0;     // weight ring position
     uint32_t buf = 0, pha = 0, a_lo = a_lo0;    // halo buffer position
     uint32_t acc = 0;                           // 0 only for the first instruction into each accumulator
@@ -235,15 +239,14 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
         mbar_wait(&b_full[st], phb);
         tcgen05_fence_after();
         if (elect_one()) {
-          umma_bf16_lh(tmem_base, a_cur, hi, b_lo, hi, idesc, acc);
-          if (kmax > 1) umma_bf16_lh(tmem_base, a_cur + 2, hi, b_lo + 2, hi, idesc, 1u);
-          if (kmax > 2) umma_bf16_lh(tmem_base, a_cur + 4, hi, b_lo + 4, hi, idesc, 1u);
-          if (kmax > 3) umma_bf16_lh(tmem_base, a_cur + 6, hi, b_lo + 6, hi, idesc, 1u);
-          if (two) {   // second 128-row sub-tile: halo rows + 128 (16 KB further), its own accumulator columns
-            umma_bf16_lh(tmem_base + n_tile, a_cur + 1024, hi, b_lo, hi, idesc, acc);
-            if (kmax > 1) umma_bf16_lh(tmem_base + n_tile, a_cur + 1026, hi, b_lo + 2, hi, idesc, 1u);
-            if (kmax > 2) umma_bf16_lh(tmem_base + n_tile, a_cur + 1028, hi, b_lo + 4, hi, idesc, 1u);
-            if (kmax > 3) umma_bf16_lh(tmem_base + n_tile, a_cur + 1030, hi, b_lo + 6, hi, idesc, 1u);
+          // every 128-row sub-tile (halo rows + 128 * sub = 16 KB further) has its own accumulator columns and shares
+          // the step's weight tile
+          for (uint32_t sub = 0; sub < m_sub; ++sub) {
+            const uint32_t a_s = a_cur + sub * 1024u, t_s = tmem_base + sub * n_tile;
+            umma_bf16_lh(t_s, a_s, hi, b_lo, hi, idesc, acc);
+            if (kmax > 1) umma_bf16_lh(t_s, a_s + 2, hi, b_lo + 2, hi, idesc, 1u);
+            if (kmax > 2) umma_bf16_lh(t_s, a_s + 4, hi, b_lo + 4, hi, idesc, 1u);
+            if (kmax > 3) umma_bf16_lh(t_s, a_s + 6, hi, b_lo + 6, hi, idesc, 1u);
           }
           umma_commit(&b_empty[st]);
         }
@@ -338,7 +341,7 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
                                      const float* bias, void* y, catb_stream_t s) {
   CATB_REQUIRE(d != nullptr && h != nullptr, "null descriptor");
   CATB_REQUIRE(d->n_tile % 16 == 0 && d->n_tile >= 16 && d->n_tile <= 256, "n_tile must be a multiple of 16 in [16,256]");
-  CATB_REQUIRE(h->m_sub >= 1 && h->m_sub <= 2 && h->m_sub * d->n_tile <= 512, "m_sub * n_tile must fit 512 TMEM columns");
+  CATB_REQUIRE(h->m_sub >= 1 && h->m_sub <= 4 && h->m_sub * d->n_tile <= 512, "m_sub * n_tile must fit 512 TMEM columns");
   CATB_REQUIRE(h->n_planes >= 1 && h->n_planes <= 4 && h->n_steps > 0 && h->n_chunks > 0, "bad halo plan");
   CATB_REQUIRE(h->TW > 0 && h->n_strips == (d->OWs + h->TW - 1) / h->TW && h->Wf == h->TW + h->Xmax &&
                    h->Lh == 128 * h->m_sub + h->Ymax * h->Wf + h->Xmax,
@@ -355,6 +358,7 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   p.bias = bias;
   p.y = y;
   p.dbg = g_halo_dbg;
+  p.dbg_mode = g_halo_dbg_mode;
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
   p.tab_bytes = halo_table_bytes(h->n_steps, h->n_chunks);
   size_t smem = 0;
@@ -391,5 +395,10 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
 // halo-fprop CTA with blockIdx.x < 4096 records %globaltimer at its phase boundaries.  Pass NULL to switch it off.
 extern "C" int catb_debug_timeline(void* device_buffer) {
   g_halo_dbg = static_cast<unsigned long long*>(device_buffer);
+  return CATB_OK;
+}
+
+extern "C" int catb_debug_mode(int mode) {
+  g_halo_dbg_mode = mode;
   return CATB_OK;
 }

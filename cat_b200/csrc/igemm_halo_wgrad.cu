@@ -28,6 +28,7 @@ struct WHaloParams {
   const __nv_bfloat16* x;
   const __nv_bfloat16* y;
   float* grad;
+  float* ws;   // two-stage mode (see igemm.cu): partial tiles [split][n_rows][n_steps * 64]
   int tiles_per_strip, tiles_total, tiles_per_cta, bufs, halo_bytes, cy_p;
 };
 
@@ -113,31 +114,18 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
       }
       // ---- X halo of the chunk (same fill as the forward kernel)
       const size_t img_base = static_cast<size_t>(n_img) * d.H * d.W;
-      for (int plane = 0; plane < h.n_planes; ++plane) {
-        const int y0 = h.plane_y0[plane], x0 = h.plane_x0[plane] + strip_x;
-        const int pa = h.plane_pa[plane], pb = h.plane_pb[plane];
-        int fy = (m0 + rsub) / h.Wf;
-        int fx = (m0 + rsub) - fy * h.Wf;
-        uint8_t* prow = hal + static_cast<size_t>(plane) * h.Lh * 128;
-        for (int hr = rsub; hr < h.Lh; hr += 16) {
-          int iy = h.mul * (fy + y0) + pa;
-          int ix = h.mul * (fx + x0) + pb;
-          bool ok = uvalid & (fy < Hf);
-          if (d.pad_mode == CATB_PAD_REFLECT) {
-            ok &= (iy > -d.H) & (iy < 2 * d.H - 1) & (ix > -d.W) & (ix < 2 * d.W - 1);
-            iy = reflect_idx(iy, d.H);
-            ix = reflect_idx(ix, d.W);
-          } else {
-            ok &= (iy >= 0) & (iy < d.H) & (ix >= 0) & (ix < d.W);
-          }
-          const __nv_bfloat16* src = ok ? xc + (img_base + static_cast<size_t>(iy) * d.W + ix) * d.ldx : p.x;
-          const int row = plane * h.Lh + hr;
-          cp16_zfill(prow + static_cast<size_t>(hr) * 128 + ((ul ^ (row & 7)) << 4), src, ok);
-          fx += 16;
-          while (fx >= h.Wf) {
-            fx -= h.Wf;
-            ++fy;
-          }
+      {
+        const uint32_t hal_s = smem_u32(hal);
+        for (int plane = 0; plane < h.n_planes; ++plane) {
+          const uint32_t plane_smem = hal_s + static_cast<uint32_t>(plane) * h.Lh * 128u;
+          if (d.pad_mode == CATB_PAD_REFLECT)
+            halo_fill_plane<true>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+                                  h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
+                                  h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
+          else
+            halo_fill_plane<false>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+                                   h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
+                                   h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
         }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
@@ -152,6 +140,23 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
       const int row = m_tile * 128 + warp * 32 + lane;   // channel of dY
       const bool rvalid = row < d.n_rows;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+      if (p.ws != nullptr) {
+        // two-stage mode: plain 64-byte runs into the split's workspace tile (column = step * 64 + channel), no atomics
+        float* wrow = p.ws + (static_cast<size_t>(blockIdx.x) * d.n_rows + row) * (static_cast<size_t>(h.n_steps) * 64) +
+                      static_cast<size_t>(grp.first_step) * 64;
+        for (int s = 0; s < grp.n_steps; ++s) {
+          for (int cc = 0; cc < 4; ++cc) {
+            float acc[16];
+            tmem_ld16(trow + s * 64 + cc * 16, acc);
+            if (rvalid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(wrow + s * 64 + cc * 16 + q * 4) =
+                    make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            }
+          }
+        }
+      } else
       for (int s = 0; s < grp.n_steps; ++s) {
         for (int cc = 0; cc < 4; ++cc) {
           float acc[16];
@@ -236,10 +241,23 @@ extern "C" int catb_igemm_halo_wgrad_fits(int n_planes, int Lh) {
   return kWHeader + 1024 + kDyBytes + halo_bytes <= 227 * 1024 ? 1 : 0;
 }
 
-extern "C" int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
-                                     const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
-                                     const catb_weight_unit* wunits, const void* x, const void* y, float* arena_grad,
-                                     catb_stream_t s) {
+static void halo_wgrad_split_plan(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int* tiles_total,
+                                  int* tiles_per_strip, int* tiles_per_cta, int* splits) {
+  *tiles_per_strip = (d->OHs * h->Wf + kWPos - 1) / kWPos;
+  *tiles_total = *tiles_per_strip * h->n_strips * d->N;
+  const int m_tiles = (d->n_rows + 127) / 128;
+  // split the position tiles so that the grid has ~3 CTAs per SM, at least 2 tiles per CTA
+  int sp = (148 * 3 + m_tiles * n_groups - 1) / (m_tiles * n_groups);
+  if (sp > (*tiles_total + 1) / 2) sp = (*tiles_total + 1) / 2;
+  if (sp < 1) sp = 1;
+  *tiles_per_cta = (*tiles_total + sp - 1) / sp;
+  *splits = (*tiles_total + *tiles_per_cta - 1) / *tiles_per_cta;
+}
+
+static int launch_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
+                             const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
+                             const catb_weight_unit* wunits, const void* x, const void* y, float* arena_grad, float* ws,
+                             catb_stream_t s) {
   CATB_REQUIRE(d != nullptr && h != nullptr && n_groups > 0, "null descriptor");
   CATB_REQUIRE(h->m_sub == 1, "the weight-gradient halo kernel uses single 128-position tiles");
   CATB_REQUIRE(h->n_planes >= 1 && h->n_planes <= 4 && h->n_steps > 0 && h->n_chunks > 0, "bad halo plan");
@@ -257,23 +275,41 @@ extern "C" int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_d
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.y = static_cast<const __nv_bfloat16*>(y);
   p.grad = arena_grad;
+  p.ws = ws;
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
   const int buf_bytes = kDyBytes + p.halo_bytes;
   CATB_REQUIRE(kWHeader + 1024 + buf_bytes <= 227 * 1024, "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
   p.bufs = (kWHeader + 1024 + 2 * buf_bytes <= 227 * 1024) ? 2 : 1;
   p.cy_p = (d->n_rows + 7) / 8 * 8;
-  p.tiles_per_strip = (d->OHs * h->Wf + kWPos - 1) / kWPos;
-  p.tiles_total = p.tiles_per_strip * h->n_strips * d->N;
+  int splits;
+  halo_wgrad_split_plan(d, h, n_groups, &p.tiles_total, &p.tiles_per_strip, &p.tiles_per_cta, &splits);
   const int m_tiles = (d->n_rows + 127) / 128;
-  // split the position tiles so that the grid has ~3 CTAs per SM, at least 2 tiles per CTA
-  int splits = (148 * 3 + m_tiles * n_groups - 1) / (m_tiles * n_groups);
-  if (splits > (p.tiles_total + 1) / 2) splits = (p.tiles_total + 1) / 2;
-  if (splits < 1) splits = 1;
-  p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
-  splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   if (p.tiles_per_cta == 1) p.bufs = 1;
   dim3 grid(splits, m_tiles, n_groups);
   const size_t smem = 1024 + kWHeader + static_cast<size_t>(p.bufs) * buf_bytes;
   igemm_halo_wgrad_kernel<<<grid, kWThreads, smem, static_cast<cudaStream_t>(s)>>>(p);
   return check_launch("igemm_halo_wgrad");
+}
+
+extern "C" int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
+                                     const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
+                                     const catb_weight_unit* wunits, const void* x, const void* y, float* arena_grad,
+                                     catb_stream_t s) {
+  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, wunits, x, y, arena_grad, nullptr, s);
+}
+
+extern "C" int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int* splits,
+                                              int* ws_k) {
+  CATB_REQUIRE(d != nullptr && h != nullptr && n_groups > 0 && splits != nullptr && ws_k != nullptr, "null pointer");
+  int tt, tps, tpc;
+  halo_wgrad_split_plan(d, h, n_groups, &tt, &tps, &tpc, splits);
+  *ws_k = h->n_steps * 64;
+  return CATB_OK;
+}
+
+extern "C" int catb_igemm_halo_wgrad_ws(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
+                                        const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
+                                        const void* x, const void* y, float* ws, catb_stream_t s) {
+  CATB_REQUIRE(ws != nullptr, "null workspace");
+  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, nullptr, x, y, nullptr, ws, s);
 }

@@ -128,7 +128,7 @@ class Gemm:
                     cands = [force_tile]
                 else:   # widest strip that fits, with 2 and 1 sub-tiles; one narrower strip as alternative
                     widths = [geo.OWs] + [t for t in (64, 32, 16) if t < geo.OWs]
-                    cands = [(tw, ms) for tw in widths for ms in (2, 1)]
+                    cands = [(tw, ms) for tw in widths for ms in ((4, 2, 1) if self.n_tile <= 128 else (2, 1))]
                 n_strip_widths = 0
                 # short weight tiles (thin GEMMs): a second variant with a small weight ring, so that 2-4 CTAs share
                 # an SM and the fill / MMA / epilogue phases of neighbouring tiles overlap
@@ -315,26 +315,57 @@ class Gemm:
         self.w_groups = torch.from_numpy(np.array(groups, dtype=np.int32)).to(dev)
         self.w_ngroups = len(groups)
         self.w_wt = units_to_device(plan.units, dev)[1]
+        self.w_nunits = len(plan.units)
 
-    def wgrad(self, x, y, grad_arena, force_v1=False):
+    def _ws_for(self, kind, d):
+        """Workspace of the two-stage weight gradient: [splits][n_rows][ws_k] fp32, owned by this Gemm (its contents only
+        live between the two launches of one wgrad call)."""
+        key = '_ws_' + kind
+        if getattr(self, key, None) is None:
+            splits, ws_k = C.c_int(0), C.c_int(0)
+            if kind == 'v1':
+                _C.check(_C.load().catb_igemm_wgrad_ws_shape(C.byref(d), C.byref(splits), C.byref(ws_k)), 'ws_shape')
+            else:
+                _C.check(_C.load().catb_igemm_halo_wgrad_ws_shape(C.byref(d), C.byref(self.w_hdesc), self.w_ngroups,
+                                                                  C.byref(splits), C.byref(ws_k)), 'halo ws_shape')
+            ws = torch.empty(splits.value * self.n_rows * ws_k.value, dtype=torch.float32, device=self.gt.device)
+            setattr(self, key, (ws, splits.value, ws_k.value))
+        return getattr(self, key)
+
+    def wgrad(self, x, y, grad_arena, force_v1=False, atomic=False):
+        """grad_arena[w] += sum_rows y[row, c] * gather(x)[row, k].  Default: the deterministic two-stage form (partial
+        tiles per row split into a workspace with plain stores, then catb_wgrad_unpack); atomic=True keeps the
+        one-launch form with fp32 atomics from the accumulators (tests compare the two)."""
         self._wgrad_plan()
         d = self.desc()
 
         def v1(g):
-            _C.call('catb_igemm_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(g), _stream())
+            if atomic:
+                _C.call('catb_igemm_wgrad', C.byref(d), _p(self.gt), _p(self.wt), _p(x), _p(y), _p(g), _stream())
+                return
+            ws, splits, ws_k = self._ws_for('v1', d)
+            _C.call('catb_igemm_wgrad_ws', C.byref(d), _p(self.gt), _p(x), _p(y), _p(ws), _stream())
+            _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, self.n_units, ws_k, _p(self.wt), _p(g), _stream())
 
         def v2(g):
-            _C.call('catb_igemm_halo_wgrad', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
-                    _p(self.w_groups), self.w_ngroups, _p(self.w_wt), _p(x), _p(y), _p(g), _stream())
+            if atomic:
+                _C.call('catb_igemm_halo_wgrad', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
+                        _p(self.w_groups), self.w_ngroups, _p(self.w_wt), _p(x), _p(y), _p(g), _stream())
+                return
+            ws, splits, ws_k = self._ws_for('v2', d)
+            _C.call('catb_igemm_halo_wgrad_ws', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
+                    _p(self.w_groups), self.w_ngroups, _p(x), _p(y), _p(ws), _stream())
+            _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, self.w_nunits, ws_k, _p(self.w_wt), _p(g), _stream())
 
         if AUTOTUNE and self.w_halo is not None and self.w_choice is None and not force_v1 \
                 and not torch.cuda.is_current_stream_capturing():
-            # wgrad accumulates with atomics, so the two kernels are timed on a scratch copy of the arena
+            # the result is accumulated into the arena, so the two kernels are timed on a scratch copy of it
             scratch = _scratch_like(grad_arena)
             t2 = self._launch_timed(lambda: v2(scratch))
             t1 = self._launch_timed(lambda: v1(scratch))
             self.w_choice = 'v2' if t2 <= t1 else 'v1'
             self.w_tuned_ms = (t1, t2)
+            setattr(self, '_ws_v1' if self.w_choice == 'v2' else '_ws_v2', None)     # drop the loser's workspace
         if self.w_halo is not None and not force_v1 and self.w_choice != 'v1':
             v2(grad_arena)
         else:

@@ -55,7 +55,7 @@ CASES = [
 
 
 @pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,N,H,W', CASES)
-@pytest.mark.parametrize('tile', ['auto', 'msub2', 'strips'])
+@pytest.mark.parametrize('tile', ['auto', 'msub2', 'msub4', 'strips'])
 def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
     from cat_b200 import ops
     torch.manual_seed(k * 100 + Cin)
@@ -71,8 +71,12 @@ def test_halo_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, tile):
     units = P.conv_fprop_units(5, Cout, Cin, k, k, pad)
     ldy = P.cpad(Cout) + 8
     geo = P.Geometry(N, H, W, P.cpad(Cin), 0, OH, OW, ldy, 8, sn=stride, pad_mode=pm)
-    force = {'auto': None, 'msub2': (OW, 2), 'strips': (max(4, OW // 3), 1)}[tile]
+    force = {'auto': None, 'msub2': (OW, 2), 'msub4': (OW, 4), 'strips': (max(4, OW // 3), 1)}[tile]
+    if tile == 'msub4' and 4 * P.choose_n_tile(Cout) > 512:
+        pytest.skip('four sub-tiles need 4 * n_tile <= 512 TMEM columns')
     gm = ops.Gemm(geo, units, Cout, DEV, force_tile=force)
+    if tile == 'msub4' and gm.halo is None:
+        pytest.skip('four sub-tiles of this shape do not fit in shared memory')
     assert gm.halo is not None, 'every conv of the path must qualify for the halo kernel'
     gm.pack(arena)     # packs both weight images (v1: compact table, v2: chunk-aligned table)
     gm.choice = 'v2'   # then pin the kernel under test (the engine autotunes v1 / v2 per GEMM)
@@ -152,6 +156,20 @@ def test_halo_wgrad(k, stride, pad, mode, Cin, Cout, N, H, W):
     assert rel_err(got1, wb.grad) < 2e-4, 'v1 wgrad'
     assert rel_err(got2, wb.grad) < 2e-4, 'v2 (halo) wgrad'
     assert float(g2[:5].abs().max()) == 0 and float(g2[5 + w.numel():].abs().max()) == 0
+    # the default path is the two-stage form (workspace + catb_wgrad_unpack): bit-identical from run to run, and equal to
+    # the one-launch atomic form up to the summation order of the row splits
+    g3, g4, g5 = torch.zeros_like(g2), torch.zeros_like(g2), torch.zeros_like(g2)
+    gw.wgrad(xd, dyd, g3)
+    gw.wgrad(xd, dyd, g4, atomic=True)
+    gw.wgrad(xd, dyd, g5, force_v1=True, atomic=True)
+    torch.cuda.synchronize()
+    assert torch.equal(g3, g2), 'two-stage weight gradient must be deterministic'
+    for ga in (g4, g5):
+        assert rel_err(ga[5:5 + w.numel()].view_as(w).double().cpu(), wb.grad) < 2e-4, 'atomic form'
+    # accumulation semantics: a second call adds
+    gw.wgrad(xd, dyd, g3)
+    torch.cuda.synchronize()
+    assert rel_err(g3[5:5 + w.numel()].view_as(w).double().cpu(), 2 * wb.grad) < 2e-4
 
 
 def test_halo_k_concat_block_stage2():

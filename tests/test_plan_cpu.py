@@ -161,7 +161,7 @@ def test_choose_n_tile():
     (3, 1, 1, 'zero', 5, 7, 10, 12), (5, 1, 2, 'reflect', 70, 4, 12, 9), (7, 1, 3, 'reflect', 3, 17, 9, 11),
     (1, 1, 0, 'zero', 130, 10, 8, 8), (3, 2, 1, 'zero', 6, 11, 10, 12), (4, 2, 1, 'zero', 72, 8, 12, 10),
     (4, 1, 1, 'zero', 8, 1, 7, 9)])
-@pytest.mark.parametrize('m_sub', [1, 2])
+@pytest.mark.parametrize('m_sub', [1, 2, 4])
 def test_halo_plan_conv_and_dgrad(k, stride, pad, mode, Cin, Cout, H, W, m_sub):
     torch.manual_seed(0)
     N = 2

@@ -86,6 +86,14 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
     if timeline and kind != 'wgrad':
         import ctypes as C
         from cat_b200 import _C
+        if tiling is None:          # let the autotune pick, then insist on the halo kernel (the timeline is its instrumentation)
+            fn()
+            torch.cuda.synchronize()
+            g.choice = 'v2'
+            if g.packed is None:
+                g.packed = torch.zeros(_C.load().catb_packed_weight_bytes(Cout, len(g.f_units), g.n_tile), dtype=torch.uint8, device=dev)
+                g.pack(arena)
+            print(f'{name}: tiling TW{g.halo.TW} m{g.halo.m_sub} b{g.hdesc.b_budget // 1024}K')
         buf = torch.zeros(4096 * 8, dtype=torch.int64, device=dev)
         fn()
         torch.cuda.synchronize()
@@ -95,17 +103,16 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
         _C.load().catb_debug_timeline(None)
         t = buf.view(4096, 8).cpu()
         t = t[t[:, 0] > 0]
-        t0 = t[:, 0].min()
-        rel = (t[:, :7] - t[:, 0:1]).float() / 1e3
-        names = ['fill done', 'mma start', 'last mma issued', 'accum complete', 'epilogue done', 'exit']
-        print(f'{name}: {t.shape[0]} CTAs recorded; kernel span {(t[:, 6].max() - t0).item() / 1e3:.1f} us; per-CTA phase times (us after prologue) median / p90:')
+        t0 = t[:, 7].min()
+        rel = (t[:, :7] - t[:, 7:8]).float() / 1e3
+        names = ['prologue done', 'fill done', 'mma start', 'last mma issued', 'accum complete', 'epilogue done', 'exit']
+        print(f'{name}: {t.shape[0]} CTAs recorded; kernel span {(t[:, 6].max() - t0).item() / 1e3:.1f} us; per-CTA phase times (us after kernel entry) median / p90:')
         for i, nme in enumerate(names):
-            col = rel[:, i + 1]
+            col = rel[:, i]
             print(f'    {nme:18s} {col.median().item():8.2f} {col.quantile(0.9).item():8.2f}')
-        print(f'    MMA thread: cycles waiting for weight tiles (median) {t[:, 7].float().median().item():.0f} '
-              f'= {t[:, 7].float().median().item() / 1.965e3:.2f} us')
-        start = (t[:, 0] - t0).float() / 1e3
-        print('    CTA start times (us): first 8', [round(v, 1) for v in start[:8].tolist()], ' median', round(start.median().item(), 1))
+        start = (t[:, 7] - t0).float() / 1e3
+        srt = start.sort().values
+        print('    CTA entry times (us): sorted every 10%', [round(srt[int(q * (len(srt) - 1) / 10)].item(), 1) for q in range(11)])
         return
 
     flops = 2.0 * N * OH * OW * Cout * Cin * k * k
@@ -134,8 +141,16 @@ if __name__ == '__main__':
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--tiling', default=None, help="pin a v2 variant: 'TW,m_sub,budgetK'")
     ap.add_argument('--timeline', action='store_true', help='per-CTA phase timestamps of the halo kernel')
+    ap.add_argument('--dbg-mode', type=int, default=0, help='catb_debug_mode bits (epilogue experiments)')
+    ap.add_argument('--dbg-sweep', default=None, help='comma separated catb_debug_mode values, run one after the other')
     ap.add_argument('--variants', action='store_true', help='time v1 and every v2 tiling / weight-ring variant')
     a = ap.parse_args()
     ops.require_cuda()
-    for c in a.cases:
-        run(c, a.iters, a.variants, a.tiling, a.timeline)
+    from cat_b200 import _C as _CC
+    for mode in ([a.dbg_mode] if a.dbg_sweep is None else [int(v) for v in a.dbg_sweep.split(',')]):
+        _CC.load().catb_debug_mode(mode)
+        if a.dbg_sweep is not None:
+            print(f'--- catb_debug_mode {mode}')
+        for c in a.cases:
+            run(c, a.iters, a.variants, a.tiling, a.timeline)
+    _CC.load().catb_debug_mode(0)
