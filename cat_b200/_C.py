@@ -66,7 +66,7 @@ _PROTOS = {
     'catb_igemm_wgrad_ws': [_DP, _P, _P, _P, _P, _P],
     'catb_igemm_halo_wgrad_ws_shape': [_DP, C.POINTER(HaloDesc), _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'catb_igemm_halo_wgrad_ws': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P],
-    'catb_wgrad_unpack': [_P, _I, _I, _I, _I, _P, _P, _P],
+    'catb_wgrad_unpack': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],

@@ -243,6 +243,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait with the 16 destination registers of an earlier tmem_ld16_nowait as in/out operands: no use of them can be
+// scheduled before the wait.
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // Epilogue of the 32 accumulator rows a warp owns (TMEM lanes 32w .. 32w+31, thread <-> row), bf16 output, no
 // accumulation: bias, activation, then a COALESCED store.  With one thread per output pixel a direct store makes every
@@ -255,64 +264,92 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 //   col_base  global output column of tile column 0 (tile_n * n_tile)
 //   rvalid / ypix  of THIS thread's row (ypix = pixel index in Y, < 2^31)
 //   stg       4 KB, 128-byte aligned, private to the warp, free of any async-proxy traffic
+__device__ __forceinline__ void sts16(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void epilogue_rows_bf16(uint32_t trow, int n_tile, int col_base, int n_store, int n_rows,
                                                    const float* __restrict__ bias, int act, bool rvalid, uint32_t ypix,
                                                    __nv_bfloat16* __restrict__ y, int ldy, int y_coff, uint8_t* stg,
-                                                   int lane, int dbg_mode = 0) {
-  for (int c64 = 0; c64 < n_tile; c64 += 64) {
+                                                   uint32_t* pixtab, int lane, int dbg_mode = 0,
+                                                   long long* dbg_cyc = nullptr) {
+  // dbg_cyc (development aid, one thread): cycles spent in [0] waiting for TMEM loads, [1] bias / activation / pack /
+  // staging stores, [2] the coalesced copy-out.
+  // pixtab: 32 words private to the warp: the output pixel of every row (0xffffffff: row not stored), so that the
+  // copy-out needs one shared-memory load per chunk instead of two shuffles.
+  const uint32_t stg_s = smem_u32(stg), pix_s = smem_u32(pixtab);
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(pix_s + lane * 4), "r"(rvalid ? ypix : 0xffffffffu) : "memory");
+  const float slope = act_slope(act);
+  const uint32_t row_s = stg_s + lane * 128;
+  const int swz = lane & 7;
+  uint32_t acc[2][16];
+  tmem_ld16_nowait(trow, acc[0]);                              // 16-column pieces, the next one in flight while this
+  for (int c64 = 0; c64 < n_tile; c64 += 64) {                 // one is converted
     const int ncol = n_tile - c64 < 64 ? n_tile - c64 : 64;   // multiple of 16
-    const int n16 = ncol >> 4;
-    // two halves of 32 columns: 32 accumulator registers live at a time (the kernels rely on 3-4 resident CTAs per SM)
+    long long tc0 = dbg_cyc != nullptr ? clock64() : 0;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      if (2 * hf < n16) {
-        uint32_t acc[32];
-        if (dbg_mode & 2) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = 0u;
-        } else {
-          tmem_ld16_nowait(trow + c64 + hf * 32, acc);
-          if (2 * hf + 1 < n16) tmem_ld16_nowait(trow + c64 + hf * 32 + 16, acc + 16);
-          tmem_wait_ld();
+    for (int q = 0; q < 4; ++q) {
+      if (q * 16 < ncol) {
+        tmem_wait_ld16(acc[q & 1]);
+        if (c64 + q * 16 + 16 < n_tile && !(dbg_mode & 2)) tmem_ld16_nowait(trow + c64 + q * 16 + 16, acc[(q + 1) & 1]);
+        if (dbg_cyc != nullptr) {
+          const long long t = clock64();
+          dbg_cyc[0] += t - tc0;
+          tc0 = t;
         }
 #pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          if (2 * hf + (q8 >> 1) < n16) {
-            const int col = col_base + c64 + hf * 32 + q8 * 8;
-            f8 o;
+        for (int g = 0; g < 2; ++g) {
+          const int col = col_base + c64 + q * 16 + g * 8;
+          f8 o;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o.v[e] = __uint_as_float(acc[q8 * 8 + e]);
-            if (bias != nullptr) {
+          for (int e = 0; e < 8; ++e) o.v[e] = __uint_as_float(acc[q & 1][g * 8 + e]);
+          if (bias != nullptr) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (col + e < n_rows) o.v[e] += __ldg(bias + col + e);
-            }
-            if (act == CATB_ACT_TANH) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o.v[e] = tanhf(o.v[e]);
-            } else if (act != CATB_ACT_NONE) {
-              const float slope = act_slope(act);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(o.v[e], slope * o.v[e]);
-            }
-            st16(stg + lane * 128 + (((hf * 4 + q8) ^ (lane & 7)) << 4), pack8(o));
+            for (int e = 0; e < 8; ++e)
+              if (col + e < n_rows) o.v[e] += __ldg(bias + col + e);
           }
+          if (act == CATB_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o.v[e] = tanhf(o.v[e]);
+          } else if (act != CATB_ACT_NONE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o.v[e] = fmaxf(o.v[e], slope * o.v[e]);
+          }
+          sts16(row_s + (((q * 2 + g) ^ swz) << 4), pack8(o));
+        }
+        if (dbg_cyc != nullptr) {
+          const long long t = clock64();
+          dbg_cyc[1] += t - tc0;
+          tc0 = t;
         }
       }
     }
     __syncwarp();
-    const int nch = ncol >> 3;   // 16-byte chunks per row: 2, 4, 6 or 8
+    const int nch = ncol >> 3;                                  // 16-byte chunks per row: 2, 4, 6 or 8
+    const uint32_t inv = (65536u + nch - 1) / nch;              // idx / nch == (idx * inv) >> 16 for idx < 256
+    const int colb = col_base + c64;
     for (int it = 0; it < nch; ++it) {
-      const int idx = it * 32 + lane;
-      const int row = idx / nch, ch = idx - row * nch;
-      const uint4 v = ld16(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-      const bool rv = __shfl_sync(0xffffffffu, static_cast<int>(rvalid), row) != 0;
-      const uint32_t pix = __shfl_sync(0xffffffffu, ypix, row);
-      const int col = col_base + c64 + ch * 8;
-      if (rv && col < n_store && !(dbg_mode & 1)) st16(y + static_cast<size_t>(pix) * ldy + y_coff + col, v);
+      const uint32_t idx = it * 32 + lane;
+      const uint32_t row = (idx * inv) >> 16, ch = idx - row * nch;
+      const uint4 v = lds16(stg_s + row * 128 + ((ch ^ (row & 7)) << 4));
+      const uint32_t pix = lds32(pix_s + row * 4);
+      const int col = colb + ch * 8;
+      if (pix != 0xffffffffu && col < n_store && !(dbg_mode & 1)) st16(y + static_cast<size_t>(pix) * ldy + y_coff + col, v);
     }
     __syncwarp();
+    if (dbg_cyc != nullptr) dbg_cyc[2] += clock64() - tc0;
   }
+  tmem_wait_ld();
 }
 
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_fprop_kernel(const FpropPar
       // every stage has been consumed (accum barrier): stage 0's activation tile is the staging area (4 KB per warp)
       epilogue_rows_bf16(trow, d.n_tile, tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
                          static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff,
-                         tiles + warp * 4096, lane);
+                         tiles + warp * 4096, reinterpret_cast<uint32_t*>(smem + 512) + warp * 32, lane);
     } else
     for (int cc = 0; cc < d.n_tile / 16; ++cc) {
       float acc[16];
@@ -728,11 +728,13 @@ extern "C" int catb_igemm_wgrad_ws(const catb_igemm_desc* d, const catb_gather_u
 }
 
 // Second stage of the two-stage weight gradient: arena_grad[w(row, unit, q)] += sum over splits (in split order) of
-// ws[split][row][unit * 8 + q].  One thread per workspace column: coalesced reads, one atomic add per real element (the
+// ws[split][row0 + row][unit * 8 + q] for the rows [row0, row0 + n_rows) of the workspace (one call per row segment when
+// the GEMM is an N-concatenation of several convolutions: each segment has its own weight-unit table).  One thread per workspace column: coalesced reads, one atomic add per real element (the
 // add itself is ordered by the stream, so the result is deterministic).
-__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, int n_splits, int n_rows, int n_units, int ws_k,
-                                    const catb_weight_unit* __restrict__ wunits, float* __restrict__ grad) {
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, int n_splits, int ws_rows, int ws_k, int row0, int n_rows,
+                                    int n_units, const catb_weight_unit* __restrict__ wunits, float* __restrict__ grad) {
   const long long total = static_cast<long long>(n_rows) * n_units * 8;
+  const size_t split_stride = static_cast<size_t>(ws_rows) * ws_k;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int q = static_cast<int>(idx & 7);
@@ -740,22 +742,22 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ ws, int n_splits, 
     const int row = static_cast<int>((idx >> 3) / n_units);
     const catb_weight_unit wu = wunits[u];
     if (q >= wu.nvalid) continue;
-    const float* src = ws + static_cast<size_t>(row) * ws_k + u * 8 + q;
-    const size_t split_stride = static_cast<size_t>(n_rows) * ws_k;
+    const float* src = ws + static_cast<size_t>(row0 + row) * ws_k + u * 8 + q;
     float acc = 0.f;
     for (int sp = 0; sp < n_splits; ++sp) acc += src[sp * split_stride];
     atomicAdd(grad + wu.w_off + static_cast<long long>(row) * wu.sn_w + q * wu.sc_w, acc);
   }
 }
 
-extern "C" int catb_wgrad_unpack(const float* ws, int n_splits, int n_rows, int n_units, int ws_k,
+extern "C" int catb_wgrad_unpack(const float* ws, int n_splits, int ws_rows, int ws_k, int row0, int n_rows, int n_units,
                                  const catb_weight_unit* wunits, float* arena_grad, catb_stream_t s) {
   CATB_REQUIRE(ws != nullptr && wunits != nullptr && arena_grad != nullptr, "null pointer");
-  CATB_REQUIRE(n_splits > 0 && n_rows > 0 && n_units > 0 && ws_k >= n_units * 8, "bad workspace shape");
+  CATB_REQUIRE(n_splits > 0 && n_rows > 0 && n_units > 0 && ws_k >= n_units * 8 && row0 >= 0 && row0 + n_rows <= ws_rows,
+               "bad workspace shape");
   const long long total = static_cast<long long>(n_rows) * n_units * 8;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  wgrad_unpack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(ws, n_splits, n_rows, n_units, ws_k, wunits,
-                                                                        arena_grad);
+  wgrad_unpack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(s)>>>(ws, n_splits, ws_rows, ws_k, row0, n_rows, n_units,
+                                                                        wunits, arena_grad);
   return check_launch("wgrad_unpack");
 }
 

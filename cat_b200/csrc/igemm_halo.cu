@@ -44,7 +44,7 @@ struct HaloParams {
 
 static unsigned long long* g_halo_dbg = nullptr;
 static int g_halo_dbg_mode = 0;   // experiment switches of the epilogue (catb_debug_mode): 1 no global stores, 2 no TMEM loads, 4 direct stores
-constexpr int kDbgSlots = 8, kDbgCtas = 4096;
+constexpr int kDbgSlots = 16, kDbgCtas = 4096;
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -159,9 +159,14 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
       if (!d.y_is_f32 && !d.accumulate && !(p.dbg_mode & 4)) {
         // all MMAs have completed (accum barrier), every fill of this CTA is consumed: the halo buffers are free and
         // serve as the staging area of the coalesced store (4 KB per warp)
+        long long cyc[3] = {0, 0, 0};
+        const bool rec = p.dbg != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < kDbgCtas;
         epilogue_rows_bf16(trow, d.n_tile, tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
                            static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff,
-                           a_base + warp * 4096, lane, p.dbg_mode);
+                           a_base + warp * 4096, reinterpret_cast<uint32_t*>(smem + 512) + warp * 32, lane, p.dbg_mode,
+                           rec ? cyc : nullptr);
+        if (rec)
+          for (int q = 0; q < 3; ++q) p.dbg[blockIdx.x * kDbgSlots + 8 + q] += static_cast<unsigned long long>(cyc[q]);
         continue;
       }
       for (int cc = 0; cc < d.n_tile / 16; ++cc) {

@@ -471,6 +471,18 @@ class GenNet:
                 g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0), base, rows, dev, segments=segs)
                 b.s1_fwd.insert(0, g)
                 self.fprop_gemms.append(g)
+            # weight gradients of stage 1: all first convs read x, so when their output slices fit ONE 128-row MMA tile
+            # (pruned students: 6 branches x <= 24 channels) they are a single GEMM -- rows = the slices of the mid-buffer
+            # gradient, K = the tap grid of the largest kernel over x -- at the cost of the largest kernel's gradient
+            # alone (the M side of the MMA is free up to 128 rows); the 1x1 / 3x3 branches simply ignore the taps outside
+            # their kernel when the workspace is added to the arena (catb_wgrad_unpack per row segment).
+            b.s1w = None
+            if ng and len(b.s1) > 1 and b.LA <= 128 and os.environ.get('CATB_NO_WFUSE', '0') != '1':
+                kmax = max(k for (_g, _sl, _m, k, _wn) in b.s1)
+                segs = [(sl, cpad(m), m, P.conv_embedded_units(ar.off(wn), m, C, k, kmax)) for (_g, sl, m, k, wn) in b.s1]
+                b.s1w = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0, pad_mode=P.PAD_REFLECT),
+                             P.conv_fprop_units(0, b.LA, C, kmax, kmax, (kmax - 1) // 2), b.LA, dev, need_pack=False,
+                             segments=segs)
             grpA = [(f'{pre}.res_ops.{j}.1.1' if kind == 'res' else f'{pre}.dw_ops.{j}.0.1', m) for (kind, j, m, _k) in b.order]
             b.nA = self.ns.make(dev, B, H4 * W4, grpA, tr)
             # depthwise convs over the dw slices
@@ -742,6 +754,9 @@ class GenNet:
                           dmid_raw.slice(0, b.LA), relu)
 
             def s1_wgrads(b=b, dmid_raw=dmid_raw):
+                if b.s1w is not None:
+                    b.s1w.wgrad(b.x.t, dmid_raw.t, ar.g)
+                    return
                 for (g, sl, m, k, wn) in b.s1:
                     g.wgrad(b.x.t, dmid_raw.t, ar.g)
             on_side(s1_wgrads)

@@ -109,6 +109,7 @@ class Gemm:
         side of `units` and supplies its own weight side for image rows [row0, row0+span)."""
         assert len(units) > 0 and n_rows > 0
         self.segments = None
+        self.seg_raw = segments      # also drives the per-segment second stage of the weight gradient
         self.geo, self.units, self.n_rows = geo, units, n_rows
         self.n_units = len(units)
         self.n_tile = choose_n_tile(n_rows)
@@ -316,6 +317,8 @@ class Gemm:
         self.w_ngroups = len(groups)
         self.w_wt = units_to_device(plan.units, dev)[1]
         self.w_nunits = len(plan.units)
+        if self.seg_raw is not None:
+            self.w_seg_wt = [units_to_device(make_halo_plan(self.geo, su).units, dev)[1] for (_r0, _sp, _nr, su) in self.seg_raw]
 
     def _ws_for(self, kind, d):
         """Workspace of the two-stage weight gradient: [splits][n_rows][ws_k] fp32, owned by this Gemm (its contents only
@@ -338,6 +341,7 @@ class Gemm:
         one-launch form with fp32 atomics from the accumulators (tests compare the two)."""
         self._wgrad_plan()
         d = self.desc()
+        assert not (atomic and self.seg_raw is not None), 'N-concatenated weight gradients only exist in the two-stage form'
 
         def v1(g):
             if atomic:
@@ -345,7 +349,15 @@ class Gemm:
                 return
             ws, splits, ws_k = self._ws_for('v1', d)
             _C.call('catb_igemm_wgrad_ws', C.byref(d), _p(self.gt), _p(x), _p(y), _p(ws), _stream())
-            _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, self.n_units, ws_k, _p(self.wt), _p(g), _stream())
+            if self.seg_raw is None:
+                _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, 0, self.n_rows, self.n_units, _p(self.wt), _p(g),
+                        _stream())
+            else:
+                if getattr(self, 'v1_seg_wt', None) is None:
+                    self.v1_seg_wt = [units_to_device(su, self.gt.device)[1] for (_r0, _sp, _nr, su) in self.seg_raw]
+                for (row0, _sp, nreal, _su), wt in zip(self.seg_raw, self.v1_seg_wt):
+                    _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, row0, nreal, self.n_units, _p(wt), _p(g),
+                            _stream())
 
         def v2(g):
             if atomic:
@@ -355,7 +367,13 @@ class Gemm:
             ws, splits, ws_k = self._ws_for('v2', d)
             _C.call('catb_igemm_halo_wgrad_ws', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
                     _p(self.w_groups), self.w_ngroups, _p(x), _p(y), _p(ws), _stream())
-            _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, self.w_nunits, ws_k, _p(self.w_wt), _p(g), _stream())
+            if self.seg_raw is None:
+                _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, 0, self.n_rows, self.w_nunits, _p(self.w_wt),
+                        _p(g), _stream())
+            else:
+                for (row0, _sp, nreal, _su), wt in zip(self.seg_raw, self.w_seg_wt):
+                    _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, row0, nreal, self.w_nunits, _p(wt), _p(g),
+                            _stream())
 
         if AUTOTUNE and self.w_halo is not None and self.w_choice is None and not force_v1 \
                 and not torch.cuda.is_current_stream_capturing():

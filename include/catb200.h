@@ -155,7 +155,9 @@ int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, con
  * product path: stage 1 writes every row split's partial tile to a caller-owned fp32 workspace
  * [splits][n_rows][ws_k] in GEMM order (column = unit * 8 + element; the halo variant uses its chunk-aligned unit
  * table, 8 units per step) with plain coalesced stores; stage 2 (catb_wgrad_unpack) sums the splits in split order and
- * adds the result to the gradient arena through the same weight-unit table.  *_ws_shape return the split count and
+ * adds rows [row0, row0 + n_rows) of it to the gradient arena through a weight-unit table (one call per row segment of
+ * an N-concatenated GEMM: the first-stage convs of a residual block share one weight-gradient GEMM, with the 1x1 and
+ * 3x3 kernels embedded in the 5x5 tap grid).  *_ws_shape return the split count and
  * the column pitch for a descriptor (workspace elements = splits * n_rows * ws_k). */
 int catb_igemm_wgrad_ws_shape(const catb_igemm_desc* d, int* splits, int* ws_k);
 int catb_igemm_wgrad_ws(const catb_igemm_desc* d, const catb_gather_unit* units, const void* x, const void* y, float* ws,
@@ -165,12 +167,12 @@ int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_des
 int catb_igemm_halo_wgrad_ws(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
                              const catb_halo_chunk* chunks /*device*/, const catb_halo_wgroup* groups /*device*/,
                              int n_groups, const void* x, const void* y, float* ws, catb_stream_t s);
-int catb_wgrad_unpack(const float* ws, int n_splits, int n_rows, int n_units, int ws_k,
-                      const catb_weight_unit* wunits /*device*/, float* arena_grad, catb_stream_t s);
+int catb_wgrad_unpack(const float* ws, int n_splits, int ws_rows /* rows per split */, int ws_k, int row0, int n_rows,
+                      int n_units, const catb_weight_unit* wunits /*device*/, float* arena_grad, catb_stream_t s);
 
-/* Development aid: with a device buffer of 4096 x 8 uint64 registered, every catb_igemm_halo_fprop CTA with
+/* Development aid: with a device buffer of 4096 x 16 uint64 registered (zeroed by the caller), every catb_igemm_halo_fprop CTA with
  * blockIdx.x < 4096 records %globaltimer (ns) at its phase boundaries: 0 prologue done, 1 first halo chunk filled,
- * 2 MMA warp released, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit, 7 kernel entry.  NULL: off. */
+ * 2 MMA warp released, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit, 7 kernel entry; 8-10 cycles of thread 0 in the epilogue's TMEM loads / pack + staging / copy-out.  NULL: off. */
 int catb_debug_timeline(void* device_buffer);
 /* Experiment switches of the halo-fprop epilogue (results become wrong): 1 no global stores, 2 no TMEM loads, 4 direct
  * per-thread stores instead of the staged coalesced ones.  0: production. */

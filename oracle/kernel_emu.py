@@ -93,8 +93,13 @@ def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, 
     y.copy_(yf.to(y.dtype))
 
 
-def _gemm_wgrad(self, x, y, grad_arena, force_v1=False):
-    P.emulate_wgrad(self.geo, self.units, self.n_rows, x.float(), y.float(), grad_arena)
+def _gemm_wgrad(self, x, y, grad_arena, force_v1=False, atomic=False):
+    if self._emu_segments is None:
+        P.emulate_wgrad(self.geo, self.units, self.n_rows, x.float(), y.float(), grad_arena)
+        return
+    for (row0, span, nreal, su) in self._emu_segments:       # N-concatenated weight gradient: one unpack per row segment
+        g2 = dataclasses.replace(self.geo, y_coff=self.geo.y_coff + row0)
+        P.emulate_wgrad(g2, su, nreal, x.float(), y.float(), grad_arena)
 
 
 # ---- layout / element-wise -----------------------------------------------------------------------

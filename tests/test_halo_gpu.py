@@ -199,3 +199,46 @@ def test_halo_k_concat_block_stage2():
     gm.fprop(buf.to(DEV), y)
     torch.cuda.synchronize()
     assert rel_err(from_dev_nhwc(y, C), ref) < 6e-3
+
+
+@pytest.mark.parametrize('force_v1', [False, True])
+def test_fused_stage1_wgrad(force_v1):
+    """Weight gradients of the first-stage convs of a residual block (kernel sizes 1 / 3 / 5 reading the same input) as
+    ONE N-concatenated GEMM on the 5x5 tap grid, unpacked per row segment (cat_b200/engine.py: b.s1w)."""
+    from cat_b200 import ops
+    torch.manual_seed(5)
+    N, H, W, C = 2, 16, 16, 62
+    mids, ks = [17, 9, 12, 5], [1, 3, 5, 1]
+    x = torch.randn(N, C, H, W)
+    ws = [(torch.randn(m, C, k, k) / math.sqrt(C * k * k)) for m, k in zip(mids, ks)]
+    dys = [torch.randn(N, m, H, W) for m in mids]
+    xb = bf(x)
+    refs = []
+    for w, k, dy in zip(ws, ks, dys):
+        wb = bf(w).requires_grad_(True)
+        xin = F.pad(xb, ((k - 1) // 2,) * 4, mode='reflect') if k > 1 else xb
+        F.conv2d(xin, wb).backward(bf(dy))
+        refs.append(wb.grad)
+    L = sum(P.cpad(m) for m in mids)
+    dyb = torch.zeros(N, H, W, L, dtype=torch.bfloat16)
+    segs, sl, off = [], 0, 7
+    for w, k, m, dy in zip(ws, ks, mids, dys):
+        dyb[..., sl:sl + m] = dy.permute(0, 2, 3, 1).to(torch.bfloat16)
+        segs.append((sl, P.cpad(m), m, P.conv_embedded_units(off, m, C, k, 5)))
+        sl += P.cpad(m)
+        off += w.numel()
+    geo = P.Geometry(N, H, W, P.cpad(C), 0, H, W, L, 0, pad_mode=P.PAD_REFLECT)
+    gw = ops.Gemm(geo, P.conv_fprop_units(0, L, C, 5, 5, 2), L, DEV, need_pack=False, segments=segs)
+    gw._wgrad_plan()
+    assert gw.w_halo is not None
+    gw.w_choice = 'v1' if force_v1 else 'v2'
+    g = torch.zeros(off + 9, device=DEV)
+    gw.wgrad(to_dev_nhwc(x), dyb.to(DEV), g, force_v1=force_v1)
+    torch.cuda.synchronize()
+    off = 7
+    assert float(g[:7].abs().max()) == 0
+    for w, ref in zip(ws, refs):
+        got = g[off:off + w.numel()].view_as(w).double().cpu()
+        assert rel_err(got, ref) < 2e-4
+        off += w.numel()
+    assert float(g[off:].abs().max()) == 0

@@ -94,14 +94,14 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
                 g.packed = torch.zeros(_C.load().catb_packed_weight_bytes(Cout, len(g.f_units), g.n_tile), dtype=torch.uint8, device=dev)
                 g.pack(arena)
             print(f'{name}: tiling TW{g.halo.TW} m{g.halo.m_sub} b{g.hdesc.b_budget // 1024}K')
-        buf = torch.zeros(4096 * 8, dtype=torch.int64, device=dev)
+        buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
         fn()
         torch.cuda.synchronize()
         _C.load().catb_debug_timeline(C.c_void_p(buf.data_ptr()))
         fn()
         torch.cuda.synchronize()
         _C.load().catb_debug_timeline(None)
-        t = buf.view(4096, 8).cpu()
+        t = buf.view(4096, 16).cpu()
         t = t[t[:, 0] > 0]
         t0 = t[:, 7].min()
         rel = (t[:, :7] - t[:, 7:8]).float() / 1e3
@@ -110,6 +110,7 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
         for i, nme in enumerate(names):
             col = rel[:, i]
             print(f'    {nme:18s} {col.median().item():8.2f} {col.quantile(0.9).item():8.2f}')
+        print('    epilogue cycles of thread 0 (median): TMEM loads %d, pack + staging %d, copy-out %d' % tuple(int(t[:, 8 + q].float().median().item()) for q in range(3)))
         start = (t[:, 7] - t0).float() / 1e3
         srt = start.sort().values
         print('    CTA entry times (us): sorted every 10%', [round(srt[int(q * (len(srt) - 1) / 10)].item(), 1) for q in range(11)])
