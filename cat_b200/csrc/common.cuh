@@ -393,7 +393,7 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major
 // ------------------------------------------------------------------------------------------
 // One parity plane of a halo chunk: frame rows [m0, m0 + Lh) in pitch space (row pitch Wf), 128 bytes (one <= 64
 // channel chunk) per row, 16-byte units XOR-swizzled with the absolute row inside the 1024-byte aligned buffer.
-// 128 threads: thread -> (row residue rsub = tid / 8 of 16, unit ul = tid % 8); every thread issues its 16-byte
+// 8 * STEP threads: thread -> (row residue rsub = tid / 8 of STEP, unit ul = tid % 8); every thread issues its 16-byte
 // cp.async copies (zero fill outside the image / frame) back to back.  All geometry arrives in registers and the
 // addresses advance incrementally: ~30 instructions per copy instead of the ~85 of the first version, whose loop
 // re-read the descriptor from constant memory and rebuilt every address from scratch (the fill of a 25 KB tile took
@@ -405,7 +405,7 @@ __device__ __forceinline__ int in_reg(int v) {
   return r;
 }
 
-template <bool REFLECT>
+template <bool REFLECT, int STEP = 16>
 __device__ __forceinline__ void halo_fill_plane(uint32_t plane_smem, int row_phase, const __nv_bfloat16* xc,
                                                 const __nv_bfloat16* xsafe, long long img_base, int m0, int rsub, int ul,
                                                 int Lh_, int Wf_, int Hf_, int mul_, int y0, int x0, int pa, int pb,
@@ -417,9 +417,10 @@ __device__ __forceinline__ void halo_fill_plane(uint32_t plane_smem, int row_pha
   int fx = (m0 + rsub) - fy * Wf;
   int iy0 = mul * (fy + y0) + pa;                           // advanced together with (fy, fx)
   int ix0 = mul * (fx + x0) + pb;
-  const int dix16 = mul * 16, dixw = mul * Wf;
-  uint32_t dst = plane_smem + rsub * 128 + ((ul ^ ((row_phase + rsub) & 7)) << 4);   // hr += 16 keeps the swizzle phase
-  for (int hr = rsub; hr < Lh; hr += 16) {
+  const int dix16 = mul * STEP, dixw = mul * Wf;
+  uint32_t dst = plane_smem + rsub * 128 + ((ul ^ ((row_phase + rsub) & 7)) << 4);   // hr += STEP (a multiple of 8) keeps the swizzle phase
+  static_assert(STEP % 8 == 0, "row step must keep the swizzle phase");
+  for (int hr = rsub; hr < Lh; hr += STEP) {
     int iy = iy0, ix = ix0;
     bool ok = uvalid & (fy < Hf);
     if (REFLECT) {
@@ -433,8 +434,8 @@ __device__ __forceinline__ void halo_fill_plane(uint32_t plane_smem, int row_pha
     const void* src = ok ? static_cast<const void*>(img + off) : static_cast<const void*>(xsafe);
     const int sz = ok ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-    dst += 2048;
-    fx += 16;
+    dst += STEP * 128;
+    fx += STEP;
     ix0 += dix16;
     while (fx >= Wf) {
       fx -= Wf;

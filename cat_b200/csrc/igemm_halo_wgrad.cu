@@ -13,7 +13,12 @@
 
 namespace catb {
 
-constexpr int kWThreads = 160;      // warps 0-3: producers + epilogue, warp 4: MMA issuer
+// One CTA per SM (two ~60 KB operand buffers), so the producers' issue rate is what feeds the tensor pipe: 16 producer
+// warps (4 per scheduler) instead of 4 -- a lone warp per scheduler issues one dependent instruction every 4-6 cycles.
+constexpr int kWProdWarps = 16;
+constexpr int kWProdThreads = kWProdWarps * 32;
+constexpr int kWRowStep = kWProdThreads / 8;   // halo / dY rows advanced per producer iteration
+constexpr int kWThreads = kWProdThreads + 32;  // + the MMA-issuing warp
 constexpr int kWHeader = 1024;
 constexpr int kWPos = 128;          // lattice positions (GEMM K) per tile
 constexpr int kDyBytes = 2 * kWPos * 128;   // [2 chunks of 64 channels][128 positions][128 B]
@@ -60,13 +65,13 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 128);
+      mbar_init(&full[i], kWProdThreads);
       mbar_init(&empty[i], 1);
     }
     mbar_init(accum, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kWProdWarps) {
     tmem_alloc_dyn(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kWProdWarps) {
     const int ul = threadIdx.x & 7, rsub = threadIdx.x >> 3;
     const int Hf = d.OHs + h.Ymax;
     const bool uvalid = ul < ch.n_units;
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
       // ---- dY tile: rows = positions (zero rows for garbage positions), 2 chunks of 64 channels
       {
         int i = (m0 + rsub) / h.Wf, j = (m0 + rsub) - i * h.Wf;
-        for (int r = rsub; r < kWPos; r += 16) {
+        for (int r = rsub; r < kWPos; r += kWRowStep) {
           const bool pv = (i < d.OHs) & (j < h.TW) & (strip_x + j < d.OWs);
           const size_t ypix = (static_cast<size_t>(n_img) * d.OH + (d.o_ph + i * d.o_step)) * d.OW + (d.o_pw + (strip_x + j) * d.o_step);
 #pragma unroll
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
             const __nv_bfloat16* src = ok ? p.y + ypix * d.ldy + d.y_coff + c : p.y;
             cp16_zfill(dyb + ca * (kWPos * 128) + r * 128 + ((ul ^ (r & 7)) << 4), src, ok);
           }
-          j += 16;
+          j += kWRowStep;
           while (j >= h.Wf) {
             j -= h.Wf;
             ++i;
@@ -119,11 +124,11 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
         for (int plane = 0; plane < h.n_planes; ++plane) {
           const uint32_t plane_smem = hal_s + static_cast<uint32_t>(plane) * h.Lh * 128u;
           if (d.pad_mode == CATB_PAD_REFLECT)
-            halo_fill_plane<true>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+            halo_fill_plane<true, kWRowStep>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
                                   h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
                                   h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
           else
-            halo_fill_plane<false>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
+            halo_fill_plane<false, kWRowStep>(plane_smem, plane * h.Lh, xc, p.x, static_cast<long long>(img_base), m0, rsub, ul, h.Lh,
                                    h.Wf, Hf, h.mul, h.plane_y0[plane], h.plane_x0[plane] + strip_x, h.plane_pa[plane],
                                    h.plane_pb[plane], d.H, d.W, d.ldx, uvalid);
         }
@@ -137,14 +142,16 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
     if (t1 > t0) {
       mbar_wait(accum, 0);
       tcgen05_fence_after();
-      const int row = m_tile * 128 + warp * 32 + lane;   // channel of dY
+      // warp w reads TMEM lanes 32 * (w % 4) ..; the four warps of a lane quarter take the taps round robin
+      const int quarter = warp & 3, part = warp >> 2;
+      const int row = m_tile * 128 + quarter * 32 + lane;   // channel of dY
       const bool rvalid = row < d.n_rows;
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       if (p.ws != nullptr) {
         // two-stage mode: plain 64-byte runs into the split's workspace tile (column = step * 64 + channel), no atomics
         float* wrow = p.ws + (static_cast<size_t>(blockIdx.x) * d.n_rows + row) * (static_cast<size_t>(h.n_steps) * 64) +
                       static_cast<size_t>(grp.first_step) * 64;
-        for (int s = 0; s < grp.n_steps; ++s) {
+        for (int s = part; s < grp.n_steps; s += kWProdWarps / 4) {
           for (int cc = 0; cc < 4; ++cc) {
             float acc[16];
             tmem_ld16(trow + s * 64 + cc * 16, acc);
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
           }
         }
       } else
-      for (int s = 0; s < grp.n_steps; ++s) {
+      for (int s = part; s < grp.n_steps; s += kWProdWarps / 4) {
         for (int cc = 0; cc < 4; ++cc) {
           float acc[16];
           tmem_ld16(trow + s * 64 + cc * 16, acc);
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc_dyn(tmem_base, tmem_cols);
+  if (warp == kWProdWarps) tmem_dealloc_dyn(tmem_base, tmem_cols);
 }
 
 int init_halo_wgrad_attributes() {
