@@ -80,6 +80,20 @@ class DistillStep:
         if self.A is not None:
             self.A.load_state_dicts(netA_sds)
 
+    def persistent_state(self):
+        """Everything that persists between steps, by name (cat_b200/optim.py: carry_engine_state)."""
+        from .optim import engine_state_from_nets
+        return engine_state_from_nets({'T': self.T, 'S': self.S, 'D': self.D, 'A': self.A},
+                                      {'step_G': self.step_G, 'step_D': self.step_D, 'step_A': self.step_A,
+                                       'lr_G': self.lr_G, 'lr_D': self.lr_D})
+
+    def after_state_load(self):
+        for net in (self.T, self.S, self.D, self.A):
+            if net is not None:
+                net.pack_weights()
+                for n in getattr(getattr(net, 'ns', None), 'created', []):
+                    n._frozen = False          # eval-mode affine of a frozen net is recomputed from the new gamma / beta
+
     def set_input(self, real_A, real_B):
         """Host or device NCHW fp32 tensors -> the persistent device buffers (the H2D copy of
         BaseInceptionDistiller.set_input, base_inception_distiller.py:271-280)."""

@@ -22,35 +22,13 @@ from ..distill_engine import DistillStep
 from ..engine import MAPPING_LAYERS
 from ..models import networks
 from ..models.base_model import MetricBook, image_names
+from ..optim import ArenaAdam, EngineOwner
 
 
-class _ArenaOptimizer:
-    """Stand-in for torch.optim.Adam over an engine arena: exposes what the reference touches
-    (param_groups[0]['lr'], state_dict / load_state_dict for save_networks / load_optimizer)."""
-
-    def __init__(self, lr, betas):
-        self.param_groups = [{'lr': lr, 'betas': betas}]
-        self.net = None
-        self.step_counter = None
-
-    def bind(self, net, step_counter):
-        self.net, self.step_counter = net, step_counter
-
-    def state_dict(self):
-        if self.net is None:
-            return {'state': {}, 'param_groups': self.param_groups}
-        a = self.net.arena
-        return {'exp_avg': a.m.detach().cpu(), 'exp_avg_sq': a.v.detach().cpu(), 'step': int(self.step_counter.item()),
-                'layout': {k: (v[0], v[1]) for k, v in a.entries.items()}, 'param_groups': self.param_groups}
-
-    def load_state_dict(self, sd):
-        if self.net is not None and 'exp_avg' in sd:
-            self.net.arena.m.copy_(sd['exp_avg'])
-            self.net.arena.v.copy_(sd['exp_avg_sq'])
-            self.step_counter.fill_(int(sd['step']))
+_ArenaOptimizer = ArenaAdam    # former name
 
 
-class InceptionDistiller:
+class InceptionDistiller(EngineOwner):
     @staticmethod
     def modify_commandline_options(parser, is_train):
         """The flags of base_inception_distiller.py:30-101 and inception_distiller.py:34-76 that the step uses."""
@@ -62,6 +40,7 @@ class InceptionDistiller:
         parser.add_argument('--restore_teacher_G_path', type=str, required=True)
         parser.add_argument('--restore_student_G_path', type=str, default=None)
         parser.add_argument('--restore_D_path', type=str, default=None)
+        parser.add_argument('--restore_A_path', type=str, default=None)
         parser.add_argument('--restore_O_path', type=str, default=None)
         parser.add_argument('--recon_loss_type', type=str, default='l1', choices=['l1', 'l2', 'smooth_l1'])
         parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka', 'mse'])
@@ -109,8 +88,9 @@ class InceptionDistiller:
         # input width follows the (pruned) student like utils/common.py:154-161
         c_s = self.netG_student.arch()['widths'][2]
         self.netAs = [nn.Conv2d(c_s, opt.teacher_ngf * 4, kernel_size=1).to(self.device) for _ in range(4)]
-        self.optimizer_G = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
-        self.optimizer_D = _ArenaOptimizer(opt.lr, (opt.beta1, 0.999))
+        # optimizer_G: group 0 = the student, group 1 = the adaptor convs (base_inception_distiller.py:205-214)
+        self.optimizer_G = ArenaAdam(opt.lr, (opt.beta1, 0.999), n_groups=2)
+        self.optimizer_D = ArenaAdam(opt.lr, (opt.beta1, 0.999))
         self.optimizers = [self.optimizer_G, self.optimizer_D]
         self.Tacts, self.Sacts = {}, {}
         self.engine = None
@@ -137,12 +117,12 @@ class InceptionDistiller:
                     student_training=self.netG_student.training, recon_loss_type=o.recon_loss_type,
                     ka_scale=float(getattr(o, 'world_size', 1)), distill_loss_type=getattr(o, 'distill_G_loss_type', 'ka'))
 
-    def _ensure_engine(self, B, H, W):
-        if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
-            return
-        eng = DistillStep(self.netG_teacher.arch(), self.netG_student.arch(), self.netD.arch(), self._hp(), B, H, W,
-                          device=str(self.device), world_size=int(getattr(self.opt, 'world_size', 1)),
-                          use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
+    def _make_engine(self, B, H, W):
+        return DistillStep(self.netG_teacher.arch(), self.netG_student.arch(), self.netD.arch(), self._hp(), B, H, W,
+                           device=str(self.device), world_size=int(getattr(self.opt, 'world_size', 1)),
+                           use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
+
+    def _bind_engine(self, eng):
         for module, net in ((self.netG_teacher, eng.T), (self.netG_student, eng.S), (self.netD, eng.D)):
             module.bind(net)               # copies the module's weights in, then re-points them at the arena
             net.pack_weights()
@@ -151,9 +131,10 @@ class InceptionDistiller:
             for i, net in enumerate(self.netAs):
                 net.weight.data = eng.A.arena.view('%d.weight' % i)
                 net.bias.data = eng.A.arena.view('%d.bias' % i)
-        self.optimizer_G.bind(eng.S, eng.step_G)
-        self.optimizer_D.bind(eng.D, eng.step_D)
-        self.engine = eng
+        a_params = [p for net in self.netAs for p in net.parameters()]
+        self.optimizer_G.bind([[(self.netG_student.parameters(), eng.S.arena, eng.step_G)],
+                               [(a_params, eng.A.arena if eng.A is not None else None, eng.step_A if eng.A is not None else None)]])
+        self.optimizer_D.bind([[(self.netD.parameters(), eng.D.arena, eng.step_D)]])
 
     def set_input(self, input):
         AtoB = getattr(self.opt, 'direction', 'AtoB') == 'AtoB'
@@ -195,7 +176,8 @@ class InceptionDistiller:
         scale = 1.0 - max(0, self._epoch + 1 - o.nepochs) / float(o.nepochs_decay + 1)
         lr = o.lr * scale
         for opt_ in self.optimizers:
-            opt_.param_groups[0]['lr'] = lr
+            for pg in opt_.param_groups:
+                pg['lr'] = lr
         if self.engine is not None:
             self.engine.set_lr(lr)
         msg = 'learning rate = %.7f' % lr
@@ -242,6 +224,15 @@ class InceptionDistiller:
         load(self.netG_teacher, getattr(self.opt, 'restore_teacher_G_path', None))
         load(self.netG_student, getattr(self.opt, 'restore_student_G_path', None))
         load(self.netD, getattr(self.opt, 'restore_D_path', None))
+        if getattr(self.opt, 'restore_A_path', None) is not None:      # base_inception_distiller.py:356-359
+            for i, netA in enumerate(self.netAs):
+                load(netA, '%s-%d.pth' % (self.opt.restore_A_path, i))
+        if getattr(self.opt, 'restore_O_path', None) is not None:      # :360-365 (applied when the engine is compiled)
+            for i, optimizer in enumerate(self.optimizers):
+                optimizer.load_state_dict(torch.load('%s-%d.pth' % (self.opt.restore_O_path, i), map_location='cpu',
+                                                     weights_only=False))
+                for param_group in optimizer.param_groups:
+                    param_group['lr'] = self.opt.lr
 
     def save_networks(self, epoch):
         os.makedirs(self.save_dir, exist_ok=True)

@@ -23,7 +23,7 @@ from .. import ops
 from ..models import networks
 from ..spade_distill_engine import SpadeDistillStep
 from ..spade_engine import MAPPING_LAYERS
-from .inception_distiller import _ArenaOptimizer
+from ..optim import ArenaAdam, EngineOwner
 
 
 class SPADEDistillerModules(nn.Module):
@@ -56,7 +56,7 @@ class SPADEDistillerModules(nn.Module):
         self.netG_teacher.eval()
 
 
-class SPADEDistiller:
+class SPADEDistiller(EngineOwner):
     @staticmethod
     def modify_commandline_options(parser, is_train):
         """The flags of base_spade_distiller.py:28-130 / spade_distiller.py:25-84 that the step uses."""
@@ -71,6 +71,7 @@ class SPADEDistiller:
         parser.add_argument('--restore_teacher_G_path', type=str, required=True)
         parser.add_argument('--restore_student_G_path', type=str, default=None)
         parser.add_argument('--restore_D_path', type=str, default=None)
+        parser.add_argument('--restore_A_path', type=str, default=None)
         parser.add_argument('--restore_O_path', type=str, default=None)
         parser.add_argument('--lambda_gan', type=float, default=1)
         parser.add_argument('--lambda_feat', type=float, default=10)
@@ -107,8 +108,8 @@ class SPADEDistiller:
             self.betas, self.lr_G, self.lr_D = (opt.beta1, opt.beta2), opt.lr, opt.lr
         else:   # base_spade_distiller_modules.py:91-105
             self.betas, self.lr_G, self.lr_D = (0.0, 0.9), opt.lr / 2, opt.lr * 2
-        self.optimizer_G = _ArenaOptimizer(self.lr_G, self.betas)
-        self.optimizer_D = _ArenaOptimizer(self.lr_D, self.betas)
+        self.optimizer_G = ArenaAdam(self.lr_G, self.betas)
+        self.optimizer_D = ArenaAdam(self.lr_D, self.betas)
         self.optimizers = [self.optimizer_G, self.optimizer_D]
         self.engine = None
         self.is_best = False
@@ -130,14 +131,14 @@ class SPADEDistiller:
                     lr_G=self.lr_G, lr_D=self.lr_D, beta1=self.betas[0], beta2=self.betas[1], n_label=int(o.input_nc), ka_scale=1.0,
                     distill_loss_type=getattr(o, 'distill_G_loss_type', 'ka'))
 
-    def _ensure_engine(self, B, H, W):
-        if self.engine is not None and (self.engine.B, self.engine.H, self.engine.W) == (B, H, W):
-            return
+    def _make_engine(self, B, H, W):
         mm = self.modules_on_one_gpu
-        t_arch, s_arch = mm.netG_teacher.arch(), mm.netG_student.arch()
-        eng = SpadeDistillStep(t_arch, s_arch, mm.netD.arch(), self._hp(), B, H, W, device=str(self.device),
-                               world_size=int(getattr(self.opt, 'world_size', 1)),
-                               use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
+        return SpadeDistillStep(mm.netG_teacher.arch(), mm.netG_student.arch(), mm.netD.arch(), self._hp(), B, H, W,
+                                device=str(self.device), world_size=int(getattr(self.opt, 'world_size', 1)),
+                                use_cuda_graph=bool(getattr(self.opt, 'cuda_graph', True)))
+
+    def _bind_engine(self, eng):
+        mm = self.modules_on_one_gpu
         mm.netG_teacher.bind(eng.T)        # copies the module's weights in, then re-points them at the arena
         mm.netG_student.bind(eng.S)
         mm.netD._alias_into(eng.D)
@@ -151,9 +152,11 @@ class SPADEDistiller:
             for i, net in enumerate(mm.netAs):
                 net.weight.data = eng.A.arena.view('%d.weight' % i)
                 net.bias.data = eng.A.arena.view('%d.bias' % i)
-        self.optimizer_G.bind(eng.S, eng.step_G)
-        self.optimizer_D.bind(eng.D, eng.step_D)
-        self.engine = eng
+        # base_spade_distiller_modules.py:91-105: one parameter group, the student followed by the adaptor convs
+        a_params = [p for net in mm.netAs for p in net.parameters()]
+        self.optimizer_G.bind([[(mm.netG_student.parameters(), eng.S.arena, eng.step_G),
+                                (a_params, eng.A.arena if eng.A is not None else None, eng.step_A if eng.A is not None else None)]])
+        self.optimizer_D.bind([[(mm.netD.parameters(), eng.D.arena, eng.step_D)]])
 
     def set_input(self, input):
         """models/spade_model.py:132-136 (the one-hot / edge preprocessing itself runs inside the step)."""
@@ -242,6 +245,15 @@ class SPADEDistiller:
             return
         load(mm.netG_student, getattr(self.opt, 'restore_student_G_path', None))
         load(mm.netD, getattr(self.opt, 'restore_D_path', None))
+        if getattr(self.opt, 'restore_A_path', None) is not None:      # base_spade_distiller_modules.py:187-190
+            for i, netA in enumerate(mm.netAs):
+                load(netA, '%s-%d.pth' % (self.opt.restore_A_path, i))
+        if getattr(self.opt, 'restore_O_path', None) is not None:      # base_spade_distiller.py:209-214; the reference
+            for i, optimizer in enumerate(self.optimizers):            # puts BOTH optimisers at opt.lr afterwards (TTUR or not)
+                optimizer.load_state_dict(torch.load('%s-%d.pth' % (self.opt.restore_O_path, i), map_location='cpu',
+                                                     weights_only=False))
+                for param_group in optimizer.param_groups:
+                    param_group['lr'] = self.opt.lr
 
     def save_networks(self, epoch):
         os.makedirs(self.save_dir, exist_ok=True)

@@ -15,33 +15,10 @@ from collections import OrderedDict
 import torch
 
 from .. import ops
+from ..optim import ArenaAdam, EngineOwner
 
 
-class ArenaOptimizer:
-    """Stand-in for one torch.optim.Adam over one or several engine arenas (CycleGAN's optimizer_G owns both generators,
-    cycle_gan_model.py:165-174): exposes what the reference touches (param_groups[0]['lr'], state_dict /
-    load_state_dict for checkpoints)."""
-
-    def __init__(self, lr, betas):
-        self.param_groups = [{'lr': lr, 'betas': betas}]
-        self.nets, self.counters = [], []
-
-    def bind(self, nets, counters):
-        self.nets, self.counters = list(nets), list(counters)
-
-    def state_dict(self):
-        out = {'param_groups': self.param_groups, 'arenas': []}
-        for net, c in zip(self.nets, self.counters):
-            a = net.arena
-            out['arenas'].append({'exp_avg': a.m.detach().cpu(), 'exp_avg_sq': a.v.detach().cpu(), 'step': int(c.item()),
-                                  'layout': {k: (v[0], v[1]) for k, v in a.entries.items()}})
-        return out
-
-    def load_state_dict(self, sd):
-        for net, c, s in zip(self.nets, self.counters, sd.get('arenas', [])):
-            net.arena.m.copy_(s['exp_avg'])
-            net.arena.v.copy_(s['exp_avg_sq'])
-            c.fill_(int(s['step']))
+ArenaOptimizer = ArenaAdam     # former name
 
 
 class MetricBook:
@@ -74,7 +51,7 @@ def image_names(paths):
     return [os.path.splitext(os.path.basename(p))[0] for p in paths]
 
 
-class BaseModel:
+class BaseModel(EngineOwner):
     """Subclasses define ``model_names`` (net<name> attributes), ``loss_names``, ``_make_engine(B, H, W)`` and
     ``_set_engine_input(input)``."""
 
@@ -110,10 +87,6 @@ class BaseModel:
         if verbose:
             self.print_networks()
 
-    def _ensure_engine(self, B, H, W):
-        if self.engine is None or (self.engine.B, self.engine.H, self.engine.W) != (B, H, W):
-            self.engine = self._make_engine(B, H, W)
-
     def optimize_parameters(self, steps):
         self.engine.step()
 
@@ -141,7 +114,8 @@ class BaseModel:
         scale = self._lr_scale()
         lrs = [base * scale for base in self._base_lrs()]
         for opt_, lr in zip(self.optimizers, lrs):
-            opt_.param_groups[0]['lr'] = lr
+            for pg in opt_.param_groups:
+                pg['lr'] = lr
         if self.engine is not None:
             self.engine.set_lr(*lrs)
         msg = 'learning rate = %.7f' % lrs[0]
@@ -197,6 +171,12 @@ class BaseModel:
                 self._net(name).load_state_dict(torch.load(path, map_location='cpu'))
                 if verbose:
                     print('Load network at %s' % path)
+        if getattr(self.opt, 'restore_O_path', None) is not None:      # models/spade_model.py:316-322 (applied at compile time)
+            for i, optimizer in enumerate(self.optimizers):
+                optimizer.load_state_dict(torch.load('%s-%d.pth' % (self.opt.restore_O_path, i), map_location='cpu',
+                                                     weights_only=False))
+                for param_group in optimizer.param_groups:
+                    param_group['lr'] = self.opt.lr
 
     def save_networks(self, epoch):
         os.makedirs(self.save_dir, exist_ok=True)

@@ -47,14 +47,19 @@ class CycleGANModel(BaseModel):
                   beta1=o.beta1, pool_size=int(getattr(o, 'pool_size', 50)))
         eng = CycleGANTrainStep(self.netG_A.arch(), self.netD_A.arch(), hp, B, H, W, device=str(self.device),
                                 world_size=int(getattr(o, 'world_size', 1)), use_cuda_graph=bool(getattr(o, 'cuda_graph', True)))
+        return eng
+
+    def _bind_engine(self, eng):
         for module, net in ((self.netG_A, eng.G_A), (self.netG_B, eng.G_B), (self.netD_A, eng.D_A), (self.netD_B, eng.D_B)):
             module.bind(net)               # copies the module's weights in, then re-points them at the arena
         eng._pack_generators()             # every application of a generator packs its own GEMM images from the arena
         eng.D_A.pack_weights()
         eng.D_B.pack_weights()
-        self.optimizer_G.bind([eng.G_A, eng.G_B], [eng.step_GA, eng.step_GB])
-        self.optimizer_D.bind([eng.D_A, eng.D_B], [eng.step_DA, eng.step_DB])
-        return eng
+        # cycle_gan_model.py:165-174: one Adam over chain(netG_A, netG_B) / chain(netD_A, netD_B)
+        self.optimizer_G.bind([[(self.netG_A.parameters(), eng.G_A.arena, eng.step_GA),
+                                (self.netG_B.parameters(), eng.G_B.arena, eng.step_GB)]])
+        self.optimizer_D.bind([[(self.netD_A.parameters(), eng.D_A.arena, eng.step_DA),
+                                (self.netD_B.parameters(), eng.D_B.arena, eng.step_DB)]])
 
     def set_input(self, input):
         self.real_A, self.real_B = input['A'], input['B']

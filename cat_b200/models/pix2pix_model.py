@@ -42,12 +42,14 @@ class Pix2PixModel(BaseModel):
                   recon_loss_type=o.recon_loss_type)
         eng = Pix2PixTrainStep(self.netG.arch(), self.netD.arch(), hp, B, H, W, device=str(self.device),
                                world_size=int(getattr(o, 'world_size', 1)), use_cuda_graph=bool(getattr(o, 'cuda_graph', True)))
+        return eng
+
+    def _bind_engine(self, eng):
         for module, net in ((self.netG, eng.G), (self.netD, eng.D)):
             module.bind(net)               # copies the module's weights in, then re-points them at the arena
             net.pack_weights()
-        self.optimizer_G.bind([eng.G], [eng.step_G])
-        self.optimizer_D.bind([eng.D], [eng.step_D])
-        return eng
+        self.optimizer_G.bind([[(self.netG.parameters(), eng.G.arena, eng.step_G)]])
+        self.optimizer_D.bind([[(self.netD.parameters(), eng.D.arena, eng.step_D)]])
 
     def set_input(self, input):
         AtoB = getattr(self.opt, 'direction', 'AtoB') == 'AtoB'

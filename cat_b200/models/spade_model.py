@@ -84,6 +84,10 @@ class SPADEModel(BaseModel):
                   beta1=self.betas[0], beta2=self.betas[1], n_label=int(o.input_nc))
         eng = SpadeTrainStep(mm.netG.arch(), mm.netD.arch(), hp, B, H, W, device=str(self.device),
                              world_size=int(getattr(o, 'world_size', 1)), use_cuda_graph=bool(getattr(o, 'cuda_graph', True)))
+        return eng
+
+    def _bind_engine(self, eng):
+        o, mm = self.opt, self.modules_on_one_gpu
         mm.netG.bind(eng.G)                # copies the module's weights in, then re-points them at the arena
         mm.netD._alias_into(eng.D)
         vgg = getattr(o, 'vgg_state_dict', None)
@@ -91,9 +95,8 @@ class SPADEModel(BaseModel):
             raise RuntimeError('opt.vgg_state_dict (torchvision vgg19().features state_dict) is required: the pretrained '
                                'VGG19 of models/modules/loss.py:154 cannot be downloaded here')
         eng.V.load_state_dict(vgg)
-        self.optimizer_G.bind([eng.G], [eng.step_G])
-        self.optimizer_D.bind([eng.D], [eng.step_D])
-        return eng
+        self.optimizer_G.bind([[(mm.netG.parameters(), eng.G.arena, eng.step_G)]])
+        self.optimizer_D.bind([[(mm.netD.parameters(), eng.D.arena, eng.step_D)]])
 
     def set_input(self, input):
         """spade_model.py:132-136 (the one-hot / edge preprocessing itself runs inside the step)."""

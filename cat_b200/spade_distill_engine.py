@@ -85,6 +85,21 @@ class SpadeDistillStep:
         if self.A is not None:
             self.A.load_state_dicts(netA_sds)
 
+    def persistent_state(self):
+        """Everything that persists between steps, by name (cat_b200/optim.py: carry_engine_state)."""
+        from .optim import engine_state_from_nets
+        return engine_state_from_nets({'T': self.T, 'S': self.S, 'D': self.D, 'V': self.V, 'A': self.A},
+                                      {'step_G': self.step_G, 'step_D': self.step_D, 'step_A': self.step_A,
+                                       'lr_G': self.lr_G, 'lr_D': self.lr_D})
+
+    def after_state_load(self):
+        for net in (self.T, self.S, self.V, self.A):
+            if net is not None:
+                net.pack_weights()
+                for n in getattr(net, 'norms', []):
+                    n._frozen = False          # eval-mode affine of a frozen net is recomputed from the new gamma / beta
+        self.D.spectral_forward(training=False)     # effective weights + GEMM images from weight_orig / u / v
+
     def set_input(self, label, instance, image):
         """label / instance: [B,1,H,W] (any integer or float dtype, host or device), image: [B,3,H,W] fp32 in
         [-1,1] -- the dict entries of SPADEModel.set_input (models/spade_model.py:132-136)."""

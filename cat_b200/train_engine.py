@@ -133,6 +133,25 @@ class CycleGANTrainStep:
         self.D_A.load_state_dict(D_A_sd)
         self.D_B.load_state_dict(D_B_sd)
 
+    def persistent_state(self):
+        """Everything that persists between steps, by name (cat_b200/optim.py: carry_engine_state)."""
+        from .optim import engine_state_from_nets
+        extra = {'step_GA': self.step_GA, 'step_GB': self.step_GB, 'step_DA': self.step_DA, 'step_DB': self.step_DB,
+                 'lr_G': self.lr_G, 'lr_D': self.lr_D}
+        for name in ('pool_A', 'pool_B'):
+            pool = getattr(self, name)
+            if pool.pool_size > 0:
+                extra[name + '.images'] = pool.images
+        return engine_state_from_nets({'G_A': self.G_A, 'G_B': self.G_B, 'D_A': self.D_A, 'D_B': self.D_B}, extra)
+
+    def after_state_load(self):
+        self._pack_generators()
+        self.D_A.pack_weights()
+        self.D_B.pack_weights()
+        for g in self._gens('A') + self._gens('B'):
+            for n in g.ns.created:
+                n._frozen = False
+
     def _pack_generators(self):
         for w in 'AB':
             for g in self._gens(w):
