@@ -34,16 +34,22 @@ def parse():
     ap.add_argument('--height', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
     ap.add_argument('--width', type=int, default=None, help='default 256 (gaugan_5p6B: 512)')
     ap.add_argument('--cpu-batch', type=int, default=None,
-                    help='images per step of the bounded CPU sample (default 4; gaugan_5p6B: 2 -- KA is degenerate at 1)')
+                    help='images per step of the CPU arm (default: the GPU batch; gaugan_5p6B: 2 -- KA is degenerate at 1)')
+    ap.add_argument('--cpu-threads', type=int, default=None, help='threads of the CPU arm (default: all host cores)')
+    ap.add_argument('--nvtx', action='store_true', help='wrap the timed steps in the NVTX range "catb_step" (ncu --nvtx --nvtx-include "catb_step/")')
+    ap.add_argument('--engine-e2e', action='store_true', help='end-to-end loop on the bare step engine instead of the distiller protocol')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity-probe', action='store_true')
     ap.add_argument('--profile-gemms', action='store_true', help='print the per-GEMM timing table to stderr')
     args = ap.parse_args()
     spade = is_spade(args.workload)
     args.batch = args.batch or (4 if spade else (8 if args.workload.startswith('cyclegan') else 16))
     args.height = args.height or (512 if spade else 256)
     args.width = args.width or (512 if spade else 256)
-    args.cpu_batch = args.cpu_batch or (2 if spade else 4)
+    # CPU arm: the GPU arm's batch where a step stays around 5 s (pix2pix 16, CycleGAN 8); the SPADE step (~10 s for two
+    # 512x512 images) is sampled at batch 2 (KA is degenerate at batch 1)
+    args.cpu_batch = args.cpu_batch or (2 if spade else args.batch)
     return args
 
 
@@ -126,22 +132,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU baseline (the oracle port of the reference path, timed on the host cores)
 # ----------------------------------------------------------------------------------------------------
-def _best_thread_count():
-    """All host cores unless a quick conv probe shows that fewer threads are faster (shared / SMT hosts)."""
-    import torch.nn.functional as F
-    n = os.cpu_count() or 1
-    x, w = torch.randn(1, 256, 64, 64), torch.randn(256, 256, 5, 5)
-    best, best_t = n, None
-    for cand in sorted({n, max(1, n // 2), max(1, n // 4), min(n, 16)}, reverse=True):
-        torch.set_num_threads(cand)
-        F.conv2d(x, w, padding=2)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            F.conv2d(x, w, padding=2)
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < 0.9 * best_t:
-            best, best_t = cand, dt
-    return best
+CPU_THREADS = [None]
+
+
+def _pin_threads():
+    """The CPU arm runs on ALL host cores of the box (or --cpu-threads), stated in `cores`: no probing, so two runs on the
+    same host use the same thread count."""
+    n = CPU_THREADS[0] or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
 
 
 def cpu_reference_steps(arch, hp, B, H, W, steps, warmup):
@@ -149,7 +148,7 @@ def cpu_reference_steps(arch, hp, B, H, W, steps, warmup):
     of the workload: same networks and resolution, `B` images per step."""
     from cat_b200 import workload as WL
     from oracle import cat_oracle as O
-    torch.set_num_threads(_best_thread_count())
+    _pin_threads()
     state = dict(teacher_sd=WL.init_generator(arch['teacher_arch'], 0, 'uniform'),
                  student_sd=WL.init_generator(arch['student_arch'], 1), D_sd=WL.init_discriminator(arch['D_arch'], 2),
                  teacher_arch=arch['teacher_arch'], student_arch=arch['student_arch'], D_arch=arch['D_arch'],
@@ -169,7 +168,7 @@ def cpu_reference_spade_steps(arch, hp, B, H, W, steps, warmup):
     bounded sample of the workload: same networks and resolution, `B` images per step."""
     from cat_b200 import workload as WL
     from oracle import spade_oracle as SO
-    torch.set_num_threads(_best_thread_count())
+    _pin_threads()
     arch = WL.spade_arch_for(arch, H, W)
     state = dict(teacher_sd=WL.init_spade_reference_sd(arch['teacher_arch'], 0), student_sd=WL.init_spade_reference_sd(arch['student_arch'], 1),
                  D_sd=WL.init_multiscale_D_sd(arch['D_arch'], 2), vgg_sd=WL.init_vgg(3), teacher_arch=arch['teacher_arch'],
@@ -191,7 +190,7 @@ def cpu_teacher_steps(workload, arch, hp, B, H, W, steps, warmup):
     sample of the workload: same networks and resolution, `B` images per step."""
     from cat_b200 import workload as WL
     from oracle import train_oracle as TO
-    torch.set_num_threads(_best_thread_count())
+    _pin_threads()
     G_arch, D_arch = arch['teacher_arch'], arch['D_arch']
     if workload == 'gaugan_teacher':
         from oracle import spade_oracle as SO
@@ -226,23 +225,77 @@ def cpu_steps_fn(workload):
     return cpu_reference_spade_steps if is_spade(workload) else cpu_reference_steps
 
 
+def real_reference_available(workload):
+    """The reference's own modules staged under oracle/_ref/ by oracle/make_ref.py (the Inception distiller workloads)."""
+    return workload in ('pix2pix_5p6B', 'cyclegan_2p6B') and os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'distillers'))
+
+
+def real_reference_steps(workload, B, H, W, steps, warmup, budget_s):
+    """Times the REFERENCE's InceptionDistiller.optimize_parameters (distillers/inception_distiller.py:179-188) on the host
+    cores: the real distiller object built by oracle/ref_harness.py from oracle/_ref/ with the flags of the published
+    script, its own shrink() producing the benchmark student, set_input + optimize_parameters per step.  When the
+    projected run exceeds `budget_s` the per-step sample is halved (stated in the result)."""
+    import contextlib
+    os.environ['CATB_REF_ROOT'] = os.path.join(ROOT, 'oracle', '_ref')
+    cores = _pin_threads()
+    from cat_b200 import workload as WL
+    with contextlib.redirect_stdout(sys.stderr):          # the reference prints its options / networks
+        from oracle.make_bench_arch import CONFIGS
+        from oracle.ref_harness import build_reference_distiller
+        model, _opt = build_reference_distiller(batch_size=B, **CONFIGS[workload])
+        model.netG_student.train()       # steady state (the reference's first step of a run is in eval mode)
+        a, b = WL.synthetic_batch(B, H, W, 233)
+
+        def one(n):
+            model.set_input({'A': a[:n], 'B': b[:n], 'A_paths': ['x'] * n, 'B_paths': ['x'] * n})
+            model.optimize_parameters(0)
+        n = B
+        while True:
+            t0 = time.perf_counter()
+            one(n)
+            t = time.perf_counter() - t0
+            if n <= 2 or t * (steps + max(warmup - 1, 0)) <= budget_s:
+                break
+            n = max(2, n // 2)
+        for _ in range(max(warmup - 1, 0)):
+            one(n)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one(n)
+        dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt, cores, n
+
+
+def cpu_arm(args, arch, steps, warmup, budget_s):
+    """The CPU arm of the benchmark: the reference itself when it is staged (kind 'reference'), else the CPU oracle port
+    (kind 'port'), on all host cores, on a per-step sample of at most --cpu-batch images at the GPU arm's resolution."""
+    H, W, B = args.height, args.width, args.cpu_batch
+    if real_reference_available(args.workload):
+        ips, dt, cores, n = real_reference_steps(args.workload, B, H, W, steps, warmup, budget_s)
+        kind, what = 'reference', "the reference's InceptionDistiller.set_input + optimize_parameters (oracle/_ref)"
+    else:
+        fn = cpu_steps_fn(args.workload)
+        ips, dt, cores = fn(arch, dict(arch['hp']), B, H, W, steps, warmup)
+        kind, n, what = 'port', B, 'CPU oracle port of optimize_parameters'
+    return {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': kind, 'batch': n, 'same_config': n == args.batch,
+            'sample': f'{n} images/step at {H}x{W}, {warmup} warm-up + {steps} timed steps, {dt:.2f} s/step, fp32, '
+                      f'{cores} threads; {what}'}, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from cat_b200 import workload as WL
     arch = WL.load_arch(arch_name(args.workload))
-    hp = dict(arch['hp'])
-    B = args.cpu_batch
-    fn = cpu_steps_fn(args.workload)
-    ips, dt, cores = fn(arch, hp, B, args.height, args.width, args.steps, args.warmup)
-    sample = f'{B} images/step at {args.height}x{args.width}, same networks; CPU oracle port of optimize_parameters'
+    cpu, dt = cpu_arm(args, arch, args.steps, args.warmup, budget_s=240.0)
+    ips, B = cpu['value'], cpu['batch']
     print(json.dumps({
         'impl': 'reference', 'metric': metric_name(args.workload), 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, arch, B, 1),
-        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': cpu,
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
@@ -278,16 +331,48 @@ def workload_config(args, arch, B, world):
 # ----------------------------------------------------------------------------------------------------
 # per-GEMM instrumentation (roofline of the dominant kernel)
 # ----------------------------------------------------------------------------------------------------
+def tag_gemms(root, owner, seen=None, depth=0):
+    """Mark every ops.Gemm reachable from a compiled network with the network it belongs to (per-network rooflines)."""
+    from cat_b200 import ops
+    seen = set() if seen is None else seen
+    if id(root) in seen or depth > 6:
+        return
+    seen.add(id(root))
+    if isinstance(root, ops.Gemm):
+        root._owner = owner
+        return
+    if isinstance(root, (list, tuple)):
+        for v in root:
+            tag_gemms(v, owner, seen, depth + 1)
+    elif isinstance(root, dict):
+        for v in root.values():
+            tag_gemms(v, owner, seen, depth + 1)
+    elif hasattr(root, '__dict__') and not isinstance(root, torch.Tensor) and type(root).__module__.startswith('cat_b200'):
+        for v in vars(root).values():
+            tag_gemms(v, owner, seen, depth + 1)
+
+
+# HBM-bound CUDA-core kernels: wrapper name -> algorithmic bytes per element of the activation they stream (DESIGN.md 3.2:
+# bf16 reads + writes that cannot be avoided), evaluated on the first Act argument
+HBM_KERNELS = {'norm_stats': 2, 'norm_apply': 4, 'norm_bwd_reduce': 6, 'norm_bwd_apply': 8, 'dwconv_fwd': 4,
+               'dwconv_bwd_data': 4, 'dwconv_bwd_weight': 4, 'gram': 2, 'ka_bwd': 6, 'reflect_fold': 4, 'act_bwd': 6}
+
+
 class GemmProfiler:
+    """CUDA events around every GEMM launch (and every HBM-bound CUDA-core kernel of HBM_KERNELS) of ONE eager step."""
+
     def __init__(self):
-        self.records = []
+        self.records, self.hbm = [], []
 
     def install(self):
         from cat_b200 import ops
         prof = self
         self._orig = (ops.Gemm.fprop, ops.Gemm.wgrad)
+        self._orig_hbm = {n: getattr(ops, n) for n in HBM_KERNELS}
 
         def flops(g):
+            if g.seg_raw is not None:     # N-concatenation: each row segment only owns the taps of its own kernel
+                return sum(2.0 * g.geo.N * g.geo.OHs * g.geo.OWs * nreal * sum(w[3] for w in su.w) for (_r, _s, nreal, su) in g.seg_raw)
             nv = sum(w[3] for w in g.units.w)
             return 2.0 * g.geo.N * g.geo.OHs * g.geo.OWs * g.n_rows * nv
 
@@ -299,28 +384,108 @@ class GemmProfiler:
                 e1.record()
                 prof.records.append((kind, g, flops(g), e0, e1))
             return inner
+
+        def wrap_hbm(fn, name, bpe):
+            def inner(x, *a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(x, *a, **k)
+                e1.record()
+                prof.hbm.append((name, float(x.pixels) * x.C * bpe, e0, e1))
+                return r
+            return inner
         ops.Gemm.fprop, ops.Gemm.wgrad = wrap(self._orig[0], 'fprop'), wrap(self._orig[1], 'wgrad')
+        for n, bpe in HBM_KERNELS.items():
+            setattr(ops, n, wrap_hbm(self._orig_hbm[n], n, bpe))
 
     def remove(self):
         from cat_b200 import ops
         ops.Gemm.fprop, ops.Gemm.wgrad = self._orig
+        for n, fn in self._orig_hbm.items():
+            setattr(ops, n, fn)
 
     def summary(self):
         torch.cuda.synchronize()
-        agg = {}
-        per = {}
+        agg, per, net = {}, {}, {}
         for kind, g, fl, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            a = agg.setdefault(kind, [0.0, 0.0, 0])
-            a[0] += fl
-            a[1] += ms
+            for table, key in ((agg, kind), (per, (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs)),
+                               (net, (getattr(g, '_owner', 'other'), kind))):
+                a = table.setdefault(key, [0.0, 0.0, 0])
+                a[0] += fl
+                a[1] += ms
+                a[2] += 1
+        hbm = {}
+        for name, nbytes, e0, e1 in self.hbm:
+            a = hbm.setdefault(name, [0.0, 0.0, 0])
+            a[0] += nbytes
+            a[1] += e0.elapsed_time(e1)
             a[2] += 1
-            key = (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs)
-            p = per.setdefault(key, [0.0, 0.0, 0])
-            p[0] += fl
-            p[1] += ms
-            p[2] += 1
-        return agg, per
+        return agg, per, net, hbm
+
+
+def parity_probe(workload, dev):
+    """One step of the benchmarked library on the small committed fixture of the workload's distiller against the CPU
+    oracle; returns the measured deviations (and raises if they exceed the tolerances of the GPU test-suite)."""
+    from oracle import cat_oracle as O
+    out = {}
+    if is_spade(workload) or workload == 'gaugan_teacher':
+        from cat_b200 import ops
+        from cat_b200.spade_distill_engine import SpadeDistillStep
+        from oracle import spade_oracle as SO
+        fix = torch.load(os.path.join(ROOT, 'tests', 'golden', 'spade_more.pt'), weights_only=False)
+        s, hp = fix['steps'][0], fix['hp']
+        vgg = SO.make_vgg_sd(fix['vgg_seed'])
+        B, _, H, W = s['image'].shape
+        eng = SpadeDistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device=dev)
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'], vgg)
+        eng.set_input(s['label'], s['instance'], s['image'])
+        eng.step()
+        torch.cuda.synchronize()
+        got = eng.get_losses()
+        state = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+                     vgg_sd=vgg, teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'],
+                     adam_G={}, adam_D={})
+        seg = SO.preprocess_input(s['label'], s['instance'], hp['n_label'])
+        ref = SO.spade_distill_step(state, seg, s['image'], hp)
+        pairs = (('G_gan', 'loss_G_gan'), ('G_feat', 'loss_G_feat'), ('G_vgg', 'loss_G_vgg'), ('G_distill', 'loss_G_distill'),
+                 ('D_fake', 'loss_D_fake'), ('D_real', 'loss_D_real'))
+        out['onehot_edges_bit_exact'] = bool(torch.equal(ops.nhwc_to_nchw(eng.seg, eng.snc).cpu(), seg))
+        tol = 3e-2
+    else:
+        from cat_b200 import ops
+        from cat_b200.distill_engine import DistillStep
+        name = 'cyclegan_in_lsgan' if workload.startswith('cyclegan') else 'pix2pix_bn_hinge'
+        path = os.path.join(ROOT, 'tests', 'golden', name + '.pt')
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, 'tests', 'golden', 'pix2pix_bn_hinge.pt')
+        fix = torch.load(path, weights_only=False)
+        s = fix['steps'][0]
+        B, _, H, W = s['real_A'].shape
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device=dev)
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        torch.cuda.synchronize()
+        got = eng.get_losses()
+        state = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']), D_sd=O.clone_sd(fix['D_sd0']),
+                     teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={})
+        ref = O.distill_step(state, s['real_A'], s['real_B'], fix['hp'])
+        sfake = ops.nhwc_to_nchw(eng.S.out, 3).cpu()
+        out['student_output_rel_l2'] = float((sfake - ref['Sfake_B']).norm() / ref['Sfake_B'].norm())
+        assert out['student_output_rel_l2'] < 3e-2, out
+        pairs = (('G_recon', 'loss_G_recon'), ('G_gan', 'loss_G_gan'), ('G_distill', 'loss_G_distill'), ('D_fake', 'loss_D_fake'),
+                 ('D_real', 'loss_D_real'))
+        tol = 2e-2
+    worst = 0.0
+    for mine, theirs in pairs:
+        r = float(ref[theirs])
+        worst = max(worst, abs(got[mine] - r) / max(1.0, abs(r)))
+    out['max_loss_deviation'] = worst
+    out['tolerance'] = tol
+    out['fixture'] = os.path.basename(path) if not (is_spade(workload) or workload == 'gaugan_teacher') else 'spade_more.pt'
+    assert worst <= tol, out
+    return out
 
 
 def main():
@@ -370,8 +535,59 @@ def main():
         macs = WL.spade_macs_per_image(arch, H, W)
     else:
         hp['ka_scale'] = float(world)   # the reference sums the per-replica KA terms (inception_distiller.py:145-148)
-        eng, host, h2d_bytes, macs = build_pix2pix(args, arch, hp, B, H, W, dev, world, rank)
+        if args.engine_e2e:
+            eng, host, h2d_bytes, macs = build_pix2pix(args, arch, hp, B, H, W, dev, world, rank)
+        else:
+            model, eng, host, h2d_bytes, macs = build_inception_distiller(args, arch, hp, B, H, W, dev, world, rank, local)
+            return run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local, model=model)
     return run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local)
+
+
+def build_inception_distiller(args, arch, hp, B, H, W, dev, world, rank, local):
+    """The user-facing path: cat_b200.distillers.InceptionDistiller driven like trainer.py:79-175 (create_distiller ->
+    setup -> set_input -> optimize_parameters -> get_current_losses), with the published script's options, the pruned
+    student architecture of the benchmark and a synthetic trained teacher restored through --restore_teacher_G_path."""
+    import tempfile
+    from cat_b200 import ops
+    from cat_b200 import workload as WL
+    from cat_b200.distillers import create_distiller
+    from cat_b200.engine import GenNet
+    Ta, Da = arch['teacher_arch'], arch['D_arch']
+    t_sd = WL.init_generator(Ta, 0, 'uniform')
+    a_host, b_host = WL.synthetic_batch(B, H, W, 233 + rank, pin=True)
+    if Ta['norm'] == 'batch' and Ta['track_running_stats']:
+        # synthetic "trained" teacher: running statistics calibrated on one synthetic batch
+        cal = GenNet(dict(Ta, momentum=1.0), B, H, W, dev, training=True, need_grad=False)
+        cal.load_state_dict(t_sd)
+        xa = ops.Act.empty(B, H, W, 3, dev, zero=True)
+        ops.nchw_to_nhwc(a_host.to(dev), xa)
+        cal.forward(xa)
+        torch.cuda.synchronize()
+        t_sd = {k: v.cpu() for k, v in cal.state_dict().items()}
+        del cal, xa
+    work = tempfile.mkdtemp(prefix='catb_bench_')
+    tpath = os.path.join(work, 'teacher_net_G.pth')
+    torch.save(t_sd, tpath)
+    opt = argparse.Namespace(
+        isTrain=True, gpu_ids=[local], log_dir=work, distiller='inception', input_nc=3, output_nc=3,
+        teacher_ngf=Ta['widths'][0], student_ngf=arch['student_arch']['widths'][0], teacher_netG='inception_9blocks',
+        student_netG='inception_9blocks', norm=Ta['norm'], norm_affine=Ta['affine'], norm_affine_D=Da['affine'],
+        norm_track_running_stats=Ta['track_running_stats'], norm_momentum=Ta['momentum'], norm_epsilon=Ta['eps'], channels=None,
+        channels_reduction_factor=6, kernel_sizes=list(Ta['kernel_sizes']), active_fn='nn.ReLU', active_fn_D='nn.LeakyReLU',
+        init_type='normal', init_gain=0.02, netD='n_layers', ndf=Da['ndf'], n_layers_D=Da['n_layers'],
+        dataset_mode='aligned' if hp['aligned'] else 'unaligned', direction='AtoB', gan_mode=hp['gan_mode'],
+        recon_loss_type=hp.get('recon_loss_type', 'l1'), distill_G_loss_type='ka', lambda_distill=hp['lambda_distill'],
+        lambda_recon=hp['lambda_recon'], lambda_gan=hp['lambda_gan'], lr=hp['lr'], beta1=hp['beta1'], nepochs=5, nepochs_decay=15,
+        student_arch=arch['student_arch'], restore_teacher_G_path=tpath, restore_student_G_path=None, restore_D_path=None,
+        restore_A_path=None, restore_O_path=None, cuda_graph=not args.no_graph, world_size=world)
+    model = create_distiller(opt, verbose=False)
+    model.setup(opt, verbose=False)
+    model.netG_student.load_state_dict(WL.init_generator(arch['student_arch'], 1))    # reference-style init, fixed seeds
+    model.netD.load_state_dict(WL.init_discriminator(Da, 2))
+    model.netG_student.train()          # steady state: the reference's eval-mode first step is over
+    host = {'A': a_host, 'B': b_host, 'A_paths': ['synthetic'] * B, 'B_paths': ['synthetic'] * B}
+    model.set_input(host)               # compiles the step engine for this batch shape
+    return model, model.engine, host, 2 * B * 3 * H * W * 4, WL.macs_per_image(arch, H, W)
 
 
 def build_teacher(args, arch, hp, B, H, W, dev, world, rank):
@@ -421,11 +637,22 @@ def build_pix2pix(args, arch, hp, B, H, W, dev, world, rank):
     return eng, (a_host, b_host), 2 * B * 3 * H * W * 4, WL.macs_per_image(arch, H, W)
 
 
-def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local):
+def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, local, model=None):
+    """model: the distiller mirror the end-to-end loop goes through (None: the bare step engine)."""
     from cat_b200 import _C
     if world > 1:
         import torch.distributed as dist
     torch.cuda.synchronize()
+    if model is not None:
+        feed, one_step, read_losses = (lambda: model.set_input(host)), (lambda i: model.optimize_parameters(i)), model.get_current_losses
+        through = 'cat_b200.distillers.%s: set_input -> optimize_parameters -> get_current_losses' % type(model).__name__
+    else:
+        feed, one_step, read_losses = (lambda: eng.set_input(*host)), (lambda i: eng.step()), eng.get_losses
+        through = '%s: set_input -> step -> get_losses' % type(eng).__name__
+    for owner, net in (('teacher', getattr(eng, 'T', None)), ('student', getattr(eng, 'S', None)), ('D', getattr(eng, 'D', None)),
+                       ('vgg', getattr(eng, 'V', None)), ('adaptors', getattr(eng, 'A', None))):
+        if net is not None:
+            tag_gemms(net, owner)
 
     def barrier():
         if world > 1:
@@ -433,7 +660,7 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    eng.set_input(*host)
+    feed()
     for _ in range(args.warmup):
         eng.step()
     launches0 = _C.LAUNCH_COUNT[0]
@@ -444,11 +671,15 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.nvtx:
+        torch.cuda.nvtx.range_push('catb_step')
     e0.record()
     for _ in range(args.steps):
         eng.step()
     e1.record()
     barrier()
+    if args.nvtx:
+        torch.cuda.nvtx.range_pop()
     ms = e0.elapsed_time(e1)
     if args.no_graph:
         launches_per_step = (_C.LAUNCH_COUNT[0] - launches0) // args.steps
@@ -457,10 +688,10 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        eng.set_input(*host)
-        eng.step()
-        losses = eng.get_losses()
+    for i in range(args.steps):
+        feed()
+        one_step(i)
+        losses = read_losses()
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -495,7 +726,7 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         for g, v in zip(gens, saved_w):
             g.overlap_wgrad = v
         eng.world_size = ws
-        agg, per = prof.summary()
+        agg, per, net, hbm_k = prof.summary()
         prof.remove()
         eng.use_cuda_graph = not args.no_graph
         peaks = {}
@@ -525,21 +756,41 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
                 'share_of_gemm_time': tms / step_ms_eager,
                 'wgrad': {'achieved': agg['wgrad'][0] / (agg['wgrad'][1] * 1e-3) / 1e12, 'launches': agg['wgrad'][2],
                           'kernel_ms_per_step': agg['wgrad'][1]} if 'wgrad' in agg else None}
+        # per network (never a single blended number): the frozen teacher's forward GEMMs, the student's
+        # forward + input-gradient GEMMs, the discriminator's, and every weight gradient, each against the tensor peak
+        per_net = {}
+        for (owner, kind), (f_, t_, c_) in sorted(net.items()):
+            per_net['%s.%s' % (owner, kind)] = {'achieved': f_ / (t_ * 1e-3) / 1e12, 'frac': f_ / (t_ * 1e-3) / 1e12 / peak,
+                                                'launches': c_, 'kernel_ms_per_step': t_}
+        roof['per_network'] = per_net
+        # HBM-bound CUDA-core kernels against the measured copy bandwidth
+        hbm_peak = peaks.get('hbm_gbs', 6500.0)
+        roof['hbm_kernels'] = {'peak': hbm_peak, 'unit': 'GB/s',
+                               'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.5 TB/s',
+                               'kernels': {k: {'achieved': b_ / (t_ * 1e-3) / 1e9, 'frac': b_ / (t_ * 1e-3) / 1e9 / hbm_peak,
+                                               'launches': c_, 'kernel_ms_per_step': t_,
+                                               'algorithmic_bytes_per_launch': b_ / c_}
+                                           for k, (b_, t_, c_) in sorted(hbm_k.items())}}
         if args.profile_gemms:
+            for k, v in per_net.items():
+                print(f'network {k:18s} {v["launches"]:4d} launches {v["kernel_ms_per_step"]:8.3f} ms {v["achieved"]:8.1f} TF/s', file=sys.stderr)
+            for k, v in roof['hbm_kernels']['kernels'].items():
+                print(f'hbm     {k:18s} {v["launches"]:4d} launches {v["kernel_ms_per_step"]:8.3f} ms {v["achieved"]:8.1f} GB/s', file=sys.stderr)
             rows = sorted(per.items(), key=lambda kv: -kv[1][1])[:40]
             for (kind, n_rows, n_units, M), (f, t, c) in rows:
                 print(f'{kind:6s} rows {n_rows:5d} units {n_units:5d} M {M:8d} x{c:3d}  {t:8.3f} ms  {f / (t * 1e-3) / 1e12:8.1f} TF/s',
                       file=sys.stderr)
 
-    # ---- CPU baseline beside it (rank 0, single-GPU run only)
+    # ---- CPU baseline beside it (rank 0, single-GPU run only): a bounded sample (~30 s) of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fn = cpu_steps_fn(args.workload)
-        cpu_steps = 2 if is_spade(args.workload) else 3
-        ips, dt, cores = fn(arch, dict(arch['hp']), args.cpu_batch, H, W, cpu_steps, 1)
-        cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'{args.cpu_batch} images/step at {H}x{W}, 1 warm-up + {cpu_steps} timed steps of the CPU oracle '
-                         f'(same networks), {dt:.2f} s/step'}
+        cpu, _dt = cpu_arm(args, arch, 2 if is_spade(args.workload) else 3, 1, budget_s=30.0)
+
+    # ---- the benchmarked binary is the checked one: one step of the same engine classes on two images of the committed
+    # fixture against the CPU oracle (stated tolerances of tests/test_distill_gpu.py)
+    parity = None
+    if rank == 0 and not args.no_parity_probe:
+        parity = parity_probe(args.workload, dev)
 
     if rank == 0:
         imgs = B * world * args.steps
@@ -550,13 +801,13 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(args, arch, B, world),
             'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
-                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': (16 + 4) * 4},
+                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': (16 + 4) * 4, 'through': through},
             'gpu_launches': launches_per_step * args.steps * 2 + launches_per_step,
             'launches_per_step': launches_per_step,
             'algorithmic_gflop_per_image': 2 * macs['step'] / 1e9,
             'model_tflops': 2 * macs['step'] * value / 1e12,
-            'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
-            'losses': {k: round(v, 5) for k, v in losses.items()},
+            'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'parity_probe': parity,
+            'losses': {k: round(float(v), 5) for k, v in losses.items()},
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -31,24 +31,36 @@ _ArenaOptimizer = ArenaAdam    # former name
 class InceptionDistiller(EngineOwner):
     @staticmethod
     def modify_commandline_options(parser, is_train):
-        """The flags of base_inception_distiller.py:30-101 and inception_distiller.py:34-76 that the step uses."""
+        """Every flag of base_inception_distiller.py:30-101 and inception_distiller.py:34-76, with the reference's types,
+        defaults and choices, so that the published scripts parse unchanged (flags of features outside the hot path --
+        weight transfer from a pretrained generator, dropout -- are accepted and reported when used)."""
         assert is_train
-        parser.add_argument('--teacher_netG', type=str, default='inception_9blocks')
-        parser.add_argument('--student_netG', type=str, default='inception_9blocks')
+        parser.add_argument('--teacher_netG', type=str, default='inception_9blocks', choices=['inception_9blocks'])
+        parser.add_argument('--student_netG', type=str, default='inception_9blocks', choices=['inception_9blocks'])
         parser.add_argument('--teacher_ngf', type=int, default=64)
         parser.add_argument('--student_ngf', type=int, default=48)
         parser.add_argument('--restore_teacher_G_path', type=str, required=True)
         parser.add_argument('--restore_student_G_path', type=str, default=None)
-        parser.add_argument('--restore_D_path', type=str, default=None)
         parser.add_argument('--restore_A_path', type=str, default=None)
+        parser.add_argument('--restore_D_path', type=str, default=None)
         parser.add_argument('--restore_O_path', type=str, default=None)
-        parser.add_argument('--recon_loss_type', type=str, default='l1', choices=['l1', 'l2', 'smooth_l1'])
-        parser.add_argument('--distill_G_loss_type', type=str, default='ka', choices=['ka', 'mse'])
+        parser.add_argument('--recon_loss_type', type=str, default='l1', choices=['l1', 'l2', 'smooth_l1', 'vgg'])
+        parser.add_argument('--distill_G_loss_type', type=str, default='mse', choices=['mse', 'ka'])
         parser.add_argument('--lambda_distill', type=float, default=1)
         parser.add_argument('--lambda_recon', type=float, default=100)
         parser.add_argument('--lambda_gan', type=float, default=1)
+        parser.add_argument('--teacher_dropout_rate', type=float, default=0)
+        parser.add_argument('--student_dropout_rate', type=float, default=0)
+        parser.add_argument('--restore_pretrained_G_path', type=str, default=None)
+        parser.add_argument('--pretrained_netG', type=str, default='inception_9blocks', choices=['inception_9blocks'])
+        parser.add_argument('--pretrained_ngf', type=int, default=64)
         parser.add_argument('--target_flops', type=float, default=0)
-        parser.set_defaults(norm='instance', dataset_mode='aligned', teacher_netG='inception_9blocks',
+        parser.add_argument('--prune_cin_lb', type=int, default=0)
+        parser.add_argument('--pretrained_student_G_path', type=str, default=None)
+        parser.add_argument('--prune_only', action='store_true')
+        parser.add_argument('--prune_continue', action='store_true')
+        parser.add_argument('--prune_logging_verbose', action='store_true')
+        parser.set_defaults(norm='instance', dataset_mode='aligned', log_dir='logs/inception', teacher_netG='inception_9blocks',
                             student_netG='inception_9blocks')
         return parser
 
@@ -65,6 +77,13 @@ class InceptionDistiller(EngineOwner):
             raise NotImplementedError('--distill_G_loss_type [%s]: ka | mse' % opt.distill_G_loss_type)
         if opt.recon_loss_type == 'vgg':
             raise NotImplementedError('VGG reconstruction loss is not on the inception distillation scripts')
+        if getattr(opt, 'teacher_dropout_rate', 0) or getattr(opt, 'student_dropout_rate', 0):
+            raise NotImplementedError('dropout (the CAT scripts run with rate 0)')
+        if getattr(opt, 'restore_pretrained_G_path', None) or getattr(opt, 'pretrained_student_G_path', None):
+            raise NotImplementedError('weight transfer from a pretrained generator (utils/weight_transfer.py) is outside the '
+                                      'hot path: initialise the student with the reference and pass --restore_student_G_path')
+        if getattr(opt, 'world_size', None) is None:      # one process per GPU under torchrun (cat_b200.install)
+            opt.world_size = int(os.environ.get('WORLD_SIZE', '1'))
         self.loss_names = ['G_gan', 'G_distill', 'G_recon', 'D_fake', 'D_real'] + ['G_distill%d' % i for i in range(4)]
         self.model_names = ['netG_student', 'netG_teacher', 'netD']
         self.visual_names = ['real_A', 'Sfake_B', 'Tfake_B', 'real_B']

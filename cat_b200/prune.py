@@ -14,8 +14,9 @@ identical to the reference's (tests/test_prune_cpu.py, fixtures written by the r
 import torch
 
 
-def generator_macs(arch, H, W):
-    """n_macs of an InceptionGenerator as utils.model_profiling.model_profiling reports it (batch 1)."""
+def generator_macs(arch, H, W, parts=False):
+    """n_macs of an InceptionGenerator as utils.model_profiling.model_profiling reports it (batch 1); parts=True returns
+    (down_sampling, features, up_sampling), the per-section figures trainer.py:121-123 logs."""
     c0, c1, c2, c3, c4 = arch['widths']
     cin, cout, ks = arch['input_nc'], arch['output_nc'], arch['kernel_sizes']
     norm_macs = not arch['track_running_stats']      # model_profiling.py:101-128: norm layers count when they do not track
@@ -26,6 +27,7 @@ def generator_macs(arch, H, W):
     m = cin * c0 * 49 * H * W + norm(c0, H, W)
     m += c0 * c1 * 9 * H2 * W2 + norm(c1, H2, W2)
     m += c1 * c2 * 9 * H4 * W4 + norm(c2, H4, W4)
+    m_down = m
     hw = H4 * W4
     for blk in arch['blocks']:
         any_branch = False
@@ -42,9 +44,12 @@ def generator_macs(arch, H, W):
         # pw_bn exists (and is profiled) for every block; its forward hook only fires when the block has a branch
         if any_branch:
             m += norm(c2, H4, W4)
+    m_feat = m - m_down
     m += c2 * c3 * 9 * H2 * W2 + norm(c3, H2, W2)
     m += c3 * c4 * 9 * H * W + norm(c4, H, W)
     m += c4 * cout * 49 * H * W
+    if parts:
+        return int(m_down), int(m_feat), int(m - m_down - m_feat)
     return int(m)
 
 
@@ -154,7 +159,7 @@ def shrink_spade(model, opt):
                                            prune_cin_ub=getattr(opt, 'prune_cin_ub', float('inf')))
     s_opt = copy.deepcopy(teacher.opt)
     s_opt.ngf = student_arch['fc_out'] // 16
-    gpu_ids = list(getattr(model, 'gpu_ids', []))[:1]
+    gpu_ids = list(getattr(model, 'gpu_ids', []))[:1] if getattr(model, 'device', torch.device('cpu')).type == 'cuda' else []
     mm.netG_student = networks.init_net(InceptionSPADEGenerator.from_arch(student_arch, s_opt), opt.init_type, opt.init_gain, gpu_ids)
     mm.netG_student.n_macs = info['macs']
     mm.netG_student.eval()         # shrink_spade_model profiles the new student, which leaves it in eval() (utils/common.py:829)
@@ -167,6 +172,7 @@ def shrink_spade(model, opt):
     mm.netAs = netAs
     if hasattr(model, 'engine'):
         model.engine = None
+        model.__dict__.pop('_engine_cache', None)      # engines compiled for the old architecture
     print('scale threshold: %g, searched flops: %d, target flops: %g' % (info['threshold'], info['macs'], target))
     return info
 
@@ -185,9 +191,12 @@ def shrink_inception(model, opt):
                                      prune_cin_lb=int(getattr(opt, 'prune_cin_lb', 1)),
                                      prune_cin_ub=getattr(opt, 'prune_cin_ub', float('inf')),
                                      prune_ft_cin_lb=int(getattr(opt, 'prune_ft_cin_lb', 1)))
-    gpu_ids = list(getattr(model, 'gpu_ids', []))[:1]
+    gpu_ids = list(getattr(model, 'gpu_ids', []))[:1] if getattr(model, 'device', torch.device('cpu')).type == 'cuda' else []
     model.netG_student = networks.init_net(networks.InceptionGenerator.from_arch(student_arch), opt.init_type, opt.init_gain, gpu_ids)
     model.netG_student.n_macs = info['macs']
+    for sec, v in zip(('down_sampling', 'features', 'up_sampling'),
+                      generator_macs(student_arch, int(opt.data_height), int(opt.data_width), parts=True)):
+        getattr(model.netG_student, sec).n_macs = v        # logged by trainer.py:121-123
     model.netG_student.eval()      # shrink_model profiles the new student, which leaves it in eval() (utils/common.py:148)
     teacher.n_macs = generator_macs(teacher.arch(), int(opt.data_height), int(opt.data_width))
     if getattr(model, 'netAs', None):       # adaptor convs follow the pruned width (utils/common.py:154-161)
@@ -196,6 +205,7 @@ def shrink_inception(model, opt):
         model.netAs = [nn.Conv2d(student_arch['widths'][2], a.out_channels, kernel_size=1).to(dev) for a in model.netAs]
     if hasattr(model, 'engine'):
         model.engine = None
+        model.__dict__.pop('_engine_cache', None)      # engines compiled for the old architecture
     print('scale threshold: %g, searched flops: %d, target flops: %g' % (info['threshold'], info['macs'], target))
     return info
 

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- drives the *real* reference (snap-research/CAT mounted read-only at
 /root/reference) on CPU so that golden vectors for the distillation hot path can be generated.
 
-This file only works in the build container (it needs /root/reference).  Nothing that runs on the GPU
-box imports it; the vectors it produces are committed under tests/golden/ by oracle/make_golden.py.
+It needs the reference: /root/reference in the build container, or the copy staged under oracle/_ref/ by
+oracle/make_ref.py (the CPU arm of bench.py on the GPU box).  The golden vectors it produces are committed under
+tests/golden/ by oracle/make_golden.py; no test on the GPU box imports it.
 
 The shims below are the harness-side stubs listed in SURVEY.md section 8(c); the reference tree is
 never modified:
@@ -22,7 +23,9 @@ import torch
 import torchvision  # noqa: F401  (must be imported before the reference is put on sys.path)
 import torch.nn as nn
 
-REF_ROOT = '/root/reference'
+# the read-only checkout in the build container; on the GPU box the copy staged by oracle/make_ref.py (oracle/_ref/)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+REF_ROOT = os.environ.get('CATB_REF_ROOT') or ('/root/reference' if os.path.isdir('/root/reference') else _STAGED)
 
 
 def _install_shims():
