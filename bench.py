@@ -505,6 +505,7 @@ def main():
     from cat_b200 import workload as WL
     from cat_b200.distill_engine import DistillStep
     from cat_b200.engine import GenNet
+    ops.require_cuda()      # raises without an sm_100 device / libcatb200.so (sets the kernels' shared-memory attributes)
 
     arch = WL.load_arch(arch_name(args.workload))
     hp = dict(arch['hp'])

@@ -43,6 +43,11 @@ class PackJob(C.Structure):
                 ('n_chunks', C.c_int32), ('row0', C.c_int32), ('span', C.c_int32), ('nreal', C.c_int32)]
 
 
+class UnpackJob(C.Structure):
+    _fields_ = [('ws', C.c_void_p), ('wunits', C.c_void_p), ('grad', C.c_void_p), ('n_splits', C.c_int32),
+                ('ws_rows', C.c_int32), ('ws_k', C.c_int32), ('row0', C.c_int32), ('n_rows', C.c_int32), ('n_units', C.c_int32)]
+
+
 class CatbError(RuntimeError):
     pass
 
@@ -67,6 +72,7 @@ _PROTOS = {
     'catb_igemm_halo_wgrad_ws_shape': [_DP, C.POINTER(HaloDesc), _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'catb_igemm_halo_wgrad_ws': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P],
     'catb_wgrad_unpack': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    'catb_wgrad_unpack_batch': [_P, _I, _I, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
     'catb_ref_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_dwconv_fwd': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
@@ -88,6 +94,7 @@ _PROTOS = {
     'catb_gan_loss': [_P, _L, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P],
     'catb_recon_loss': [_P, _I, _I, _P, _I, _I, _L, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _I, _P],
     'catb_gram': [_P, _I, _I, _I, _L, _I, _P, _P],
+    'catb_gram_ref': [_P, _I, _I, _I, _L, _I, _P, _P],
     'catb_ka_finish': [_P, _P, _I, _F, _P, _P, _P, _P],
     'catb_ka_bwd': [_P, _I, _I, _I, _L, _I, _P, _P, _I, _I, _I, _P],
     'catb_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P],

@@ -84,6 +84,15 @@ __device__ __forceinline__ int reflect_idx(int i, int L) {
   return i;
 }
 
+// Adjoint of reflect_idx: the padded-frame coordinates j (in [-p, L-1+p]) that mirror onto i (at most three)
+__device__ __forceinline__ int reflect_sources(int i, int L, int p, int* src) {
+  int n = 0;
+  src[n++] = i;
+  if (i >= 1 && i <= p) src[n++] = -i;
+  if (i <= L - 2 && i >= L - 1 - p) src[n++] = 2 * (L - 1) - i;
+  return n;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

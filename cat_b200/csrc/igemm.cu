@@ -761,6 +761,35 @@ extern "C" int catb_wgrad_unpack(const float* ws, int n_splits, int ws_rows, int
   return check_launch("wgrad_unpack");
 }
 
+// Batched form: blockIdx.y selects a job of a device-resident table, so that the second stage of every weight gradient
+// of a backward pass is ONE launch (small jobs run side by side instead of one ~5 us launch each).
+__global__ void wgrad_unpack_batch_kernel(const catb_unpack_job* __restrict__ jobs) {
+  const catb_unpack_job j = jobs[blockIdx.y];
+  const long long total = static_cast<long long>(j.n_rows) * j.n_units * 8;
+  const float* ws = reinterpret_cast<const float*>(j.ws);
+  const catb_weight_unit* wunits = reinterpret_cast<const catb_weight_unit*>(j.wunits);
+  float* grad = reinterpret_cast<float*>(j.grad);
+  const size_t split_stride = static_cast<size_t>(j.ws_rows) * j.ws_k;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(idx & 7);
+    const int u = static_cast<int>((idx >> 3) % j.n_units);
+    const int row = static_cast<int>((idx >> 3) / j.n_units);
+    const catb_weight_unit wu = wunits[u];
+    if (q >= wu.nvalid) continue;
+    const float* src = ws + static_cast<size_t>(j.row0 + row) * j.ws_k + u * 8 + q;
+    float acc = 0.f;
+    for (int sp = 0; sp < j.n_splits; ++sp) acc += src[sp * split_stride];
+    atomicAdd(grad + wu.w_off + static_cast<long long>(row) * wu.sn_w + q * wu.sc_w, acc);
+  }
+}
+
+extern "C" int catb_wgrad_unpack_batch(const catb_unpack_job* jobs, int n_jobs, int blocks_per_job, catb_stream_t s) {
+  CATB_REQUIRE(jobs != nullptr && n_jobs > 0 && n_jobs <= 65535 && blocks_per_job > 0, "bad unpack job table (%d jobs)", n_jobs);
+  wgrad_unpack_batch_kernel<<<dim3(blocks_per_job, n_jobs), 256, 0, static_cast<cudaStream_t>(s)>>>(jobs);
+  return check_launch("wgrad_unpack_batch");
+}
+
 extern "C" int catb_ref_fprop(const catb_igemm_desc* d, const catb_gather_unit* units, const catb_weight_unit* wunits,
                               const float* arena, const void* x, const float* bias, void* y, catb_stream_t s) {
   if (int e = validate_desc(d)) return e;

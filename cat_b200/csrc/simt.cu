@@ -17,154 +17,6 @@ static inline int grid_for(long long work, int block, int max_blocks = 148 * 16)
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise convolution, reflect padding (k-1)/2, per-unit kernel size
-// ------------------------------------------------------------------------------------------------
-// Filters of the whole channel range are staged once per block in shared memory as w_s[tap][C]
-// (49 taps max, zero for padding channels / unused taps), then every thread handles one (pixel, 8-channel
-// unit): 16-byte activation loads, two float4 filter loads per tap.
-constexpr int kDwMaxTaps = 49;
-__device__ __forceinline__ void dw_stage_filters(float* w_s, int C, const int32_t* ksize, const int32_t* w_off,
-                                                 const float* arena) {
-  for (int i = threadIdx.x; i < C * kDwMaxTaps; i += blockDim.x) {
-    const int tap = i / C, c = i - tap * C;
-    const int k = ksize[c], wo = w_off[c];
-    w_s[i] = (wo >= 0 && tap < k * k) ? arena[wo + tap] : 0.f;
-  }
-  __syncthreads();
-}
-
-__global__ void dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, __nv_bfloat16* __restrict__ y,
-                                  int ldy, int y_coff, int N, int H, int W, int C, const int32_t* __restrict__ ksize,
-                                  const int32_t* __restrict__ w_off, const float* __restrict__ arena, int zero_pad) {
-  extern __shared__ float w_s[];
-  dw_stage_filters(w_s, C, ksize, w_off, arena);
-  const int U = C / 8;
-  const long long total = static_cast<long long>(N) * H * W * U;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(idx % U);
-    long long pix = idx / U;
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const int k = ksize[u * 8];
-    const int p = (k - 1) / 2;
-    f8 acc;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
-    for (int r = 0; r < k; ++r) {
-      if (zero_pad && (h - p + r < 0 || h - p + r >= H)) continue;
-      const int ih = zero_pad ? h - p + r : reflect_idx(h - p + r, H);
-      for (int s = 0; s < k; ++s) {
-        if (zero_pad && (w - p + s < 0 || w - p + s >= W)) continue;
-        const int iw = zero_pad ? w - p + s : reflect_idx(w - p + s, W);
-        const f8 xv = unpack8(ldg16(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * ldx + x_coff + u * 8));
-        const float4 wa = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8);
-        const float4 wb = *reinterpret_cast<const float4*>(w_s + (r * k + s) * C + u * 8 + 4);
-        acc.v[0] += xv.v[0] * wa.x; acc.v[1] += xv.v[1] * wa.y; acc.v[2] += xv.v[2] * wa.z; acc.v[3] += xv.v[3] * wa.w;
-        acc.v[4] += xv.v[4] * wb.x; acc.v[5] += xv.v[5] * wb.y; acc.v[6] += xv.v[6] * wb.z; acc.v[7] += xv.v[7] * wb.w;
-      }
-    }
-    st16(y + static_cast<size_t>(pix) * ldy + y_coff + u * 8, pack8(acc));
-  }
-}
-
-// dx[ih,iw] = sum over (oh,r),(ow,s) with reflect(oh-p+r)=ih, reflect(ow-p+s)=iw of dy[oh,ow]*w[r,s]
-__device__ __forceinline__ int reflect_sources(int i, int L, int p, int* src) {
-  // padded-frame coordinates j (in [-p, L-1+p]) that mirror onto i
-  int n = 0;
-  src[n++] = i;
-  if (i >= 1 && i <= p) src[n++] = -i;
-  if (i <= L - 2 && i >= L - 1 - p) src[n++] = 2 * (L - 1) - i;
-  return n;
-}
-
-__global__ void dwconv_bwd_data_kernel(const __nv_bfloat16* __restrict__ dy, int ldy, int y_coff,
-                                       __nv_bfloat16* __restrict__ dx, int ldx, int x_coff, int N, int H, int W, int C,
-                                       const int32_t* __restrict__ ksize, const int32_t* __restrict__ w_off,
-                                       const float* __restrict__ arena, int zero_pad) {
-  extern __shared__ float w_s[];
-  dw_stage_filters(w_s, C, ksize, w_off, arena);
-  const int U = C / 8;
-  const long long total = static_cast<long long>(N) * H * W * U;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(idx % U);
-    long long pix = idx / U;
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const int k = ksize[u * 8];
-    const int p = (k - 1) / 2;
-    f8 acc;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
-    int hs[3], ws[3];
-    // zero padding: only the pixel itself maps onto (h, w)
-    const int nh = reflect_sources(h, H, zero_pad ? 0 : p, hs), nw = reflect_sources(w, W, zero_pad ? 0 : p, ws);
-    for (int a = 0; a < nh; ++a)
-      for (int r = 0; r < k; ++r) {
-        const int oh = hs[a] + p - r;
-        if (oh < 0 || oh >= H) continue;
-        for (int b = 0; b < nw; ++b)
-          for (int s = 0; s < k; ++s) {
-            const int ow = ws[b] + p - s;
-            if (ow < 0 || ow >= W) continue;
-            const f8 g = unpack8(ldg16(dy + ((static_cast<size_t>(n) * H + oh) * W + ow) * ldy + y_coff + u * 8));
-            const float* wp = w_s + (r * k + s) * C + u * 8;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc.v[q] += g.v[q] * wp[q];
-          }
-      }
-    st16(dx + static_cast<size_t>(pix) * ldx + x_coff + u * 8, pack8(acc));
-  }
-}
-
-// grid = (pixel blocks, units); each block reduces its pixels for every tap of one 8-channel unit
-__global__ void dwconv_bwd_weight_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff,
-                                         const __nv_bfloat16* __restrict__ dy, int ldy, int y_coff, int N, int H, int W,
-                                         const int32_t* __restrict__ ksize, const int32_t* __restrict__ w_off,
-                                         float* __restrict__ grad, int zero_pad) {
-  __shared__ float part[8][8];
-  const int u = blockIdx.y;
-  const int k = ksize[u * 8];
-  const int p = (k - 1) / 2;
-  const long long pixels = static_cast<long long>(N) * H * W;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = 0; r < k; ++r)
-    for (int s = 0; s < k; ++s) {
-      f8 acc;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
-      for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < pixels;
-           pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int w = static_cast<int>(pix % W);
-        const int h = static_cast<int>((pix / W) % H);
-        const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-        if (zero_pad && (h - p + r < 0 || h - p + r >= H || w - p + s < 0 || w - p + s >= W)) continue;
-        const int ih = zero_pad ? h - p + r : reflect_idx(h - p + r, H), iw = zero_pad ? w - p + s : reflect_idx(w - p + s, W);
-        const f8 g = unpack8(ldg16(dy + static_cast<size_t>(pix) * ldy + y_coff + u * 8));
-        const f8 xv = unpack8(ldg16(x + ((static_cast<size_t>(n) * H + ih) * W + iw) * ldx + x_coff + u * 8));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc.v[q] += g.v[q] * xv.v[q];
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float v = warp_sum(acc.v[q]);
-        if (lane == 0) part[warp][q] = v;
-      }
-      __syncthreads();
-      if (threadIdx.x < 8) {
-        float v = 0.f;
-        for (int wi = 0; wi < static_cast<int>(blockDim.x >> 5); ++wi) v += part[wi][threadIdx.x];
-        const int wo = w_off[u * 8 + threadIdx.x];
-        if (wo >= 0) atomicAdd(grad + wo + r * k + s, v);
-      }
-      __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // normalisation
 // ------------------------------------------------------------------------------------------------
 // Generic per-channel reduction skeleton: thread <-> (pixel lane, unit); block partials in smem.
@@ -631,7 +483,71 @@ __global__ void recon_loss_kernel(const __nv_bfloat16* __restrict__ a, int lda, 
   if (threadIdx.x == 0) atomicAdd(loss, t * inv);
 }
 
-// Gram matrix of B samples over K = pixels*C elements; tile of KT elements per iteration in smem.
+// Gram matrix of B samples over K = pixels * C elements on the tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32): the
+// reduction runs over K, so X is both operands -- A = X (16 samples x 16 k), B = X^T -- and the SAME registers serve as
+// the A and the B fragments.  A warp takes one (pixel, 32-channel group) per iteration: lane (g, t) loads 16 bytes
+// (channels 8t .. 8t+7) of samples g and g + 8 of every 16-sample block, i.e. four lanes cover 64 contiguous bytes of a
+// sample; the order of k inside an MMA is irrelevant as long as both operands use the same one, which they do by
+// construction.  Two loads + four MMAs per KB of activations: HBM bound.  (The round-1 kernel formed every pair's dot
+// product with scalar FMAs out of shared memory: 370 GB/s.)
+__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NB>   // 16-sample blocks: 1 (B <= 16) or 2 (B <= 32)
+__global__ void __launch_bounds__(256) gram_mma_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, int B,
+                                                        long long pps, int C, float* __restrict__ G) {
+  __shared__ float red[32 * 32];
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cg = (C + 31) / 32;                      // 32-channel groups per pixel
+  const long long blocks = pps * cg;
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  float acc[NB][NB][2][4];
+#pragma unroll
+  for (int i = 0; i < NB * NB * 8; ++i) (&acc[0][0][0][0])[i] = 0.f;
+  for (long long blk = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < blocks; blk += wstride) {
+    const long long pix = blk / cg;
+    const int c0 = static_cast<int>(blk - pix * cg) * 32 + t * 8;
+    uint4 r[NB][2];
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int smp = bi * 16 + hf * 8 + g;
+        r[bi][hf] = (smp < B && c0 < C) ? ldg16(x + (static_cast<size_t>(smp) * pps + pix) * ldx + x_coff + c0) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+    for (int I = 0; I < NB; ++I)
+#pragma unroll
+      for (int J = 0; J < NB; ++J)
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh) {
+          mma_bf16_16816(acc[I][J][nh], r[I][0].x, r[I][1].x, r[I][0].y, r[I][1].y, r[J][nh].x, r[J][nh].y);
+          mma_bf16_16816(acc[I][J][nh], r[I][0].z, r[I][1].z, r[I][0].w, r[I][1].w, r[J][nh].z, r[J][nh].w);
+        }
+  }
+  // accumulator layout: d0, d1 = (row g, cols 2t, 2t+1), d2, d3 = (row g + 8, same cols)
+#pragma unroll
+  for (int I = 0; I < NB; ++I)
+#pragma unroll
+    for (int J = 0; J < NB; ++J)
+#pragma unroll
+      for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = I * 16 + g + (e >> 1) * 8, j = J * 16 + nh * 8 + 2 * t + (e & 1);
+          if (i < B && j < B) atomicAdd(&red[i * B + j], acc[I][J][nh][e]);
+        }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) atomicAdd(G + i, red[i]);
+}
+
+// SIMT restatement of the Gram matrix (the round-1 kernel; kept for on-device bisection in tests: catb_gram_ref).
 constexpr int kGramKT = 256;
 __global__ void gram_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, int B, long long pps, int C,
                             float* __restrict__ G) {
@@ -766,15 +682,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-int init_simt_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(dwconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(dwconv): %s", cudaGetErrorString(e));
-    return CATB_ERR_CUDA;
-  }
-  return CATB_OK;
-}
+int init_dwconv_attributes();
+int init_simt_attributes() { return init_dwconv_attributes(); }
 
 }  // namespace catb
 
@@ -783,45 +692,6 @@ using namespace catb;
 #define CHK_SLICE(ld, coff, C)                                                                     \
   CATB_REQUIRE((ld) % 8 == 0 && (coff) % 8 == 0 && (C) % 8 == 0 && (C) > 0 && (coff) + (C) <= (ld), \
                "bad channel slice (ld=%d coff=%d C=%d)", (int)(ld), (int)(coff), (int)(C))
-
-extern "C" int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int N, int H, int W,
-                               int C, const int32_t* ksize, const int32_t* w_off, const float* arena, int pad_mode,
-                               catb_stream_t s) {
-  CHK_SLICE(ldx, x_coff, C);
-  CHK_SLICE(ldy, y_coff, C);
-  const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
-  dwconv_fwd_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
-                                                             static_cast<__nv_bfloat16*>(y), ldy, y_coff, N, H, W, C,
-                                                             ksize, w_off, arena, pad_mode == CATB_PAD_ZERO);
-  return check_launch("dwconv_fwd");
-}
-
-extern "C" int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* dx, int ldx, int x_coff, int N, int H,
-                                    int W, int C, const int32_t* ksize, const int32_t* w_off, const float* arena,
-                                    int pad_mode, catb_stream_t s) {
-  CHK_SLICE(ldx, x_coff, C);
-  CHK_SLICE(ldy, y_coff, C);
-  const long long total = static_cast<long long>(N) * H * W * (C / 8);
-  CATB_REQUIRE(C * kDwMaxTaps * 4 <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
-  dwconv_bwd_data_kernel<<<grid_for(total, 256, 148 * 8), 256, C * kDwMaxTaps * sizeof(float), S(s)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, y_coff,
-                                                                  static_cast<__nv_bfloat16*>(dx), ldx, x_coff, N, H, W,
-                                                                  C, ksize, w_off, arena, pad_mode == CATB_PAD_ZERO);
-  return check_launch("dwconv_bwd_data");
-}
-
-extern "C" int catb_dwconv_bwd_weight(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, int N,
-                                      int H, int W, int C, const int32_t* ksize, const int32_t* w_off,
-                                      float* arena_grad, int pad_mode, catb_stream_t s) {
-  CHK_SLICE(ldx, x_coff, C);
-  CHK_SLICE(ldy, y_coff, C);
-  const long long pixels = static_cast<long long>(N) * H * W;
-  dim3 grid(grid_for(pixels, 256, 64), C / 8, 1);
-  dwconv_bwd_weight_kernel<<<grid, 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff,
-                                                    static_cast<const __nv_bfloat16*>(dy), ldy, y_coff, N, H, W, ksize,
-                                                    w_off, arena_grad, pad_mode == CATB_PAD_ZERO);
-  return check_launch("dwconv_bwd_weight");
-}
 
 static dim3 reduce_grid(long long pixels_per_group, int C, int groups) {
   const int U = C / 8;
@@ -1009,11 +879,24 @@ extern "C" int catb_gram(const void* x, int ldx, int x_coff, int B, long long pi
                          catb_stream_t s) {
   CHK_SLICE(ldx, x_coff, C);
   CATB_REQUIRE(B >= 1 && B <= 32, "KA kernels support 1 <= batch <= 32 per device (got %d)", B);
+  const long long blocks = pixels_per_sample * ((C + 31) / 32);      // one per warp iteration
+  const int grid = grid_for(blocks, 8, 148 * 4);
+  if (B <= 16)
+    gram_mma_kernel<1><<<grid, 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff, B, pixels_per_sample, C, G);
+  else
+    gram_mma_kernel<2><<<grid, 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff, B, pixels_per_sample, C, G);
+  return check_launch("gram");
+}
+
+extern "C" int catb_gram_ref(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G,
+                             catb_stream_t s) {
+  CHK_SLICE(ldx, x_coff, C);
+  CATB_REQUIRE(B >= 1 && B <= 32, "KA kernels support 1 <= batch <= 32 per device (got %d)", B);
   const long long tiles = (pixels_per_sample * C + kGramKT - 1) / kGramKT;
   const size_t smem = static_cast<size_t>(B) * (kGramKT + 1) * sizeof(float);
   gram_kernel<<<grid_for(tiles, 1, 148 * 4), 256, smem, S(s)>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_coff, B,
                                                                  pixels_per_sample, C, G);
-  return check_launch("gram");
+  return check_launch("gram_ref");
 }
 
 extern "C" int catb_ka_finish(const float* Gx, const float* Gy, int B, float loss_scale, float* loss, float* ka_value,

@@ -661,6 +661,13 @@ class GenNet:
 
     # ---- backward ------------------------------------------------------------------------------
     def backward(self, d_out: Act, act_grads=None):
+        """See _backward; the second stages of all weight gradients run as one launch when the pass is left."""
+        if getattr(self, '_unpack', None) is None:
+            self._unpack = ops.UnpackQueue(self.dev)
+        with self._unpack:
+            return self._backward(d_out, act_grads)
+
+    def _backward(self, d_out: Act, act_grads=None):
         """d_out: gradient w.r.t. the tanh output.  act_grads: {mapping layer: callable(Act)} invoked to
         accumulate extra gradient (the KA loss) into d(activation) at the four mapping layers."""
         assert self.need_grad
@@ -786,6 +793,7 @@ class GenNet:
         self.n_stem.backward(self.d_a0, self.a0, self.y0, self.d_y0, relu)
         if self.packx:
             self.g_stem.wgrad(self.x_stem.t, self.d_y0.t, self.aux.g)
+            ops.flush_unpack()                                  # the two aux weight gradients must have landed in aux.g
             ops.scatter_add(self.aux.g, self.aux_idx, ar.g)     # d(stem.wx), d(head.wx) -> the 7x7 parameter gradients
         else:
             self.g_stem.wgrad(self.x_in.t, self.d_y0.t, ar.g)
@@ -926,6 +934,13 @@ class DisNet:
         return self.pred
 
     def backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None):
+        """See _backward; the second stages of all weight gradients run as one launch when the pass is left."""
+        if getattr(self, '_unpack', None) is None:
+            self._unpack = ops.UnpackQueue(self.dev)
+        with self._unpack:
+            return self._backward(dpred, param_grads, input_grad, act_grad_hook)
+
+    def _backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None):
         """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0).
         act_grad_hook(li, d): called with the gradient w.r.t. the activation output of layer li before it is
         back-propagated (the feature-matching loss of the SPADE path adds its term there)."""

@@ -94,6 +94,68 @@ def _scratch_like(t):
     return _SCRATCH[key]
 
 
+_UNPACK = [None]      # the UnpackQueue of the backward pass that is being issued (None: second stages run immediately)
+
+
+class UnpackQueue:
+    """Second stage of every two-stage weight gradient of one backward pass as ONE launch.
+
+    ``with net.unpack_queue:`` around a backward pass makes Gemm.wgrad launch only its first stage (partial tiles into
+    the GEMM's own workspace) and register the second stage here; leaving the block -- after every side stream has been
+    joined -- runs them all through catb_wgrad_unpack_batch.  The job table lives on the device and is rebuilt only when
+    the set of jobs changes (never during graph capture: the eager tuning step of an engine builds it first)."""
+
+    def __init__(self, device):
+        self.dev, self.jobs, self.tables, self.depth, self._outer = device, [], {}, 0, None
+
+    def __enter__(self):
+        if self.depth == 0:
+            self._outer, _UNPACK[0] = _UNPACK[0], self
+            self.jobs = []
+        self.depth += 1
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self.depth -= 1
+        if self.depth == 0:
+            _UNPACK[0] = self._outer
+            if exc_type is None:
+                self.flush()
+        return False
+
+    def add(self, ws, splits, ws_rows, ws_k, row0, n_rows, n_units, wt, grad):
+        self.jobs.append((ws.data_ptr(), wt.data_ptr(), grad.data_ptr(), splits, ws_rows, ws_k, row0, n_rows, n_units))
+
+    def flush(self):
+        """Run (and forget) the jobs registered so far; called implicitly when the block is left."""
+        if not self.jobs:
+            return
+        if str(self.dev) == 'cpu':       # kernel emulation: second stages were applied immediately
+            self.jobs = []
+            return
+        key = tuple(self.jobs)
+        entry = self.tables.get(key)
+        if entry is None:
+            assert not torch.cuda.is_current_stream_capturing(), 'unpack table must be built before graph capture'
+            arr = (_C.UnpackJob * len(key))()
+            big = 1
+            for i, j in enumerate(key):
+                arr[i] = _C.UnpackJob(*j)
+                big = max(big, j[7] * j[8] * 8)
+            table = torch.from_numpy(np.frombuffer(arr, dtype=np.uint8).copy()).to(self.dev)
+            entry = (table, len(key), max(1, min(148 * 4, (big + 2047) // 2048)))
+            self.tables[key] = entry
+        table, n, blocks = entry
+        _C.call('catb_wgrad_unpack_batch', _p(table), n, blocks, _stream())
+        self.jobs = []
+
+
+def flush_unpack():
+    """Run the second stages registered so far (a consumer of the gradients follows inside the same backward pass)."""
+    if _UNPACK[0] is not None:
+        _UNPACK[0].flush()
+
+
 class Gemm:
     """One implicit GEMM: geometry + unit tables (+ packed bf16 weights for the fprop direction).
 
@@ -342,6 +404,13 @@ class Gemm:
         self._wgrad_plan()
         d = self.desc()
         assert not (atomic and self.seg_raw is not None), 'N-concatenated weight gradients only exist in the two-stage form'
+        queue = [None]      # second stages go to the backward pass's UnpackQueue, except while the two kernels are being timed
+
+        def second(ws, splits, ws_k, row0, n_rows, n_units, wt, g):
+            if queue[0] is not None:
+                queue[0].add(ws, splits, self.n_rows, ws_k, row0, n_rows, n_units, wt, g)
+            else:
+                _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, row0, n_rows, n_units, _p(wt), _p(g), _stream())
 
         def v1(g):
             if atomic:
@@ -350,14 +419,12 @@ class Gemm:
             ws, splits, ws_k = self._ws_for('v1', d)
             _C.call('catb_igemm_wgrad_ws', C.byref(d), _p(self.gt), _p(x), _p(y), _p(ws), _stream())
             if self.seg_raw is None:
-                _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, 0, self.n_rows, self.n_units, _p(self.wt), _p(g),
-                        _stream())
+                second(ws, splits, ws_k, 0, self.n_rows, self.n_units, self.wt, g)
             else:
                 if getattr(self, 'v1_seg_wt', None) is None:
                     self.v1_seg_wt = [units_to_device(su, self.gt.device)[1] for (_r0, _sp, _nr, su) in self.seg_raw]
                 for (row0, _sp, nreal, _su), wt in zip(self.seg_raw, self.v1_seg_wt):
-                    _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, row0, nreal, self.n_units, _p(wt), _p(g),
-                            _stream())
+                    second(ws, splits, ws_k, row0, nreal, self.n_units, wt, g)
 
         def v2(g):
             if atomic:
@@ -368,12 +435,10 @@ class Gemm:
             _C.call('catb_igemm_halo_wgrad_ws', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
                     _p(self.w_groups), self.w_ngroups, _p(x), _p(y), _p(ws), _stream())
             if self.seg_raw is None:
-                _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, 0, self.n_rows, self.w_nunits, _p(self.w_wt),
-                        _p(g), _stream())
+                second(ws, splits, ws_k, 0, self.n_rows, self.w_nunits, self.w_wt, g)
             else:
                 for (row0, _sp, nreal, _su), wt in zip(self.seg_raw, self.w_seg_wt):
-                    _C.call('catb_wgrad_unpack', _p(ws), splits, self.n_rows, ws_k, row0, nreal, self.w_nunits, _p(wt), _p(g),
-                            _stream())
+                    second(ws, splits, ws_k, row0, nreal, self.w_nunits, wt, g)
 
         if AUTOTUNE and self.w_halo is not None and self.w_choice is None and not force_v1 \
                 and not torch.cuda.is_current_stream_capturing():
@@ -384,6 +449,7 @@ class Gemm:
             self.w_choice = 'v2' if t2 <= t1 else 'v1'
             self.w_tuned_ms = (t1, t2)
             setattr(self, '_ws_v1' if self.w_choice == 'v2' else '_ws_v2', None)     # drop the loser's workspace
+        queue[0] = _UNPACK[0]
         if self.w_halo is not None and not force_v1 and self.w_choice != 'v1':
             v2(grad_arena)
         else:

@@ -668,6 +668,13 @@ class SpadeGenNet(_Net):
 
     # ---- backward ------------------------------------------------------------------------------
     def backward(self, d_out: Act, act_grads=None):
+        """See _backward; the second stages of all weight gradients run as one launch when the pass is left."""
+        if getattr(self, '_unpack', None) is None:
+            self._unpack = ops.UnpackQueue(self.dev)
+        with self._unpack:
+            return self._backward(d_out, act_grads)
+
+    def _backward(self, d_out: Act, act_grads=None):
         """d_out: gradient w.r.t. the tanh output; act_grads: {mapping layer: callable(Act)} accumulating the KA
         gradient into d(block output)."""
         assert self.need_grad
@@ -814,6 +821,13 @@ class MultiScaleDis:
         return self.nets
 
     def backward(self, dpreds, param_grads, input_grad, act_grad_hook=None):
+        """See _backward; the second stages of all weight gradients run as one launch when the pass is left."""
+        if getattr(self, '_unpack', None) is None:
+            self._unpack = ops.UnpackQueue(self.arena.p.device)
+        with self._unpack:
+            return self._backward(dpreds, param_grads, input_grad, act_grad_hook)
+
+    def _backward(self, dpreds, param_grads, input_grad, act_grad_hook=None):
         """dpreds[i]: gradient w.r.t. the prediction of scale i.  Returns d(input) (scale-0 resolution)."""
         for i in range(len(self.nets) - 1, -1, -1):
             net = self.nets[i]

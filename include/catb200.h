@@ -170,6 +170,16 @@ int catb_igemm_halo_wgrad_ws(const catb_igemm_desc* d, const catb_halo_desc* h, 
 int catb_wgrad_unpack(const float* ws, int n_splits, int ws_rows /* rows per split */, int ws_k, int row0, int n_rows,
                       int n_units, const catb_weight_unit* wunits /*device*/, float* arena_grad, catb_stream_t s);
 
+/* All second stages of one backward pass in ONE launch: a device-resident job table (fields as the arguments of
+ * catb_wgrad_unpack, plus the gradient arena each job adds to). */
+typedef struct {
+  const void* ws;      /* const float* (device) */
+  const void* wunits;  /* const catb_weight_unit* (device) */
+  void* grad;          /* float* gradient arena (device) */
+  int32_t n_splits, ws_rows, ws_k, row0, n_rows, n_units;
+} catb_unpack_job;
+int catb_wgrad_unpack_batch(const catb_unpack_job* jobs /*device*/, int n_jobs, int blocks_per_job, catb_stream_t s);
+
 /* Development aid: with a device buffer of 4096 x 16 uint64 registered (zeroed by the caller), every catb_igemm_halo_fprop CTA with
  * blockIdx.x < 4096 records %globaltimer (ns) at its phase boundaries: 0 prologue done, 1 first halo chunk filled,
  * 2 MMA warp released, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit, 7 kernel entry; 8-10 cycles of thread 0 in the epilogue's TMEM loads / pack + staging / copy-out.  NULL: off. */
@@ -273,6 +283,8 @@ int catb_recon_loss(const void* a, int lda, int a_coff, const void* b, int ldb, 
 /* KA (utils/common.py:38-46).  gram: G[B,B] += X X^T over K = pixels*C elements per sample (caller
  * zeroes G).  ka_finish: value and the B x B coefficient matrix of dX = coef * X.  ka_bwd: dX (+)= coef X. */
 int catb_gram(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G, catb_stream_t s);
+/* SIMT restatement of catb_gram (the round-1 kernel), kept for on-device bisection in tests. */
+int catb_gram_ref(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, float* G, catb_stream_t s);
 int catb_ka_finish(const float* Gx, const float* Gy, int B, float loss_scale, float* loss /* += */,
                    float* ka_value, float* coef, catb_stream_t s);
 int catb_ka_bwd(const void* x, int ldx, int x_coff, int B, long long pixels_per_sample, int C, const float* coef,

@@ -93,7 +93,7 @@ def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, 
     y.copy_(yf.to(y.dtype))
 
 
-def _gemm_wgrad(self, x, y, grad_arena, force_v1=False, atomic=False):
+def _gemm_wgrad(self, x, y, grad_arena, force_v1=False, atomic=False):      # second stage applied immediately
     if self._emu_segments is None:
         P.emulate_wgrad(self.geo, self.units, self.n_rows, x.float(), y.float(), grad_arena)
         return
