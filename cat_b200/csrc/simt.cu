@@ -23,7 +23,7 @@ static inline int grid_for(long long work, int block, int max_blocks = 148 * 16)
 // MODE 0: sum x, sum x^2            (forward statistics)
 // MODE 1: sum dz, sum dz*xhat        (backward reduction)
 template <int MODE>
-__global__ void channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff,
+__global__ void __launch_bounds__(512, 1) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff,
                                       const __nv_bfloat16* __restrict__ dout, int ldd, int d_coff,
                                       const __nv_bfloat16* __restrict__ out, int ldo, int o_coff, int HW, int C,
                                       int per_sample, const float* __restrict__ mean_rstd, int act,
@@ -52,25 +52,45 @@ __global__ void channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, int l
           rs.v[q] = mean_rstd[(static_cast<size_t>(g) * 2 + 1) * C + u * 8 + q];
         }
       }
+      // four pixels in flight per thread: all loads of an iteration are issued before the first use (at ~40 % occupancy
+      // one outstanding 16-byte load per thread left the memory system two thirds idle)
+      constexpr int kIn = MODE == 0 ? 4 : 2;      // MODE 1 streams three tensors per pixel
+      const long long pstep = static_cast<long long>(gridDim.x) * lanes;
       for (long long pp = static_cast<long long>(blockIdx.x) * lanes + (U >= static_cast<int>(blockDim.x) ? 0 : pl);
-           pp < npix; pp += static_cast<long long>(gridDim.x) * lanes) {
-        const size_t pix = static_cast<size_t>(pix0 + pp);
-        const f8 xv = unpack8(ldg16(x + pix * ldx + x_coff + u * 8));
-        if (MODE == 0) {
+           pp < npix; pp += kIn * pstep) {
+        uint4 xr[kIn], dr[kIn], orr[kIn];
+        bool ok[kIn];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            a.v[q] += xv.v[q];
-            b.v[q] += xv.v[q] * xv.v[q];
+        for (int j = 0; j < kIn; ++j) {
+          const long long pj = pp + j * pstep;
+          ok[j] = pj < npix;
+          const size_t pix = static_cast<size_t>(pix0 + (ok[j] ? pj : pp));
+          xr[j] = ldg16(x + pix * ldx + x_coff + u * 8);
+          if (MODE == 1) {
+            dr[j] = ldg16(dout + pix * ldd + d_coff + u * 8);
+            if (act != CATB_ACT_NONE) orr[j] = ldg16(out + pix * ldo + o_coff + u * 8);
           }
-        } else {
-          const f8 dv = unpack8(ldg16(dout + pix * ldd + d_coff + u * 8));
-          f8 ov;
-          if (act != CATB_ACT_NONE) ov = unpack8(ldg16(out + pix * ldo + o_coff + u * 8));
+        }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
-            a.v[q] += dz;
-            b.v[q] += dz * (xv.v[q] - mu.v[q]) * rs.v[q];
+        for (int j = 0; j < kIn; ++j) {
+          if (!ok[j]) continue;
+          const f8 xv = unpack8(xr[j]);
+          if (MODE == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              a.v[q] += xv.v[q];
+              b.v[q] += xv.v[q] * xv.v[q];
+            }
+          } else {
+            const f8 dv = unpack8(dr[j]);
+            f8 ov;
+            if (act != CATB_ACT_NONE) ov = unpack8(orr[j]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
+              a.v[q] += dz;
+              b.v[q] += dz * (xv.v[q] - mu.v[q]) * rs.v[q];
+            }
           }
         }
       }
@@ -153,28 +173,30 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, 
     *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + static_cast<size_t>(g) * C + u * 8 + 4));
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8 + 4));
-    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += 2 * stride) {
-      const size_t p0 = static_cast<size_t>(pix0 + pp), p1 = p0 + stride;
-      const bool two = pp + stride < npix;
-      f8 v0 = unpack8(ldg16(x + p0 * ldx + x_coff + u * 8)), v1, r0, r1;
-      if (two) v1 = unpack8(ldg16(x + p1 * ldx + x_coff + u * 8));
-      if (res != nullptr) {
-        r0 = unpack8(ldg16(res + p0 * ldr + r_coff + u * 8));
-        if (two) r1 = unpack8(ldg16(res + p1 * ldr + r_coff + u * 8));
+    constexpr int kIn = 4;      // pixels in flight per thread (loads issued before the first use)
+    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += kIn * stride) {
+      uint4 xr[kIn], rr[kIn];
+      bool ok[kIn];
+#pragma unroll
+      for (int j = 0; j < kIn; ++j) {
+        const long long pj = pp + j * stride;
+        ok[j] = pj < npix;
+        const size_t pj_ = static_cast<size_t>(pix0 + (ok[j] ? pj : pp));
+        xr[j] = ldg16(x + pj_ * ldx + x_coff + u * 8);
+        if (res != nullptr) rr[j] = ldg16(res + pj_ * ldr + r_coff + u * 8);
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        v0.v[q] = apply_act(v0.v[q] * sc[q] + sh[q], act);
-        if (res != nullptr) v0.v[q] += r0.v[q];
-      }
-      st16(y + p0 * ldy + y_coff + u * 8, pack8(v0));
-      if (two) {
+      for (int j = 0; j < kIn; ++j) {
+        if (!ok[j]) continue;
+        f8 v = unpack8(xr[j]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v1.v[q] = apply_act(v1.v[q] * sc[q] + sh[q], act);
-          if (res != nullptr) v1.v[q] += r1.v[q];
+        for (int q = 0; q < 8; ++q) v.v[q] = apply_act(v.v[q] * sc[q] + sh[q], act);
+        if (res != nullptr) {
+          const f8 r = unpack8(rr[j]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v.v[q] += r.v[q];
         }
-        st16(y + p1 * ldy + y_coff + u * 8, pack8(v1));
+        st16(y + static_cast<size_t>(pix0 + pp + j * stride) * ldy + y_coff + u * 8, pack8(v));
       }
     }
   }
@@ -222,19 +244,33 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, in
       k2[q] = -ga * rs * rs * s2;
       k3[q] = -ga * rs * s1 + ga * rs * rs * mu * s2;
     }
-    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += stride) {
-      const size_t pix = static_cast<size_t>(pix0 + pp);
-      const f8 dv = unpack8(ldg16(dout + pix * ldd + d_coff + u * 8));
-      const f8 xv = unpack8(ldg16(x + pix * ldx + x_coff + u * 8));
-      f8 ov;
-      if (act != CATB_ACT_NONE) ov = unpack8(ldg16(out + pix * ldo + o_coff + u * 8));
-      f8 r;
+    constexpr int kIn = 3;      // pixels in flight per thread (up to nine 16-byte loads issued before the first use)
+    for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += kIn * stride) {
+      uint4 dr[kIn], xr[kIn], orr[kIn];
+      bool ok[kIn];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
-        r.v[q] = k1[q] * dz + k2[q] * xv.v[q] + k3[q];
+      for (int j = 0; j < kIn; ++j) {
+        const long long pj = pp + j * stride;
+        ok[j] = pj < npix;
+        const size_t pix = static_cast<size_t>(pix0 + (ok[j] ? pj : pp));
+        dr[j] = ldg16(dout + pix * ldd + d_coff + u * 8);
+        xr[j] = ldg16(x + pix * ldx + x_coff + u * 8);
+        if (act != CATB_ACT_NONE) orr[j] = ldg16(out + pix * ldo + o_coff + u * 8);
       }
-      st16(dx + pix * ldg + g_coff + u * 8, pack8(r));
+#pragma unroll
+      for (int j = 0; j < kIn; ++j) {
+        if (!ok[j]) continue;
+        const f8 dv = unpack8(dr[j]), xv = unpack8(xr[j]);
+        f8 ov;
+        if (act != CATB_ACT_NONE) ov = unpack8(orr[j]);
+        f8 r;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float dz = act != CATB_ACT_NONE ? dv.v[q] * act_grad_from_out(ov.v[q], act) : dv.v[q];
+          r.v[q] = k1[q] * dz + k2[q] * xv.v[q] + k3[q];
+        }
+        st16(dx + static_cast<size_t>(pix0 + pp + j * stride) * ldg + g_coff + u * 8, pack8(r));
+      }
     }
   }
 }
@@ -693,11 +729,15 @@ using namespace catb;
   CATB_REQUIRE((ld) % 8 == 0 && (coff) % 8 == 0 && (C) % 8 == 0 && (C) > 0 && (coff) + (C) <= (ld), \
                "bad channel slice (ld=%d coff=%d C=%d)", (int)(ld), (int)(coff), (int)(C))
 
+// Blocks of 512 threads, at most one per SM in total: every block ends with 2*C atomic adds onto the SAME 2*C addresses
+// (per group), and same-address atomics from different SMs serialise in L2 (~20-30 ns each) -- with 592 blocks that tail
+// was a fixed ~10 us per launch, more than the streaming part of most of these reductions.
+constexpr int kReduceThreads = 512;
 static dim3 reduce_grid(long long pixels_per_group, int C, int groups) {
   const int U = C / 8;
-  const int lanes = U >= 256 ? 1 : 256 / U;
+  const int lanes = U >= kReduceThreads ? 1 : kReduceThreads / U;
   long long gx = (pixels_per_group + static_cast<long long>(lanes) * 8 - 1) / (static_cast<long long>(lanes) * 8);
-  const long long cap = std::max(1, 148 * 4 / groups);
+  const long long cap = std::max(1, 148 / groups);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3(static_cast<unsigned>(gx), groups, 1);
@@ -719,7 +759,7 @@ extern "C" int catb_norm_stats(const void* x, int ldx, int x_coff, int N, int HW
   CHK_SLICE(ldx, x_coff, C);
   const long long pixels = static_cast<long long>(N) * HW;
   const dim3 grid = reduce_grid(per_sample ? HW : pixels, C, per_sample ? N : 1);
-  channel_reduce_kernel<0><<<grid, 256, 2 * C * sizeof(float), S(s)>>>(
+  channel_reduce_kernel<0><<<grid, kReduceThreads, 2 * C * sizeof(float), S(s)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, nullptr, 0, 0, nullptr, 0, 0, HW, C, per_sample, nullptr, 0,
       sums, pixels);
   return check_launch("norm_stats");
@@ -755,7 +795,7 @@ extern "C" int catb_norm_bwd_reduce(const void* dout, int ldd, int d_coff, const
   CHK_SLICE(ldd, d_coff, C);
   const long long pixels = static_cast<long long>(N) * HW;
   const dim3 grid = reduce_grid(per_sample ? HW : pixels, C, per_sample ? N : 1);
-  channel_reduce_kernel<1><<<grid, 256, 2 * C * sizeof(float), S(s)>>>(
+  channel_reduce_kernel<1><<<grid, kReduceThreads, 2 * C * sizeof(float), S(s)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<const __nv_bfloat16*>(dout), ldd, d_coff,
       static_cast<const __nv_bfloat16*>(out), ldo, o_coff, HW, C, per_sample, mean_rstd, act, red, pixels);
   return check_launch("norm_bwd_reduce");
