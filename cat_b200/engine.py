@@ -452,19 +452,29 @@ class GenNet:
             # are kept for the weight gradients.
             b.s1, b.s1_fwd = [], []
             ones = [(kind, j, m) for (kind, j, m, k) in b.order if k == 1]
+            # pruned students (all first-stage slices within one 128-row N tile): every first conv in ONE GEMM on the tap
+            # grid of the largest kernel -- the block is launch / latency bound, and an N = 128 MMA costs ~1.5x an N = 24 one
+            fuse_all = len(b.order) > 1 and b.LA <= 128 and os.environ.get('CATB_NO_S1FUSE', '0') != '1'
             for (kind, j, m, k) in b.order:
                 if kind == 'res':
                     wn, sl = f'{pre}.res_ops.{j}.1.0.weight', b.res_sl[j]
                 else:
                     wn, sl = f'{pre}.dw_ops.{j}.0.0.weight', b.dw1_sl[j]
-                fused = k == 1 and len(ones) > 1
+                fused = fuse_all or (k == 1 and len(ones) > 1)
                 g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl, pad_mode=P.PAD_REFLECT),
                          P.conv_fprop_units(ar.off(wn), m, C, k, k, (k - 1) // 2), m, dev, need_pack=not fused)
                 b.s1.append((g, sl, m, k, wn))
                 if not fused:
                     b.s1_fwd.append(g)
                     self.fprop_gemms.append(g)
-            if len(ones) > 1:
+            if fuse_all:
+                kmax = max(k for (_g, _sl, _m, k, _wn) in b.s1)
+                segs = [(sl, cpad(m), m, P.conv_embedded_units(ar.off(wn), m, C, k, kmax)) for (_g, sl, m, k, wn) in b.s1]
+                g = Gemm(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, 0, pad_mode=P.PAD_REFLECT),
+                         P.conv_fprop_units(0, b.LA, C, kmax, kmax, (kmax - 1) // 2), b.LA, dev, segments=segs)
+                b.s1_fwd = [g]
+                self.fprop_gemms.append(g)
+            elif len(ones) > 1:
                 rows = sum(cpad(m) for (_, _, m) in ones)      # the 1x1 slices start at channel 0 and are contiguous
                 base = P.conv_fprop_units(0, rows, C, 1, 1, 0)
                 segs = [(sl, cpad(m), m, P.conv_fprop_units(ar.off(wn), m, C, 1, 1, 0)) for (_, sl, m, k, wn) in b.s1 if k == 1]
@@ -504,7 +514,25 @@ class GenNet:
                 u2.extend(P.conv_fprop_units(ar.off(f'{pre}.dw_ops.{j}.4.weight'), C, m, 1, 1, 0, cu0=sl // 8))
             b.g2 = G(P.Geometry(B, H4, W4, b.L, 0, H4, W4, Cp, 0, pad_mode=P.PAD_REFLECT), u2, C)
             b.npw = self.ns.make(dev, B, H4 * W4, [(f'{pre}.pw_bn', C)], tr)
-            if ng:
+            b.d2f = None
+            if ng and (len(b.res) + len(b.dw)) > 1 and b.L <= 256 and os.environ.get('CATB_NO_D2FUSE', '0') != '1':
+                # stage-2 input gradients of all branches as ONE N-concatenated GEMM into the frame of the largest kernel
+                # (rows = the branches' slices of d(mid); the dw first-stage slices in between get zero rows and are
+                # written by the depthwise input gradient afterwards), folded once
+                k2 = max([k for _, _, k in b.res] + [1])
+                b.P2 = (k2 - 1) // 2
+                segs = [(sl, cpad(m), m, P.conv_dgrad_embedded_units(ar.off(f'{pre}.res_ops.{j}.4.weight'), C, m, k, k2))
+                        for (j, m, k), sl in zip(b.res, b.res_sl)]
+                segs += [(sl, cpad(m), m, P.conv_dgrad_embedded_units(ar.off(f'{pre}.dw_ops.{j}.4.weight'), C, m, 1, k2))
+                         for (j, m, k), sl in zip(b.dw, b.dw2_sl)]
+                Hp, Wp = H4 + 2 * b.P2, W4 + 2 * b.P2
+                if b.P2 > 0:
+                    maxLpad = max(maxLpad, Hp * Wp * b.L)
+                b.d2f = Gemm(P.Geometry(B, H4, W4, Cp, 0, Hp, Wp, b.L, 0), P.conv_dgrad_units(0, C, b.L, k2, k2, 0), b.L, dev,
+                             segments=segs)
+                self.bwd_gemms.append(b.d2f)
+                b.d2 = []
+            elif ng:
                 # stage-2 input gradients: one GEMM per branch (padded frame + fold for k > 1)
                 b.d2 = []
                 for (j, m, k), sl in zip(b.res, b.res_sl):
@@ -519,6 +547,7 @@ class GenNet:
                 for (j, m, k), sl in zip(b.dw, b.dw2_sl):
                     un = P.conv_dgrad_units(ar.off(f'{pre}.dw_ops.{j}.4.weight'), C, m, 1, 1, 0)
                     b.d2.append((G(P.Geometry(B, H4, W4, Cp, 0, H4, W4, b.L, sl), un, m, bwd=True), sl, m, 0))
+            if ng:
                 # stage-1 input gradient: ONE GEMM over the concatenated first-stage gradients
                 b.P1 = max([(k - 1) // 2 for _, _, k in b.res] + [0])
                 u1 = P.Units()
@@ -741,6 +770,13 @@ class GenNet:
             b.npw.backward(cur, None, b.tmp, self.ws_dtmp, none)
             on_side(lambda: b.g2.wgrad(b.mid_act.t, self.ws_dtmp.t, ar.g))
             ev_tmp = mark()
+            if b.d2f is not None:
+                if b.P2 > 0:
+                    fr = self._ws(self.ws_frame, H4 + 2 * b.P2, W4 + 2 * b.P2, b.L)
+                    b.d2f.fprop(self.ws_dtmp.t, fr.t)
+                    ops.reflect_fold(fr, dmid_act, b.P2)
+                else:
+                    b.d2f.fprop(self.ws_dtmp.t, dmid_act.t)
             for (g, sl, m, p) in b.d2:
                 if p > 0:
                     fr = self._ws(self.ws_frame, H4 + 2 * p, W4 + 2 * p, cpad(m))

@@ -100,6 +100,28 @@ def conv_dgrad_units(w_off, Cout, Cin, R, S, q, cu0=0, q_s=None) -> Units:
     return u
 
 
+def conv_dgrad_embedded_units(w_off, Cout, Cin, k, Kmax, cu0=0) -> Units:
+    """Input gradient of a k x k conv (reflect padding (k-1)/2, result = gradient w.r.t. its padded frame) expressed on
+    the frame of a Kmax x Kmax conv: same gather side as conv_dgrad_units(., Cout, ., Kmax, Kmax, 0); the small conv's
+    frame sits (Kmax - k) / 2 pixels inside the large one, so its tap (r', s') is the large tap (r' + off, s' + off) and
+    the outer ring carries no weight.  Used to N-concatenate the last-conv input gradients of a residual block (one GEMM
+    producing d(mid) of all six branches in the frame of the largest kernel, folded once)."""
+    assert (Kmax - k) % 2 == 0 and k <= Kmax
+    off = (Kmax - k) // 2
+    u = Units()
+    for r in range(Kmax):
+        for s in range(Kmax):
+            rb, sb = r - off, s - off
+            inside = 0 <= rb < k and 0 <= sb < k
+            for nu in range(cpad(Cout) // 8):
+                u.g.append((-r, -s, cu0 + nu))
+                if inside:
+                    u.w.append((w_off + nu * 8 * Cin * k * k + rb * k + sb, k * k, Cin * k * k, max(0, min(8, Cout - nu * 8))))
+                else:
+                    u.w.append((0, 0, 0, 0))
+    return u
+
+
 def convT_fprop_units(w_off, Cin, Cout, R, S, pad, cu0=0) -> Units:
     """nn.ConvTranspose2d weight [Cin, Cout, R, S]: Y[oh] = sum X[(oh + pad - r)/stride] W[c, n, r]
     (use with sn=1, sd=stride).  GEMM rows = output channels."""
