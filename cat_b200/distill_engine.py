@@ -66,6 +66,9 @@ class DistillStep:
         self.step_A = torch.zeros(1, dtype=torch.int32, device=device)
         self._graphs = None
         self.use_cuda_graph = use_cuda_graph
+        # data parallel: the discriminator's gradient slices are all-reduced layer by layer during its last backward pass
+        self.early_reduce = world_size > 1 and os.environ.get('CATB_EARLY_REDUCE', '1') != '0'
+        self._reducer = parallel.LayerwiseReducer(world_size)
         self.overlap_teacher = os.environ.get('CATB_NO_OVERLAP', '0') != '1'
         self._side = None
 
@@ -154,7 +157,11 @@ class DistillStep:
         D.backward(self.dpred, param_grads=True, input_grad=False)
         D.forward(real)
         ops.gan_loss(D.pred, D.pred_n, 8, hp['gan_mode'], True, True, 0.5, self.losses[1:2], self.dpred)
-        D.backward(self.dpred, param_grads=True, input_grad=False)
+        if self.early_reduce:       # the gradients are final layer by layer in this (second) pass
+            D.backward(self.dpred, param_grads=True, input_grad=False, grads_final_hook=self._reducer.reduce_async)
+            self._reducer.join()
+        else:
+            D.backward(self.dpred, param_grads=True, input_grad=False)
 
     def _adam(self, net, lr, step):
         a = net.arena
@@ -229,6 +236,8 @@ class DistillStep:
             self._part3()
 
     def _allreduce(self, net):
+        if net is self.D and self.early_reduce:
+            return                      # already reduced layer by layer inside the D phase
         parallel.reduce_gradients(net.arena.g, self.world_size)
         if net is self.S and self.A is not None:
             parallel.reduce_gradients(self.A.arena.g, self.world_size)

@@ -969,14 +969,25 @@ class DisNet:
                 cur = L.yraw
         return self.pred
 
-    def backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None):
-        """See _backward; the second stages of all weight gradients run as one launch when the pass is left."""
+    def backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None, grads_final_hook=None):
+        """See _backward; the second stages of all weight gradients run as one launch when the pass is left.
+        grads_final_hook(grad_slice): called right after a layer's parameter gradients are complete (its weight-gradient
+        second stage flushed) with that layer's contiguous slice of the gradient arena -- the data-parallel step starts
+        the slice's all-reduce there (cat_b200/parallel.py: LayerwiseReducer)."""
         if getattr(self, '_unpack', None) is None:
             self._unpack = ops.UnpackQueue(self.dev)
         with self._unpack:
-            return self._backward(dpred, param_grads, input_grad, act_grad_hook)
+            return self._backward(dpred, param_grads, input_grad, act_grad_hook, grads_final_hook)
 
-    def _backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None):
+    def layer_grad_slice(self, li):
+        """Contiguous slice of the gradient arena holding every parameter of layer li (conv weight, bias, norm scale /
+        shift: allocated back to back per layer)."""
+        a = self.arena
+        start = a.off(self.layers[li].wn)
+        end = a.off(self.layers[li + 1].wn) if li + 1 < len(self.layers) else a.size
+        return a.g[start:end]
+
+    def _backward(self, dpred: Act, param_grads, input_grad, act_grad_hook=None, grads_final_hook=None):
         """dpred: bf16 [B,oh,ow,8] gradient of the loss w.r.t. the prediction (channel 0).
         act_grad_hook(li, d): called with the gradient w.r.t. the activation output of layer li before it is
         back-propagated (the feature-matching loss of the SPADE path adds its term there)."""
@@ -1000,6 +1011,9 @@ class DisNet:
                 L.gw.wgrad(x_in.t, dy.t, ar.g)
                 if L.has_bias:
                     ops.channel_sum(dy, L.dbias)
+                if grads_final_hook is not None:
+                    ops.flush_unpack()
+                    grads_final_hook(self.layer_grad_slice(li))
             if li > 0:
                 tgt = self.layers[li - 1].da
                 for g in L.gb:
