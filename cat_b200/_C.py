@@ -66,6 +66,7 @@ _PROTOS = {
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],
+    'catb_igemm_halo_fprop_persist': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _I, _I, _P],
     'catb_igemm_halo_wgrad': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad_ws_shape': [_DP, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'catb_igemm_wgrad_ws': [_DP, _P, _P, _P, _P, _P],
@@ -125,6 +126,7 @@ _SPECIAL = {
     'catb_packed_weight_bytes': ([_I, _I, _I], C.c_size_t),
     'catb_igemm_halo_fits': ([_I, _I, _I, _I, _I, _I], C.c_int),
     'catb_igemm_halo_wgrad_fits': ([_I, _I], C.c_int),
+    'catb_igemm_halo_persist_fits': ([_I] * 10, C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))
 

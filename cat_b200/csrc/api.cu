@@ -28,6 +28,7 @@ int init_igemm_attributes();
 int init_halo_attributes();
 int init_simt_attributes();
 int init_halo_wgrad_attributes();
+int init_halo_persist_attributes();
 
 }  // namespace catb
 
@@ -57,5 +58,6 @@ extern "C" int catb_init(int device) {
   if (int e = catb::init_igemm_attributes()) return e;
   if (int e = catb::init_halo_attributes()) return e;
   if (int e = catb::init_simt_attributes()) return e;
+  if (int e = catb::init_halo_persist_attributes()) return e;
   return catb::init_halo_wgrad_attributes();
 }

@@ -46,11 +46,15 @@ __device__ __forceinline__ void dw_prepare(DwGroups* grp, float* w_s, int C, con
     grp->n = n;
   }
   if (w_s != nullptr) {
-    for (int i = threadIdx.x; i < U * kDwMaxTaps * 8; i += blockDim.x) {
-      const int q = i & 7, tap = (i >> 3) % kDwMaxTaps, u = (i >> 3) / kDwMaxTaps;
-      const int c = u * 8 + q;
+    // one thread per channel: its kernel size and arena offset are loaded ONCE, then the (up to 49) taps are independent
+    // loads (the element-wise form -- three dependent global loads for each of the C * 49 table entries -- made this
+    // prologue the whole kernel: ~40 us per launch whatever the tensor size, profiles/r02_bench_v2_1gpu.json hbm_kernels)
+    for (int c = threadIdx.x; c < U * 8; c += blockDim.x) {
       const int k = ksize[c], wo = w_off[c];
-      w_s[i] = (wo >= 0 && tap < k * k) ? arena[wo + tap] : 0.f;
+      const int taps = wo >= 0 ? k * k : 0;
+      float* dst = w_s + (static_cast<size_t>(c >> 3) * kDwMaxTaps) * 8 + (c & 7);
+#pragma unroll 7
+      for (int tap = 0; tap < kDwMaxTaps; ++tap) dst[tap * 8] = tap < taps ? __ldg(arena + wo + tap) : 0.f;
     }
   }
   __syncthreads();
@@ -306,7 +310,7 @@ extern "C" int catb_dwconv_fwd(const void* x, int ldx, int x_coff, void* y, int 
   const size_t smem = static_cast<size_t>(C) * kDwMaxTaps * sizeof(float);
   CATB_REQUIRE(smem <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
   const long long work = static_cast<long long>(N) * H * ((W + 3) / 4) * (C / 8);
-  dwconv_grouped_kernel<0><<<dw_grid(work, 148 * 8), 256, smem, static_cast<cudaStream_t>(s)>>>(
+  dwconv_grouped_kernel<0><<<dw_grid(work, 148 * 4), 256, smem, static_cast<cudaStream_t>(s)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<__nv_bfloat16*>(y), ldy, y_coff, N, H, W, C, ksize, w_off,
       arena, pad_mode == CATB_PAD_ZERO);
   return check_launch("dwconv_fwd");
@@ -320,7 +324,7 @@ extern "C" int catb_dwconv_bwd_data(const void* dy, int ldy, int y_coff, void* d
   const size_t smem = static_cast<size_t>(C) * kDwMaxTaps * sizeof(float);
   CATB_REQUIRE(smem <= 200 * 1024, "too many depthwise channels (%d) for the shared-memory filter stage", C);
   const long long work = static_cast<long long>(N) * H * W * (C / 8);
-  dwconv_grouped_kernel<1><<<dw_grid(work, 148 * 8), 256, smem, static_cast<cudaStream_t>(s)>>>(
+  dwconv_grouped_kernel<1><<<dw_grid(work, 148 * 4), 256, smem, static_cast<cudaStream_t>(s)>>>(
       static_cast<const __nv_bfloat16*>(dy), ldy, y_coff, static_cast<__nv_bfloat16*>(dx), ldx, x_coff, N, H, W, C, ksize,
       w_off, arena, pad_mode == CATB_PAD_ZERO);
   return check_launch("dwconv_bwd_data");

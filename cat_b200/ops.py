@@ -80,6 +80,8 @@ def units_to_device(units: Units, device):
 
 USE_HALO = os.environ.get('CATB_NO_HALO', '0') != '1'   # v2 (halo) forward kernel unless disabled
 AUTOTUNE = os.environ.get('CATB_NO_AUTOTUNE', '0') != '1'  # pick v1 / v2 per GEMM by timing the first call
+USE_PERSIST = os.environ.get('CATB_NO_PERSIST', '0') != '1'   # v3 (persistent halo kernel) variants offered to the autotune
+USE_TMA = os.environ.get('CATB_NO_TMA', '0') != '1'           # v3 stages zero-padded halos with cp.async.bulk.tensor
 
 
 _SCRATCH = {}
@@ -164,11 +166,13 @@ class Gemm:
     kernel.  Both read the same packed weights; wgrad always uses the original unit order."""
 
     def __init__(self, geo: Geometry, units: Units, n_rows: int, device, need_pack=True, halo=None, force_tile=None,
-                 segments=None):
+                 segments=None, force_mode=None):
         """force_tile=(TW, m_sub) pins the halo tiling (tests); by default the widest strip / largest
         sub-tile count that fits in shared memory and still fills the GPU is chosen.
         segments=[(row0, span, nreal, Units)] describes an N-concatenation: every segment shares the gather
-        side of `units` and supplies its own weight side for image rows [row0, row0+span)."""
+        side of `units` and supplies its own weight side for image rows [row0, row0+span).
+        force_mode pins the forward kernel of the halo tilings (tests): 0 = v2 (one tile per CTA), 1 = v3 persistent with
+        cp.async producers, 2 = v3 persistent with TMA-staged tiles; by default every applicable one is a candidate."""
         assert len(units) > 0 and n_rows > 0
         self.segments = None
         self.seg_raw = segments      # also drives the per-segment second stage of the weight gradient
@@ -185,7 +189,7 @@ class Gemm:
         if need_pack:
             lib = _C.load()
             plan = make_halo_plan(geo, units) if (USE_HALO if halo is None else halo) else None
-            self.tilings = []   # [(TW, m_sub, HaloDesc, steps tensor)]: candidates, the autotune keeps one
+            self.tilings = []   # [(TW, m_sub, HaloDesc, steps tensor, mode)]: candidates, the autotune keeps one
             if plan is not None:
                 if force_tile is not None:
                     cands = [force_tile]
@@ -196,9 +200,25 @@ class Gemm:
                 # short weight tiles (thin GEMMs): a second variant with a small weight ring, so that 2-4 CTAs share
                 # an SM and the fill / MMA / epilogue phases of neighbouring tiles overlap
                 budgets = (0, 16 * 1024) if (force_tile is None and self.n_tile <= 128) else (0,)
+                # v3 stages the halo with TMA where out-of-bounds = zero is the padding rule (or no tap leaves the image)
+                tma_ok = USE_TMA and (geo.pad_mode != _C.PAD_REFLECT or (plan.Ymax == 0 and plan.Xmax == 0 and
+                                                                     all(pl[2] == 0 and pl[3] == 0 for pl in plan.planes)))
+                self.c_visible = 8 * max(cu0 + nu for (cu0, nu, _, _) in plan.chunks)
                 for tw, ms in cands:
                     plan.TW, plan.m_sub = tw, ms
-                    if not lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms, len(plan.steps), len(plan.chunks)):
+                    modes = []
+                    if lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms, len(plan.steps), len(plan.chunks)):
+                        modes.append(0)
+                    if USE_PERSIST or force_mode:
+                        m3s = ((2, 1) if tma_ok else (1,)) if not force_mode else ((force_mode,) if (force_mode == 1 or tma_ok) else ())
+                        for m3 in m3s:
+                            if lib.catb_igemm_halo_persist_fits(len(plan.planes), plan.Lh, plan.Wf, plan.mul, self.n_tile, ms,
+                                                                len(plan.steps), len(plan.chunks), 0, int(m3 == 2)):
+                                modes.append(m3)
+                                break
+                    if force_mode is not None:
+                        modes = [m for m in modes if m == force_mode]
+                    if not modes:
                         continue
                     if force_tile is None and tw not in [t[0] for t in self.tilings]:
                         n_strip_widths += 1
@@ -206,14 +226,15 @@ class Gemm:
                             break
                     st = np.array([[pl * plan.Lh + dy * plan.Wf + dx, ci] for (ci, pl, dy, dx) in plan.steps], dtype=np.int32)
                     st = torch.from_numpy(st).to(device)
-                    for budget in budgets:
-                        hd = _C.HaloDesc()
-                        hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
-                        for i, (pa, pb, y0, x0) in enumerate(plan.planes):
-                            hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
-                        hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
-                        hd.Ymax, hd.Xmax, hd.m_sub, hd.b_budget = plan.Ymax, plan.Xmax, plan.m_sub, budget
-                        self.tilings.append((tw, ms, hd, st))
+                    for mode in modes:
+                        for budget in budgets:
+                            hd = _C.HaloDesc()
+                            hd.n_steps, hd.n_chunks, hd.n_planes = len(plan.steps), len(plan.chunks), len(plan.planes)
+                            for i, (pa, pb, y0, x0) in enumerate(plan.planes):
+                                hd.plane_pa[i], hd.plane_pb[i], hd.plane_y0[i], hd.plane_x0[i] = pa, pb, y0, x0
+                            hd.mul, hd.TW, hd.n_strips, hd.Wf, hd.Lh = plan.mul, plan.TW, plan.n_strips, plan.Wf, plan.Lh
+                            hd.Ymax, hd.Xmax, hd.m_sub, hd.b_budget = plan.Ymax, plan.Xmax, plan.m_sub, budget
+                            self.tilings.append((tw, ms, hd, st, mode))
                 if not self.tilings:
                     plan = None
             if plan is not None:
@@ -246,9 +267,9 @@ class Gemm:
                     self.segments.append((row0, span, nreal, wt1, wt2))
 
     def _use_tiling(self, t):
-        tw, ms, hd, steps = t
+        tw, ms, hd, steps, mode = t
         self.halo.TW, self.halo.m_sub = tw, ms
-        self.hdesc, self.h_steps = hd, steps
+        self.hdesc, self.h_steps, self.h_mode = hd, steps, mode
 
     def desc(self, act=0, accumulate=False, y_is_f32=False, geo=None, n_units=None):
         g = geo or self.geo
@@ -314,6 +335,10 @@ class Gemm:
             _C.call('catb_igemm_fprop', C.byref(d1), _p(self.gt), _p(x), _p(self.packed_v1), _p(bias), _p(y), _stream())
 
         def v2():
+            if self.h_mode:   # v3: persistent pipeline, halo staged by TMA (mode 2) or cp.async producers (mode 1)
+                _C.call('catb_igemm_halo_fprop_persist', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
+                        _p(x), _p(self.packed), _p(bias), _p(y), int(self.h_mode == 2), self.c_visible, _stream())
+                return
             _C.call('catb_igemm_halo_fprop', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
                     _p(x), _p(self.packed), _p(bias), _p(y), _stream())
 

@@ -138,6 +138,21 @@ int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, con
                           const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
                           const float* bias /*nullable*/, void* y, catb_stream_t s);
 
+/* v3 forward kernel: the same halo GEMM as a persistent, warp-specialised pipeline (cat_b200/csrc/igemm_halo_persist.cu):
+ * every CTA walks output tiles with the halo ring, the weight ring and TWO tensor-memory accumulator stages running
+ * across tile boundaries, so the epilogue of one tile overlaps the fill and the MMAs of the next.  use_tma = 1 stages
+ * the activation halo with cp.async.bulk.tensor from a 4-D tiled tensor map over the NHWC input (zero padding = the
+ * map's out-of-bounds fill, parity planes of stride-2 convs = traversal stride 2); it needs zero padding (or a GEMM
+ * without border taps) and c_visible = the channel count of the GEMM's input slice (channels past it read as zero).
+ * use_tma = 0 keeps the cp.async producers (reflection padding).  Same tables and packed weights as
+ * catb_igemm_halo_fprop; replaces the same ATen conv / conv-transpose / conv-backward-input call sites
+ * (models/modules/inception_modules.py:22-44, models/modules/discriminators.py:37-75 of the reference). */
+int catb_igemm_halo_persist_fits(int n_planes, int Lh, int Wf, int mul, int n_tile, int m_sub, int n_steps, int n_chunks,
+                                 int b_budget, int use_tma);
+int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
+                                  const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
+                                  const float* bias /*nullable*/, void* y, int use_tma, int c_visible, catb_stream_t s);
+
 /* v2 weight gradient on the same halo plan (m_sub = 1): a CTA handles one 128-channel tile of the lattice
  * tensor, one channel chunk of X and one group of <= 8 consecutive steps (taps) of that chunk, each tap
  * accumulating in its own 64 TMEM columns (cat_b200/csrc/igemm_halo_wgrad.cu).  `wunits` holds 8 weight

@@ -1,0 +1,155 @@
+"""GPU parity of the v3 forward kernel (persistent halo pipeline, cat_b200/csrc/igemm_halo_persist.cu): both halo
+producers -- cp.async.bulk.tensor tiles from a 4-D tensor map (mode 2) and the cp.async threads (mode 1) -- against torch
+(fp64 on bf16-rounded operands) and against the v1 gather-per-tap kernel, on shapes with several tiles per CTA (the
+rings and the two accumulator stages wrap), several N tiles, parity planes, channel slices and partial chunks."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cat_b200 import igemm_plan as P
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _init():
+    from cat_b200 import ops
+    ops.require_cuda()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def to_dev_nhwc(x, ld=None, coff=0, fill=0.0):
+    N, C, H, W = x.shape
+    ld = ld or P.cpad(C)
+    out = torch.full((N, H, W, ld), fill, dtype=torch.bfloat16)
+    out[..., coff:coff + P.cpad(C)] = 0
+    out[..., coff:coff + C] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.to(DEV)
+
+
+def from_dev_nhwc(t, C, coff=0):
+    return t[..., coff:coff + C].permute(0, 3, 1, 2).to(torch.float64).cpu()
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+CASES = [
+    # k, stride, pad, mode, Cin, Cout, N, H, W
+    (3, 1, 1, 'zero', 5, 7, 2, 10, 12),
+    (5, 1, 2, 'reflect', 72, 42, 2, 16, 16),     # two channel chunks, second one partial
+    (7, 1, 3, 'reflect', 64, 3, 1, 24, 40),      # generator head
+    (1, 1, 0, 'reflect', 72, 40, 2, 8, 8),       # 1x1: no border taps, TMA although the padding rule is reflection
+    (1, 1, 0, 'zero', 24, 40, 2, 8, 8),
+    (3, 2, 1, 'zero', 17, 31, 2, 16, 16),        # 4 parity planes (traversal stride 2)
+    (4, 2, 1, 'zero', 64, 128, 2, 16, 16),
+    (4, 1, 1, 'zero', 128, 1, 2, 9, 9),
+    (4, 1, 1, 'zero', 128, 300, 1, 12, 12),      # two N tiles
+    (3, 1, 1, 'zero', 64, 64, 4, 96, 96),        # 288+ tiles: every CTA walks several (rings / accumulator stages wrap)
+    (1, 1, 0, 'zero', 128, 24, 8, 128, 128),     # short K, 1024 tiles
+    (4, 2, 1, 'zero', 24, 64, 4, 128, 128),      # stride 2 with many tiles
+    (5, 1, 2, 'reflect', 40, 24, 4, 64, 64),     # reflection: cp.async producers in the persistent pipeline
+]
+
+
+def _tile_forms(OW, Cout):
+    forms = [('auto', None), ('msub2', (OW, 2)), ('strips', (max(4, OW // 3), 1))]
+    return forms
+
+
+@pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,N,H,W', CASES)
+@pytest.mark.parametrize('pmode', [1, 2])
+@pytest.mark.parametrize('tile', ['auto', 'msub2', 'strips'])
+def test_persistent_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, pmode, tile):
+    from cat_b200 import ops
+    torch.manual_seed(k * 100 + Cin)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, k, k) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout)
+    xb, wb = bf(x).requires_grad_(True), bf(w)
+    xin = F.pad(xb, (pad,) * 4, mode='reflect') if mode == 'reflect' else xb
+    y_ref = F.conv2d(xin, wb, b.double(), stride=stride, padding=0 if mode == 'reflect' else pad)
+    OH, OW = y_ref.shape[2:]
+    arena = torch.cat([torch.zeros(5), w.flatten()]).to(DEV)
+    pm = P.PAD_REFLECT if mode == 'reflect' else P.PAD_ZERO
+    units = P.conv_fprop_units(5, Cout, Cin, k, k, pad)
+    ldy = P.cpad(Cout) + 8
+    # the input is a channel slice [16, 16 + Cin) of a wider buffer whose other channels hold a large value: nothing of
+    # it may leak into the result (tensor-map base / visible channel count, zero fill of partial chunks)
+    ldx, xc = P.cpad(Cin) + 24, 16
+    geo = P.Geometry(N, H, W, ldx, xc, OH, OW, ldy, 8, sn=stride, pad_mode=pm)
+    force = dict(_tile_forms(OW, Cout))[tile]
+    if force is not None and force[1] * 2 * P.choose_n_tile(Cout) > 512:
+        pytest.skip('two accumulator stages of this tiling exceed 512 TMEM columns')
+    gm = ops.Gemm(geo, units, Cout, DEV, force_tile=force, force_mode=pmode)
+    if gm.halo is None or not gm.tilings:
+        pytest.skip('mode %d does not apply to this shape (reflection padding with border taps / does not fit)' % pmode)
+    assert all(t[4] == pmode for t in gm.tilings)
+    gm.pack(arena)
+    gm.choice = 'v2'
+    xd, bias = to_dev_nhwc(x, ldx, xc, fill=1000.0), b.to(DEV)
+    ref = F.leaky_relu(y_ref.detach(), 0.2)
+    y1 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
+    gm.fprop(xd, y1, bias=bias, act=ops.ACT['leaky'], force_v1=True)
+    for cand in gm.tilings:
+        gm._use_tiling(cand)
+        y3 = torch.full((N, OH, OW, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
+        gm.fprop(xd, y3, bias=bias, act=ops.ACT['leaky'])
+        torch.cuda.synchronize()
+        assert rel_err(from_dev_nhwc(y3, Cout, 8), ref) < 6e-3, 'v3 persistent kernel vs torch'
+        assert float((y1.float() - y3.float()).abs().max()) <= 2 ** -7 * float(ref.abs().max()), 'v3 vs v1'
+        assert float(y3[..., :8].float().min()) == 7.0 and float(y3[..., :8].float().max()) == 7.0
+        # run it again into the same buffer: a persistent kernel must leave no state behind
+        gm.fprop(xd, y3, bias=bias, act=ops.ACT['leaky'])
+        torch.cuda.synchronize()
+        assert rel_err(from_dev_nhwc(y3, Cout, 8), ref) < 6e-3
+    # fp32 output with accumulate (the epilogue's second path)
+    yf = torch.ones(N, OH, OW, ldy, dtype=torch.float32, device=DEV)
+    gm.fprop(xd, yf, bias=bias, accumulate=True, y_is_f32=True)
+    torch.cuda.synchronize()
+    assert rel_err(yf[..., 8:8 + Cout].permute(0, 3, 1, 2).double().cpu(), y_ref.detach() + 1.0) < 2e-5
+    # input gradient (zero-padded convs: direct / 4 sub-pixel phases)
+    if mode == 'zero' and N * H * W <= 40000:
+        dy = torch.randn(N, Cout, OH, OW)
+        y_ref.backward(bf(dy))
+        dyd = to_dev_nhwc(dy)
+        du = P.conv_dgrad_units(5, Cout, Cin, k, k, pad)
+        dx = torch.zeros(N, H, W, P.cpad(Cin), dtype=torch.bfloat16, device=DEV)
+        if stride == 1:
+            gd = ops.Gemm(P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0), du, Cin, DEV, force_mode=pmode)
+            assert gd.halo is not None
+            gd.choice = 'v2'
+            gd.pack(arena)
+            gd.fprop(dyd, dx)
+        else:
+            for a in range(2):
+                for c in range(2):
+                    ph = du.phase(a, c)
+                    if len(ph) == 0:
+                        continue
+                    g = P.Geometry(N, OH, OW, P.cpad(Cout), 0, H, W, P.cpad(Cin), 0, sn=1, sd=2, o_step=2, o_ph=a, o_pw=c)
+                    gd = ops.Gemm(g, ph, Cin, DEV, force_mode=pmode)
+                    assert gd.halo is not None
+                    gd.choice = 'v2'
+                    gd.pack(arena)
+                    gd.fprop(dyd, dx)
+        torch.cuda.synchronize()
+        assert rel_err(from_dev_nhwc(dx, Cin), xb.grad) < 6e-3, 'v3 dgrad'
+
+
+def test_autotune_offers_the_persistent_variants():
+    """Without force_mode every Gemm of a zero-padded conv lists v2, and v3 with TMA; a reflection-padded 3x3 lists v3 with
+    the cp.async producers."""
+    from cat_b200 import ops
+    units = P.conv_fprop_units(0, 64, 64, 3, 3, 1)
+    g0 = ops.Gemm(P.Geometry(2, 32, 32, 64, 0, 32, 32, 64, 0, pad_mode=P.PAD_ZERO), units, 64, DEV)
+    g1 = ops.Gemm(P.Geometry(2, 32, 32, 64, 0, 32, 32, 64, 0, pad_mode=P.PAD_REFLECT), units, 64, DEV)
+    assert {t[4] for t in g0.tilings} == {0, 2}
+    assert {t[4] for t in g1.tilings} == {0, 1}

@@ -65,10 +65,10 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
     else:
         fn = lambda: g.wgrad(x, y, grad)  # noqa: E731
     if tiling is not None and kind != 'wgrad':      # pin one v2 variant (for ncu): 'TW,m_sub,budgetK'
-        tw, ms_, bk = (int(v) for v in tiling.split(','))
+        tw, ms_, bk, PIN_MODE = ([int(v) for v in tiling.split(',')] + [0])[:4]   # mode: 0 v2, 1 v3 cp.async, 2 v3 TMA
         ops.AUTOTUNE = False
-        pick = [t for t in g.tilings if (t[0], t[1], t[2].b_budget // 1024) == (tw, ms_, bk)]
-        assert pick, [(t[0], t[1], t[2].b_budget // 1024) for t in g.tilings]
+        pick = [t for t in g.tilings if (t[0], t[1], t[2].b_budget // 1024) == (tw, ms_, bk) and t[4] == PIN_MODE]
+        assert pick, [(t[0], t[1], t[2].b_budget // 1024, t[4]) for t in g.tilings]
         g._use_tiling(pick[0])
 
     def timed(f):
@@ -123,7 +123,7 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
         rows = [('v1', timed(lambda: g.fprop(x, y, force_v1=True)))]
         for t in (g.tilings if g.halo is not None else []):
             g._use_tiling(t)
-            rows.append((f'v2 TW{t[0]} m{t[1]} b{t[2].b_budget // 1024}K', timed(lambda: g.fprop(x, y))))
+            rows.append((f'{("v2", "v3-cpasync", "v3-tma")[t[4]]} TW{t[0]} m{t[1]} b{t[2].b_budget // 1024}K', timed(lambda: g.fprop(x, y))))
         best = min(r[1] for r in rows)
         print(f'{name:6s} M={N * OH * OW} N={Cout} K={Cin * k * k} n_tile {g.n_tile}  HBM floor {hbm_us:6.1f} us  best {best * 1e3:7.1f} us '
               f'({flops / best / 1e9:6.1f} TF/s, {hbm_us / (best * 1e3) * 100:4.1f}% of the HBM floor rate)')
@@ -140,7 +140,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('cases', nargs='*', default=list(CASES))
     ap.add_argument('--iters', type=int, default=20)
-    ap.add_argument('--tiling', default=None, help="pin a v2 variant: 'TW,m_sub,budgetK'")
+    ap.add_argument('--tiling', default=None, help="pin a halo variant: 'TW,m_sub,budgetK[,mode]' (mode 0 v2, 1 v3 persistent + cp.async, 2 v3 persistent + TMA)")
     ap.add_argument('--timeline', action='store_true', help='per-CTA phase timestamps of the halo kernel')
     ap.add_argument('--dbg-mode', type=int, default=0, help='catb_debug_mode bits (epilogue experiments)')
     ap.add_argument('--dbg-sweep', default=None, help='comma separated catb_debug_mode values, run one after the other')
