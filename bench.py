@@ -354,7 +354,7 @@ def tag_gemms(root, owner, seen=None, depth=0):
 
 # HBM-bound CUDA-core kernels: wrapper name -> algorithmic bytes per element of the activation they stream (DESIGN.md 3.2:
 # bf16 reads + writes that cannot be avoided), evaluated on the first Act argument
-HBM_KERNELS = {'norm_stats': 2, 'norm_apply': 4, 'norm_bwd_reduce': 6, 'norm_bwd_apply': 8, 'dwconv_fwd': 4,
+HBM_KERNELS = {'norm_stats': 2, 'norm_apply': 4, 'norm_apply_fused': 4, 'norm_bwd_reduce': 6, 'norm_bwd_apply': 8, 'dwconv_fwd': 4,
                'dwconv_bwd_data': 4, 'dwconv_bwd_weight': 4, 'gram': 2, 'ka_bwd': 6, 'reflect_fold': 4, 'act_bwd': 6}
 
 
@@ -380,9 +380,10 @@ class GemmProfiler:
             def inner(g, *a, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                fn(g, *a, **k)
+                r = fn(g, *a, **k)
                 e1.record()
                 prof.records.append((kind, g, flops(g), e0, e1))
+                return r
             return inner
 
         def wrap_hbm(fn, name, bpe):
@@ -407,9 +408,15 @@ class GemmProfiler:
     def summary(self):
         torch.cuda.synchronize()
         agg, per, net = {}, {}, {}
+        def variant(kind, g):
+            if kind != 'fprop':
+                return 'halo' if getattr(g, 'w_halo', None) is not None else 'v1'
+            if g.halo is None or g.choice == 'v1':
+                return 'v1'
+            return f"{('v2', 'v3-cpasync', 'v3-tma')[g.h_mode]} TW{g.halo.TW} m{g.halo.m_sub} b{g.hdesc.b_budget // 1024}K"
         for kind, g, fl, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            for table, key in ((agg, kind), (per, (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs)),
+            for table, key in ((agg, kind), (per, (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs, variant(kind, g))),
                                (net, (getattr(g, '_owner', 'other'), kind))):
                 a = table.setdefault(key, [0.0, 0.0, 0])
                 a[0] += fl
@@ -745,12 +752,12 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, 'profiles', f'traffic_{args.workload}.json')))
-            ks = [v for k, v in tj['kernels'].items() if k in ('igemm_halo_fprop_kernel', 'igemm_fprop_kernel')]
+            ks = [v for k, v in tj['kernels'].items() if k in ('igemm_halo_fprop_kernel', 'igemm_halo_persist_kernel', 'igemm_fprop_kernel')]
             traffic = sum(v['dram_read'] + v['dram_write'] for v in ks) / max(1, sum(v['launches'] for v in ks))
             traffic_src = f'profiles/traffic_{args.workload}.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)'
         except (OSError, KeyError, ValueError):
             pass
-        roof = {'bound': 'tensor', 'kernel': 'igemm_halo_fprop_kernel + igemm_fprop_kernel (tcgen05 implicit-GEMM conv/dgrad)',
+        roof = {'bound': 'tensor', 'kernel': 'igemm_halo_persist_kernel + igemm_halo_fprop_kernel + igemm_fprop_kernel (tcgen05 implicit-GEMM conv/dgrad)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                 'traffic_source': traffic_src, 'algorithmic_flop_per_launch': fl / n,
                 'peak_source': peak_src, 'launches': n, 'kernel_ms_per_step': tms,
@@ -777,9 +784,9 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
                 print(f'network {k:18s} {v["launches"]:4d} launches {v["kernel_ms_per_step"]:8.3f} ms {v["achieved"]:8.1f} TF/s', file=sys.stderr)
             for k, v in roof['hbm_kernels']['kernels'].items():
                 print(f'hbm     {k:18s} {v["launches"]:4d} launches {v["kernel_ms_per_step"]:8.3f} ms {v["achieved"]:8.1f} GB/s', file=sys.stderr)
-            rows = sorted(per.items(), key=lambda kv: -kv[1][1])[:40]
-            for (kind, n_rows, n_units, M), (f, t, c) in rows:
-                print(f'{kind:6s} rows {n_rows:5d} units {n_units:5d} M {M:8d} x{c:3d}  {t:8.3f} ms  {f / (t * 1e-3) / 1e12:8.1f} TF/s',
+            rows = sorted(per.items(), key=lambda kv: -kv[1][1])[:60]
+            for (kind, n_rows, n_units, M, var), (f, t, c) in rows:
+                print(f'{kind:6s} rows {n_rows:5d} units {n_units:5d} M {M:8d} x{c:3d}  {t:8.3f} ms  {f / (t * 1e-3) / 1e12:8.1f} TF/s  {var}',
                       file=sys.stderr)
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only): a bounded sample (~30 s) of the same workload

@@ -38,6 +38,11 @@ class HaloDesc(C.Structure):
                 ('Ymax', C.c_int32), ('Xmax', C.c_int32), ('m_sub', C.c_int32), ('b_budget', C.c_int32)]
 
 
+class EpilogueStats(C.Structure):
+    _fields_ = [('sums', C.c_void_p), ('C', C.c_int32), ('coff', C.c_int32), ('per_sample', C.c_int32),
+                ('reserved', C.c_int32)]
+
+
 class PackJob(C.Structure):
     _fields_ = [('wunits', C.c_void_p), ('packed', C.c_void_p), ('n_tile', C.c_int32), ('n_units', C.c_int32),
                 ('n_chunks', C.c_int32), ('row0', C.c_int32), ('span', C.c_int32), ('nreal', C.c_int32)]
@@ -65,8 +70,8 @@ _PROTOS = {
     'catb_pack_weights_batch': [_P, _I, _I, _P, _P],
     'catb_igemm_fprop': [_DP, _P, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad': [_DP, _P, _P, _P, _P, _P, _P],
-    'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P],
-    'catb_igemm_halo_fprop_persist': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    'catb_igemm_halo_fprop': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    'catb_igemm_halo_fprop_persist': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     'catb_igemm_halo_wgrad': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad_ws_shape': [_DP, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'catb_igemm_wgrad_ws': [_DP, _P, _P, _P, _P, _P],
@@ -82,6 +87,8 @@ _PROTOS = {
     'catb_norm_stats': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     'catb_norm_finalize': [_P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     'catb_norm_apply': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    'catb_norm_apply_fused': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P,
+                              _I, _P],
     'catb_norm_bwd_reduce': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     'catb_norm_bwd_apply': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I,
                             _P, _P, _P],
@@ -119,6 +126,8 @@ _PROTOS = {
     'catb_expand_x': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'catb_shift_sum': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     'catb_shift_expand': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'catb_tap_sum': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    'catb_tap_expand': [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 _SPECIAL = {
     'catb_version': ([], C.c_char_p),

@@ -291,7 +291,10 @@ __device__ __forceinline__ void epilogue_rows_bf16(uint32_t trow, int n_tile, in
                                                    const float* __restrict__ bias, int act, bool rvalid, uint32_t ypix,
                                                    __nv_bfloat16* __restrict__ y, int ldy, int y_coff, uint8_t* stg,
                                                    uint32_t* pixtab, int lane, int dbg_mode = 0,
-                                                   long long* dbg_cyc = nullptr) {
+                                                   long long* dbg_cyc = nullptr, float* stat_s = nullptr) {
+  // stat_s (optional, shared by the CTA's epilogue warps): [2][n_tile] floats, column sums and sums of squares of the
+  // STORED (bf16-rounded, post-activation) values of the rows that are written -- the statistics pass of the
+  // normalisation layer behind this conv, taken from the staging tile while it is in shared memory anyway.
   // dbg_cyc (development aid, one thread): cycles spent in [0] waiting for TMEM loads, [1] bias / activation / pack /
   // staging stores, [2] the coalesced copy-out.
   // pixtab: 32 words private to the warp: the output pixel of every row (0xffffffff: row not stored), so that the
@@ -344,6 +347,28 @@ __device__ __forceinline__ void epilogue_rows_bf16(uint32_t trow, int n_tile, in
       }
     }
     __syncwarp();
+    if (stat_s != nullptr && 2 * lane < ncol) {
+      // lane <-> the two channels in word `lane` of every staged row (a row's 32 words sit in 32 different banks)
+      const uint32_t word_s = stg_s + ((lane & 3) << 2);
+      const int chunk = lane >> 2;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+      for (int row = 0; row < 32; ++row) {
+        const uint32_t pix = lds32(pix_s + row * 4);
+        const uint32_t v = lds32(word_s + row * 128 + ((chunk ^ (row & 7)) << 4));
+        if (pix != 0xffffffffu) {
+          const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+          s0 += a;
+          q0 += a * a;
+          s1 += b;
+          q1 += b * b;
+        }
+      }
+      atomicAdd(stat_s + c64 + 2 * lane, s0);
+      atomicAdd(stat_s + c64 + 2 * lane + 1, s1);
+      atomicAdd(stat_s + n_tile + c64 + 2 * lane, q0);
+      atomicAdd(stat_s + n_tile + c64 + 2 * lane + 1, q1);
+    }
     const int nch = ncol >> 3;                                  // 16-byte chunks per row: 2, 4, 6 or 8
     const uint32_t inv = (65536u + nch - 1) / nch;              // idx / nch == (idx * inv) >> 16 for idx < 256
     const int colb = col_base + c64;
@@ -359,6 +384,24 @@ __device__ __forceinline__ void epilogue_rows_bf16(uint32_t trow, int n_tile, in
     if (dbg_cyc != nullptr) dbg_cyc[2] += clock64() - tc0;
   }
   tmem_wait_ld();
+}
+
+// Named barrier among `count` threads (the epilogue warps of a warp-specialised kernel).
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Flush a CTA's [2][n_tile] statistics tile (see epilogue_rows_bf16) into the layer's sums [G][2][C] and clear it.
+// Called by `nthreads` threads (tid = 0 .. nthreads-1) after a barrier among them.
+__device__ __forceinline__ void flush_epilogue_stats(float* stat_s, int n_tile, int col_base, int n_store,
+                                                     const catb_epilogue_stats& st, int n_img, int tid, int nthreads) {
+  float* dst = st.sums + static_cast<size_t>(st.per_sample ? n_img : 0) * 2 * st.C + st.coff;
+  for (int i = tid; i < 2 * n_tile; i += nthreads) {
+    const int which = i >= n_tile ? 1 : 0, c = i - which * n_tile;
+    const float v = stat_s[i];
+    stat_s[i] = 0.f;
+    if (col_base + c < n_store && v != 0.f) atomicAdd(dst + which * st.C + col_base + c, v);
+  }
 }
 
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).

@@ -19,6 +19,7 @@
 // chip); sharing the tile between sub-tiles divides that traffic.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -26,6 +27,7 @@ namespace catb {
 
 constexpr int kHThreads = 192;
 constexpr int kHHeader = 1024;
+constexpr int kHStatBytes = 2048;   // fused statistics tile [2][n_tile <= 256] floats, between the tables and the halo
 constexpr int kHMaxBStages = 24;  // small weight tiles need many copies in flight (a 6 KB tile per ~1.5 us round trip otherwise)
 
 struct HaloParams {
@@ -40,6 +42,7 @@ struct HaloParams {
   int tiles_per_image, a_bufs, b_stages, tmem_cols, n_store, halo_bytes, tab_bytes, dbg_mode;
   uint32_t idesc;
   unsigned long long* dbg;  // optional per-CTA phase timestamps (catb_debug_timeline), null in production
+  catb_epilogue_stats st;   // st.sums == nullptr: no fused statistics
 };
 
 static unsigned long long* g_halo_dbg = nullptr;
@@ -55,7 +58,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.dbg != nullptr && blockIdx.y == 0 && blockIdx.x < kDbgCtas) p.dbg[blockIdx.x * kDbgSlots + (slot)] = gtimer(); \
   } while (0)
 
-__global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const HaloParams p) {
+__global__ void __maxnreg__(112) igemm_halo_fprop_kernel(const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);  // [2]
@@ -67,7 +70,8 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
   // step / chunk tables in shared memory: the MMA thread must not wait for global loads between instructions
   uint32_t* s_aoff = reinterpret_cast<uint32_t*>(smem + kHHeader);                        // [n_steps] a_row * 8
   int4* s_chunks = reinterpret_cast<int4*>(smem + kHHeader + ((p.h.n_steps * 4 + 15) & ~15));  // [n_chunks]
-  uint8_t* a_base = smem + kHHeader + p.tab_bytes;
+  float* stat_s = reinterpret_cast<float*>(smem + kHHeader + p.tab_bytes);
+  uint8_t* a_base = smem + kHHeader + p.tab_bytes + kHStatBytes;
   uint8_t* b_base = a_base + static_cast<size_t>(p.a_bufs) * p.halo_bytes;
 
   const catb_igemm_desc& d = p.d;
@@ -100,6 +104,8 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
   }
   for (int i = threadIdx.x; i < h.n_steps; i += kHThreads) s_aoff[i] = static_cast<uint32_t>(p.steps[i].a_row) * 8u;
   for (int i = threadIdx.x; i < h.n_chunks; i += kHThreads) s_chunks[i] = reinterpret_cast<const int4*>(p.chunks)[i];
+  if (p.st.sums != nullptr)
+    for (int i = threadIdx.x; i < 2 * d.n_tile; i += kHThreads) stat_s[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
         epilogue_rows_bf16(trow, d.n_tile, tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
                            static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff,
                            a_base + warp * 4096, reinterpret_cast<uint32_t*>(smem + 512) + warp * 32, lane, p.dbg_mode,
-                           rec ? cyc : nullptr);
+                           rec ? cyc : nullptr, p.st.sums != nullptr ? stat_s : nullptr);
         if (rec)
           for (int q = 0; q < 3; ++q) p.dbg[blockIdx.x * kDbgSlots + 8 + q] += static_cast<unsigned long long>(cyc[q]);
         continue;
@@ -212,6 +218,10 @@ __global__ void __launch_bounds__(kHThreads, 1) igemm_halo_fprop_kernel(const Ha
           }
         }
       }
+    }
+    if (p.st.sums != nullptr) {   // fused statistics of the conv + norm blocks: one atomic per column and CTA
+      named_bar_sync(1, 128);
+      flush_epilogue_stats(stat_s, d.n_tile, tile_n * d.n_tile, p.n_store, p.st, n_img, threadIdx.x, 128);
     }
   } else if (warp == 4) {
     // ---------------------------------------------------------------- MMA issuer
@@ -321,7 +331,7 @@ static int halo_table_bytes(int n_steps, int n_chunks) {
 }
 
 static int halo_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int* a_bufs, int* b_stages, size_t* total) {
-  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kHHeader - tab_bytes;
+  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kHHeader - tab_bytes - kHStatBytes;
   int ab = 2;
   if (2 * halo_bytes + 3 * b_bytes > limit) ab = 1;
   int bs = (limit - ab * halo_bytes) / b_bytes;
@@ -329,7 +339,7 @@ static int halo_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int* a_buf
   if (bs < 2) return -1;
   *a_bufs = ab;
   *b_stages = bs;
-  *total = 1024 + kHHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes;
+  *total = 1024 + kHHeader + tab_bytes + kHStatBytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes;
   return 0;
 }
 
@@ -343,7 +353,7 @@ extern "C" int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub,
 
 extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
                                      const catb_halo_chunk* chunks, const void* x, const void* packed_w,
-                                     const float* bias, void* y, catb_stream_t s) {
+                                     const float* bias, void* y, const catb_epilogue_stats* stats, catb_stream_t s) {
   CATB_REQUIRE(d != nullptr && h != nullptr, "null descriptor");
   CATB_REQUIRE(d->n_tile % 16 == 0 && d->n_tile >= 16 && d->n_tile <= 256, "n_tile must be a multiple of 16 in [16,256]");
   CATB_REQUIRE(h->m_sub >= 1 && h->m_sub <= 4 && h->m_sub * d->n_tile <= 512, "m_sub * n_tile must fit 512 TMEM columns");
@@ -364,6 +374,12 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
   p.y = y;
   p.dbg = g_halo_dbg;
   p.dbg_mode = g_halo_dbg_mode;
+  memset(&p.st, 0, sizeof(p.st));
+  if (stats != nullptr && stats->sums != nullptr) {
+    CATB_REQUIRE(!d->y_is_f32 && !d->accumulate && !(g_halo_dbg_mode & 4), "fused statistics need the plain bf16 store");
+    CATB_REQUIRE(stats->C > 0 && stats->coff >= 0 && stats->coff + (d->n_rows + 7) / 8 * 8 <= stats->C, "bad statistics slice");
+    p.st = *stats;
+  }
   p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
   p.tab_bytes = halo_table_bytes(h->n_steps, h->n_chunks);
   size_t smem = 0;
@@ -381,7 +397,7 @@ extern "C" int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_d
     if (want < (h->b_budget > 0 ? 2 : 4)) want = h->b_budget > 0 ? 2 : 4;
     if (p.b_stages > want) p.b_stages = want;
   }
-  smem = 1024 + kHHeader + p.tab_bytes + static_cast<size_t>(p.a_bufs) * p.halo_bytes +
+  smem = 1024 + kHHeader + p.tab_bytes + kHStatBytes + static_cast<size_t>(p.a_bufs) * p.halo_bytes +
          static_cast<size_t>(p.b_stages) * d->n_tile * 128;
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);

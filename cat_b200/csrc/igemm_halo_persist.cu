@@ -26,6 +26,7 @@ constexpr int kPHeader = 1024;      // barriers [0, 512), per-warp pixel tables 
 constexpr int kPMaxA = 4;
 constexpr int kPMaxBStages = 24;
 constexpr int kPStageBytes = 4 * 4096;   // epilogue staging: 4 KB per epilogue warp
+constexpr int kPStatBytes = 2 * 2 * 256 * 4;   // fused statistics: two (tile parity) x [2][n_tile <= 256] floats
 
 struct PersistParams {
   catb_igemm_desc d;
@@ -39,6 +40,7 @@ struct PersistParams {
   int tiles_per_image, tiles_x, tiles_total, a_bufs, b_stages, tmem_cols, acc_cols, n_store, halo_bytes, tab_bytes;
   int use_tma, plane_rows, plane_bytes;   // TMA mode: frame rows per plane box, bytes per plane (1024-aligned)
   uint32_t idesc;
+  catb_epilogue_stats st;                 // st.sums == nullptr: no fused statistics
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
@@ -81,6 +83,7 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
   uint8_t* a_base = smem + kPHeader + p.tab_bytes;
   uint8_t* b_base = a_base + static_cast<size_t>(p.a_bufs) * p.halo_bytes;
   uint8_t* stg_base = b_base + static_cast<size_t>(p.b_stages) * (p.d.n_tile * 128);
+  float* stat_base = reinterpret_cast<float*>(stg_base + kPStageBytes);   // [2][2][n_tile]
 
   const catb_igemm_desc& d = p.d;
   const catb_halo_desc& h = p.h;
@@ -117,6 +120,8 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
     }
   }
   for (int i = threadIdx.x; i < h.n_chunks; i += kPThreads) s_chunks[i] = reinterpret_cast<const int4*>(p.chunks)[i];
+  if (p.st.sums != nullptr)
+    for (int i = threadIdx.x; i < 4 * d.n_tile; i += kPThreads) stat_base[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -271,6 +276,7 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const TileCoord t = decode_tile(p, tile);
+      float* stat_s = p.st.sums != nullptr ? stat_base + as * 2 * d.n_tile : nullptr;
       mbar_wait(&acc_full[as], aph);
       tcgen05_fence_after();
       for (int sub = 0; sub < h.m_sub; ++sub) {
@@ -282,7 +288,8 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
         const uint32_t trow = tmem_base + as * static_cast<uint32_t>(p.acc_cols) + (static_cast<uint32_t>(q * 32) << 16) + sub * d.n_tile;
         if (!d.y_is_f32 && !d.accumulate) {
           epilogue_rows_bf16(trow, d.n_tile, t.tile_n * d.n_tile, p.n_store, d.n_rows, p.bias, d.act, rvalid,
-                             static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff, stg, pixtab, lane);
+                             static_cast<uint32_t>(ypix), reinterpret_cast<__nv_bfloat16*>(p.y), d.ldy, d.y_coff, stg, pixtab, lane,
+                             0, nullptr, stat_s);
           continue;
         }
         for (int cc = 0; cc < d.n_tile / 16; ++cc) {
@@ -328,6 +335,12 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (stat_s != nullptr) {
+        // the four warps have added their rows of this tile: one of the two tiles (by parity, so the next tile's adds need
+        // no second barrier) goes out with one atomic per column, image and CTA
+        named_bar_sync(1, 128);
+        flush_epilogue_stats(stat_s, d.n_tile, t.tile_n * d.n_tile, p.n_store, p.st, t.n_img, threadIdx.x - 192, 128);
+      }
     }
   }
 
@@ -384,7 +397,7 @@ static int persist_halo_bytes(int n_planes, int Lh, int Wf, int use_tma, int* pl
 // Shared-memory plan: 0 and a_bufs / b_stages / total bytes, or -1 when it does not fit.
 static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int budget, int n_chunks, int* a_bufs, int* b_stages,
                              size_t* total) {
-  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kPHeader - tab_bytes - kPStageBytes;
+  const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kPHeader - tab_bytes - kPStageBytes - kPStatBytes;
   // weight ring: >= ~64 KB in flight (bulk-copy latency), or the caller's smaller budget (thin GEMMs: more CTAs per SM)
   const int bud = budget > 0 ? budget : 64 * 1024;
   int want_b = (bud + b_bytes - 1) / b_bytes;
@@ -401,7 +414,8 @@ static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int bud
   if (n_chunks == 1 && ab == 2 && 3 * halo_bytes <= 28 * 1024 && 3 * halo_bytes + bs * b_bytes <= limit) ab = 3;
   *a_bufs = ab;
   *b_stages = bs;
-  *total = 1024 + kPHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes + kPStageBytes;
+  *total = 1024 + kPHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes + kPStageBytes +
+           kPStatBytes;
   return 0;
 }
 
@@ -418,7 +432,8 @@ extern "C" int catb_igemm_halo_persist_fits(int n_planes, int Lh, int Wf, int mu
 
 extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
                                              const catb_halo_chunk* chunks, const void* x, const void* packed_w,
-                                             const float* bias, void* y, int use_tma, int c_visible, catb_stream_t s) {
+                                             const float* bias, void* y, int use_tma, int c_visible,
+                                             const catb_epilogue_stats* stats, catb_stream_t s) {
   CATB_REQUIRE(d != nullptr && h != nullptr, "null descriptor");
   CATB_REQUIRE(d->n_tile % 16 == 0 && d->n_tile >= 16 && d->n_tile <= 256, "n_tile must be a multiple of 16 in [16,256]");
   CATB_REQUIRE(h->m_sub >= 1 && h->m_sub <= 4 && 2 * h->m_sub * d->n_tile <= 512,
@@ -438,6 +453,12 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
   p.wpk = static_cast<const uint8_t*>(packed_w);
   p.bias = bias;
   p.y = y;
+  memset(&p.st, 0, sizeof(p.st));
+  if (stats != nullptr && stats->sums != nullptr) {
+    CATB_REQUIRE(!d->y_is_f32 && !d->accumulate, "fused statistics need the plain bf16 store");
+    CATB_REQUIRE(stats->C > 0 && stats->coff >= 0 && stats->coff + (d->n_rows + 7) / 8 * 8 <= stats->C, "bad statistics slice");
+    p.st = *stats;
+  }
   p.use_tma = use_tma ? 1 : 0;
   p.plane_rows = persist_plane_rows(h->Lh, h->Wf);
   p.halo_bytes = persist_halo_bytes(h->n_planes, h->Lh, h->Wf, p.use_tma, &p.plane_bytes);

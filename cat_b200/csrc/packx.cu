@@ -92,6 +92,58 @@ __global__ void shift_expand_kernel(const __nv_bfloat16* __restrict__ dz, int ld
   }
 }
 
+// ---- "tap-split" form of a conv with ONE output channel (PatchGAN head, discriminators.py:72-73) -------------------
+// A 4x4 conv Cin -> 1 on a 128 x 16 tensor-core tile wastes 15/16 of every instruction and re-reads each input pixel
+// once per tap.  Instead  P[n, iy, ix, t] = sum_c X[n, iy, ix, c] W[0, c, t]  is ONE 1x1 GEMM with the R*S taps as its
+// output channels (each input pixel read once), and the conv is the shifted sum of P below; the adjoint spreads dY
+// over the taps (tap_expand), after which the weight / input gradients are 1x1 GEMMs as well.
+__global__ void tap_sum_kernel(const float* __restrict__ P, int ldp, int p_coff, float* __restrict__ out, int ldo, int o_coff,
+                               int N, int H, int W, int OH, int OW, int R, int S, int pad, const float* __restrict__ bias) {
+  const long long total = static_cast<long long>(N) * OH * OW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % OW);
+    const int oy = static_cast<int>((idx / OW) % OH);
+    const long long n = idx / (static_cast<long long>(OW) * OH);
+    float acc = bias != nullptr ? bias[0] : 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int iy = oy + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < S; ++s) {
+        const int ix = ox + s - pad;
+        if (ix < 0 || ix >= W) continue;
+        acc += P[((n * H + iy) * W + ix) * ldp + p_coff + r * S + s];
+      }
+    }
+    out[idx * ldo + o_coff] = acc;
+  }
+}
+
+// dP[n, iy, ix, r*S + s] = dY[n, iy - r + pad, ix - s + pad] (0 outside the output), one 8-tap unit per thread
+__global__ void tap_expand_kernel(const __nv_bfloat16* __restrict__ dy, int ldy, int y_coff, __nv_bfloat16* __restrict__ dP, int ldp,
+                                  int p_coff, int N, int H, int W, int OH, int OW, int R, int S, int pad) {
+  const int U = (R * S + 7) / 8;
+  const long long total = static_cast<long long>(N) * H * W * U;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx % U);
+    const long long pix = idx / U;
+    const int ix = static_cast<int>(pix % W);
+    const int iy = static_cast<int>((pix / W) % H);
+    const long long n = pix / (static_cast<long long>(W) * H);
+    f8 o;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = u * 8 + q;
+      const int r = t / S, s = t - r * S;
+      const int oy = iy - r + pad, ox = ix - s + pad;
+      o.v[q] = (t < R * S && oy >= 0 && oy < OH && ox >= 0 && ox < OW)
+                   ? __bfloat162float(dy[((n * OH + oy) * OW + ox) * ldy + y_coff]) : 0.f;
+    }
+    st16(dP + pix * ldp + p_coff + u * 8, pack8(o));
+  }
+}
+
 }  // namespace catb
 
 using namespace catb;
@@ -131,4 +183,24 @@ extern "C" int catb_shift_expand(const void* dz, int ldz, int z_coff, void* dP, 
   shift_expand_kernel<<<grid_for(total, 256), 256, 0, S(s)>>>(static_cast<const __nv_bfloat16*>(dz), ldz, z_coff,
                                                               static_cast<__nv_bfloat16*>(dP), ldp, p_coff, N, H, W, Cout, taps);
   return check_launch("shift_expand");
+}
+
+extern "C" int catb_tap_sum(const float* P, int ldp, int p_coff, float* out, int ldo, int o_coff, int N, int H, int W, int OH,
+                            int OW, int R, int S, int pad, const float* bias, catb_stream_t s) {
+  CATB_REQUIRE(R >= 1 && S >= 1 && p_coff + R * S <= ldp && o_coff < ldo && OH == H + 2 * pad - R + 1 && OW == W + 2 * pad - S + 1,
+               "bad tap-sum geometry (R=%d S=%d pad=%d)", R, S, pad);
+  const long long total = static_cast<long long>(N) * OH * OW;
+  tap_sum_kernel<<<grid_for(total, 128), 128, 0, static_cast<cudaStream_t>(s)>>>(P, ldp, p_coff, out, ldo, o_coff, N, H, W, OH, OW, R, S, pad, bias);
+  return check_launch("tap_sum");
+}
+
+extern "C" int catb_tap_expand(const void* dy, int ldy, int y_coff, void* dP, int ldp, int p_coff, int N, int H, int W, int OH,
+                               int OW, int R, int S, int pad, catb_stream_t s) {
+  CATB_REQUIRE(R >= 1 && S >= 1 && ldp % 8 == 0 && p_coff % 8 == 0 && p_coff + (R * S + 7) / 8 * 8 <= ldp && y_coff < ldy &&
+                   OH == H + 2 * pad - R + 1 && OW == W + 2 * pad - S + 1,
+               "bad tap-expand geometry (R=%d S=%d pad=%d)", R, S, pad);
+  const long long total = static_cast<long long>(N) * H * W * ((R * S + 7) / 8);
+  tap_expand_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(s)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, y_coff,
+                                                            static_cast<__nv_bfloat16*>(dP), ldp, p_coff, N, H, W, OH, OW, R, S, pad);
+  return check_launch("tap_expand");
 }

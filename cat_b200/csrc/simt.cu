@@ -3,6 +3,7 @@
 // All activations are NHWC bf16 slices (pixel pitch `ld`, channel offset `coff`, 8 channels = 16 bytes
 // per access); reductions use warp shuffles + shared-memory partials + one global atomic per block.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -156,23 +157,78 @@ __device__ __forceinline__ UnitMap unit_map(int U) {
   return m;
 }
 
+// Optional "finalize" folded into the apply kernel (fin.sums != nullptr): every thread derives scale / shift of its own
+// 8 channels from the accumulated sums (the same arithmetic as norm_finalize_kernel), and the first pixel block of each
+// group also writes scale / shift / mean_rstd for the backward pass and moves the running statistics -- one launch less
+// per normalisation layer.
+struct NormFin {
+  const float* sums;   // [G][2][C] or nullptr (scale / shift are read from memory)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* scale_out;
+  float* shift_out;
+  float* mean_rstd;
+  float count, eps, momentum;
+};
+
 __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int x_coff, __nv_bfloat16* __restrict__ y,
                                   int ldy, int y_coff, const __nv_bfloat16* __restrict__ res, int ldr, int r_coff, int HW,
                                   int C, int per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  int act, long long pixels) {
+                                  int act, long long pixels, const NormFin fin) {
+  extern __shared__ float fin_s[];   // fused finalize: [2][C] scale / shift of this block's group
   const int U = C / 8;
   const UnitMap m = unit_map(U);
-  if (!m.active) return;
   const int g = per_sample ? blockIdx.y : 0;
+  if (fin.sums != nullptr) {
+    // one channel per thread, ONCE per block (fp64 only here: E[x^2] - E[x]^2 cancels; per-thread copies of this for all
+    // 8 channels of every thread cost more than the whole element-wise pass -- fp64 runs at 1/64 rate)
+    const double inv = 1.0 / static_cast<double>(fin.count);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double mu = fin.sums[static_cast<size_t>(g) * 2 * C + c] * inv;
+      double v = fin.sums[static_cast<size_t>(g) * 2 * C + C + c] * inv - mu * mu;
+      if (v < 0) v = 0;
+      const float mean = static_cast<float>(mu), var = static_cast<float>(v);
+      const float rstd = rsqrtf(var + fin.eps);
+      const float ga = fin.gamma ? fin.gamma[c] : 1.f, be = fin.beta ? fin.beta[c] : 0.f;
+      const float sc1 = ga * rstd, sh1 = be - mean * ga * rstd;
+      fin_s[c] = sc1;
+      fin_s[C + c] = sh1;
+      if (blockIdx.x == 0) {
+        if (fin.running_mean != nullptr && !per_sample) {
+          const float unbiased = fin.count > 1.f ? var * fin.count / (fin.count - 1.f) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mean;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * unbiased;
+        }
+        fin.scale_out[static_cast<size_t>(g) * C + c] = sc1;
+        fin.shift_out[static_cast<size_t>(g) * C + c] = sh1;
+        if (fin.mean_rstd != nullptr) {
+          fin.mean_rstd[(static_cast<size_t>(g) * 2 + 0) * C + c] = mean;
+          fin.mean_rstd[(static_cast<size_t>(g) * 2 + 1) * C + c] = rstd;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!m.active) return;
   const long long pix0 = per_sample ? static_cast<long long>(g) * HW : 0;
   const long long npix = per_sample ? HW : pixels;
   const long long stride = static_cast<long long>(gridDim.x) * m.lanes;
   for (int u = m.u; u < U; u += blockDim.x) {  // only loops when U > blockDim.x
     float sc[8], sh[8];
+    if (fin.sums != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        sc[q] = fin_s[u * 8 + q];
+        sh[q] = fin_s[C + u * 8 + q];
+      }
+    } else {
     *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + static_cast<size_t>(g) * C + u * 8));
     *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + static_cast<size_t>(g) * C + u * 8 + 4));
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + static_cast<size_t>(g) * C + u * 8 + 4));
+    }
     constexpr int kIn = 4;      // pixels in flight per thread (loads issued before the first use)
     for (long long pp = static_cast<long long>(blockIdx.x) * m.lanes + m.pl; pp < npix; pp += kIn * stride) {
       uint4 xr[kIn], rr[kIn];
@@ -744,11 +800,11 @@ static dim3 reduce_grid(long long pixels_per_group, int C, int groups) {
 }
 
 // grid of the unit-mapped element-wise kernels: x = pixel blocks (two pixels per thread iteration), y = groups
-static dim3 elementwise_grid(long long pixels_per_group, int C, int groups) {
+static dim3 elementwise_grid(long long pixels_per_group, int C, int groups, int blocks_per_sm = 8) {
   const int U = C / 8;
   const int lanes = U >= 256 ? 1 : 256 / U;
   long long gx = (pixels_per_group + static_cast<long long>(lanes) * 2 - 1) / (static_cast<long long>(lanes) * 2);
-  const long long cap = std::max(1, 148 * 8 / groups);
+  const long long cap = std::max(1, 148 * blocks_per_sm / groups);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3(static_cast<unsigned>(gx), groups, 1);
@@ -782,10 +838,41 @@ extern "C" int catb_norm_apply(const void* x, int ldx, int x_coff, void* y, int 
   CHK_SLICE(ldx, x_coff, C);
   CHK_SLICE(ldy, y_coff, C);
   const long long pixels = static_cast<long long>(N) * HW;
+  NormFin fin;
+  memset(&fin, 0, sizeof(fin));
   norm_apply_kernel<<<elementwise_grid(per_sample ? HW : pixels, C, per_sample ? N : 1), 256, 0, S(s)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<__nv_bfloat16*>(y), ldy, y_coff,
-      static_cast<const __nv_bfloat16*>(residual), ldr, r_coff, HW, C, per_sample, scale, shift, act, pixels);
+      static_cast<const __nv_bfloat16*>(residual), ldr, r_coff, HW, C, per_sample, scale, shift, act, pixels, fin);
   return check_launch("norm_apply");
+}
+
+extern "C" int catb_norm_apply_fused(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, const void* residual,
+                                     int ldr, int r_coff, int N, int HW, int C, int per_sample, const float* sums, float count,
+                                     float eps, float momentum, const float* gamma, const float* beta, float* running_mean,
+                                     float* running_var, float* scale, float* shift, float* mean_rstd, int act,
+                                     catb_stream_t s) {
+  CHK_SLICE(ldx, x_coff, C);
+  CHK_SLICE(ldy, y_coff, C);
+  CATB_REQUIRE(sums != nullptr && scale != nullptr && shift != nullptr, "fused finalize needs the sums and the scale / shift outputs");
+  const long long pixels = static_cast<long long>(N) * HW;
+  NormFin fin;
+  fin.sums = sums;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale_out = scale;
+  fin.shift_out = shift;
+  fin.mean_rstd = mean_rstd;
+  fin.count = count;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  CATB_REQUIRE(2 * C * sizeof(float) <= 48 * 1024, "too many channels (%d) for the fused finalize", C);
+  // fewer, longer-lived blocks than the plain apply: every block derives the group's scale / shift once
+  norm_apply_kernel<<<elementwise_grid(per_sample ? HW : pixels, C, per_sample ? N : 1, 3), 256, 2 * C * sizeof(float), S(s)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, x_coff, static_cast<__nv_bfloat16*>(y), ldy, y_coff,
+      static_cast<const __nv_bfloat16*>(residual), ldr, r_coff, HW, C, per_sample, nullptr, nullptr, act, pixels, fin);
+  return check_launch("norm_apply_fused");
 }
 
 extern "C" int catb_norm_bwd_reduce(const void* dout, int ldd, int d_coff, const void* out, int ldo, int o_coff,

@@ -124,15 +124,27 @@ class Norm:
         self.batch_stats = self.per_sample or training or not self.track
         self._frozen = False
 
-    def forward(self, x: Act, y: Act, act, residual=None):
+    def stats_for(self, x: Act, y_coff):
+        """The `stats` argument of Gemm.fprop for a conv that writes channels [y_coff, ...) of the buffer this layer
+        normalises as slice `x` (None when the layer uses running statistics: nothing to accumulate)."""
+        if not self.batch_stats:
+            return None
+        return (self.sums, self.Cp, y_coff - x.coff, self.per_sample)
+
+    def forward(self, x: Act, y: Act, act, residual=None, have_stats=False):
+        """have_stats: the producing convs accumulated sum / sum of squares in their epilogues (Gemm.fprop(stats=...)
+        returned True for every one of them), so the statistics pass over x is skipped."""
         if self.batch_stats:
-            if not self.pooled:
-                self.sums.zero_()
-            ops.norm_stats(x, self.per_sample, self.sums)
+            if not have_stats:
+                if not self.pooled:
+                    self.sums.zero_()
+                ops.norm_stats(x, self.per_sample, self.sums)
             upd = self.training and self.track
-            ops.norm_finalize(self.sums, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
-                              self.rmean if upd else None, self.rvar if upd else None, self.scale, self.shift,
-                              self.mean_rstd)
+            # finalize folded into the apply kernel: one launch
+            ops.norm_apply_fused(x, y, self.sums, self.count, self.eps, self.momentum, self.gamma, self.beta,
+                                 self.rmean if upd else None, self.rvar if upd else None, self.scale, self.shift,
+                                 self.mean_rstd, self.per_sample, act, residual)
+            return
         elif not self._frozen:
             ops.norm_finalize(None, self.G, self.Cp, self.count, self.eps, self.momentum, self.gamma, self.beta,
                               self.rmean, self.rvar, self.scale, self.shift, self.mean_rstd)
@@ -153,6 +165,20 @@ class Norm:
         count = self.count if self.batch_stats else float('inf')
         ops.norm_bwd_apply(dout, out, x, dx, self.per_sample, self.mean_rstd, self.gamma, self.red, count, act,
                            self.dgamma if param_grads else None, self.dbeta if param_grads else None)
+
+
+def conv_norm(gemms, x_t, y: Act, norm: Norm, nx: Act, ny: Act, act, residual=None, **fprop_kw):
+    """conv (one GEMM, or several writing disjoint pixels / channels of y) + norm + activation: the GEMM epilogues
+    accumulate the layer's statistics when every one of them can (halo kernels); otherwise the statistics pass runs."""
+    if not isinstance(gemms, (list, tuple)):
+        gemms = [gemms]
+    fused = []
+    for g in gemms:
+        fused.append(g.fprop(x_t, y.t, stats=norm.stats_for(nx, g.geo.y_coff), **fprop_kw))
+    ok = all(fused)
+    if any(fused) and not ok:      # mixed: discard the partial sums, the statistics pass recomputes them
+        norm.sums.zero_()
+    norm.forward(nx, ny, act, residual=residual, have_stats=ok)
 
 
 def pool_norm_buffers(norms, dev):
@@ -655,32 +681,22 @@ class GenNet:
         self.pool_sums.zero_()
         if self.packx:
             ops.expand_x(x_in, self.x_stem, self.arch['input_nc'], 7)
-            self.g_stem.fprop(self.x_stem.t, self.y0.t)
+            conv_norm(self.g_stem, self.x_stem.t, self.y0, self.n_stem, self.y0, self.a0, relu)
         else:
-            self.g_stem.fprop(x_in.t, self.y0.t)
-        self.n_stem.forward(self.y0, self.a0, relu)
-        self.g_d1.fprop(self.a0.t, self.y1.t)
-        self.n_d1.forward(self.y1, self.a1, relu)
-        self.g_d2.fprop(self.a1.t, self.y2.t)
-        self.n_d2.forward(self.y2, self.a2, relu)
+            conv_norm(self.g_stem, x_in.t, self.y0, self.n_stem, self.y0, self.a0, relu)
+        conv_norm(self.g_d1, self.a0.t, self.y1, self.n_d1, self.y1, self.a1, relu)
+        conv_norm(self.g_d2, self.a1.t, self.y2, self.n_d2, self.y2, self.a2, relu)
         for b in self.blocks:
             if b.empty:
                 continue
-            for g in b.s1_fwd:
-                g.fprop(b.x.t, b.mid_raw.t)
-            b.nA.forward(b.mid_raw.slice(0, b.LA), b.mid_act.slice(0, b.LA), relu)
+            conv_norm(b.s1_fwd, b.x.t, b.mid_raw, b.nA, b.mid_raw.slice(0, b.LA), b.mid_act.slice(0, b.LA), relu)
             if b.dw:
                 ops.dwconv_fwd(b.mid_act.slice(b.D0, b.D1 - b.D0), b.mid_raw.slice(b.LA, b.L - b.LA), b.dw_k, b.dw_w,
                                self.arena.p)
                 b.nB.forward(b.mid_raw.slice(b.LA, b.L - b.LA), b.mid_act.slice(b.LA, b.L - b.LA), relu)
-            b.g2.fprop(b.mid_act.t, b.tmp.t)
-            b.npw.forward(b.tmp, b.out, none, residual=b.x)
-        for g in self.g_u1:
-            g.fprop(self.feat_out.t, self.yu1.t)
-        self.n_u1.forward(self.yu1, self.au1, relu)
-        for g in self.g_u2:
-            g.fprop(self.au1.t, self.yu2.t)
-        self.n_u2.forward(self.yu2, self.au2, relu)
+            conv_norm(b.g2, b.mid_act.t, b.tmp, b.npw, b.tmp, b.out, none, residual=b.x)
+        conv_norm(self.g_u1, self.feat_out.t, self.yu1, self.n_u1, self.yu1, self.au1, relu)
+        conv_norm(self.g_u2, self.au1.t, self.yu2, self.n_u2, self.yu2, self.au2, relu)
         if self.packx:
             self.g_head.fprop(self.au2.t, self.head_P.t)
             ops.shift_sum(self.head_P, self.out, self.arch['output_nc'], 7, self.head_bias, ACT['tanh'])
@@ -911,6 +927,25 @@ class DisNet:
             wn = L.wn
             L.units = P.conv_fprop_units(ar.off(wn), L.cout, L.cin, 4, 4, pad)
             L.y_f32 = last
+            L.tap = bool(last and L.cout == 1 and L.stride == 1 and ops.TAP_HEAD)
+            if L.tap:
+                # one output channel: the conv in "tap-split" form (csrc/packx.cu) -- P = X . W[taps] is a 1x1 GEMM with the
+                # 16 taps as output channels (each input pixel read once), the prediction is the shifted tap sum; the
+                # adjoint spreads d(prediction) over the taps and both gradients are 1x1 GEMMs too
+                L.y = torch.zeros(B, L.oh, L.ow, 8, dtype=torch.float32, device=dev)
+                L.P = torch.zeros(B, L.h, L.w, 16, dtype=torch.float32, device=dev)
+                L.dP = Act.empty(B, L.h, L.w, 16, dev, zero=True)
+                L.units = P.tap_split_units(ar.off(wn), L.cin, 4, 4)
+                L.g = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.h, L.w, 16, 0), L.units, 16, dev)
+                self.fprop_gemms.append(L.g)
+                L.bias = ar.view(L.bn) if L.has_bias else None
+                L.dbias = ar.view(L.bn, 'g') if L.has_bias else None
+                L.dy, L.da = None, None
+                L.gb = [Gemm(P.Geometry(B, L.h, L.w, 16, 0, L.h, L.w, cpad(L.cin), 0),
+                             P.tap_split_dgrad_units(ar.off(wn), L.cin, 4, 4), L.cin, dev)]
+                self.bwd_gemms += L.gb
+                L.gw = Gemm(P.Geometry(B, L.h, L.w, cpad(L.cin), 0, L.h, L.w, 16, 0), L.units, 16, dev, need_pack=False)
+                continue
             if last:
                 L.y = torch.zeros(B, L.oh, L.ow, 8, dtype=torch.float32, device=dev)
                 ldy = 8
@@ -958,11 +993,13 @@ class DisNet:
         cur = x
         self.pool_sums.zero_()
         for L in self.layers:
-            if L.y_f32:
+            if L.tap:
+                L.g.fprop(cur.t, L.P, y_is_f32=True)
+                ops.tap_sum(L.P, L.y, L.h, L.w, L.oh, L.ow, 4, 4, self.pad, L.bias)
+            elif L.y_f32:
                 L.g.fprop(cur.t, L.y, bias=L.bias, y_is_f32=True)
             elif L.has_norm:
-                L.g.fprop(cur.t, L.yraw.t)
-                L.norm.forward(L.yraw, L.a, ACT['leaky'])
+                conv_norm(L.g, cur.t, L.yraw, L.norm, L.yraw, L.a, ACT['leaky'])
                 cur = L.a
             else:
                 L.g.fprop(cur.t, L.yraw.t, bias=L.bias, act=ACT['leaky'])
@@ -1007,8 +1044,13 @@ class DisNet:
             else:
                 ops.act_bwd(d, L.yraw, L.dy, ACT['leaky'])
                 dy = L.dy
+            if L.tap:
+                ops.tap_expand(d, L.dP, 4, 4, self.pad)
+                dy_w = L.dP        # lattice tensor of the 1x1 weight / input gradients
+            else:
+                dy_w = dy
             if param_grads:
-                L.gw.wgrad(x_in.t, dy.t, ar.g)
+                L.gw.wgrad(x_in.t, dy_w.t, ar.g)
                 if L.has_bias:
                     ops.channel_sum(dy, L.dbias)
                 if grads_final_hook is not None:
@@ -1017,9 +1059,9 @@ class DisNet:
             if li > 0:
                 tgt = self.layers[li - 1].da
                 for g in L.gb:
-                    g.fprop(dy.t, tgt.t)
+                    g.fprop(dy_w.t, tgt.t)
                 d = tgt
             elif input_grad:
                 for g in L.gb:
-                    g.fprop(dy.t, self.d_in.t)
+                    g.fprop(dy_w.t, self.d_in.t)
         return self.d_in

@@ -64,6 +64,25 @@ def conv_fprop_units(w_off, Cout, Cin, R, S, pad, cu0=0, pad_s=None) -> Units:
     return u
 
 
+def tap_split_units(w_off, Cin, R, S, cu0=0) -> Units:
+    """Conv weight [1, Cin, R, S] read as the 1x1 "tap-product" GEMM P[pix, t] = sum_c X[pix, c] W[0, c, t]: GEMM rows =
+    the R*S taps, K = input channels.  The same table drives the weight gradient with dP as the lattice tensor."""
+    u = Units()
+    for cu in range(cpad(Cin) // 8):
+        u.g.append((0, 0, cu0 + cu))
+        u.w.append((w_off + cu * 8 * R * S, 1, R * S, max(0, min(8, Cin - cu * 8))))
+    return u
+
+
+def tap_split_dgrad_units(w_off, Cin, R, S, cu0=0) -> Units:
+    """Input gradient of the tap-split conv: dX[pix, c] = sum_t dP[pix, t] W[0, c, t]: GEMM rows = input channels, K = taps."""
+    u = Units()
+    for tu in range(cpad(R * S) // 8):
+        u.g.append((0, 0, cu0 + tu))
+        u.w.append((w_off + tu * 8, R * S, 1, max(0, min(8, R * S - tu * 8))))
+    return u
+
+
 def conv_embedded_units(w_off, Cout, Cin, k, Kmax, cu0=0) -> Units:
     """A k x k conv (padding (k-1)/2) expressed on the tap grid of a Kmax x Kmax conv (padding (Kmax-1)/2):
     same gather side as conv_fprop_units(., ., Cin, Kmax, Kmax, (Kmax-1)/2), weight side pointing at the

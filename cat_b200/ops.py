@@ -81,7 +81,9 @@ def units_to_device(units: Units, device):
 USE_HALO = os.environ.get('CATB_NO_HALO', '0') != '1'   # v2 (halo) forward kernel unless disabled
 AUTOTUNE = os.environ.get('CATB_NO_AUTOTUNE', '0') != '1'  # pick v1 / v2 per GEMM by timing the first call
 USE_PERSIST = os.environ.get('CATB_NO_PERSIST', '0') != '1'   # v3 (persistent halo kernel) variants offered to the autotune
-USE_TMA = os.environ.get('CATB_NO_TMA', '0') != '1'           # v3 stages zero-padded halos with cp.async.bulk.tensor
+FUSE_STATS = os.environ.get('CATB_NO_FUSED_STATS', '0') != '1'   # norm statistics accumulated by the conv epilogue
+USE_TMA = os.environ.get('CATB_NO_TMA', '0') != '1'
+TAP_HEAD = os.environ.get('CATB_NO_TAP_HEAD', '0') != '1'     # one-output-channel convs (PatchGAN head) in tap-split form           # v3 stages zero-padded halos with cp.async.bulk.tensor
 
 
 _SCRATCH = {}
@@ -327,20 +329,29 @@ class Gemm:
         e1.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
+    def fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False, stats=None):
+        """stats=(sums, C, coff, per_sample): ask the epilogue to add the per-channel sum / sum of squares of the stored
+        values to sums[g, 0 / 1, coff + channel] (the statistics pass of the norm layer behind the conv).  Returns True
+        when the launched kernel did so (the halo kernels v2 / v3; not the gather-per-tap kernel v1)."""
         d1 = self.desc(act, accumulate, y_is_f32)
         d2 = self.desc(act, accumulate, y_is_f32, n_units=len(self.f_units))
+        st = [None]    # the timing launches of the autotune run without statistics
 
         def v1():
             _C.call('catb_igemm_fprop', C.byref(d1), _p(self.gt), _p(x), _p(self.packed_v1), _p(bias), _p(y), _stream())
 
         def v2():
+            es = None
+            if st[0] is not None:
+                es = _C.EpilogueStats()
+                es.sums, es.C, es.coff, es.per_sample = st[0][0].data_ptr(), int(st[0][1]), int(st[0][2]), int(bool(st[0][3]))
+                es = C.byref(es)
             if self.h_mode:   # v3: persistent pipeline, halo staged by TMA (mode 2) or cp.async producers (mode 1)
                 _C.call('catb_igemm_halo_fprop_persist', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
-                        _p(x), _p(self.packed), _p(bias), _p(y), int(self.h_mode == 2), self.c_visible, _stream())
+                        _p(x), _p(self.packed), _p(bias), _p(y), int(self.h_mode == 2), self.c_visible, es, _stream())
                 return
             _C.call('catb_igemm_halo_fprop', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
-                    _p(x), _p(self.packed), _p(bias), _p(y), _stream())
+                    _p(x), _p(self.packed), _p(bias), _p(y), es, _stream())
 
         if AUTOTUNE and self.halo is not None and self.choice is None and not force_v1 and not accumulate \
                 and not torch.cuda.is_current_stream_capturing():
@@ -361,9 +372,11 @@ class Gemm:
             else:
                 self.packed = None
         if self.halo is not None and not force_v1 and self.choice != 'v1':
+            st[0] = stats if (FUSE_STATS and not accumulate and not y_is_f32) else None
             v2()
-        else:
-            v1()
+            return st[0] is not None
+        v1()
+        return False
 
     def _wgrad_plan(self):
         """Halo plan of the weight-gradient direction (built lazily: not every Gemm computes one)."""
@@ -522,6 +535,15 @@ def norm_finalize(sums, G, Cc, count, eps, momentum, gamma, beta, rmean, rvar, s
 def norm_apply(x: Act, y: Act, scale, shift, per_sample, act, residual: Act = None):
     r = residual.args() if residual is not None else (None, 0, 0)
     _C.call('catb_norm_apply', *x.args(), *y.args(), *r, x.N, x.HW, x.C, int(per_sample), _p(scale), _p(shift),
+            int(act), _stream())
+
+
+def norm_apply_fused(x: Act, y: Act, sums, count, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_rstd,
+                     per_sample, act, residual: Act = None):
+    """norm_finalize + norm_apply in one launch (scale / shift derived per thread from the sums)."""
+    r = residual.args() if residual is not None else (None, 0, 0)
+    _C.call('catb_norm_apply_fused', *x.args(), *y.args(), *r, x.N, x.HW, x.C, int(per_sample), _p(sums), float(count),
+            float(eps), float(momentum), _p(gamma), _p(beta), _p(rmean), _p(rvar), _p(scale), _p(shift), _p(mean_rstd),
             int(act), _stream())
 
 
@@ -693,6 +715,17 @@ def shift_sum(P: Act, out: Act, Cout, taps, bias, act):
 def shift_expand(dz: Act, dP: Act, Cout, taps):
     assert dP.W == dz.W + taps - 1 and (dP.N, dP.H) == (dz.N, dz.H)
     _C.call('catb_shift_expand', *dz.args(), *dP.args(), dz.N, dz.H, dz.W, int(Cout), int(taps), _stream())
+
+
+def tap_sum(P, out, H, W, OH, OW, R, S, pad, bias):
+    """P: fp32 [N,H,W,ldp] (taps in channels 0 .. R*S-1), out: fp32 [N,OH,OW,ldo], channel 0 = bias + shifted tap sum."""
+    _C.call('catb_tap_sum', _p(P), P.shape[-1], 0, _p(out), out.shape[-1], 0, P.shape[0], H, W, OH, OW, R, S, pad, _p(bias),
+            _stream())
+
+
+def tap_expand(dy: Act, dP: Act, R, S, pad):
+    """dP[n,iy,ix,r*S+s] = dy[n, iy-r+pad, ix-s+pad, channel 0 of the slice] (0 outside)."""
+    _C.call('catb_tap_expand', *dy.args(), *dP.args(), dy.N, dP.H, dP.W, dy.H, dy.W, R, S, pad, _stream())
 
 
 class PackBatch:

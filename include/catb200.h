@@ -134,9 +134,20 @@ typedef struct {
 /* 1 when the halo tile + weight ring + the step / chunk tables (kept in shared memory for the MMA-issuing warp)
  * fit in shared memory / TMEM for these parameters, else 0. */
 int catb_igemm_halo_fits(int n_planes, int Lh, int n_tile, int m_sub, int n_steps, int n_chunks);
+/* Optional fused statistics of the halo kernels' bf16 epilogue: the per-channel sum and sum of squares of the values the
+ * launch stores, added atomically to sums[g][0][coff + column] / sums[g][1][coff + column] (g = image when per_sample,
+ * else 0) -- the statistics pass of the InstanceNorm / BatchNorm layer that follows the conv
+ * (models/modules/inception_modules.py:22-44 ConvBNReLU: conv + norm + activation), so catb_norm_stats is not launched. */
+typedef struct {
+  float* sums;        /* [G][2][C] fp32, zeroed by the caller before the producing launches */
+  int32_t C, coff;    /* channels per statistics row; column of the GEMM's output channel 0 in it */
+  int32_t per_sample; /* 1: one group per image (InstanceNorm); 0: one group (BatchNorm) */
+  int32_t reserved;
+} catb_epilogue_stats;
 int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
                           const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
-                          const float* bias /*nullable*/, void* y, catb_stream_t s);
+                          const float* bias /*nullable*/, void* y, const catb_epilogue_stats* stats /*nullable*/,
+                          catb_stream_t s);
 
 /* v3 forward kernel: the same halo GEMM as a persistent, warp-specialised pipeline (cat_b200/csrc/igemm_halo_persist.cu):
  * every CTA walks output tiles with the halo ring, the weight ring and TWO tensor-memory accumulator stages running
@@ -151,7 +162,8 @@ int catb_igemm_halo_persist_fits(int n_planes, int Lh, int Wf, int mul, int n_ti
                                  int b_budget, int use_tma);
 int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
                                   const catb_halo_chunk* chunks /*device*/, const void* x, const void* packed_w,
-                                  const float* bias /*nullable*/, void* y, int use_tma, int c_visible, catb_stream_t s);
+                                  const float* bias /*nullable*/, void* y, int use_tma, int c_visible,
+                                  const catb_epilogue_stats* stats /*nullable*/, catb_stream_t s);
 
 /* v2 weight gradient on the same halo plan (m_sub = 1): a CTA handles one 128-channel tile of the lattice
  * tensor, one channel chunk of X and one group of <= 8 consecutive steps (taps) of that chunk, each tap
@@ -252,6 +264,14 @@ int catb_norm_finalize(const float* sums, int G, int C, float count, float eps, 
 int catb_norm_apply(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, const void* residual,
                     int ldr, int r_coff, int N, int HW, int C, int per_sample, const float* scale,
                     const float* shift, int act, catb_stream_t s);
+/* catb_norm_finalize + catb_norm_apply in one launch: every thread derives scale / shift of its channels from the sums;
+ * the first pixel block of each group also writes scale / shift / mean_rstd (for the backward pass) and moves the
+ * running statistics.  With the sums produced by the conv epilogue (catb_epilogue_stats) a conv + norm + activation
+ * block of the reference (inception_modules.py:22-44) is two launches. */
+int catb_norm_apply_fused(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, const void* residual,
+                          int ldr, int r_coff, int N, int HW, int C, int per_sample, const float* sums, float count,
+                          float eps, float momentum, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float* scale, float* shift, float* mean_rstd, int act, catb_stream_t s);
 /* Backward of act(norm(x)): pass 1 reduces sum(dz) and sum(dz*xhat) into red[G,2,C] (zeroed by the
  * caller), pass 2 writes dx.  `out` is the saved activation output (act' is taken from it);
  * act == NONE ignores it. */
@@ -386,6 +406,15 @@ int catb_shift_sum(const void* P, int ldp, int p_coff, void* out, int ldo, int o
                    int taps, const float* bias /*nullable*/, int act, catb_stream_t s);
 int catb_shift_expand(const void* dz, int ldz, int z_coff, void* dP, int ldp, int p_coff, int N, int H, int W, int Cout,
                       int taps, catb_stream_t s);
+
+/* "Tap-split" form of a conv with one output channel (the PatchGAN head, models/modules/discriminators.py:72-73, and
+ * the last conv of the SPADE sub-discriminators :160-161): P[n,iy,ix,t] = sum_c X[n,iy,ix,c] W[0,c,t] is a 1x1 GEMM with
+ * the R*S taps as output channels; catb_tap_sum adds bias + the shifted taps into channel o_coff of the fp32 prediction,
+ * catb_tap_expand spreads dY (channel y_coff of a bf16 buffer) back over the taps for the 1x1 weight / input gradients. */
+int catb_tap_sum(const float* P, int ldp, int p_coff, float* out, int ldo, int o_coff, int N, int H, int W, int OH, int OW,
+                 int R, int S, int pad, const float* bias /*nullable, 1 element*/, catb_stream_t s);
+int catb_tap_expand(const void* dy, int ldy, int y_coff, void* dP, int ldp, int p_coff, int N, int H, int W, int OH, int OW,
+                    int R, int S, int pad, catb_stream_t s);
 
 #ifdef __cplusplus
 }

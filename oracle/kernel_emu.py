@@ -57,7 +57,7 @@ def _act_grad_from_out(o, act):
 
 # ---- implicit GEMMs ------------------------------------------------------------------------------
 def _gemm_init(orig):
-    def init(self, geo, units, n_rows, device, need_pack=True, halo=None, force_tile=None, segments=None):
+    def init(self, geo, units, n_rows, device, need_pack=True, halo=None, force_tile=None, segments=None, force_mode=None):
         orig(self, geo, units, n_rows, device, need_pack=need_pack, halo=False, force_tile=None, segments=segments)
         self._emu_segments = segments
         self._emu_w = None
@@ -69,7 +69,7 @@ def _gemm_pack(self, arena):
     self._emu_w = arena.detach().to(ops.BF16).float()
 
 
-def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False):
+def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False, stats=None):
     assert self._emu_w is not None, 'fprop before pack()'
     assert y.dtype == (torch.float32 if y_is_f32 else ops.BF16)
     geo = self.geo
@@ -91,6 +91,19 @@ def _gemm_fprop(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, 
         top = min(c0 + cpad(self.n_rows), geo.ldy)
         yf[n, oh, ow, c0 + self.n_rows:top] = 0
     y.copy_(yf.to(y.dtype))
+    if stats is None or accumulate or y_is_f32 or not ops.FUSE_STATS:
+        return False
+    # fused statistics of the halo kernels' epilogue: sums of the STORED values of the rows this GEMM writes
+    sums, Cn, coff, per_sample = stats
+    v = y.float()[:, geo.o_ph::geo.o_step, geo.o_pw::geo.o_step, c0:c0 + cpad(self.n_rows)][:, :geo.OHs, :geo.OWs]
+    top = coff + v.shape[-1]
+    if per_sample:
+        sums[:, 0, coff:top] += v.sum((1, 2))
+        sums[:, 1, coff:top] += (v * v).sum((1, 2))
+    else:
+        sums[0, 0, coff:top] += v.sum((0, 1, 2))
+        sums[0, 1, coff:top] += (v * v).sum((0, 1, 2))
+    return True
 
 
 def _gemm_wgrad(self, x, y, grad_arena, force_v1=False, atomic=False):      # second stage applied immediately
@@ -188,6 +201,13 @@ def norm_apply(x, y, scale, shift, per_sample, act, residual=None):
     if residual is not None:
         v = v + _get(residual)
     _put(y, v)
+
+
+def norm_apply_fused(x, y, sums, count, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_rstd, per_sample, act,
+                     residual=None):
+    G = x.N if per_sample else 1
+    norm_finalize(sums, G, x.C, count, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_rstd)
+    norm_apply(x, y, scale, shift, per_sample, act, residual)
 
 
 def _dz_xhat(dout, out, x, per_sample, mean_rstd, act):
@@ -477,6 +497,34 @@ def sn_backward(table, n, max_rows, max_cols, grad, w_eff, bufs, sigma, cdot):
         g.copy_((g - c * torch.outer(u, v)) / sigma[d])
 
 
+def tap_sum(P, out, H, W, OH, OW, R, S, pad, bias):
+    acc = torch.zeros(P.shape[0], OH, OW, dtype=torch.float32)
+    Pp = torch.nn.functional.pad(P.float(), (0, 0, pad, pad, pad, pad))
+    for r in range(R):
+        for s in range(S):
+            acc += Pp[:, r:r + OH, s:s + OW, r * S + s]
+    if bias is not None:
+        acc += bias.view(-1)[0]
+    out[..., 0] = acc
+
+
+def tap_expand(dy, dP, R, S, pad):
+    g = dy.t[..., dy.coff].float()
+    N, OH, OW = g.shape
+    H, W = dP.H, dP.W
+    gp = torch.nn.functional.pad(g, (R, R, R, R))       # generous frame: index (oy + R, ox + R)
+    val = torch.zeros(N, H, W, dP.C, dtype=torch.float32)
+    iy = torch.arange(H).view(-1, 1)
+    ix = torch.arange(W).view(1, -1)
+    for r in range(R):
+        for s in range(S):
+            oy, ox = iy - r + pad, ix - s + pad
+            ok = (oy >= 0) & (oy < OH) & (ox >= 0) & (ox < OW)
+            v = gp[:, (oy.clamp(-R, OH + R - 1) + R).expand(H, W), (ox.clamp(-R, OW + R - 1) + R).expand(H, W)]
+            val[..., r * S + s] = v * ok
+    _put(dP, val)
+
+
 def expand_x(x, y, Cin, taps):
     v = _get(x)[..., :Cin]
     W, p = x.W, (taps - 1) // 2
@@ -513,10 +561,10 @@ def shift_expand(dz, dP, Cout, taps):
     _put(dP, res)
 
 
-_PATCHED = ['expand_x', 'shift_sum', 'shift_expand', 'resize_nearest', 'upsample2x_bwd', 'spade_modulate', 'spade_modulate_bwd', 'act_fwd', 'avgpool3s2',
+_PATCHED = ['expand_x', 'shift_sum', 'shift_expand', 'tap_sum', 'tap_expand', 'resize_nearest', 'upsample2x_bwd', 'spade_modulate', 'spade_modulate_bwd', 'act_fwd', 'avgpool3s2',
             'avgpool3s2_bwd', 'maxpool2', 'maxpool2_bwd', 'onehot_edges', 'gather_sum', 'scatter_add', 'fma_vec',
             'sn_forward', 'sn_backward', 'nchw_to_nhwc', 'nhwc_to_nchw', 'copy_channels', 'act_bwd', 'channel_sum', 'reflect_fold', 'add',
-            'norm_stats', 'norm_finalize', 'norm_apply', 'norm_bwd_reduce', 'norm_bwd_apply', 'dwconv_fwd',
+            'norm_stats', 'norm_finalize', 'norm_apply', 'norm_apply_fused', 'norm_bwd_reduce', 'norm_bwd_apply', 'dwconv_fwd',
             'dwconv_bwd_data', 'dwconv_bwd_weight', 'gan_loss', 'recon_loss', 'gram', 'ka_finish', 'ka_bwd', 'adam']
 
 

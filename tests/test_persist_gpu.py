@@ -153,3 +153,75 @@ def test_autotune_offers_the_persistent_variants():
     g1 = ops.Gemm(P.Geometry(2, 32, 32, 64, 0, 32, 32, 64, 0, pad_mode=P.PAD_REFLECT), units, 64, DEV)
     assert {t[4] for t in g0.tilings} == {0, 2}
     assert {t[4] for t in g1.tilings} == {0, 1}
+
+
+@pytest.mark.parametrize('k,stride,pad,Cin,Cout,N,H,W', [
+    (3, 1, 1, 24, 40, 3, 20, 28),       # several tiles per image, garbage positions in pitch space
+    (1, 1, 0, 64, 300, 2, 16, 16),      # two N tiles
+    (4, 2, 1, 16, 72, 4, 64, 64),       # stride 2, many tiles per CTA in the persistent kernel
+    (3, 1, 1, 64, 64, 4, 96, 96),
+])
+@pytest.mark.parametrize('pmode', [0, 1, 2])
+@pytest.mark.parametrize('per_sample', [False, True])
+def test_fused_epilogue_statistics(k, stride, pad, Cin, Cout, N, H, W, pmode, per_sample):
+    """Sum / sum of squares accumulated by the conv epilogue (v2 and both v3 producers) == catb_norm_stats over the
+    stored output (same bf16 values; fp32 summation order differs), into a channel slice of a wider statistics row."""
+    from cat_b200 import ops
+    torch.manual_seed(k + Cout)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, k, k) / math.sqrt(Cin * k * k)
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    arena = w.flatten().to(DEV)
+    units = P.conv_fprop_units(0, Cout, Cin, k, k, pad)
+    Cp = P.cpad(Cout)
+    ldy, yc = Cp + 16, 8
+    geo = P.Geometry(N, H, W, P.cpad(Cin), 0, OH, OW, ldy, yc, sn=stride, pad_mode=P.PAD_ZERO)
+    gm = ops.Gemm(geo, units, Cout, DEV, force_mode=pmode)
+    assert gm.halo is not None and gm.tilings
+    gm.pack(arena)
+    gm.choice = 'v2'
+    xd = to_dev_nhwc(x)
+    G = N if per_sample else 1
+    Cs, coff = Cp + 24, 16          # statistics row wider than the GEMM's channels
+    for cand in gm.tilings:
+        gm._use_tiling(cand)
+        y = torch.zeros(N, OH, OW, ldy, dtype=torch.bfloat16, device=DEV)
+        sums = torch.zeros(G, 2, Cs, device=DEV)
+        assert gm.fprop(xd, y, act=ops.ACT['leaky'], stats=(sums, Cs, coff, per_sample)) is True
+        ref = torch.zeros(G, 2, Cp, device=DEV)
+        ops.norm_stats(ops.Act(y, yc, Cp), per_sample, ref)
+        torch.cuda.synchronize()
+        got = sums[:, :, coff:coff + Cp]
+        assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max()), (cand[0], cand[1], cand[4])
+        assert float(sums[:, :, :coff].abs().max()) == 0 and float(sums[:, :, coff + Cp:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('per_sample,track,residual', [(False, True, False), (True, False, True), (False, False, True)])
+def test_norm_apply_fused_matches_finalize_plus_apply(per_sample, track, residual):
+    from cat_b200 import ops
+    torch.manual_seed(3)
+    N, H, W, C = 3, 12, 20, 40
+    x = ops.Act((torch.randn(N, H, W, C, device=DEV) * 2 + 0.5).to(torch.bfloat16))
+    r = ops.Act(torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)) if residual else None
+    G = N if per_sample else 1
+    count = H * W if per_sample else N * H * W
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    sums = torch.zeros(G, 2, C, device=DEV)
+    ops.norm_stats(x, per_sample, sums)
+    out = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        scale, shift, mr = (torch.zeros(G, C, device=DEV), torch.zeros(G, C, device=DEV), torch.zeros(G, 2, C, device=DEV))
+        y = ops.Act(torch.zeros(N, H, W, C, dtype=torch.bfloat16, device=DEV))
+        a = (rm if track else None, rv if track else None)
+        if fused:
+            ops.norm_apply_fused(x, y, sums, count, 1e-5, 0.1, gamma, beta, a[0], a[1], scale, shift, mr, per_sample,
+                                 ops.ACT['relu'], r)
+        else:
+            ops.norm_finalize(sums, G, C, count, 1e-5, 0.1, gamma, beta, a[0], a[1], scale, shift, mr)
+            ops.norm_apply(x, y, scale, shift, per_sample, ops.ACT['relu'], r)
+        torch.cuda.synchronize()
+        out.append((y.t.float(), scale, shift, mr, rm, rv))
+    assert float((out[0][0] - out[1][0]).abs().max()) <= 2 ** -7 * float(out[0][0].abs().max())   # bf16 outputs: one ulp
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
