@@ -75,8 +75,8 @@ _PROTOS = {
     'catb_igemm_halo_wgrad': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P, _P],
     'catb_igemm_wgrad_ws_shape': [_DP, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'catb_igemm_wgrad_ws': [_DP, _P, _P, _P, _P, _P],
-    'catb_igemm_halo_wgrad_ws_shape': [_DP, C.POINTER(HaloDesc), _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
-    'catb_igemm_halo_wgrad_ws': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _P],
+    'catb_igemm_halo_wgrad_ws_shape': [_DP, C.POINTER(HaloDesc), _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    'catb_igemm_halo_wgrad_ws': [_DP, C.POINTER(HaloDesc), _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     'catb_wgrad_unpack': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     'catb_wgrad_unpack_batch': [_P, _I, _I, _P],
     'catb_ref_fprop': [_DP, _P, _P, _P, _P, _P, _P, _P],
@@ -136,6 +136,7 @@ _SPECIAL = {
     'catb_igemm_halo_fits': ([_I, _I, _I, _I, _I, _I], C.c_int),
     'catb_igemm_halo_wgrad_fits': ([_I, _I], C.c_int),
     'catb_igemm_halo_persist_fits': ([_I] * 10, C.c_int),
+    'catb_igemm_halo_wgrad_tma_fits': ([C.POINTER(HaloDesc)], C.c_int),
 }
 EXPORTED_SYMBOLS = sorted(list(_PROTOS) + list(_SPECIAL))
 

@@ -375,6 +375,25 @@ static TensorMapEncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
+// 4-D tiled tensor map over an NHWC bf16 activation slice: dims (C = c_visible, W, H, N), box 64 channels x box_w x box_h
+// pixels (x 1 image) traversed with `stride` along W and H, SWIZZLE_128B, out-of-bounds elements read as zero.
+int encode_nhwc_tile_map(CUtensorMap* out, const void* base, int c_visible, int W, int H, int N, int ld, int box_w, int box_h,
+                         int stride) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  CATB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_visible), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(W) * ld * 2,
+                                 static_cast<cuuint64_t>(H) * W * ld * 2};
+  const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w * stride), static_cast<cuuint32_t>(box_h * stride), 1};
+  const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CATB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return CATB_OK;
+}
+
 }  // namespace catb
 
 using namespace catb;
@@ -474,19 +493,8 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
                  "TMA-staged tiles need zero padding (out-of-bounds fill); reflection-padded convs use the cp.async producers");
     CATB_REQUIRE(h->Wf * h->mul <= 256 && p.plane_rows * h->mul <= 256, "TMA box exceeds 256 elements per dimension");
     CATB_REQUIRE(c_visible > 0 && c_visible % 8 == 0 && d->x_coff + c_visible <= d->ldx, "bad visible channel count %d", c_visible);
-    TensorMapEncodeTiledFn enc = tensor_map_encoder();
-    CATB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     // NHWC activation as a 4-D tensor (C, W, H, N), channels beyond the GEMM's own slice out of bounds (-> zero)
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_visible), static_cast<cuuint64_t>(d->W), static_cast<cuuint64_t>(d->H),
-                                static_cast<cuuint64_t>(d->N)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->ldx) * 2, static_cast<cuuint64_t>(d->W) * d->ldx * 2,
-                                   static_cast<cuuint64_t>(d->H) * d->W * d->ldx * 2};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(h->Wf * h->mul), static_cast<cuuint32_t>(p.plane_rows * h->mul), 1};
-    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(h->mul), static_cast<cuuint32_t>(h->mul), 1};
-    void* base = const_cast<__nv_bfloat16*>(p.x + d->x_coff);
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CATB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    if (int e = encode_nhwc_tile_map(&tmap, p.x + d->x_coff, c_visible, d->W, d->H, d->N, d->ldx, h->Wf, p.plane_rows, h->mul)) return e;
   }
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);

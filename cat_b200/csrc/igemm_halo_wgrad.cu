@@ -9,6 +9,9 @@
 // (M = 128 dY channels, N = 64 X channels, K = 16 positions) whose B descriptor starts at the tap's row offset
 // inside the halo.  Both operands are MN-major (rows = positions).  Each tap accumulates in its own 64 TMEM
 // columns (8 taps = 512 columns); the epilogue adds them to the fp32 gradient arena with atomics.
+#include <cuda.h>   // CUtensorMap (types only)
+#include <cstring>
+
 #include "common.cuh"
 
 namespace catb {
@@ -20,6 +23,7 @@ constexpr int kWProdThreads = kWProdWarps * 32;
 constexpr int kWRowStep = kWProdThreads / 8;   // halo / dY rows advanced per producer iteration
 constexpr int kWThreads = kWProdThreads + 32;  // + the MMA-issuing warp
 constexpr int kWHeader = 1024;
+constexpr int kWMaxBufs = 4;        // ring depth of the operand buffers (TMA mode: 2-4; cp.async mode: 1-2)
 constexpr int kWPos = 128;          // lattice positions (GEMM K) per tile
 constexpr int kDyBytes = 2 * kWPos * 128;   // [2 chunks of 64 channels][128 positions][128 B]
 
@@ -35,7 +39,18 @@ struct WHaloParams {
   float* grad;
   float* ws;   // two-stage mode (see igemm.cu): partial tiles [split][n_rows][n_steps * 64]
   int tiles_per_strip, tiles_total, tiles_per_cta, bufs, halo_bytes, cy_p;
+  // TMA mode (zero padding, one strip): both operands arrive as tensor-map boxes of whole frame rows; pos = lattice
+  // positions (GEMM K) per tile, 128 or 64 (the smaller tile buys a deeper ring when four parity planes fill the SM)
+  int use_tma, pos, dy_chunk_bytes, dy_rows, plane_rows, plane_bytes;
 };
+
+__device__ __forceinline__ void tma_load_4d_w(uint32_t dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 
 __device__ __forceinline__ void cp16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
   const int sz = valid ? 16 : 0;
@@ -43,15 +58,18 @@ __device__ __forceinline__ void cp16_zfill(void* smem_dst, const void* gmem_src,
                : "memory");
 }
 
-__global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WHaloParams p) {
+__global__ void __launch_bounds__(kWThreads, 1)
+igemm_halo_wgrad_kernel(const __grid_constant__ WHaloParams p, const __grid_constant__ CUtensorMap tmap_x,
+                        const __grid_constant__ CUtensorMap tmap_y) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [2]
-  uint64_t* empty = full + 2;                            // [2]
-  uint64_t* accum = full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 5);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kWMaxBufs]
+  uint64_t* empty = full + kWMaxBufs;                    // [kWMaxBufs]
+  uint64_t* accum = full + 2 * kWMaxBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kWMaxBufs + 1);
   uint8_t* bufs = smem + kWHeader;
-  const int buf_bytes = kDyBytes + p.halo_bytes;
+  const int dy_bytes = 2 * p.dy_chunk_bytes;
+  const int buf_bytes = dy_bytes + p.halo_bytes;
 
   const catb_igemm_desc& d = p.d;
   const catb_halo_desc& h = p.h;
@@ -64,8 +82,8 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
   const uint32_t tmem_cols = grp.n_steps * 64 <= 64 ? 64 : (grp.n_steps * 64 <= 128 ? 128 : (grp.n_steps * 64 <= 256 ? 256 : 512));
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], kWProdThreads);
+    for (int i = 0; i < kWMaxBufs; ++i) {
+      mbar_init(&full[i], p.use_tma ? 1 : kWProdThreads);
       mbar_init(&empty[i], 1);
     }
     mbar_init(accum, 1);
@@ -86,6 +104,28 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
     const bool uvalid = ul < ch.n_units;
     const __nv_bfloat16* xc = p.x + d.x_coff + (ch.cu0 + ul) * 8;
     const int per_img = p.tiles_per_strip * h.n_strips;
+    if (p.use_tma) {
+      if (threadIdx.x == 0) {
+        const uint32_t tx_bytes = (2u * p.dy_rows + static_cast<uint32_t>(h.n_planes) * p.plane_rows) * h.Wf * 128u;
+        for (int t = t0; t < t1; ++t) {
+          const int it = t - t0;
+          const int buf = it % p.bufs;
+          const uint32_t ph = (it / p.bufs) & 1;
+          const int n_img = t / per_img;
+          const int m0 = (t - n_img * per_img) * p.pos;      // one strip per image in this mode
+          const int fy0 = m0 / h.Wf;
+          const uint32_t dst = smem_u32(bufs + static_cast<size_t>(buf) * buf_bytes);
+          mbar_wait(&empty[buf], ph ^ 1);
+          mbar_arrive_expect_tx(&full[buf], tx_bytes);
+          for (int ca = 0; ca < 2; ++ca)   // dY: positions x 64 channels, rows (i >= OHs) / columns (j >= OWs) out of bounds = 0
+            tma_load_4d_w(dst + ca * p.dy_chunk_bytes, &tmap_y, &full[buf], m_tile * 128 + ca * 64, 0, fy0, n_img);
+          for (int pl = 0; pl < h.n_planes; ++pl)
+            tma_load_4d_w(dst + dy_bytes + pl * p.plane_bytes, &tmap_x, &full[buf], ch.cu0 * 8,
+                          h.mul * h.plane_x0[pl] + h.plane_pb[pl], h.mul * (fy0 + h.plane_y0[pl]) + h.plane_pa[pl], n_img);
+        }
+      }
+      __syncwarp();
+    } else
     for (int t = t0; t < t1; ++t) {
       const int it = t - t0;
       const int buf = it % p.bufs;
@@ -95,7 +135,7 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
       const int m0 = (t - n_img * per_img - strip * p.tiles_per_strip) * kWPos;
       const int strip_x = strip * h.TW;
       uint8_t* dyb = bufs + static_cast<size_t>(buf) * buf_bytes;
-      uint8_t* hal = dyb + kDyBytes;
+      uint8_t* hal = dyb + dy_bytes;
       mbar_wait(&empty[buf], ph ^ 1);
       // ---- dY tile: rows = positions (zero rows for garbage positions), 2 chunks of 64 channels
       {
@@ -187,22 +227,41 @@ __global__ void __launch_bounds__(kWThreads, 1) igemm_halo_wgrad_kernel(const WH
       const uint32_t hi = sw128_desc_hi(1024);
       uint32_t boff[8];   // (a_row * 128) >> 4 of the group's taps
 #pragma unroll
-      for (int s = 0; s < 8; ++s) boff[s] = s < grp.n_steps ? static_cast<uint32_t>(p.steps[grp.first_step + s].a_row) * 8u : 0u;
-      const uint32_t dy_lo0 = sw128_desc_lo(smem_u32(bufs), kWPos * 128);
-      const uint32_t hal_lo0 = sw128_desc_lo(smem_u32(bufs) + kDyBytes, 1024);
+      for (int s = 0; s < 8; ++s) {
+        uint32_t a_row = s < grp.n_steps ? static_cast<uint32_t>(p.steps[grp.first_step + s].a_row) : 0u;
+        if (p.use_tma) {   // a_row = plane * Lh + (dy * Wf + dx): planes are plane_bytes apart in this mode
+          const uint32_t plane = a_row / static_cast<uint32_t>(h.Lh), rest = a_row - plane * static_cast<uint32_t>(h.Lh);
+          boff[s] = plane * (static_cast<uint32_t>(p.plane_bytes) >> 4) + rest * 8u;
+        } else {
+          boff[s] = a_row * 8u;
+        }
+      }
+      const uint32_t dy_lo0 = sw128_desc_lo(smem_u32(bufs), p.dy_chunk_bytes);
+      const uint32_t hal_lo0 = sw128_desc_lo(smem_u32(bufs) + dy_bytes, 1024);
       const uint32_t buf16 = static_cast<uint32_t>(buf_bytes) >> 4;
+      const int ksteps = p.pos / 16;
+      const int per_img_m = p.tiles_per_strip * h.n_strips;
       uint32_t buf = 0, ph = 0, dy_lo = dy_lo0, hal_lo = hal_lo0, acc = 0;
       for (int t = t0; t < t1; ++t) {
+        uint32_t toff = 0;   // TMA mode: the tile starts (m0 mod Wf) rows into its boxes
+        if (p.use_tma) {
+          const int m0 = (t - (t / per_img_m) * per_img_m) * p.pos;
+          toff = static_cast<uint32_t>(m0 - (m0 / h.Wf) * h.Wf) * 8u;
+        }
         mbar_wait(&full[buf], ph);
         tcgen05_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
             if (s < grp.n_steps) {
-              const uint32_t b_lo = hal_lo + boff[s];
+              const uint32_t a_lo = dy_lo + toff, b_lo = hal_lo + toff + boff[s];
 #pragma unroll
-              for (int k = 0; k < kWPos / 16; ++k)
-                umma_bf16_lh(tmem_base + s * 64, dy_lo + k * 128, hi, b_lo + k * 128, hi, idesc, k == 0 ? acc : 1u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lh(tmem_base + s * 64, a_lo + k * 128, hi, b_lo + k * 128, hi, idesc, k == 0 ? acc : 1u);
+              if (ksteps == 8) {
+#pragma unroll
+                for (int k = 4; k < 8; ++k) umma_bf16_lh(tmem_base + s * 64, a_lo + k * 128, hi, b_lo + k * 128, hi, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty[buf]);
@@ -239,6 +298,9 @@ int init_halo_wgrad_attributes() {
   return CATB_OK;
 }
 
+int encode_nhwc_tile_map(CUtensorMap* out, const void* base, int c_visible, int W, int H, int N, int ld, int box_w, int box_h,
+                         int stride);   // igemm_halo_persist.cu
+
 }  // namespace catb
 
 using namespace catb;
@@ -248,9 +310,50 @@ extern "C" int catb_igemm_halo_wgrad_fits(int n_planes, int Lh) {
   return kWHeader + 1024 + kDyBytes + halo_bytes <= 227 * 1024 ? 1 : 0;
 }
 
-static void halo_wgrad_split_plan(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int* tiles_total,
+// Tile plan shared by the launch and the workspace-shape query.  TMA mode: pos = 128 if at least two ring buffers fit,
+// else 64 (halves both boxes); returns false when not even that fits / the boxes exceed the 256-element box limit.
+struct WTilePlan {
+  int pos, bufs, dy_rows, dy_chunk_bytes, plane_rows, plane_bytes, halo_bytes;
+};
+static bool wgrad_tile_plan(const catb_halo_desc* h, int use_tma, WTilePlan* tp) {
+  if (!use_tma) {
+    tp->pos = kWPos;
+    tp->dy_rows = kWPos;
+    tp->dy_chunk_bytes = kWPos * 128;
+    tp->plane_rows = h->Lh;
+    tp->plane_bytes = h->Lh * 128;
+    tp->halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
+    const int buf_bytes = 2 * tp->dy_chunk_bytes + tp->halo_bytes;
+    if (kWHeader + 1024 + buf_bytes > 227 * 1024) return false;
+    tp->bufs = (kWHeader + 1024 + 2 * buf_bytes <= 227 * 1024) ? 2 : 1;
+    return true;
+  }
+  for (int pos = 128; pos >= 64; pos /= 2) {
+    const int Wf = h->Wf, Lh = h->Lh - 128 + pos;
+    tp->pos = pos;
+    tp->dy_rows = (Wf - 1 + pos + Wf - 1) / Wf;
+    tp->dy_chunk_bytes = (tp->dy_rows * Wf * 128 + 1023) / 1024 * 1024;
+    tp->plane_rows = (Wf - 1 + Lh + Wf - 1) / Wf;
+    tp->plane_bytes = (tp->plane_rows * Wf * 128 + 1023) / 1024 * 1024;
+    tp->halo_bytes = h->n_planes * tp->plane_bytes;
+    if (Wf * h->mul > 256 || tp->plane_rows * h->mul > 256 || tp->dy_rows > 256) return false;
+    const int buf_bytes = 2 * tp->dy_chunk_bytes + tp->halo_bytes;
+    int bufs = (227 * 1024 - kWHeader - 1024) / buf_bytes;
+    if (bufs > kWMaxBufs) bufs = kWMaxBufs;
+    tp->bufs = bufs;
+    if (bufs >= 2 || (pos == 64 && bufs >= 1)) return true;
+  }
+  return false;
+}
+
+extern "C" int catb_igemm_halo_wgrad_tma_fits(const catb_halo_desc* h) {
+  WTilePlan tp;
+  return h != nullptr && h->n_strips == 1 && wgrad_tile_plan(h, 1, &tp) ? 1 : 0;
+}
+
+static void halo_wgrad_split_plan(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int pos, int* tiles_total,
                                   int* tiles_per_strip, int* tiles_per_cta, int* splits) {
-  *tiles_per_strip = (d->OHs * h->Wf + kWPos - 1) / kWPos;
+  *tiles_per_strip = (d->OHs * h->Wf + pos - 1) / pos;
   *tiles_total = *tiles_per_strip * h->n_strips * d->N;
   const int m_tiles = (d->n_rows + 127) / 128;
   // split the position tiles so that the grid has ~3 CTAs per SM, at least 2 tiles per CTA
@@ -264,7 +367,7 @@ static void halo_wgrad_split_plan(const catb_igemm_desc* d, const catb_halo_desc
 static int launch_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
                              const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
                              const catb_weight_unit* wunits, const void* x, const void* y, float* arena_grad, float* ws,
-                             catb_stream_t s) {
+                             int use_tma, int c_visible, catb_stream_t s) {
   CATB_REQUIRE(d != nullptr && h != nullptr && n_groups > 0, "null descriptor");
   CATB_REQUIRE(h->m_sub == 1, "the weight-gradient halo kernel uses single 128-position tiles");
   CATB_REQUIRE(h->n_planes >= 1 && h->n_planes <= 4 && h->n_steps > 0 && h->n_chunks > 0, "bad halo plan");
@@ -283,18 +386,37 @@ static int launch_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, 
   p.y = static_cast<const __nv_bfloat16*>(y);
   p.grad = arena_grad;
   p.ws = ws;
-  p.halo_bytes = (h->n_planes * h->Lh * 128 + 1023) / 1024 * 1024;
-  const int buf_bytes = kDyBytes + p.halo_bytes;
-  CATB_REQUIRE(kWHeader + 1024 + buf_bytes <= 227 * 1024, "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
-  p.bufs = (kWHeader + 1024 + 2 * buf_bytes <= 227 * 1024) ? 2 : 1;
+  p.use_tma = use_tma ? 1 : 0;
+  WTilePlan tp;
+  CATB_REQUIRE(wgrad_tile_plan(h, p.use_tma, &tp), "halo tile does not fit in shared memory (Lh=%d planes=%d)", h->Lh, h->n_planes);
+  p.pos = tp.pos;
+  p.bufs = tp.bufs;
+  p.dy_rows = tp.dy_rows;
+  p.dy_chunk_bytes = tp.dy_chunk_bytes;
+  p.plane_rows = tp.plane_rows;
+  p.plane_bytes = tp.plane_bytes;
+  p.halo_bytes = tp.halo_bytes;
+  const int buf_bytes = 2 * p.dy_chunk_bytes + p.halo_bytes;
   p.cy_p = (d->n_rows + 7) / 8 * 8;
+  CUtensorMap tmx, tmy;
+  memset(&tmx, 0, sizeof(tmx));
+  memset(&tmy, 0, sizeof(tmy));
+  if (p.use_tma) {
+    CATB_REQUIRE(d->pad_mode != CATB_PAD_REFLECT || (h->Ymax == 0 && h->Xmax == 0),
+                 "TMA-staged weight gradient needs zero padding (out-of-bounds fill)");
+    CATB_REQUIRE(h->n_strips == 1 && d->o_step == 1 && d->o_ph == 0 && d->o_pw == 0 && d->OHs == d->OH && d->OWs == d->OW,
+                 "TMA-staged weight gradient: one strip, dense output lattice");
+    CATB_REQUIRE(c_visible > 0 && c_visible % 8 == 0 && d->x_coff + c_visible <= d->ldx, "bad visible channel count %d", c_visible);
+    if (int e = encode_nhwc_tile_map(&tmx, p.x + d->x_coff, c_visible, d->W, d->H, d->N, d->ldx, h->Wf, p.plane_rows, h->mul)) return e;
+    if (int e = encode_nhwc_tile_map(&tmy, p.y + d->y_coff, p.cy_p, d->OW, d->OH, d->N, d->ldy, h->Wf, p.dy_rows, 1)) return e;
+  }
   int splits;
-  halo_wgrad_split_plan(d, h, n_groups, &p.tiles_total, &p.tiles_per_strip, &p.tiles_per_cta, &splits);
+  halo_wgrad_split_plan(d, h, n_groups, p.pos, &p.tiles_total, &p.tiles_per_strip, &p.tiles_per_cta, &splits);
   const int m_tiles = (d->n_rows + 127) / 128;
-  if (p.tiles_per_cta == 1) p.bufs = 1;
+  if (p.bufs > p.tiles_per_cta) p.bufs = p.tiles_per_cta;
   dim3 grid(splits, m_tiles, n_groups);
   const size_t smem = 1024 + kWHeader + static_cast<size_t>(p.bufs) * buf_bytes;
-  igemm_halo_wgrad_kernel<<<grid, kWThreads, smem, static_cast<cudaStream_t>(s)>>>(p);
+  igemm_halo_wgrad_kernel<<<grid, kWThreads, smem, static_cast<cudaStream_t>(s)>>>(p, tmx, tmy);
   return check_launch("igemm_halo_wgrad");
 }
 
@@ -302,21 +424,23 @@ extern "C" int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_d
                                      const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
                                      const catb_weight_unit* wunits, const void* x, const void* y, float* arena_grad,
                                      catb_stream_t s) {
-  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, wunits, x, y, arena_grad, nullptr, s);
+  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, wunits, x, y, arena_grad, nullptr, 0, 0, s);
 }
 
-extern "C" int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int* splits,
-                                              int* ws_k) {
+extern "C" int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int use_tma,
+                                              int* splits, int* ws_k) {
   CATB_REQUIRE(d != nullptr && h != nullptr && n_groups > 0 && splits != nullptr && ws_k != nullptr, "null pointer");
+  WTilePlan tp;
+  CATB_REQUIRE(wgrad_tile_plan(h, use_tma ? 1 : 0, &tp), "halo tile does not fit in shared memory");
   int tt, tps, tpc;
-  halo_wgrad_split_plan(d, h, n_groups, &tt, &tps, &tpc, splits);
+  halo_wgrad_split_plan(d, h, n_groups, tp.pos, &tt, &tps, &tpc, splits);
   *ws_k = h->n_steps * 64;
   return CATB_OK;
 }
 
 extern "C" int catb_igemm_halo_wgrad_ws(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps,
                                         const catb_halo_chunk* chunks, const catb_halo_wgroup* groups, int n_groups,
-                                        const void* x, const void* y, float* ws, catb_stream_t s) {
+                                        const void* x, const void* y, float* ws, int use_tma, int c_visible, catb_stream_t s) {
   CATB_REQUIRE(ws != nullptr, "null workspace");
-  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, nullptr, x, y, nullptr, ws, s);
+  return launch_halo_wgrad(d, h, steps, chunks, groups, n_groups, nullptr, x, y, nullptr, ws, use_tma, c_visible, s);
 }

@@ -417,6 +417,15 @@ class Gemm:
         self.w_ngroups = len(groups)
         self.w_wt = units_to_device(plan.units, dev)[1]
         self.w_nunits = len(plan.units)
+        # TMA-staged variant (both operands as tensor-map boxes issued by one thread): zero padding or no border taps, one
+        # strip, dense output lattice
+        g = self.geo
+        no_border = plan.Ymax == 0 and plan.Xmax == 0 and all(pl[2] == 0 and pl[3] == 0 for pl in plan.planes)
+        self.w_c_visible = 8 * max(cu0 + nu for (cu0, nu, _, _) in plan.chunks)
+        self.w_tma_ok = bool(USE_TMA and (g.pad_mode != _C.PAD_REFLECT or no_border) and plan.n_strips == 1 and g.o_step == 1
+                             and g.o_ph == 0 and g.o_pw == 0 and g.OHs == g.OH and g.OWs == g.OW
+                             and lib.catb_igemm_halo_wgrad_tma_fits(C.byref(hd)))
+        self.w_tma = False
         if self.seg_raw is not None:
             self.w_seg_wt = [units_to_device(make_halo_plan(self.geo, su).units, dev)[1] for (_r0, _sp, _nr, su) in self.seg_raw]
 
@@ -430,7 +439,7 @@ class Gemm:
                 _C.check(_C.load().catb_igemm_wgrad_ws_shape(C.byref(d), C.byref(splits), C.byref(ws_k)), 'ws_shape')
             else:
                 _C.check(_C.load().catb_igemm_halo_wgrad_ws_shape(C.byref(d), C.byref(self.w_hdesc), self.w_ngroups,
-                                                                  C.byref(splits), C.byref(ws_k)), 'halo ws_shape')
+                                                                  int(kind == 'v2t'), C.byref(splits), C.byref(ws_k)), 'halo ws_shape')
             ws = torch.empty(splits.value * self.n_rows * ws_k.value, dtype=torch.float32, device=self.gt.device)
             setattr(self, key, (ws, splits.value, ws_k.value))
         return getattr(self, key)
@@ -469,9 +478,9 @@ class Gemm:
                 _C.call('catb_igemm_halo_wgrad', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
                         _p(self.w_groups), self.w_ngroups, _p(self.w_wt), _p(x), _p(y), _p(g), _stream())
                 return
-            ws, splits, ws_k = self._ws_for('v2', d)
+            ws, splits, ws_k = self._ws_for('v2t' if self.w_tma else 'v2', d)
             _C.call('catb_igemm_halo_wgrad_ws', C.byref(d), C.byref(self.w_hdesc), _p(self.w_steps), _p(self.w_chunks),
-                    _p(self.w_groups), self.w_ngroups, _p(x), _p(y), _p(ws), _stream())
+                    _p(self.w_groups), self.w_ngroups, _p(x), _p(y), _p(ws), int(self.w_tma), self.w_c_visible, _stream())
             if self.seg_raw is None:
                 second(ws, splits, ws_k, 0, self.n_rows, self.w_nunits, self.w_wt, g)
             else:
@@ -483,10 +492,20 @@ class Gemm:
             # the result is accumulated into the arena, so the two kernels are timed on a scratch copy of it
             scratch = _scratch_like(grad_arena)
             t2 = self._launch_timed(lambda: v2(scratch))
+            t2t = None
+            if self.w_tma_ok and not atomic:
+                self.w_tma = True
+                t2t = self._launch_timed(lambda: v2(scratch))
+                if t2t < t2:
+                    t2 = t2t
+                else:
+                    self.w_tma = False
             t1 = self._launch_timed(lambda: v1(scratch))
             self.w_choice = 'v2' if t2 <= t1 else 'v1'
-            self.w_tuned_ms = (t1, t2)
-            setattr(self, '_ws_v1' if self.w_choice == 'v2' else '_ws_v2', None)     # drop the loser's workspace
+            self.w_tuned_ms = (t1, t2, t2t)
+            for k in ('_ws_v1', '_ws_v2', '_ws_v2t'):      # drop the losers' workspaces
+                if k != ('_ws_v1' if self.w_choice == 'v1' else ('_ws_v2t' if self.w_tma else '_ws_v2')):
+                    setattr(self, k, None)
         queue[0] = _UNPACK[0]
         if self.w_halo is not None and not force_v1 and self.w_choice != 'v1':
             v2(grad_arena)

@@ -189,11 +189,18 @@ int catb_igemm_halo_wgrad(const catb_igemm_desc* d, const catb_halo_desc* h, con
 int catb_igemm_wgrad_ws_shape(const catb_igemm_desc* d, int* splits, int* ws_k);
 int catb_igemm_wgrad_ws(const catb_igemm_desc* d, const catb_gather_unit* units, const void* x, const void* y, float* ws,
                         catb_stream_t s);
-int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int* splits,
+/* use_tma = 1 (zero padding or no border taps, one strip, dense output lattice; catb_igemm_halo_wgrad_tma_fits): both
+ * operands of a tile -- dY[positions x 128 channels] and the X halo planes -- arrive as cp.async.bulk.tensor boxes of whole
+ * frame rows issued by one thread (positions past the image read as zero = the garbage rows of pitch space), in a 2-4
+ * deep ring of 128- or 64-position tiles; c_visible as for catb_igemm_halo_fprop_persist.  The split count depends on
+ * the tile size, so the shape query takes the same flag. */
+int catb_igemm_halo_wgrad_tma_fits(const catb_halo_desc* h);
+int catb_igemm_halo_wgrad_ws_shape(const catb_igemm_desc* d, const catb_halo_desc* h, int n_groups, int use_tma, int* splits,
                                    int* ws_k);
 int catb_igemm_halo_wgrad_ws(const catb_igemm_desc* d, const catb_halo_desc* h, const catb_halo_step* steps /*device*/,
                              const catb_halo_chunk* chunks /*device*/, const catb_halo_wgroup* groups /*device*/,
-                             int n_groups, const void* x, const void* y, float* ws, catb_stream_t s);
+                             int n_groups, const void* x, const void* y, float* ws, int use_tma, int c_visible,
+                             catb_stream_t s);
 int catb_wgrad_unpack(const float* ws, int n_splits, int ws_rows /* rows per split */, int ws_k, int row0, int n_rows,
                       int n_units, const catb_weight_unit* wunits /*device*/, float* arena_grad, catb_stream_t s);
 

@@ -225,3 +225,51 @@ def test_norm_apply_fused_matches_finalize_plus_apply(per_sample, track, residua
     assert float((out[0][0] - out[1][0]).abs().max()) <= 2 ** -7 * float(out[0][0].abs().max())   # bf16 outputs: one ulp
     for a, b in zip(out[0][1:], out[1][1:]):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('k,stride,pad,Cin,Cout,N,H,W', [
+    (3, 1, 1, 5, 7, 2, 10, 12),
+    (1, 1, 0, 72, 40, 2, 8, 8),
+    (3, 2, 1, 17, 31, 2, 16, 16),        # 4 parity planes
+    (4, 2, 1, 64, 200, 2, 32, 32),       # two channel tiles of dY, PatchGAN-like
+    (4, 1, 1, 128, 72, 2, 17, 17),
+    (4, 2, 1, 128, 256, 4, 64, 64),      # four planes fill the SM: the 64-position tile form
+    (3, 1, 1, 64, 64, 4, 96, 96),        # many tiles per CTA: the ring wraps
+    (1, 1, 0, 128, 24, 8, 64, 64),
+    (1, 1, 0, 1024, 16, 16, 31, 31),     # 16 channel chunks: few splits, 5 tiles per CTA through a 3-deep ring
+])
+def test_tma_weight_gradient(k, stride, pad, Cin, Cout, N, H, W):
+    """Weight gradient with both operands staged by cp.async.bulk.tensor (dY tile + X halo planes as tensor-map boxes)
+    against torch and, bit for bit in structure, against the cp.async form (same MMAs; the row splits may differ)."""
+    from cat_b200 import ops
+    torch.manual_seed(k * 10 + Cout)
+    x = torch.randn(N, Cin, H, W)
+    w = torch.randn(Cout, Cin, k, k)
+    xb, wb = bf(x), bf(w).requires_grad_(True)
+    y_ref = F.conv2d(xb, wb, None, stride=stride, padding=pad)
+    OH, OW = y_ref.shape[2:]
+    dy = torch.randn(N, Cout, OH, OW)
+    y_ref.backward(bf(dy))
+    units = P.conv_fprop_units(5, Cout, Cin, k, k, pad)
+    ldx, xc = P.cpad(Cin) + 24, 16           # channel slices of wider buffers on both sides
+    geo = P.Geometry(N, H, W, ldx, xc, OH, OW, P.cpad(Cout) + 8, 8, sn=stride, pad_mode=P.PAD_ZERO)
+    gw = ops.Gemm(geo, units, Cout, DEV, need_pack=False)
+    xd, dyd = to_dev_nhwc(x, ldx, xc, fill=1000.0), to_dev_nhwc(dy, P.cpad(Cout) + 8, 8, fill=1000.0)
+    gw._wgrad_plan()
+    assert gw.w_halo is not None and gw.w_tma_ok, 'the TMA form must apply to every zero-padded single-strip conv'
+    gw.w_choice = 'v2'
+    out = []
+    for tma in (False, True):
+        gw.w_tma = tma
+        g = torch.zeros(5 + w.numel() + 64, device=DEV)
+        gw.wgrad(xd, dyd, g)
+        torch.cuda.synchronize()
+        got = g[5:5 + w.numel()].view_as(w).double().cpu()
+        assert rel_err(got, wb.grad) < 2e-4, 'TMA weight gradient' if tma else 'cp.async weight gradient'
+        assert float(g[:5].abs().max()) == 0 and float(g[5 + w.numel():].abs().max()) == 0
+        g_again = torch.zeros_like(g)
+        gw.wgrad(xd, dyd, g_again)
+        torch.cuda.synchronize()
+        assert torch.equal(g, g_again), 'two-stage weight gradient must be deterministic'
+        out.append(got)
+    assert rel_err(out[1], out[0]) < 1e-5
