@@ -405,17 +405,22 @@ class GemmProfiler:
         for n, fn in self._orig_hbm.items():
             setattr(ops, n, fn)
 
-    def summary(self):
+    def summary(self, reps=2):
         torch.cuda.synchronize()
         agg, per, net = {}, {}, {}
+        # `reps` identical steps were recorded back to back: keep the faster timing of every launch
+        def fold(recs, t0, t1):
+            n = len(recs) // reps
+            if n == 0 or len(recs) != n * reps:
+                return [(r, r[t0].elapsed_time(r[t1])) for r in recs]
+            return [(recs[i], min(recs[i + k * n][t0].elapsed_time(recs[i + k * n][t1]) for k in range(reps))) for i in range(n)]
         def variant(kind, g):
             if kind != 'fprop':
                 return 'halo' if getattr(g, 'w_halo', None) is not None else 'v1'
             if g.halo is None or g.choice == 'v1':
                 return 'v1'
-            return f"{('v2', 'v3-cpasync', 'v3-tma')[g.h_mode]} TW{g.halo.TW} m{g.halo.m_sub} b{g.hdesc.b_budget // 1024}K"
-        for kind, g, fl, e0, e1 in self.records:
-            ms = e0.elapsed_time(e1)
+            return f"{('v2', 'v3-cpasync', 'v3-tma', 'v3-tma-reflect')[g.h_mode]} TW{g.halo.TW} m{g.halo.m_sub} b{g.hdesc.b_budget // 1024}K"
+        for (kind, g, fl, e0, e1), ms in fold(self.records, 3, 4):
             for table, key in ((agg, kind), (per, (kind, g.n_rows, g.n_units, g.geo.N * g.geo.OHs * g.geo.OWs, variant(kind, g))),
                                (net, (getattr(g, '_owner', 'other'), kind))):
                 a = table.setdefault(key, [0.0, 0.0, 0])
@@ -423,10 +428,10 @@ class GemmProfiler:
                 a[1] += ms
                 a[2] += 1
         hbm = {}
-        for name, nbytes, e0, e1 in self.hbm:
+        for (name, nbytes, e0, e1), ms in fold(self.hbm, 2, 3):
             a = hbm.setdefault(name, [0.0, 0.0, 0])
             a[0] += nbytes
-            a[1] += e0.elapsed_time(e1)
+            a[1] += ms
             a[2] += 1
         return agg, per, net, hbm
 
@@ -729,6 +734,8 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         for g in gens:
             g.overlap_wgrad = False
         eng.step()
+        eng.step()      # twice: every launch is reported at the faster of its two timings (one eager step is noisy --
+        #                 the same kernel variant on the same tensors was seen at 93 and 176 us in consecutive sessions)
         for k, v in saved.items():
             setattr(eng, k, v)
         for g, v in zip(gens, saved_w):

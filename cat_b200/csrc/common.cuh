@@ -498,6 +498,48 @@ __device__ __forceinline__ void halo_fill_plane(uint32_t plane_smem, int row_pha
   }
 }
 
+// Reflection padding on top of a TMA-staged plane: the tensor-map box leaves zeros where the frame reaches outside the
+// image (out-of-bounds fill); this pass overwrites exactly those halo rows with the mirrored pixels (nn.ReflectionPad2d),
+// 16 bytes per thread and row, after the box has landed.  Same row walk as halo_fill_plane; `row0` = frame pixel index of
+// the box origin (fy0 * Wf), `n_rows` = box rows * Wf, plane base 1024-byte aligned (swizzle phase = row & 7).
+template <int STEP>
+__device__ __forceinline__ void halo_patch_reflect(uint32_t plane_smem, const __nv_bfloat16* xc, const __nv_bfloat16* xsafe,
+                                                   long long img_base, int row0, int rsub, int ul, int n_rows_, int Wf_, int mul_,
+                                                   int y0, int x0, int pa, int pb, int H_, int W_, int ldx, bool uvalid) {
+  const int n_rows = in_reg(n_rows_), Wf = in_reg(Wf_), mul = in_reg(mul_), H = in_reg(H_), W = in_reg(W_);
+  const int pitch_bytes = in_reg(ldx * 2);
+  const char* img = reinterpret_cast<const char*>(xc + img_base * ldx);
+  int fy = (row0 + rsub) / Wf;
+  int fx = (row0 + rsub) - fy * Wf;
+  int iy0 = mul * (fy + y0) + pa;
+  int ix0 = mul * (fx + x0) + pb;
+  const int dixs = mul * STEP, dixw = mul * Wf;
+  uint32_t dst = plane_smem + rsub * 128 + ((ul ^ (rsub & 7)) << 4);
+  static_assert(STEP % 8 == 0, "row step must keep the swizzle phase");
+  for (int hr = rsub; hr < n_rows; hr += STEP) {
+    int iy = iy0, ix = ix0;
+    const bool inside = (static_cast<unsigned>(iy) < static_cast<unsigned>(H)) & (static_cast<unsigned>(ix) < static_cast<unsigned>(W));
+    if (!inside) {
+      const bool ok = uvalid & (iy > -H) & (iy < 2 * H - 1) & (ix > -W) & (ix < 2 * W - 1);
+      iy = reflect_idx(iy, H);
+      ix = reflect_idx(ix, W);
+      const uint32_t off = static_cast<uint32_t>(iy * W + ix) * static_cast<uint32_t>(pitch_bytes);
+      const void* src = ok ? static_cast<const void*>(img + off) : static_cast<const void*>(xsafe);
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+    dst += STEP * 128;
+    fx += STEP;
+    ix0 += dixs;
+    while (fx >= Wf) {
+      fx -= Wf;
+      ix0 -= dixw;
+      ++fy;
+      iy0 += mul;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the gather shared by every implicit-GEMM kernel (and its SIMT restatement)
 // ------------------------------------------------------------------------------------------

@@ -23,8 +23,8 @@ namespace catb {
 
 constexpr int kPThreads = 320;      // warps 0-3 halo producers, 4 MMA issuer, 5 weight loader, 6-9 epilogue
 constexpr int kPHeader = 1024;      // barriers [0, 512), per-warp pixel tables of the epilogue [512, 1024)
-constexpr int kPMaxA = 4;
-constexpr int kPMaxBStages = 24;
+constexpr int kPMaxA = 6;
+constexpr int kPMaxBStages = 18;     // (3 * 6 + 2 * 18 + 4 barriers + the TMEM slot fit the first 512 header bytes)
 constexpr int kPStageBytes = 4 * 4096;   // epilogue staging: 4 KB per epilogue warp
 constexpr int kPStatBytes = 2 * 2 * 256 * 4;   // fused statistics: two (tile parity) x [2][n_tile <= 256] floats
 
@@ -39,6 +39,7 @@ struct PersistParams {
   void* y;
   int tiles_per_image, tiles_x, tiles_total, a_bufs, b_stages, tmem_cols, acc_cols, n_store, halo_bytes, tab_bytes;
   int use_tma, plane_rows, plane_bytes;   // TMA mode: frame rows per plane box, bytes per plane (1024-aligned)
+  int patch;                              // TMA mode on a reflection-padded conv: warps 2-3 mirror the out-of-image fringe
   uint32_t idesc;
   catb_epilogue_stats st;                 // st.sums == nullptr: no fused statistics
 };
@@ -73,7 +74,8 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);   // [kPMaxA]
   uint64_t* a_empty = a_full + kPMaxA;                     // [kPMaxA]
-  uint64_t* b_full = a_empty + kPMaxA;                     // [kPMaxBStages]
+  uint64_t* a_tma = a_empty + kPMaxA;                      // [kPMaxA] patch mode: the box has landed (before the fringe pass)
+  uint64_t* b_full = a_tma + kPMaxA;                       // [kPMaxBStages]
   uint64_t* b_empty = b_full + kPMaxBStages;               // [kPMaxBStages]
   uint64_t* acc_full = b_empty + kPMaxBStages;             // [2]
   uint64_t* acc_empty = acc_full + 2;                      // [2]
@@ -92,8 +94,9 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_bufs; ++i) {
-      mbar_init(&a_full[i], p.use_tma ? 1 : 128);
+      mbar_init(&a_full[i], p.use_tma ? (p.patch ? 64 : 1) : 128);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&a_tma[i], 1);
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&b_full[i], 1);
@@ -130,8 +133,31 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
   if (warp < 4) {
     // ---------------------------------------------------------------- halo producers
     uint32_t g = 0;   // chunks staged so far by this CTA (ring position across tiles)
-    if (p.use_tma) {
+    if (p.use_tma && p.patch && warp >= 2) {
+      // ---- reflection padding: wait for the chunk's boxes, mirror the out-of-image halo rows, then release the chunk
+      const int t64 = threadIdx.x - 64, ul = t64 & 7, rsub = t64 >> 3;   // 8 rows per pass, 8 lanes per row
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const size_t img_base = static_cast<size_t>(t.n_img) * d.H * d.W;
+        const int row0 = (t.m0 / h.Wf) * h.Wf;
+        for (int c = 0; c < h.n_chunks; ++c, ++g) {
+          const uint32_t buf = g % p.a_bufs, ph = (g / p.a_bufs) & 1;
+          const int4 chv = s_chunks[c];
+          const __nv_bfloat16* xc = p.x + d.x_coff + (chv.x + ul) * 8;
+          mbar_wait(&a_tma[buf], ph);
+          const uint32_t abuf_s = smem_u32(a_base + static_cast<size_t>(buf) * p.halo_bytes);
+          for (int pl = 0; pl < h.n_planes; ++pl)
+            halo_patch_reflect<8>(abuf_s + pl * p.plane_bytes, xc, p.x, static_cast<long long>(img_base), row0, rsub, ul,
+                                  p.plane_rows * h.Wf, h.Wf, h.mul, h.plane_y0[pl], h.plane_x0[pl] + t.strip_x, h.plane_pa[pl],
+                                  h.plane_pb[pl], d.H, d.W, d.ldx, ul < chv.y);
+          cp_async_wait_all();
+          fence_proxy_async();
+          mbar_arrive(&a_full[buf]);
+        }
+      }
+    } else if (p.use_tma) {
       if (threadIdx.x == 0) {
+        uint64_t* a_land = p.patch ? a_tma : a_full;     // patch mode: the fringe pass stands between the box and the MMAs
         const uint32_t tx_bytes = static_cast<uint32_t>(h.n_planes) * p.plane_rows * h.Wf * 128u;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
           const TileCoord t = decode_tile(p, tile);
@@ -140,10 +166,10 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
             const uint32_t buf = g % p.a_bufs, ph = (g / p.a_bufs) & 1;
             const int cu0 = s_chunks[c].x;
             mbar_wait(&a_empty[buf], ph ^ 1);
-            mbar_arrive_expect_tx(&a_full[buf], tx_bytes);
+            mbar_arrive_expect_tx(&a_land[buf], tx_bytes);
             const uint32_t dst = smem_u32(a_base + static_cast<size_t>(buf) * p.halo_bytes);
             for (int pl = 0; pl < h.n_planes; ++pl)
-              tma_load_4d(dst + pl * p.plane_bytes, &tmap, &a_full[buf], cu0 * 8,
+              tma_load_4d(dst + pl * p.plane_bytes, &tmap, &a_land[buf], cu0 * 8,
                           h.mul * (h.plane_x0[pl] + t.strip_x) + h.plane_pb[pl], h.mul * (fy0 + h.plane_y0[pl]) + h.plane_pa[pl],
                           t.n_img);
           }
@@ -423,14 +449,24 @@ static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int bud
   const int min_b = budget > 0 ? 2 : 4;
   if (want_b < min_b) want_b = min_b;
   if (want_b > kPMaxBStages) want_b = kPMaxBStages;
-  int ab = 2;   // two halo buffers: the fill of the next chunk / tile runs under this one's MMAs
+  // Halo ring.  Two buffers let the fill of the next chunk run under this one's MMAs; a GEMM that streams its activations
+  // (short K: 1x1 convs, the HBM-bound student / teacher layers) needs ~96 KB of loads in flight per SM to cover the
+  // DRAM latency (ncu on the teacher's fused 1x1: two 20 KB boxes in flight = 1.7 TB/s), so small halos get a deeper
+  // ring -- unless the caller asked for the small-footprint variant (b_budget > 0: several CTAs per SM do the same job).
+  int ab = 2;
   if (2 * halo_bytes + 2 * b_bytes > limit) ab = 1;
   if (ab * halo_bytes + 2 * b_bytes > limit) return -1;
+  if (budget == 0 && ab == 2) {
+    int want_a = (96 * 1024 + halo_bytes - 1) / halo_bytes;
+    if (want_a > kPMaxA) want_a = kPMaxA;
+    const int keep_b = (want_b < 3 ? want_b : 3) * b_bytes;   // weight tiles come from L2: three stages suffice if space is short
+    while (want_a > 2 && want_a * halo_bytes + keep_b > limit) --want_a;
+    ab = want_a;
+  }
   int bs = (limit - ab * halo_bytes) / b_bytes;
   if (bs > want_b) bs = want_b;
   if (bs < 2) return -1;
-  // a third buffer for single-chunk GEMMs with a small halo, when it is cheap (< 1/8 of shared memory in total)
-  if (n_chunks == 1 && ab == 2 && 3 * halo_bytes <= 28 * 1024 && 3 * halo_bytes + bs * b_bytes <= limit) ab = 3;
+  (void)n_chunks;
   *a_bufs = ab;
   *b_stages = bs;
   *total = 1024 + kPHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes + kPStageBytes +
@@ -479,6 +515,7 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
     p.st = *stats;
   }
   p.use_tma = use_tma ? 1 : 0;
+  p.patch = use_tma == 2 ? 1 : 0;
   p.plane_rows = persist_plane_rows(h->Lh, h->Wf);
   p.halo_bytes = persist_halo_bytes(h->n_planes, h->Lh, h->Wf, p.use_tma, &p.plane_bytes);
   p.tab_bytes = persist_table_bytes(h->n_steps, h->n_chunks);
@@ -489,8 +526,8 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (p.use_tma) {
-    CATB_REQUIRE(d->pad_mode != CATB_PAD_REFLECT || (h->Ymax == 0 && h->Xmax == 0),
-                 "TMA-staged tiles need zero padding (out-of-bounds fill); reflection-padded convs use the cp.async producers");
+    CATB_REQUIRE(p.patch || d->pad_mode != CATB_PAD_REFLECT || (h->Ymax == 0 && h->Xmax == 0),
+                 "TMA-staged tiles of a reflection-padded conv need the fringe pass (use_tma = 2)");
     CATB_REQUIRE(h->Wf * h->mul <= 256 && p.plane_rows * h->mul <= 256, "TMA box exceeds 256 elements per dimension");
     CATB_REQUIRE(c_visible > 0 && c_visible % 8 == 0 && d->x_coff + c_visible <= d->ldx, "bad visible channel count %d", c_visible);
     // NHWC activation as a 4-D tensor (C, W, H, N), channels beyond the GEMM's own slice out of bounds (-> zero)

@@ -83,6 +83,7 @@ AUTOTUNE = os.environ.get('CATB_NO_AUTOTUNE', '0') != '1'  # pick v1 / v2 per GE
 USE_PERSIST = os.environ.get('CATB_NO_PERSIST', '0') != '1'   # v3 (persistent halo kernel) variants offered to the autotune
 FUSE_STATS = os.environ.get('CATB_NO_FUSED_STATS', '0') != '1'   # norm statistics accumulated by the conv epilogue
 USE_TMA = os.environ.get('CATB_NO_TMA', '0') != '1'
+TMA_REFLECT = os.environ.get('CATB_TMA_REFLECT', '0') == '1'   # offer v3 mode 3 (TMA + reflection fringe pass) to the autotune
 TAP_HEAD = os.environ.get('CATB_NO_TAP_HEAD', '0') != '1'     # one-output-channel convs (PatchGAN head) in tap-split form           # v3 stages zero-padded halos with cp.async.bulk.tensor
 
 
@@ -174,7 +175,8 @@ class Gemm:
         segments=[(row0, span, nreal, Units)] describes an N-concatenation: every segment shares the gather
         side of `units` and supplies its own weight side for image rows [row0, row0+span).
         force_mode pins the forward kernel of the halo tilings (tests): 0 = v2 (one tile per CTA), 1 = v3 persistent with
-        cp.async producers, 2 = v3 persistent with TMA-staged tiles; by default every applicable one is a candidate."""
+        cp.async producers, 2 = v3 persistent with TMA-staged tiles, 3 = v3 with TMA tiles + the reflection fringe pass; by
+        default every applicable one is a candidate."""
         assert len(units) > 0 and n_rows > 0
         self.segments = None
         self.seg_raw = segments      # also drives the per-segment second stage of the weight gradient
@@ -203,8 +205,10 @@ class Gemm:
                 # an SM and the fill / MMA / epilogue phases of neighbouring tiles overlap
                 budgets = (0, 16 * 1024) if (force_tile is None and self.n_tile <= 128) else (0,)
                 # v3 stages the halo with TMA where out-of-bounds = zero is the padding rule (or no tap leaves the image)
-                tma_ok = USE_TMA and (geo.pad_mode != _C.PAD_REFLECT or (plan.Ymax == 0 and plan.Xmax == 0 and
-                                                                     all(pl[2] == 0 and pl[3] == 0 for pl in plan.planes)))
+                no_border = plan.Ymax == 0 and plan.Xmax == 0 and all(pl[2] == 0 and pl[3] == 0 for pl in plan.planes)
+                tma_ok = USE_TMA and (geo.pad_mode != _C.PAD_REFLECT or no_border)
+                # reflection padding with border taps: TMA boxes + a fringe pass that mirrors the out-of-image halo rows (mode 3)
+                tma_reflect = USE_TMA and not tma_ok
                 self.c_visible = 8 * max(cu0 + nu for (cu0, nu, _, _) in plan.chunks)
                 for tw, ms in cands:
                     plan.TW, plan.m_sub = tw, ms
@@ -212,12 +216,20 @@ class Gemm:
                     if lib.catb_igemm_halo_fits(len(plan.planes), plan.Lh, self.n_tile, ms, len(plan.steps), len(plan.chunks)):
                         modes.append(0)
                     if USE_PERSIST or force_mode:
-                        m3s = ((2, 1) if tma_ok else (1,)) if not force_mode else ((force_mode,) if (force_mode == 1 or tma_ok) else ())
+                        if force_mode:
+                            m3s = (force_mode,) if (force_mode == 1 or (force_mode == 2 and tma_ok) or
+                                                    (force_mode == 3 and tma_reflect)) else ()
+                        else:       # zero padding: TMA (else cp.async); reflection: cp.async producers -- the TMA + fringe-pass
+                            # form lost to them and to v2 on every shape measured (profiles/r02_gemm_variants_v6.txt: the
+                            # serial box -> fringe -> MMA chain adds latency to GEMMs that are MMA-issue bound anyway), so it
+                            # is only a candidate when asked for (CATB_TMA_REFLECT=1)
+                            m3s = (2, 1) if tma_ok else ((3, 1) if (tma_reflect and TMA_REFLECT) else (1,))
                         for m3 in m3s:
                             if lib.catb_igemm_halo_persist_fits(len(plan.planes), plan.Lh, plan.Wf, plan.mul, self.n_tile, ms,
-                                                                len(plan.steps), len(plan.chunks), 0, int(m3 == 2)):
+                                                                len(plan.steps), len(plan.chunks), 0, int(m3 >= 2)):
                                 modes.append(m3)
-                                break
+                                if m3 == 2:
+                                    break
                     if force_mode is not None:
                         modes = [m for m in modes if m == force_mode]
                     if not modes:
@@ -346,9 +358,9 @@ class Gemm:
                 es = _C.EpilogueStats()
                 es.sums, es.C, es.coff, es.per_sample = st[0][0].data_ptr(), int(st[0][1]), int(st[0][2]), int(bool(st[0][3]))
                 es = C.byref(es)
-            if self.h_mode:   # v3: persistent pipeline, halo staged by TMA (mode 2) or cp.async producers (mode 1)
+            if self.h_mode:   # v3: persistent pipeline, halo staged by cp.async producers (mode 1), TMA (2), TMA + reflection fringe (3)
                 _C.call('catb_igemm_halo_fprop_persist', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
-                        _p(x), _p(self.packed), _p(bias), _p(y), int(self.h_mode == 2), self.c_visible, es, _stream())
+                        _p(x), _p(self.packed), _p(bias), _p(y), (0, 0, 1, 2)[self.h_mode], self.c_visible, es, _stream())
                 return
             _C.call('catb_igemm_halo_fprop', C.byref(d2), C.byref(self.hdesc), _p(self.h_steps), _p(self.h_chunks),
                     _p(x), _p(self.packed), _p(bias), _p(y), es, _stream())

@@ -155,7 +155,9 @@ int catb_igemm_halo_fprop(const catb_igemm_desc* d, const catb_halo_desc* h, con
  * the activation halo with cp.async.bulk.tensor from a 4-D tiled tensor map over the NHWC input (zero padding = the
  * map's out-of-bounds fill, parity planes of stride-2 convs = traversal stride 2); it needs zero padding (or a GEMM
  * without border taps) and c_visible = the channel count of the GEMM's input slice (channels past it read as zero).
- * use_tma = 0 keeps the cp.async producers (reflection padding).  Same tables and packed weights as
+ * use_tma = 2 does the same for a reflection-padded conv: the boxes land with zeros outside the image and two warps then
+ * mirror exactly those halo rows (nn.ReflectionPad2d) before the chunk is released to the MMAs.  use_tma = 0 keeps the
+ * cp.async producers.  Same tables and packed weights as
  * catb_igemm_halo_fprop; replaces the same ATen conv / conv-transpose / conv-backward-input call sites
  * (models/modules/inception_modules.py:22-44, models/modules/discriminators.py:37-75 of the reference). */
 int catb_igemm_halo_persist_fits(int n_planes, int Lh, int Wf, int mul, int n_tile, int m_sub, int n_steps, int n_chunks,

@@ -55,7 +55,9 @@ CASES = [
     (3, 1, 1, 'zero', 64, 64, 4, 96, 96),        # 288+ tiles: every CTA walks several (rings / accumulator stages wrap)
     (1, 1, 0, 'zero', 128, 24, 8, 128, 128),     # short K, 1024 tiles
     (4, 2, 1, 'zero', 24, 64, 4, 128, 128),      # stride 2 with many tiles
-    (5, 1, 2, 'reflect', 40, 24, 4, 64, 64),     # reflection: cp.async producers in the persistent pipeline
+    (5, 1, 2, 'reflect', 40, 24, 4, 64, 64),     # reflection: cp.async producers / TMA + fringe pass in the persistent pipeline
+    (3, 1, 1, 'reflect', 136, 48, 3, 40, 56),    # three channel chunks, strips touch both borders
+    (7, 1, 3, 'reflect', 24, 40, 2, 12, 12),     # halo wider than a third of the image
 ]
 
 
@@ -65,7 +67,7 @@ def _tile_forms(OW, Cout):
 
 
 @pytest.mark.parametrize('k,stride,pad,mode,Cin,Cout,N,H,W', CASES)
-@pytest.mark.parametrize('pmode', [1, 2])
+@pytest.mark.parametrize('pmode', [1, 2, 3])
 @pytest.mark.parametrize('tile', ['auto', 'msub2', 'strips'])
 def test_persistent_fprop_and_dgrad(k, stride, pad, mode, Cin, Cout, N, H, W, pmode, tile):
     from cat_b200 import ops
@@ -152,7 +154,7 @@ def test_autotune_offers_the_persistent_variants():
     g0 = ops.Gemm(P.Geometry(2, 32, 32, 64, 0, 32, 32, 64, 0, pad_mode=P.PAD_ZERO), units, 64, DEV)
     g1 = ops.Gemm(P.Geometry(2, 32, 32, 64, 0, 32, 32, 64, 0, pad_mode=P.PAD_REFLECT), units, 64, DEV)
     assert {t[4] for t in g0.tilings} == {0, 2}
-    assert {t[4] for t in g1.tilings} == {0, 1}
+    assert {t[4] for t in g1.tilings} == {0, 1}      # (+ 3, TMA with the reflection fringe pass, under CATB_TMA_REFLECT=1)
 
 
 @pytest.mark.parametrize('k,stride,pad,Cin,Cout,N,H,W', [

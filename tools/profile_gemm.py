@@ -123,7 +123,7 @@ def run(name, iters, variants=False, tiling=None, timeline=False):
         rows = [('v1', timed(lambda: g.fprop(x, y, force_v1=True)))]
         for t in (g.tilings if g.halo is not None else []):
             g._use_tiling(t)
-            rows.append((f'{("v2", "v3-cpasync", "v3-tma")[t[4]]} TW{t[0]} m{t[1]} b{t[2].b_budget // 1024}K', timed(lambda: g.fprop(x, y))))
+            rows.append((f'{("v2", "v3-cpasync", "v3-tma", "v3-tma-reflect")[t[4]]} TW{t[0]} m{t[1]} b{t[2].b_budget // 1024}K', timed(lambda: g.fprop(x, y))))
         best = min(r[1] for r in rows)
         print(f'{name:6s} M={N * OH * OW} N={Cout} K={Cin * k * k} n_tile {g.n_tile}  HBM floor {hbm_us:6.1f} us  best {best * 1e3:7.1f} us '
               f'({flops / best / 1e9:6.1f} TF/s, {hbm_us / (best * 1e3) * 100:4.1f}% of the HBM floor rate)')
