@@ -40,6 +40,7 @@ struct PersistParams {
   int tiles_per_image, tiles_x, tiles_total, a_bufs, b_stages, tmem_cols, acc_cols, n_store, halo_bytes, tab_bytes;
   int use_tma, plane_rows, plane_bytes;   // TMA mode: frame rows per plane box, bytes per plane (1024-aligned)
   int patch;                              // TMA mode on a reflection-padded conv: warps 2-3 mirror the out-of-image fringe
+  int b_stationary;                       // every weight tile of the GEMM has its own stage and is loaded ONCE per CTA
   uint32_t idesc;
   catb_epilogue_stats st;                 // st.sums == nullptr: no fused statistics
 };
@@ -252,13 +253,13 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
               if (kmax > 2) umma_bf16_lh(t_s, a_s + 4, hi, b_lo + 4, hi, idesc, 1u);
               if (kmax > 3) umma_bf16_lh(t_s, a_s + 6, hi, b_lo + 6, hi, idesc, 1u);
             }
-            umma_commit(&b_empty[st]);
+            if (!p.b_stationary) umma_commit(&b_empty[st]);
           }
           __syncwarp();
           acc = 1u;
           if (++st == static_cast<uint32_t>(p.b_stages)) {
             st = 0;
-            phb ^= 1u;
+            if (!p.b_stationary) phb ^= 1u;   // stationary tiles: every later wait on the completed phase 0 passes at once
             b_lo = b_lo0;
           } else {
             b_lo += b_step;
@@ -279,7 +280,14 @@ igemm_halo_persist_kernel(const __grid_constant__ PersistParams p, const __grid_
     }
   } else if (warp == 5) {
     // ---------------------------------------------------------------- weight loader
-    if (lane == 0) {
+    if (lane == 0 && p.b_stationary) {
+      // the whole weight matrix (one N tile, <= kPMaxBStages steps) fits: it is fetched once and stays for every tile of
+      // this CTA -- a short-K GEMM otherwise re-streams more weight bytes than activation bytes per tile
+      for (int s = 0; s < h.n_steps; ++s) {
+        mbar_arrive_expect_tx(&b_full[s], b_bytes);
+        bulk_g2s(b_base + static_cast<size_t>(s) * b_bytes, p.wpk + static_cast<size_t>(s) * b_bytes, b_bytes, &b_full[s]);
+      }
+    } else if (lane == 0) {
       uint32_t sg = 0;
       for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         const int tile_n = tile / p.tiles_x;
@@ -428,11 +436,16 @@ static int persist_table_bytes(int n_steps, int n_chunks) {
   return (((n_steps * 4 + 15) & ~15) + n_chunks * 16 + 1023) / 1024 * 1024;
 }
 
-static int persist_plane_rows(int Lh, int Wf) { return (Wf - 1 + Lh + Wf - 1) / Wf; }
+// Frame rows a plane box must hold: the tile starts (m0 mod Wf) pixels into its first row, m0 a multiple of the tile size,
+// so the largest offset is Wf - gcd(tile, Wf) (a strip as wide as a power of two needs no slack row at all).
+static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+static int persist_plane_rows(int Lh, int Wf, int tile_positions) {
+  return (Wf - gcd_int(tile_positions, Wf) + Lh + Wf - 1) / Wf;
+}
 
-static int persist_halo_bytes(int n_planes, int Lh, int Wf, int use_tma, int* plane_bytes) {
+static int persist_halo_bytes(int n_planes, int Lh, int Wf, int m_sub, int use_tma, int* plane_bytes) {
   if (use_tma) {
-    *plane_bytes = (persist_plane_rows(Lh, Wf) * Wf * 128 + 1023) / 1024 * 1024;
+    *plane_bytes = (persist_plane_rows(Lh, Wf, 128 * m_sub) * Wf * 128 + 1023) / 1024 * 1024;
     return n_planes * *plane_bytes;
   }
   *plane_bytes = Lh * 128;
@@ -440,7 +453,7 @@ static int persist_halo_bytes(int n_planes, int Lh, int Wf, int use_tma, int* pl
 }
 
 // Shared-memory plan: 0 and a_bufs / b_stages / total bytes, or -1 when it does not fit.
-static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int budget, int n_chunks, int* a_bufs, int* b_stages,
+static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int budget, int n_steps, int* a_bufs, int* b_stages,
                              size_t* total) {
   const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kPHeader - tab_bytes - kPStageBytes - kPStatBytes;
   // weight ring: >= ~64 KB in flight (bulk-copy latency), or the caller's smaller budget (thin GEMMs: more CTAs per SM)
@@ -464,9 +477,10 @@ static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int bud
     ab = want_a;
   }
   int bs = (limit - ab * halo_bytes) / b_bytes;
+  // a stage per weight tile when the whole matrix fits (the launch then keeps it resident if the GEMM has one N tile)
+  if (budget == 0 && n_steps <= kPMaxBStages && bs >= n_steps && n_steps >= 2 && n_steps * b_bytes <= 112 * 1024) want_b = n_steps;
   if (bs > want_b) bs = want_b;
   if (bs < 2) return -1;
-  (void)n_chunks;
   *a_bufs = ab;
   *b_stages = bs;
   *total = 1024 + kPHeader + tab_bytes + static_cast<size_t>(ab) * halo_bytes + static_cast<size_t>(bs) * b_bytes + kPStageBytes +
@@ -477,11 +491,11 @@ static int persist_smem_plan(int halo_bytes, int b_bytes, int tab_bytes, int bud
 extern "C" int catb_igemm_halo_persist_fits(int n_planes, int Lh, int Wf, int mul, int n_tile, int m_sub, int n_steps, int n_chunks,
                                             int b_budget, int use_tma) {
   if (2 * m_sub * n_tile > 512) return 0;
-  if (use_tma && (Wf * mul > 256 || persist_plane_rows(Lh, Wf) * mul > 256)) return 0;
+  if (use_tma && (Wf * mul > 256 || persist_plane_rows(Lh, Wf, 128 * m_sub) * mul > 256)) return 0;
   int plane_bytes, ab, bs;
   size_t total;
-  const int halo_bytes = persist_halo_bytes(n_planes, Lh, Wf, use_tma, &plane_bytes);
-  return persist_smem_plan(halo_bytes, n_tile * 128, persist_table_bytes(n_steps, n_chunks), b_budget, n_chunks, &ab, &bs, &total) == 0
+  const int halo_bytes = persist_halo_bytes(n_planes, Lh, Wf, m_sub, use_tma, &plane_bytes);
+  return persist_smem_plan(halo_bytes, n_tile * 128, persist_table_bytes(n_steps, n_chunks), b_budget, n_steps, &ab, &bs, &total) == 0
              ? 1 : 0;
 }
 
@@ -516,11 +530,11 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
   }
   p.use_tma = use_tma ? 1 : 0;
   p.patch = use_tma == 2 ? 1 : 0;
-  p.plane_rows = persist_plane_rows(h->Lh, h->Wf);
-  p.halo_bytes = persist_halo_bytes(h->n_planes, h->Lh, h->Wf, p.use_tma, &p.plane_bytes);
+  p.plane_rows = persist_plane_rows(h->Lh, h->Wf, 128 * h->m_sub);
+  p.halo_bytes = persist_halo_bytes(h->n_planes, h->Lh, h->Wf, h->m_sub, p.use_tma, &p.plane_bytes);
   p.tab_bytes = persist_table_bytes(h->n_steps, h->n_chunks);
   size_t smem = 0;
-  CATB_REQUIRE(persist_smem_plan(p.halo_bytes, d->n_tile * 128, p.tab_bytes, h->b_budget, h->n_chunks, &p.a_bufs, &p.b_stages,
+  CATB_REQUIRE(persist_smem_plan(p.halo_bytes, d->n_tile * 128, p.tab_bytes, h->b_budget, h->n_steps, &p.a_bufs, &p.b_stages,
                                  &smem) == 0,
                "halo tile (%d bytes) does not fit in shared memory", p.halo_bytes);
   CUtensorMap tmap;
@@ -533,6 +547,7 @@ extern "C" int catb_igemm_halo_fprop_persist(const catb_igemm_desc* d, const cat
     // NHWC activation as a 4-D tensor (C, W, H, N), channels beyond the GEMM's own slice out of bounds (-> zero)
     if (int e = encode_nhwc_tile_map(&tmap, p.x + d->x_coff, c_visible, d->W, d->H, d->N, d->ldx, h->Wf, p.plane_rows, h->mul)) return e;
   }
+  p.b_stationary = (p.b_stages == h->n_steps && (d->n_rows + d->n_tile - 1) / d->n_tile == 1) ? 1 : 0;
   const int positions = d->OHs * h->Wf;
   p.tiles_per_image = (positions + 128 * h->m_sub - 1) / (128 * h->m_sub);
   p.tiles_x = p.tiles_per_image * h->n_strips * d->N;

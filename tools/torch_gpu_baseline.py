@@ -1,6 +1,6 @@
 """Context number: the REFERENCE's own InceptionDistiller.optimize_parameters (oracle/_ref, stock
 PyTorch modules -> cuDNN / cuBLAS kernels) timed on the same B200 at the benchmark configuration, in fp32 (TF32 convs
-allowed) and under bf16 autocast with channels_last, eager.  This is "stock PyTorch 2.x + cuDNN on the same GPU", the bar
+allowed) and under bf16 autocast, eager (the reference's `.view` calls rule out channels_last).  This is "stock PyTorch 2.x + cuDNN on the same GPU", the bar
 SURVEY.md section 2b names; it is not part of bench.py's contract (the reference arm there is the CPU path).
 
     python tools/torch_gpu_baseline.py [--workload pix2pix_5p6B] [--batch 16] [--steps 10] > profiles/r02_torch_gpu_baseline.json
@@ -10,6 +10,7 @@ import contextlib
 import json
 import os
 import sys
+import time
 
 import torch
 import torch.nn as nn
@@ -32,7 +33,7 @@ def main():
     dev = torch.device('cuda:0')
     out = {'workload': a.workload, 'batch': a.batch, 'height': a.height, 'width': a.width, 'gpu': torch.cuda.get_device_name(0),
            'torch': torch.__version__, 'cudnn': torch.backends.cudnn.version(), 'modes': {}}
-    for mode in ('fp32_tf32', 'bf16_autocast_channels_last'):
+    for mode in ('fp32_tf32', 'bf16_autocast'):
         with contextlib.redirect_stdout(sys.stderr):
             from oracle.make_bench_arch import CONFIGS
             from oracle.ref_harness import build_reference_distiller
@@ -41,8 +42,6 @@ def main():
         for name, v in list(vars(model).items()):
             if isinstance(v, nn.Module):
                 v.to(dev)
-                if mode != 'fp32_tf32':
-                    v.to(memory_format=torch.channels_last)
         for v in vars(model).values():      # module lists (the 1x1 adaptors netAs carry the device the KA terms are keyed by)
             if isinstance(v, (list, tuple)):
                 for m in v:
@@ -53,8 +52,6 @@ def main():
         torch.backends.cudnn.allow_tf32 = True
         torch.backends.cuda.matmul.allow_tf32 = True
         xa, xb = WL.synthetic_batch(a.batch, a.height, a.width, 233)
-        if mode != 'fp32_tf32':
-            xa, xb = xa.contiguous(memory_format=torch.channels_last), xb.contiguous(memory_format=torch.channels_last)
         ctx = (lambda: torch.autocast('cuda', dtype=torch.bfloat16)) if mode != 'fp32_tf32' else contextlib.nullcontext
 
         def one():
@@ -65,13 +62,11 @@ def main():
             for _ in range(a.warmup):
                 one()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            t0 = time.perf_counter()
             for _ in range(a.steps):
                 one()
-            e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.steps
+            ms = (time.perf_counter() - t0) * 1e3 / a.steps
             out['modes'][mode] = {'ms_per_step': ms, 'images_per_s': a.batch / (ms * 1e-3),
                                   'note': 'host inputs copied to the device inside the timed loop (set_input), eager'}
         except Exception as e:      # noqa: BLE001 -- a context number: report why a mode does not run
