@@ -67,7 +67,10 @@ class DistillStep:
         self._graphs = None
         self.use_cuda_graph = use_cuda_graph
         # data parallel: the discriminator's gradient slices are all-reduced layer by layer during its last backward pass
-        self.early_reduce = world_size > 1 and os.environ.get('CATB_EARLY_REDUCE', '1') != '0'
+        # (opt-in, CATB_EARLY_REDUCE=1: exercised over gloo on CPU only -- the one 8-GPU session of round 2 that would have
+        # timed it was lost; the default keeps round 1's two all-reduces between the graph segments,
+        # measured at 0.990 weak-scaling efficiency on 8 B200)
+        self.early_reduce = world_size > 1 and os.environ.get('CATB_EARLY_REDUCE', '0') == '1'
         self._reducer = parallel.LayerwiseReducer(world_size)
         self.overlap_teacher = os.environ.get('CATB_NO_OVERLAP', '0') != '1'
         self._side = None
@@ -157,7 +160,7 @@ class DistillStep:
         D.backward(self.dpred, param_grads=True, input_grad=False)
         D.forward(real)
         ops.gan_loss(D.pred, D.pred_n, 8, hp['gan_mode'], True, True, 0.5, self.losses[1:2], self.dpred)
-        if self.early_reduce:       # the gradients are final layer by layer in this (second) pass
+        if self.early_reduce and self.world_size > 1:       # the gradients are final layer by layer in this (second) pass
             D.backward(self.dpred, param_grads=True, input_grad=False, grads_final_hook=self._reducer.reduce_async)
             self._reducer.join()
         else:
@@ -236,7 +239,7 @@ class DistillStep:
             self._part3()
 
     def _allreduce(self, net):
-        if net is self.D and self.early_reduce:
+        if net is self.D and self.early_reduce and self.world_size > 1:
             return                      # already reduced layer by layer inside the D phase
         parallel.reduce_gradients(net.arena.g, self.world_size)
         if net is self.S and self.A is not None:

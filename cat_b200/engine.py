@@ -82,11 +82,24 @@ class Arena:
         o1, _, L1, _ = self.entries[last]
         return getattr(self, which)[o0:o1 + L1]
 
-    def load_state_dict(self, sd, prefix=''):
+    def load_state_dict(self, sd, prefix='', strict=False):
+        """Copies the entries of `sd` that this arena holds.  A shape mismatch always raises (copy_ would broadcast, e.g. a
+        checkpoint of a differently pruned student); entries of the arena that `sd` lacks keep their current values and
+        are returned (strict=True raises instead) -- a network's parameters and buffers live in two arenas that are both
+        loaded from one state dict, so unexpected keys are normal and not reported."""
+        missing = []
         for name in self.entries:
             key = prefix + name
-            if key in sd:
-                self.view(name).copy_(sd[key].to(torch.float32))
+            if key not in sd:
+                missing.append(key)
+                continue
+            dst, src = self.view(name), sd[key]
+            if tuple(dst.shape) != tuple(src.shape) and dst.numel() != src.numel():
+                raise ValueError(f'{key}: checkpoint shape {tuple(src.shape)} does not match {tuple(dst.shape)}')
+            dst.copy_(src.to(torch.float32).reshape(dst.shape))
+        if strict and missing:
+            raise KeyError(f'state dict lacks {len(missing)} entries, e.g. {missing[:4]}')
+        return missing
 
     def state_dict(self, prefix=''):
         return OrderedDict((prefix + n, self.view(n).detach().clone().cpu()) for n in self.entries)

@@ -21,8 +21,8 @@ WORLD = 2
 PER_RANK = 2
 
 
-def _worker_inception(rank, port, path, out_dir):
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+def _worker_inception(rank, port, path, out_dir, early='0'):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), CATB_EARLY_REDUCE=early)
     dist.init_process_group('gloo', rank=rank, world_size=WORLD)
     torch.set_num_threads(2)
     from oracle.kernel_emu import emulated_kernels
@@ -48,11 +48,12 @@ def _worker_inception(rank, port, path, out_dir):
 
 
 @pytest.mark.timeout(900)
-def test_engine_two_ranks_inception(golden_dir, tmp_path):
+@pytest.mark.parametrize('early', ['0', '1'])      # the default two all-reduces / the layer-wise reduction inside the D backward pass
+def test_engine_two_ranks_inception(golden_dir, tmp_path, early):
     from test_data_parallel_cpu import _data_parallel_reference
     path = os.path.join(golden_dir, 'cyclegan_in_lsgan.pt')
-    port = 33500 + os.getpid() % 2000
-    mp.spawn(_worker_inception, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    port = 33500 + os.getpid() % 2000 + int(early)
+    mp.spawn(_worker_inception, args=(port, path, str(tmp_path), early), nprocs=WORLD, join=True)
     fix = torch.load(path, weights_only=False)
     S_ref, D_ref, _ = _data_parallel_reference(fix)       # fp64, single process, reference DataParallel semantics
     ranks = [torch.load(os.path.join(tmp_path, f'rank{r}.pt'), weights_only=False) for r in range(WORLD)]
