@@ -228,3 +228,56 @@ def test_engine_two_ranks_pix2pix_training(golden_dir, tmp_path):
         err = float((ranks[0]['G_g'][k] - g).abs().max())
         assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (k, err, float(g.abs().max()))
     assert n > 10
+
+
+def _worker_mirror(rank, port, path, out_dir):
+    """The user-facing distiller mirror under data parallelism: what bench.py's end-to-end loop drives at N > 1."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), WORLD_SIZE=str(WORLD), RANK=str(rank))
+    dist.init_process_group('gloo', rank=rank, world_size=WORLD)
+    torch.set_num_threads(2)
+    from oracle.kernel_emu import emulated_kernels
+    from test_data_parallel_cpu import _batch
+    from test_distiller_flow_emulated_cpu import _opt
+    fix = torch.load(path, weights_only=False)
+    a, b = _batch(fix)
+    sl = slice(rank * PER_RANK, (rank + 1) * PER_RANK)
+    with emulated_kernels(exact=True):
+        from cat_b200.distillers import create_distiller
+        opt = _opt(fix, os.path.join(out_dir, f'log{rank}'))
+        os.makedirs(opt.log_dir, exist_ok=True)
+        opt.world_size = WORLD
+        model = create_distiller(opt, verbose=False)
+        model.setup(opt, verbose=False)
+        model.netG_teacher.load_state_dict(fix['teacher_sd'])
+        model.netG_student.load_state_dict(fix['student_sd0'])
+        model.netD.load_state_dict(fix['D_sd0'])
+        model.netG_student.train()
+        losses = []
+        for it in range(2):
+            model.set_input({'A': a[sl].float(), 'B': b[sl].float(), 'A_paths': ['x'] * PER_RANK, 'B_paths': ['x'] * PER_RANK})
+            model.optimize_parameters(it)
+            losses.append(dict(model.get_current_losses()))
+        assert model.engine.world_size == WORLD
+        out = {'S': {k: v.clone() for k, v in model.netG_student.state_dict().items()},
+               'D': {k: v.clone() for k, v in model.netD.state_dict().items()}, 'losses': losses}
+    torch.save(out, os.path.join(out_dir, f'mirror{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_distiller_mirror_two_ranks(golden_dir, tmp_path):
+    """set_input -> optimize_parameters -> get_current_losses of the InceptionDistiller mirror on two ranks (gloo): no rank
+    enters a collective alone, and after two steps both ranks hold bit-identical student and discriminator weights (same
+    all-reduced gradients, same Adam) although their losses (different half batches) differ."""
+    path = os.path.join(golden_dir, 'pix2pix_bn_hinge.pt')
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_worker_mirror, args=(port, path, str(tmp_path)), nprocs=WORLD, join=True)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f'mirror{r}.pt'), weights_only=False) for r in range(WORLD))
+    for tag in ('S', 'D'):
+        for k, v in r0[tag].items():
+            if k.endswith('running_mean') or k.endswith('running_var') or k.endswith('num_batches_tracked'):
+                continue            # per-rank BatchNorm statistics (DESIGN.md section 7)
+            assert torch.equal(v, r1[tag][k]), (tag, k)
+    for L in r0['losses'] + r1['losses']:
+        assert all(v == v for v in L.values())
+    assert r0['losses'][0] != r1['losses'][0]
