@@ -281,3 +281,48 @@ def test_generator_input_gradient_exact(golden_dir, packx, monkeypatch):
         d_in = net.backward(dS)
         assert rel_l2(ops.nhwc_to_nchw(d_in, 3), x.grad) < 1e-4
         assert float(d_in.t[..., 3:].abs().max()) == 0.0          # padding channels of the gradient stay exactly zero
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('fusing', ['none', 'every_other'])
+def test_conv_norm_falls_back_to_the_statistics_pass(golden_dir, fusing, monkeypatch):
+    """engine.conv_norm: when no producing GEMM of a norm layer accumulates the statistics in its epilogue (gather-per-tap
+    kernel chosen by the autotune), or only some of them do (a layer fed by several GEMMs, e.g. the four phase GEMMs of a
+    transposed conv), the partial sums are discarded and catb_norm_stats runs -- same losses and gradients as the fused path."""
+    from oracle import cat_oracle as O
+    from oracle import kernel_emu
+    from oracle.kernel_emu import emulated_kernels
+    fix = torch.load(os.path.join(golden_dir, 'cyclegan_in_lsgan.pt'), weights_only=False)
+    step = fix['steps'][0]
+    B, _, H, W = step['real_A'].shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
+              D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
+              D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    ref = O.distill_step(st, step['real_A'], step['real_B'], fix['hp'])
+    orig, calls = kernel_emu._gemm_fprop, [0, 0]
+
+    def patched(self, x, y, bias=None, act=0, accumulate=False, y_is_f32=False, force_v1=False, stats=None):
+        calls[0] += 1
+        if stats is not None and (fusing == 'none' or calls[0] % 2):
+            stats = None            # this launch runs on a kernel that does not fuse the statistics
+            calls[1] += 1
+        return orig(self, x, y, bias=bias, act=act, accumulate=accumulate, y_is_f32=y_is_f32, force_v1=force_v1, stats=stats)
+    monkeypatch.setattr(kernel_emu, '_gemm_fprop', patched)
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], fix['hp'], B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(step['real_A'], step['real_B'])
+        eng.step()
+        L = eng.get_losses()
+        assert calls[1] > 0
+        for k_ref, k in (('loss_D_fake', 'D_fake'), ('loss_D_real', 'D_real'), ('loss_G_gan', 'G_gan'),
+                         ('loss_G_recon', 'G_recon'), ('loss_G_distill', 'G_distill')):
+            r = float(ref[k_ref])
+            assert abs(L[k] - r) <= 1e-5 * max(1.0, abs(r)), (k, L[k], r)
+        for tag, net, grads in (('S', eng.S, ref['S_grads']), ('D', eng.D, ref['D_grads'])):
+            scale = max(float(g.abs().max()) for g in grads.values())
+            for k, g in grads.items():
+                if net.arena.has(k):
+                    err = float((net.arena.view(k, 'g') - g).abs().max())
+                    assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err)
