@@ -326,3 +326,40 @@ def test_conv_norm_falls_back_to_the_statistics_pass(golden_dir, fusing, monkeyp
                 if net.arena.has(k):
                     err = float((net.arena.view(k, 'g') - g).abs().max())
                     assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (tag, k, err)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('only', ['gan', 'recon', 'distill'])
+def test_student_gradient_per_loss_component_exact(golden_dir, only):
+    """Each term of backward_G alone (the other two weights set to zero): with lambda_recon = 100 the reconstruction term
+    dominates the summed student gradient, so a mis-scaled GAN or KA term could hide inside the tolerance of the summed
+    check; here every term must reproduce the oracle's gradient on its own (exact kernel emulation, fp32 oracle)."""
+    from oracle import cat_oracle as O
+    from oracle.kernel_emu import emulated_kernels
+    fix = torch.load(os.path.join(golden_dir, 'pix2pix_bn_hinge.pt'), weights_only=False)
+    hp = dict(fix['hp'])
+    for k in ('gan', 'recon', 'distill'):
+        if k != only:
+            hp['lambda_' + k] = 0.0
+    step = fix['steps'][0]
+    B, _, H, W = step['real_A'].shape
+    st = dict(teacher_sd=O.clone_sd(fix['teacher_sd']), student_sd=O.clone_sd(fix['student_sd0']),
+              D_sd=O.clone_sd(fix['D_sd0']), teacher_arch=fix['teacher_arch'], student_arch=fix['student_arch'],
+              D_arch=fix['D_arch'], adam_G={}, adam_D={})
+    ref = O.distill_step(st, step['real_A'], step['real_B'], hp)
+    with emulated_kernels(exact=True):
+        from cat_b200.distill_engine import DistillStep
+        eng = DistillStep(fix['teacher_arch'], fix['student_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['teacher_sd'], fix['student_sd0'], fix['D_sd0'])
+        eng.set_input(step['real_A'], step['real_B'])
+        eng.step()
+        grads = ref['S_grads']
+        scale = max(float(g.abs().max()) for g in grads.values())
+        assert scale > 0
+        n = 0
+        for k, g in grads.items():
+            if eng.S.arena.has(k):
+                err = float((eng.S.arena.view(k, 'g') - g).abs().max())
+                assert err <= 2e-3 * float(g.abs().max()) + 2e-5 * scale, (only, k, err, float(g.abs().max()))
+                n += 1
+        assert n > 20

@@ -192,3 +192,35 @@ def test_cyclegan_without_identity_term_and_without_pool_exact(golden_dir):
             assert abs(v - r) <= 1e-5 * max(1.0, abs(r)), (k, v, r)
         for tag, net in (('G_A', eng.G_A), ('G_B', eng.G_B), ('D_A', eng.D_A), ('D_B', eng.D_B)):
             _check_grads(net, ref[tag + '_grads'], tag)
+
+
+@pytest.mark.timeout(600)
+def test_cyclegan_gan_terms_alone_exact(golden_dir):
+    """--lambda_A 0 --lambda_B 0: only the two GAN terms of backward_G remain (cycle and identity terms carry the weights
+    lambda_A / lambda_B, cycle_gan_model.py:262-289).  With the default weights (10) the cycle terms dominate the generators'
+    gradients; here the GAN path through the frozen discriminators must reproduce the oracle on its own."""
+    from oracle import train_oracle as TO
+    from oracle.cat_oracle import clone_sd
+    from oracle.kernel_emu import emulated_kernels
+    fix = _load(golden_dir, 'train_cyclegan_in_lsgan')
+    hp = dict(fix['hp'], lambda_A=0.0, lambda_B=0.0, pool_size=0)
+    s = fix['steps'][0]
+    B, _, H, W = s['real_A'].shape
+    st = dict(G_A_sd=clone_sd(fix['G_A_sd0']), G_B_sd=clone_sd(fix['G_B_sd0']), D_A_sd=clone_sd(fix['D_A_sd0']),
+              D_B_sd=clone_sd(fix['D_B_sd0']), G_arch=fix['G_arch'], D_arch=fix['D_arch'], adam_G={}, adam_D={},
+              pool_A=TO.ImagePool(0), pool_B=TO.ImagePool(0))
+    ref = TO.cyclegan_train_step(st, s['real_A'], s['real_B'], hp)
+    with emulated_kernels(exact=True):
+        from cat_b200.train_engine import CycleGANTrainStep
+        eng = CycleGANTrainStep(fix['G_arch'], fix['D_arch'], hp, B, H, W, device='cpu')
+        eng.load(fix['G_A_sd0'], fix['G_B_sd0'], fix['D_A_sd0'], fix['D_B_sd0'])
+        eng.set_input(s['real_A'], s['real_B'])
+        eng.step()
+        L = eng.get_losses()
+        for k in ('G_cycle_A', 'G_cycle_B', 'G_idt_A', 'G_idt_B'):
+            assert L[k] == 0.0
+        for k, v in L.items():
+            r = float(ref['loss_' + k])
+            assert abs(v - r) <= 1e-5 * max(1.0, abs(r)), (k, v, r)
+        for tag, net in (('G_A', eng.G_A), ('G_B', eng.G_B), ('D_A', eng.D_A), ('D_B', eng.D_B)):
+            _check_grads(net, ref[tag + '_grads'], tag)
