@@ -757,13 +757,15 @@ def run_job(args, arch, eng, host, h2d_bytes, macs, B, H, W, dev, world, rank, l
         # DRAM traffic of the same kernel family from the committed ncu launch list of this workload
         # (profiles/traffic_<workload>.json, tools/summarize_launches.py): bytes per launch, averaged over the step
         traffic, traffic_src = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, 'profiles', f'traffic_{args.workload}.json')))
-            ks = [v for k, v in tj['kernels'].items() if k in ('igemm_halo_fprop_kernel', 'igemm_halo_persist_kernel', 'igemm_fprop_kernel')]
-            traffic = sum(v['dram_read'] + v['dram_write'] for v in ks) / max(1, sum(v['launches'] for v in ks))
-            traffic_src = f'profiles/traffic_{args.workload}.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)'
-        except (OSError, KeyError, ValueError):
-            pass
+        for tname in (f'r02_traffic_{args.workload}.json', f'traffic_{args.workload}.json'):     # newest capture first
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', tname)))
+                ks = [v for k, v in tj['kernels'].items() if k in ('igemm_halo_fprop_kernel', 'igemm_halo_persist_kernel', 'igemm_fprop_kernel')]
+                traffic = sum(v['dram_read'] + v['dram_write'] for v in ks) / max(1, sum(v['launches'] for v in ks))
+                traffic_src = f'profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch of the family)'
+                break
+            except (OSError, KeyError, ValueError):
+                continue
         roof = {'bound': 'tensor', 'kernel': 'igemm_halo_persist_kernel + igemm_halo_fprop_kernel + igemm_fprop_kernel (tcgen05 implicit-GEMM conv/dgrad)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                 'traffic_source': traffic_src, 'algorithmic_flop_per_launch': fl / n,

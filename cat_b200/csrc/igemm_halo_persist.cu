@@ -7,9 +7,14 @@
 //   * activation halo ring (a_full / a_empty):  filled either by ONE thread with cp.async.bulk.tensor (TMA, 4-D tiled
 //     tensor map over the NHWC activation, SWIZZLE_128B, out-of-bounds = zero padding, traversal stride 2 for the
 //     parity planes of stride-2 convs)  or, for reflection-padded convs, by the 128 cp.async producer threads of v2;
-//   * weight ring (b_full / b_empty): 1-D bulk copies of the pre-swizzled weight tiles, as in v2;
+//     (use_tma = 2, opt-in: the boxes of a reflection-padded conv land with zeros outside the image and warps 2-3 mirror
+//     exactly those halo rows before the chunk is released -- parity-green, but slower than the cp.async producers);
+//   * weight ring (b_full / b_empty): 1-D bulk copies of the pre-swizzled weight tiles, as in v2 -- or, when the whole
+//     weight matrix of a one-N-tile GEMM fits, one stage per tile loaded ONCE per CTA (b_stationary);
 //   * TWO accumulator stages in tensor memory (acc_full / acc_empty): the four epilogue warps drain tile i
-//     (tcgen05.ld -> bias / activation -> staged coalesced bf16 stores) while the MMA warp already works on tile i+1.
+//     (tcgen05.ld -> bias / activation -> staged coalesced bf16 stores, optionally the per-channel sum / sum of squares
+//     of the stored values for the norm layer behind the conv: catb_epilogue_stats) while the MMA warp already works on
+//     tile i+1.
 // Shared-memory layout of a TMA-filled plane: the box is R = ceil((Wf - 1 + Lh) / Wf) full frame rows of Wf pixels
 // (128 bytes each), i.e. the same "pitch space" as v2 with the tile starting (m0 mod Wf) pixels into it, so a filter
 // tap is still a shifted shared-memory descriptor.  Each plane starts on a 1024-byte boundary, which makes the TMA
