@@ -53,3 +53,27 @@ def test_every_benchmark_gemm_has_its_kernels(no_cuda_check, name, H, W):
         tma_w.append(bool(L.gw.w_tma_ok))
     assert tma_w[-1] and sum(tma_w) >= len(tma_w) - 2, tma_w
     assert D.layers[-1].tap            # one output channel: tap-split form
+
+
+@pytest.mark.timeout(600)
+def test_every_spade_benchmark_gemm_has_its_kernels(no_cuda_check):
+    """configs[3]: the GauGAN / SPADE student and teacher at 512 x 512 (every conv of the SPADE path is zero padded, so every
+    halo GEMM must offer the TMA-staged persistent kernel)."""
+    from cat_b200 import workload as WL
+    from cat_b200.ops import Act
+    from cat_b200.spade_engine import SpadeGenNet
+    sarch = WL.spade_arch_for(WL.load_arch('gaugan_5p6B'), 512, 512)
+    seg = Act.empty(1, 512, 512, sarch['student_arch']['semantic_nc'], 'cpu', zero=True)
+    for tag, training in (('student_arch', True), ('teacher_arch', False)):
+        net = SpadeGenNet(sarch[tag], seg, 'cpu', training=training, need_grad=training)
+        gemms = net.fprop_gemms + net.bwd_gemms
+        assert len(gemms) > 50
+        n_halo = 0
+        for g in gemms:
+            if g.halo is None:
+                continue
+            n_halo += 1
+            modes = {t[4] for t in g.tilings}
+            assert 2 in modes or 1 in modes, (tag, g.n_rows, g.n_units, modes)
+            assert g.geo.pad_mode != _C.PAD_REFLECT
+        assert n_halo >= 0.9 * len(gemms), (tag, n_halo, len(gemms))
