@@ -32,7 +32,7 @@ int init_halo_persist_attributes();
 
 }  // namespace catb
 
-extern "C" const char* catb_version(void) { return "catb200 0.1 (sm_100a)"; }
+extern "C" const char* catb_version(void) { return "catb200 0.2 (sm_100a)"; }
 
 extern "C" const char* catb_last_error_string(void) { return catb::g_err; }
 
